@@ -1,0 +1,447 @@
+// oracle/ref_harness.cc -- TEST INFRASTRUCTURE, not product code.
+//
+// A thin extern "C" harness that is compiled TOGETHER WITH THE UNMODIFIED
+// REFERENCE SOURCES (camera.cc voxel_octree.cc tribox2.cc raytri.cc
+// tiny_obj_loader.cc, see oracle/build_ref.sh) into oracle/_ref/libvrt_ref.so.
+// It contains no algorithm of its own: every result it returns is produced by
+// the reference's functions
+//   gi::ray_march_init   voxel_octree.cc:67-75
+//   gi::ray_march        voxel_octree.cc:131-188
+//   Camera::gen_rays1/4  camera.cc:77-112
+//   render_mt            camera.h:41-68
+//   triBoxOverlap        tribox2.cc:112-186
+//   intersect_triangle3  raytri.cc:197-249
+// and is only re-shaped into flat arrays so that Python tests (ctypes) and
+// bench.py's `--impl reference` / `cpu_baseline` legs can read it.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's reference legs may load
+// the library built from this file.
+
+#include "voxel_octree.h"
+#include "camera.h"
+
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+struct LeafInfo {
+        uint32_t x, y, z;  // cell coordinates at level max_depth-1
+        uint32_t level;    // depth of the node below the root (root = 0)
+};
+
+struct RefScene {
+        tinyobj::material_t mtl{};
+        std::vector<gi::Triangle> tris;
+        std::vector<gi::VoxelBase*> ptrs;
+        std::unique_ptr<gi::VoxelOctree> root;
+        int max_depth = 0;
+        double build_seconds = 0;
+        // filled by index()
+        std::unordered_map<const gi::VoxelOctree*, LeafInfo> leaf_of;
+        std::unordered_map<const gi::VoxelBase*, uint32_t> tri_of;
+        uint64_t n_nodes = 0, n_interior = 0, n_nonempty_leaves = 0, n_refs = 0;
+        uint32_t max_leaf_refs = 0;
+};
+
+bool node_is_leaf(const gi::VoxelOctree* n)
+{
+        return n->children[0] == nullptr;
+}
+
+void index_walk(RefScene* s, const gi::VoxelOctree* n, uint32_t x, uint32_t y,
+                uint32_t z, uint32_t level)
+{
+        s->n_nodes++;
+        if (node_is_leaf(n)) {
+                if (!n->voxels.empty()) {
+                        s->n_nonempty_leaves++;
+                        s->n_refs += n->voxels.size();
+                        if (n->voxels.size() > s->max_leaf_refs)
+                                s->max_leaf_refs = (uint32_t)n->voxels.size();
+                        s->leaf_of[n] = LeafInfo{ x, y, z, level };
+                }
+                return;
+        }
+        s->n_interior++;
+        for (int i = 0; i < 8; ++i) {
+                // child i: x is bit 2, y is bit 1, z is bit 0 (voxel_octree.cc:33)
+                index_walk(s, n->children[i].get(), 2 * x + ((i >> 2) & 1),
+                           2 * y + ((i >> 1) & 1), 2 * z + (i & 1), level + 1);
+        }
+}
+
+struct HitRec {
+        const gi::VoxelOctree* leaf;
+        const gi::VoxelBase* voxel;
+        ISect isect;
+        uint8_t hit;
+};
+
+void store_hit(const RefScene* s, const HitRec& h, uint8_t* hit, uint32_t* cell,
+               uint32_t* tri, float* pos, float* nrm, uint64_t i)
+{
+        hit[i] = h.hit;
+        if (!h.hit) {
+                if (cell)
+                        cell[3 * i] = cell[3 * i + 1] = cell[3 * i + 2] = 0xffffffffu;
+                if (tri)
+                        tri[i] = 0xffffffffu;
+                if (pos)
+                        pos[3 * i] = pos[3 * i + 1] = pos[3 * i + 2] = 0.f;
+                if (nrm)
+                        nrm[3 * i] = nrm[3 * i + 1] = nrm[3 * i + 2] = 0.f;
+                return;
+        }
+        if (cell) {
+                auto it = s->leaf_of.find(h.leaf);
+                if (it == s->leaf_of.end()) {
+                        cell[3 * i] = cell[3 * i + 1] = cell[3 * i + 2] = 0xfffffffeu;
+                } else {
+                        cell[3 * i] = it->second.x;
+                        cell[3 * i + 1] = it->second.y;
+                        cell[3 * i + 2] = it->second.z;
+                }
+        }
+        if (tri)
+                tri[i] = s->tri_of.at(h.voxel);
+        if (pos) {
+                pos[3 * i] = h.isect.hit.x;
+                pos[3 * i + 1] = h.isect.hit.y;
+                pos[3 * i + 2] = h.isect.hit.z;
+        }
+        if (nrm) {
+                nrm[3 * i] = h.isect.normal.x;
+                nrm[3 * i + 1] = h.isect.normal.y;
+                nrm[3 * i + 2] = h.isect.normal.z;
+        }
+}
+
+Camera make_camera(const float* cam /* fov, eye3, spot3, up3 */)
+{
+        return Camera{ cam[0],
+                       Vec3{ cam[1], cam[2], cam[3] },
+                       Vec3{ cam[4], cam[5], cam[6] },
+                       Vec3{ cam[7], cam[8], cam[9] } };
+}
+
+}  // namespace
+
+extern "C" {
+
+// tri_xyz: [T][3][3] float; tri_nrm: [T][3][3] float or NULL (then the
+// geometric normal of each triangle is fed to the reference's ctor).
+void* ref_scene_create(const float* tri_xyz, const float* tri_nrm, uint32_t T)
+{
+        auto* s = new RefScene;
+        s->tris.reserve(T);
+        for (uint32_t t = 0; t < T; ++t) {
+                const float* p = tri_xyz + 9 * (size_t)t;
+                Vec3 p0{ p[0], p[1], p[2] }, p1{ p[3], p[4], p[5] },
+                        p2{ p[6], p[7], p[8] };
+                Vec3 n0, n1, n2;
+                if (tri_nrm) {
+                        const float* n = tri_nrm + 9 * (size_t)t;
+                        n0 = Vec3{ n[0], n[1], n[2] };
+                        n1 = Vec3{ n[3], n[4], n[5] };
+                        n2 = Vec3{ n[6], n[7], n[8] };
+                } else {
+                        n0 = n1 = n2 = jql::cross(p1 - p0, p2 - p0);
+                }
+                s->tris.emplace_back(p0, p1, p2, n0, n1, n2, Vec2{}, Vec2{}, Vec2{},
+                                     &s->mtl);
+        }
+        s->ptrs.reserve(T);
+        for (auto& tri : s->tris)
+                s->ptrs.push_back(&tri);
+        for (uint32_t t = 0; t < T; ++t)
+                s->tri_of[s->ptrs[t]] = t;
+        return s;
+}
+
+void ref_scene_free(void* h)
+{
+        delete static_cast<RefScene*>(h);
+}
+
+// gi::ray_march_init, timed.  Returns seconds of the reference call alone.
+double ref_scene_build(void* h, int max_depth)
+{
+        auto* s = static_cast<RefScene*>(h);
+        s->root = std::make_unique<gi::VoxelOctree>();
+        s->max_depth = max_depth;
+        auto t0 = std::chrono::steady_clock::now();
+        gi::ray_march_init(s->root.get(), s->ptrs, max_depth);
+        auto t1 = std::chrono::steady_clock::now();
+        s->build_seconds = std::chrono::duration<double>(t1 - t0).count();
+        s->leaf_of.clear();
+        s->n_nodes = s->n_interior = s->n_nonempty_leaves = s->n_refs = 0;
+        s->max_leaf_refs = 0;
+        index_walk(s, s->root.get(), 0, 0, 0, 0);
+        return s->build_seconds;
+}
+
+// out[0..5] = counts: nodes, interior, non-empty leaves, tri refs, max refs per leaf, max_depth
+void ref_scene_stats(void* h, uint64_t* out)
+{
+        auto* s = static_cast<RefScene*>(h);
+        out[0] = s->n_nodes;
+        out[1] = s->n_interior;
+        out[2] = s->n_nonempty_leaves;
+        out[3] = s->n_refs;
+        out[4] = s->max_leaf_refs;
+        out[5] = (uint64_t)s->max_depth;
+}
+
+void ref_scene_root_aabb(void* h, float* out6)
+{
+        auto* s = static_cast<RefScene*>(h);
+        out6[0] = s->root->aabb.min.x;
+        out6[1] = s->root->aabb.min.y;
+        out6[2] = s->root->aabb.min.z;
+        out6[3] = s->root->aabb.max.x;
+        out6[4] = s->root->aabb.max.y;
+        out6[5] = s->root->aabb.max.z;
+}
+
+namespace {
+void dump_walk(const RefScene* s, const gi::VoxelOctree* n, uint32_t x, uint32_t y,
+               uint32_t z, uint32_t level, uint32_t* cells, uint32_t* levels,
+               uint32_t* counts, uint32_t* refs, float* boxes, uint64_t* nl,
+               uint64_t* nr)
+{
+        if (node_is_leaf(n)) {
+                if (n->voxels.empty())
+                        return;
+                uint64_t l = (*nl)++;
+                cells[3 * l] = x;
+                cells[3 * l + 1] = y;
+                cells[3 * l + 2] = z;
+                if (levels)
+                        levels[l] = level;
+                counts[l] = (uint32_t)n->voxels.size();
+                if (boxes) {
+                        boxes[6 * l + 0] = n->aabb.min.x;
+                        boxes[6 * l + 1] = n->aabb.min.y;
+                        boxes[6 * l + 2] = n->aabb.min.z;
+                        boxes[6 * l + 3] = n->aabb.max.x;
+                        boxes[6 * l + 4] = n->aabb.max.y;
+                        boxes[6 * l + 5] = n->aabb.max.z;
+                }
+                for (auto* v : n->voxels)
+                        refs[(*nr)++] = s->tri_of.at(v);
+                return;
+        }
+        for (int i = 0; i < 8; ++i)
+                dump_walk(s, n->children[i].get(), 2 * x + ((i >> 2) & 1),
+                          2 * y + ((i >> 1) & 1), 2 * z + (i & 1), level + 1, cells,
+                          levels, counts, refs, boxes, nl, nr);
+}
+}  // namespace
+
+// Depth-first (child index order == Morton order) dump of every non-empty leaf:
+// cells[L][3], levels[L] (may be NULL), counts[L], refs[sum counts] in stored
+// order, boxes[L][6] (may be NULL) = the leaf AABBs exactly as the reference's
+// split() recurrence produced them.
+void ref_scene_dump_leaves(void* h, uint32_t* cells, uint32_t* levels,
+                           uint32_t* counts, uint32_t* refs, float* boxes)
+{
+        auto* s = static_cast<RefScene*>(h);
+        uint64_t nl = 0, nr = 0;
+        dump_walk(s, s->root.get(), 0, 0, 0, 0, cells, levels, counts, refs, boxes,
+                  &nl, &nr);
+}
+
+// gi::ray_march over an explicit ray batch.  rays: [R][8] = o3,d3,tmin,tmax,
+// copied VERBATIM into jql::Ray (no re-normalisation: the Ray ctor is bypassed
+// so that both sides see identical bits).
+void ref_trace_rays(void* h, const float* rays, uint64_t R, int nthreads,
+                    uint8_t* hit, uint32_t* cell, uint32_t* tri, float* pos,
+                    float* nrm)
+{
+        auto* s = static_cast<RefScene*>(h);
+        if (nthreads < 1)
+                nthreads = 1;
+        auto work = [&](uint64_t lo, uint64_t hi) {
+                for (uint64_t i = lo; i < hi; ++i) {
+                        const float* r = rays + 8 * i;
+                        jql::Ray ray;
+                        ray.o = Vec3{ r[0], r[1], r[2] };
+                        ray.d = Vec3{ r[3], r[4], r[5] };
+                        ray.tmin = r[6];
+                        ray.tmax = r[7];
+                        HitRec rec{};
+                        gi::VoxelOctree* leaf = nullptr;
+                        gi::VoxelBase* vox = nullptr;
+                        rec.hit = gi::ray_march(s->root.get(), ray, &leaf, &vox,
+                                                &rec.isect) ? 1 : 0;
+                        rec.leaf = leaf;
+                        rec.voxel = vox;
+                        store_hit(s, rec, hit, cell, tri, pos, nrm, i);
+                }
+        };
+        if (nthreads == 1) {
+                work(0, R);
+                return;
+        }
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t)
+                th.emplace_back(work, R * t / nthreads, R * (t + 1) / nthreads);
+        for (auto& t : th)
+                t.join();
+}
+
+// Camera::gen_rays1 / gen_rays4 for the pixel rectangle [x0,x1) x [y0,y1).
+// rays_out: [(y1-y0)][(x1-x0)][spp][8], row-major by pixel then sample.
+void ref_gen_rays(const float* cam10, float film_w, float film_h, int nx, int ny,
+                  int spp, int x0, int y0, int x1, int y1, float* rays_out)
+{
+        Camera cam = make_camera(cam10);
+        Film film(film_w, film_h, nx, ny);
+        const Film& f = film;
+        size_t k = 0;
+        for (int py = y0; py < y1; ++py)
+                for (int px = x0; px < x1; ++px) {
+                        auto rays = (spp == 4) ? cam.gen_rays4(f, px, py)
+                                               : cam.gen_rays1(f, px, py);
+                        for (auto& r : rays) {
+                                float* o = rays_out + 8 * k++;
+                                o[0] = r.o.x; o[1] = r.o.y; o[2] = r.o.z;
+                                o[3] = r.d.x; o[4] = r.d.y; o[5] = r.d.z;
+                                o[6] = r.tmin; o[7] = r.tmax;
+                        }
+                }
+}
+
+// The reference's own render loop: render_mt(&film, lambda) with the lambda
+// = gen_rays{1,4} + gi::ray_march that only records the hit (the CPU baseline
+// of SURVEY.md 8(d)).  Returns wall seconds of the render_mt call.  Outputs
+// (any may be NULL) are [ny][nx][spp] on a harness-owned y*nx+x layout.
+// NOTE render_mt only renders (nx/8*8) x (ny/8*8) pixels (camera.h:46).
+double ref_render_mt(void* h, const float* cam10, float film_w, float film_h,
+                     int nx, int ny, int spp, uint8_t* hit, uint32_t* cell,
+                     uint32_t* tri, float* pos, float* nrm, uint64_t* rays_traced)
+{
+        auto* s = static_cast<RefScene*>(h);
+        Camera cam = make_camera(cam10);
+        Film film_obj(film_w, film_h, nx, ny);
+        Film* film = &film_obj;
+        std::vector<HitRec> recs((size_t)nx * ny * spp);
+        gi::VoxelOctree* root = s->root.get();
+        HitRec* recp = recs.data();
+        auto t0 = std::chrono::steady_clock::now();
+        render_mt(film, [&cam, root, recp, spp](Film* f, int px, int py) {
+                auto rays = (spp == 4) ? cam.gen_rays4(*f, px, py)
+                                       : cam.gen_rays1(*f, px, py);
+                size_t base = ((size_t)py * f->nx + px) * spp;
+                for (size_t k = 0; k < rays.size(); ++k) {
+                        HitRec& rec = recp[base + k];
+                        gi::VoxelOctree* leaf = nullptr;
+                        gi::VoxelBase* vox = nullptr;
+                        rec.hit = gi::ray_march(root, rays[k], &leaf, &vox,
+                                                &rec.isect) ? 1 : 0;
+                        rec.leaf = leaf;
+                        rec.voxel = vox;
+                }
+        });
+        auto t1 = std::chrono::steady_clock::now();
+        if (rays_traced)
+                *rays_traced = (uint64_t)(nx / 8 * 8) * (ny / 8 * 8) * spp;
+        if (hit)
+                for (size_t i = 0; i < recs.size(); ++i)
+                        store_hit(s, recs[i], hit, cell, tri, pos, nrm, i);
+        return std::chrono::duration<double>(t1 - t0).count();
+}
+
+int ref_hardware_concurrency(void)
+{
+        return (int)std::thread::hardware_concurrency();
+}
+
+// Direct predicate access (known-answer tests).
+int ref_tribox(const float* center, const float* half, const float* tri9)
+{
+        float c[3] = { center[0], center[1], center[2] };
+        float hs[3] = { half[0], half[1], half[2] };
+        float tv[3][3];
+        std::memcpy(tv, tri9, sizeof tv);
+        return triBoxOverlap(c, hs, tv);
+}
+
+void ref_tribox_batch(const float* centers, const float* halves, const float* tris,
+                      uint64_t n, uint8_t* out)
+{
+        for (uint64_t i = 0; i < n; ++i)
+                out[i] = (uint8_t)ref_tribox(centers + 3 * i, halves + 3 * i,
+                                             tris + 9 * i);
+}
+
+// Triangle::is_overlap (voxel_octree.cc:486-492) on an explicit AABB.
+void ref_tri_overlap_aabb_batch(const float* aabbs6, const float* tris, uint64_t n,
+                                uint8_t* out)
+{
+        tinyobj::material_t mtl{};
+        for (uint64_t i = 0; i < n; ++i) {
+                const float* p = tris + 9 * i;
+                const float* b = aabbs6 + 6 * i;
+                Vec3 p0{ p[0], p[1], p[2] }, p1{ p[3], p[4], p[5] },
+                        p2{ p[6], p[7], p[8] };
+                Vec3 nn{ 0, 1, 0 };
+                gi::Triangle tri(p0, p1, p2, nn, nn, nn, Vec2{}, Vec2{}, Vec2{}, &mtl);
+                AABB3D box{ Vec3{ b[0], b[1], b[2] }, Vec3{ b[3], b[4], b[5] } };
+                out[i] = tri.is_overlap(box) ? 1 : 0;
+        }
+}
+
+// intersect_triangle3 on doubles: in [n][15] = o3,d3,v0,v1,v2 ; out [n][3]=t,u,v
+void ref_raytri_batch(const double* in, uint64_t n, uint8_t* res, double* tuv)
+{
+        for (uint64_t i = 0; i < n; ++i) {
+                double a[15];
+                std::memcpy(a, in + 15 * i, sizeof a);
+                double t = 0, u = 0, v = 0;
+                res[i] = (uint8_t)intersect_triangle3(a, a + 3, a + 6, a + 9, a + 12,
+                                                      &t, &u, &v);
+                tuv[3 * i] = t;
+                tuv[3 * i + 1] = u;
+                tuv[3 * i + 2] = v;
+        }
+}
+
+// AABB<Vec3>::isect(ray, nullptr) (graphics_math.h:1312-1332), batch.
+void ref_aabb_isect_batch(const float* aabbs6, const float* rays8, uint64_t n,
+                          uint8_t* out)
+{
+        for (uint64_t i = 0; i < n; ++i) {
+                const float* b = aabbs6 + 6 * i;
+                const float* r = rays8 + 8 * i;
+                AABB3D box{ Vec3{ b[0], b[1], b[2] }, Vec3{ b[3], b[4], b[5] } };
+                jql::Ray ray;
+                ray.o = Vec3{ r[0], r[1], r[2] };
+                ray.d = Vec3{ r[3], r[4], r[5] };
+                ray.tmin = r[6];
+                ray.tmax = r[7];
+                out[i] = box.isect(ray, nullptr) ? 1 : 0;
+        }
+}
+
+// Camera ctor (camera.cc:65-75): returns the 16 floats of C_ (column-major,
+// C_[col][row]) by probing the camera with unit vectors through gen_rays-free
+// public API is impossible (C_ is private), so we rebuild it with the same jql
+// calls the ctor uses.
+void ref_camera_matrix(const float* cam10, float* out16)
+{
+        Vec3 eye{ cam10[1], cam10[2], cam10[3] };
+        Vec3 spot{ cam10[4], cam10[5], cam10[6] };
+        Vec3 up{ cam10[7], cam10[8], cam10[9] };
+        const Vec3 forward_ = normalize(spot - eye);
+        const Vec3 s = normalize(cross(forward_, up));
+        const Vec3 up_ = normalize(cross(s, forward_));
+        Mat4 C = jql::affine_transform(Mat3{ s, up_, -forward_ }, eye);
+        std::memcpy(out16, jql::begin(C), 16 * sizeof(float));
+}
+
+}  // extern "C"

@@ -1,0 +1,782 @@
+/* oracle/vrt_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement (plain C99, scalar, FMA-free: compile with
+ * -ffp-contract=off) of the reference's hot path, written from the behaviour
+ * of jqly/VoxelRayTrace20190722 -- each function cites the reference
+ * file:line it follows (paths relative to VoxelRayTrace20190722/).
+ *
+ * Parity status: PINNED.  The reference ships no golden vectors
+ * (SURVEY.md 4), so this restatement is pinned against the reference itself,
+ * compiled unmodified into oracle/_ref/libvrt_ref.so (oracle/build_ref.sh):
+ * tests/test_oracle_vs_ref.py compares every entry point below with the
+ * reference on seeded inputs, and tests/golden/ holds vectors generated from
+ * the reference by tests/golden/make_golden.py.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load the library built from this file.  The
+ * product (libvrt.so) never links or calls it.
+ *
+ * Data layout is deliberately NOT the reference's pointer tree: nodes live in
+ * one growable pool and are exported as (Morton-sorted leaf list, per-leaf
+ * triangle index list) so the GPU result can be compared array-for-array.
+ */
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ */
+/* Predicates                                                          */
+/* ------------------------------------------------------------------ */
+
+/* tribox2.cc:42-63 planeBoxOverlap (2001 variant: normal, d, maxbox). */
+static int orc_plane_box(const float n[3], float d, const float hb[3])
+{
+        float lo[3], hi[3];
+        for (int q = 0; q < 3; ++q) {
+                if (n[q] > 0.0f) {
+                        lo[q] = -hb[q];
+                        hi[q] = hb[q];
+                } else {
+                        lo[q] = hb[q];
+                        hi[q] = -hb[q];
+                }
+        }
+        if ((n[0] * lo[0] + n[1] * lo[1] + n[2] * lo[2]) + d > 0.0f)
+                return 0;
+        if ((n[0] * hi[0] + n[1] * hi[1] + n[2] * hi[2]) + d >= 0.0f)
+                return 1;
+        return 0;
+}
+
+/* One edge-cross-axis SAT test.  pa,pb are the two projected vertices the
+ * reference macro evaluates (tribox2.cc:67-110); rad the projected box radius.
+ * `first_lt_second` semantics: the macros use  if(pa<pb){min=pa;max=pb;} else
+ * {min=pb;max=pa;}  -- for non-NaN inputs that equals plain min/max. */
+static int orc_axis_sep(float pa, float pb, float rad)
+{
+        float mn, mx;
+        if (pa < pb) {
+                mn = pa;
+                mx = pb;
+        } else {
+                mn = pb;
+                mx = pa;
+        }
+        return (mn > rad || mx < -rad);
+}
+
+/* tribox2.cc:112-186 triBoxOverlap.  tri = 9 floats v0,v1,v2. */
+int orc_tribox(const float c[3], const float h[3], const float tri[9])
+{
+        float v0[3], v1[3], v2[3], e0[3], e1[3], e2[3];
+        for (int k = 0; k < 3; ++k) {
+                v0[k] = tri[k] - c[k];
+                v1[k] = tri[3 + k] - c[k];
+                v2[k] = tri[6 + k] - c[k];
+        }
+        for (int k = 0; k < 3; ++k) {
+                e0[k] = v1[k] - v0[k];
+                e1[k] = v2[k] - v1[k];
+                e2[k] = v0[k] - v2[k];
+        }
+        float fx, fy, fz;
+        /* edge 0: X01, Y02, Z12  (tribox2.cc:139-144) */
+        fx = fabsf(e0[0]); fy = fabsf(e0[1]); fz = fabsf(e0[2]);
+        if (orc_axis_sep(e0[2] * v0[1] - e0[1] * v0[2], e0[2] * v2[1] - e0[1] * v2[2],
+                         fz * h[1] + fy * h[2])) return 0;
+        if (orc_axis_sep(-e0[2] * v0[0] + e0[0] * v0[2], -e0[2] * v2[0] + e0[0] * v2[2],
+                         fz * h[0] + fx * h[2])) return 0;
+        /* Z12 compares p2<p1 first; symmetric for min/max of non-NaN */
+        if (orc_axis_sep(e0[1] * v2[0] - e0[0] * v2[1], e0[1] * v1[0] - e0[0] * v1[1],
+                         fy * h[0] + fx * h[1])) return 0;
+        /* edge 1: X01, Y02, Z0  (tribox2.cc:146-151) */
+        fx = fabsf(e1[0]); fy = fabsf(e1[1]); fz = fabsf(e1[2]);
+        if (orc_axis_sep(e1[2] * v0[1] - e1[1] * v0[2], e1[2] * v2[1] - e1[1] * v2[2],
+                         fz * h[1] + fy * h[2])) return 0;
+        if (orc_axis_sep(-e1[2] * v0[0] + e1[0] * v0[2], -e1[2] * v2[0] + e1[0] * v2[2],
+                         fz * h[0] + fx * h[2])) return 0;
+        if (orc_axis_sep(e1[1] * v0[0] - e1[0] * v0[1], e1[1] * v1[0] - e1[0] * v1[1],
+                         fy * h[0] + fx * h[1])) return 0;
+        /* edge 2: X2, Y1, Z12  (tribox2.cc:153-158) */
+        fx = fabsf(e2[0]); fy = fabsf(e2[1]); fz = fabsf(e2[2]);
+        if (orc_axis_sep(e2[2] * v0[1] - e2[1] * v0[2], e2[2] * v1[1] - e2[1] * v1[2],
+                         fz * h[1] + fy * h[2])) return 0;
+        if (orc_axis_sep(-e2[2] * v0[0] + e2[0] * v0[2], -e2[2] * v1[0] + e2[0] * v1[2],
+                         fz * h[0] + fx * h[2])) return 0;
+        if (orc_axis_sep(e2[1] * v2[0] - e2[0] * v2[1], e2[1] * v1[0] - e2[0] * v1[1],
+                         fy * h[0] + fx * h[1])) return 0;
+        /* the three box-axis tests, strict inequalities (tribox2.cc:166-176) */
+        for (int k = 0; k < 3; ++k) {
+                float mn = v0[k], mx = v0[k];
+                if (v1[k] < mn) mn = v1[k];
+                if (v1[k] > mx) mx = v1[k];
+                if (v2[k] < mn) mn = v2[k];
+                if (v2[k] > mx) mx = v2[k];
+                if (mn > h[k] || mx < -h[k])
+                        return 0;
+        }
+        /* plane test (tribox2.cc:181-183) */
+        float n[3];
+        n[0] = e0[1] * e1[2] - e0[2] * e1[1];
+        n[1] = e0[2] * e1[0] - e0[0] * e1[2];
+        n[2] = e0[0] * e1[1] - e0[1] * e1[0];
+        float d = -(n[0] * v0[0] + n[1] * v0[1] + n[2] * v0[2]);
+        return orc_plane_box(n, d, h) ? 1 : 0;
+}
+
+/* voxel_octree.cc:486-492 Triangle::is_overlap: centre=(min+max)*.5f
+ * (graphics_math.h:1252-1255), half=(max-min)/2.f. */
+int orc_tri_overlaps_aabb(const float mn[3], const float mx[3], const float tri[9])
+{
+        float c[3], h[3];
+        for (int k = 0; k < 3; ++k) {
+                c[k] = (mn[k] + mx[k]) * .5f;
+                h[k] = (mx[k] - mn[k]) / 2.f;
+        }
+        return orc_tribox(c, h, tri) == 1;
+}
+
+/* raytri.cc:197-249 intersect_triangle3 (double, two-sided, no t test). */
+int orc_raytri(const double o[3], const double dir[3], const double a[3],
+               const double b[3], const double c[3], double* t, double* u, double* v)
+{
+        const double eps = 0.000001; /* raytri.cc:9 */
+        double e1[3], e2[3], tv[3], pv[3], qv[3];
+        for (int k = 0; k < 3; ++k) {
+                e1[k] = b[k] - a[k];
+                e2[k] = c[k] - a[k];
+        }
+        pv[0] = dir[1] * e2[2] - dir[2] * e2[1];
+        pv[1] = dir[2] * e2[0] - dir[0] * e2[2];
+        pv[2] = dir[0] * e2[1] - dir[1] * e2[0];
+        double det = e1[0] * pv[0] + e1[1] * pv[1] + e1[2] * pv[2];
+        for (int k = 0; k < 3; ++k)
+                tv[k] = o[k] - a[k];
+        double inv = 1.0 / det;
+        qv[0] = tv[1] * e1[2] - tv[2] * e1[1];
+        qv[1] = tv[2] * e1[0] - tv[0] * e1[2];
+        qv[2] = tv[0] * e1[1] - tv[1] * e1[0];
+        if (det > eps) {
+                *u = tv[0] * pv[0] + tv[1] * pv[1] + tv[2] * pv[2];
+                if (*u < 0.0 || *u > det)
+                        return 0;
+                *v = dir[0] * qv[0] + dir[1] * qv[1] + dir[2] * qv[2];
+                if (*v < 0.0 || *u + *v > det)
+                        return 0;
+        } else if (det < -eps) {
+                *u = tv[0] * pv[0] + tv[1] * pv[1] + tv[2] * pv[2];
+                if (*u > 0.0 || *u < det)
+                        return 0;
+                *v = dir[0] * qv[0] + dir[1] * qv[1] + dir[2] * qv[2];
+                if (*v > 0.0 || *u + *v < det)
+                        return 0;
+        } else {
+                return 0;
+        }
+        *t = (e2[0] * qv[0] + e2[1] * qv[1] + e2[2] * qv[2]) * inv;
+        *u *= inv;
+        *v *= inv;
+        return 1;
+}
+
+/* std::min / std::max semantics (matter only for NaN): min(a,b)=(b<a)?b:a,
+ * max(a,b)=(a<b)?b:a. */
+static float std_minf(float a, float b) { return (b < a) ? b : a; }
+static float std_maxf(float a, float b) { return (a < b) ? b : a; }
+
+/* graphics_math.h:1312-1332 AABB<Vec3>::isect(ray, nullptr).
+ * ray = o3,d3,tmin,tmax. */
+int orc_aabb_isect(const float mn[3], const float mx[3], const float ray[8])
+{
+        float lo[3], hi[3];
+        for (int k = 0; k < 3; ++k) {
+                float d = ray[3 + k];
+                if (d == 0.f) /* std::replace(...,0.f,FLT_MIN): matches -0.f too */
+                        d = FLT_MIN;
+                float dinv = 1.f / d;
+                float a = (mn[k] - ray[k]) * dinv;
+                float b = (mx[k] - ray[k]) * dinv;
+                lo[k] = std_minf(a, b);
+                hi[k] = std_maxf(a, b);
+        }
+        /* std::max_element / std::min_element: first extremum, '<' only */
+        float t0 = lo[0];
+        if (t0 < lo[1]) t0 = lo[1];
+        if (t0 < lo[2]) t0 = lo[2];
+        float t1 = hi[0];
+        if (hi[1] < t1) t1 = hi[1];
+        if (hi[2] < t1) t1 = hi[2];
+        if (t0 > t1)
+                return 0;
+        float tmin = ray[6], tmax = ray[7];
+        return ((t0 >= tmin && t0 <= tmax) || (t1 >= tmin && t1 <= tmax)) ? 1 : 0;
+}
+
+/* ------------------------------------------------------------------ */
+/* Camera                                                              */
+/* ------------------------------------------------------------------ */
+
+static void v3_normalize(float v[3])
+{
+        /* graphics_math.h:532-586: dot = ((0+x*x)+y*y)+z*z ; v / sqrtf(dot) */
+        float s = 0.f;
+        s += v[0] * v[0];
+        s += v[1] * v[1];
+        s += v[2] * v[2];
+        float l = sqrtf(s);
+        v[0] = v[0] / l;
+        v[1] = v[1] / l;
+        v[2] = v[2] / l;
+}
+
+static void v3_cross(const float p[3], const float q[3], float out[3])
+{
+        /* graphics_math.h:588-592 */
+        out[0] = p[1] * q[2] - q[1] * p[2];
+        out[1] = p[2] * q[0] - q[2] * p[0];
+        out[2] = p[0] * q[1] - q[0] * p[1];
+}
+
+/* camera.cc:65-75 Camera::Camera -> column-major C_[col][row], 16 floats.
+ * cam10 = fov, eye3, spot3, up3. */
+void orc_camera_matrix(const float cam10[10], float C[16])
+{
+        const float* eye = cam10 + 1;
+        const float* spot = cam10 + 4;
+        const float* up = cam10 + 7;
+        float f[3] = { spot[0] - eye[0], spot[1] - eye[1], spot[2] - eye[2] };
+        v3_normalize(f);
+        float s[3], u[3];
+        v3_cross(f, up, s);
+        v3_normalize(s);
+        v3_cross(s, f, u);
+        v3_normalize(u);
+        memset(C, 0, 16 * sizeof(float));
+        for (int r = 0; r < 3; ++r) {
+                C[0 + r] = s[r];
+                C[4 + r] = u[r];
+                C[8 + r] = -f[r];
+                C[12 + r] = eye[r];
+        }
+        C[15] = 1.f;
+}
+
+/* z of camera.cc:82,100:  -(film.h / (2*tanf(fov/2)))  (host libm tanf). */
+float orc_camera_z(float fov, float film_h)
+{
+        return -(film_h / (2 * tanf(fov / 2)));
+}
+
+/* camera.cc:77-112 gen_rays1/gen_rays4 for one pixel; out = spp rays x 8. */
+void orc_gen_rays_pixel(const float C[16], float z, int nx, int ny, int spp, int px,
+                        int py, float* out)
+{
+        static const float s4[4][2] = { { 1, 5 }, { 3, 1 }, { 7, 3 }, { 5, 7 } };
+        const float x = (float)(px - nx / 2);
+        const float y = (float)((ny - 1 - py) - ny / 2);
+        for (int k = 0; k < spp; ++k) {
+                float sx = (spp == 4 ? s4[k][0] : 4.f) / 8.f;
+                float sy = (spp == 4 ? s4[k][1] : 4.f) / 8.f;
+                float x_ = (x + sx) / (float)nx;
+                float y_ = (y + sy) / (float)ny;
+                /* point_transform(C,{0,0,0}) graphics_math.h:1063-1070:
+                 * acc = 0; acc += C[i]*v[i] for i=0..3 with v=(0,0,0,1); /= w */
+                float o4[4], d4[4];
+                for (int r = 0; r < 4; ++r) {
+                        float a = 0.f;
+                        a += C[0 + r] * 0.f;
+                        a += C[4 + r] * 0.f;
+                        a += C[8 + r] * 0.f;
+                        a += C[12 + r] * 1.f;
+                        o4[r] = a;
+                        float b = 0.f;
+                        b += C[0 + r] * x_;
+                        b += C[4 + r] * y_;
+                        b += C[8 + r] * z;
+                        b += C[12 + r] * 0.f;
+                        d4[r] = b;
+                }
+                float* r8 = out + 8 * k;
+                r8[0] = o4[0] / o4[3];
+                r8[1] = o4[1] / o4[3];
+                r8[2] = o4[2] / o4[3];
+                float d[3] = { d4[0], d4[1], d4[2] };
+                v3_normalize(d); /* Ray ctor graphics_math.h:1159-1166 */
+                r8[3] = d[0];
+                r8[4] = d[1];
+                r8[5] = d[2];
+                r8[6] = 0.f;     /* Camera near default camera.h:76 */
+                r8[7] = FLT_MAX; /* Camera far default  camera.h:77 */
+        }
+}
+
+void orc_gen_rays(const float C[16], float z, int nx, int ny, int spp, int x0, int y0,
+                  int x1, int y1, float* out)
+{
+        size_t k = 0;
+        for (int py = y0; py < y1; ++py)
+                for (int px = x0; px < x1; ++px) {
+                        orc_gen_rays_pixel(C, z, nx, ny, spp, px, py, out + 8 * k);
+                        k += (size_t)spp;
+                }
+}
+
+/* ------------------------------------------------------------------ */
+/* Octree build (voxel_octree.cc:22-75)                                */
+/* ------------------------------------------------------------------ */
+
+typedef struct {
+        float mn[3], mx[3];
+        int32_t child[8]; /* -1 = this node is a leaf (never split) */
+        uint32_t* refs;   /* triangle indices, insertion (= ascending) order */
+        uint32_t nrefs, cap;
+} orc_node;
+
+typedef struct {
+        orc_node* nodes;
+        size_t n_nodes, cap_nodes;
+        const float* tri; /* borrowed [T][9] */
+        float* nrm;       /* owned, NORMALISED per-vertex normals [T][9] */
+        float* tri_own;   /* owned copy of the vertices */
+        uint32_t T;
+        int max_depth;
+} orc_tree;
+
+static int32_t orc_new_node(orc_tree* t, const float mn[3], const float mx[3])
+{
+        if (t->n_nodes == t->cap_nodes) {
+                t->cap_nodes = t->cap_nodes ? t->cap_nodes * 2 : 1024;
+                t->nodes = (orc_node*)realloc(t->nodes, t->cap_nodes * sizeof(orc_node));
+        }
+        orc_node* n = &t->nodes[t->n_nodes];
+        memcpy(n->mn, mn, sizeof n->mn);
+        memcpy(n->mx, mx, sizeof n->mx);
+        for (int i = 0; i < 8; ++i)
+                n->child[i] = -1;
+        n->refs = NULL;
+        n->nrefs = n->cap = 0;
+        return (int32_t)t->n_nodes++;
+}
+
+/* voxel_octree.cc:27-39 split: size=(max-min)/2 ; child i: mask=(i&4,i&2,i&1)
+ * -> min'=min+mask*size ; max'=min'+size  (float recurrence, NOT closed form). */
+static void orc_split(orc_tree* t, int32_t ni)
+{
+        float mn[3], mx[3], sz[3];
+        memcpy(mn, t->nodes[ni].mn, sizeof mn);
+        memcpy(mx, t->nodes[ni].mx, sizeof mx);
+        for (int k = 0; k < 3; ++k)
+                sz[k] = (mx[k] - mn[k]) / 2; /* Vec3 / int -> float division */
+        for (int i = 0; i < 8; ++i) {
+                float cmn[3], cmx[3];
+                int m[3] = { (i & 4) ? 1 : 0, (i & 2) ? 1 : 0, (i & 1) ? 1 : 0 };
+                for (int k = 0; k < 3; ++k) {
+                        cmn[k] = mn[k] + (float)m[k] * sz[k];
+                        cmx[k] = cmn[k] + sz[k];
+                }
+                int32_t c = orc_new_node(t, cmn, cmx); /* may realloc */
+                t->nodes[ni].child[i] = c;
+        }
+}
+
+/* voxel_octree.cc:41-65 insert */
+static void orc_insert(orc_tree* t, int32_t ni, uint32_t tri_idx, int cur, int maxd)
+{
+        const float* tv = t->tri + 9 * (size_t)tri_idx;
+        if (!orc_tri_overlaps_aabb(t->nodes[ni].mn, t->nodes[ni].mx, tv))
+                return;
+        if (t->nodes[ni].child[0] < 0) {
+                if (cur == maxd) {
+                        orc_node* n = &t->nodes[ni];
+                        if (n->nrefs == n->cap) {
+                                n->cap = n->cap ? n->cap * 2 : 4;
+                                n->refs = (uint32_t*)realloc(n->refs, n->cap * sizeof(uint32_t));
+                        }
+                        n->refs[n->nrefs++] = tri_idx;
+                        return;
+                }
+                orc_split(t, ni);
+        }
+        for (int i = 0; i < 8; ++i)
+                orc_insert(t, t->nodes[ni].child[i], tri_idx, cur + 1, maxd);
+}
+
+/* voxel_octree.cc:67-75 ray_march_init.  nrm may be NULL (geometric normal
+ * cross(p1-p0,p2-p0) is used for all three vertices, as the harness does).
+ * Normals are normalised once here like the Triangle ctor (voxel_octree.cc:426). */
+orc_tree* orc_build(const float* tri, const float* nrm, uint32_t T, int max_depth)
+{
+        orc_tree* t = (orc_tree*)calloc(1, sizeof(orc_tree));
+        t->T = T;
+        t->max_depth = max_depth;
+        t->tri_own = (float*)malloc(sizeof(float) * 9 * (size_t)(T ? T : 1));
+        memcpy(t->tri_own, tri, sizeof(float) * 9 * (size_t)T);
+        t->tri = t->tri_own;
+        t->nrm = (float*)malloc(sizeof(float) * 9 * (size_t)(T ? T : 1));
+        for (uint32_t i = 0; i < T; ++i) {
+                const float* p = tri + 9 * (size_t)i;
+                float* n = t->nrm + 9 * (size_t)i;
+                if (nrm) {
+                        memcpy(n, nrm + 9 * (size_t)i, 9 * sizeof(float));
+                } else {
+                        float a[3] = { p[3] - p[0], p[4] - p[1], p[5] - p[2] };
+                        float b[3] = { p[6] - p[0], p[7] - p[1], p[8] - p[2] };
+                        float g[3];
+                        v3_cross(a, b, g);
+                        for (int v = 0; v < 3; ++v)
+                                memcpy(n + 3 * v, g, sizeof g);
+                }
+                for (int v = 0; v < 3; ++v)
+                        v3_normalize(n + 3 * v);
+        }
+        /* root AABB = merge of triangle AABBs from the empty box
+         * (graphics_math.h:1228-1266) */
+        float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX };
+        float mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+        for (uint32_t i = 0; i < T; ++i) {
+                const float* p = tri + 9 * (size_t)i;
+                float tmn[3] = { FLT_MAX, FLT_MAX, FLT_MAX };
+                float tmx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+                for (int v = 0; v < 3; ++v)
+                        for (int k = 0; k < 3; ++k) {
+                                tmn[k] = std_minf(tmn[k], p[3 * v + k]);
+                                tmx[k] = std_maxf(tmx[k], p[3 * v + k]);
+                        }
+                for (int k = 0; k < 3; ++k) {
+                        mn[k] = std_minf(mn[k], tmn[k]);
+                        mx[k] = std_maxf(mx[k], tmx[k]);
+                }
+        }
+        orc_new_node(t, mn, mx);
+        for (uint32_t i = 0; i < T; ++i)
+                orc_insert(t, 0, i, 1, max_depth);
+        return t;
+}
+
+void orc_free(orc_tree* t)
+{
+        if (!t)
+                return;
+        for (size_t i = 0; i < t->n_nodes; ++i)
+                free(t->nodes[i].refs);
+        free(t->nodes);
+        free(t->nrm);
+        free(t->tri_own);
+        free(t);
+}
+
+void orc_root_aabb(const orc_tree* t, float out6[6])
+{
+        memcpy(out6, t->nodes[0].mn, 12);
+        memcpy(out6 + 3, t->nodes[0].mx, 12);
+}
+
+/* counts: [0]=nodes (incl. empty leaves) [1]=interior [2]=non-empty leaves
+ * [3]=tri refs [4]=max refs/leaf [5]=non-empty nodes (interior+non-empty leaves) */
+void orc_stats(const orc_tree* t, uint64_t out[6])
+{
+        memset(out, 0, 6 * sizeof(uint64_t));
+        out[0] = t->n_nodes;
+        for (size_t i = 0; i < t->n_nodes; ++i) {
+                const orc_node* n = &t->nodes[i];
+                if (n->child[0] >= 0)
+                        out[1]++;
+                else if (n->nrefs) {
+                        out[2]++;
+                        out[3] += n->nrefs;
+                        if (n->nrefs > out[4])
+                                out[4] = n->nrefs;
+                }
+        }
+        out[5] = out[1] + out[2];
+}
+
+static void orc_dump_walk(const orc_tree* t, int32_t ni, uint32_t x, uint32_t y,
+                          uint32_t z, uint32_t* cells, uint32_t* counts,
+                          uint32_t* refs, float* boxes, uint64_t* nl, uint64_t* nr)
+{
+        const orc_node* n = &t->nodes[ni];
+        if (n->child[0] < 0) {
+                if (!n->nrefs)
+                        return;
+                uint64_t l = (*nl)++;
+                cells[3 * l] = x;
+                cells[3 * l + 1] = y;
+                cells[3 * l + 2] = z;
+                counts[l] = n->nrefs;
+                if (boxes) {
+                        memcpy(boxes + 6 * l, n->mn, 12);
+                        memcpy(boxes + 6 * l + 3, n->mx, 12);
+                }
+                memcpy(refs + *nr, n->refs, n->nrefs * sizeof(uint32_t));
+                *nr += n->nrefs;
+                return;
+        }
+        for (int i = 0; i < 8; ++i)
+                orc_dump_walk(t, n->child[i], 2 * x + ((i >> 2) & 1),
+                              2 * y + ((i >> 1) & 1), 2 * z + (i & 1), cells, counts,
+                              refs, boxes, nl, nr);
+}
+
+/* Morton-order (child index order) dump of non-empty leaves. */
+void orc_dump_leaves(const orc_tree* t, uint32_t* cells, uint32_t* counts,
+                     uint32_t* refs, float* boxes)
+{
+        uint64_t nl = 0, nr = 0;
+        orc_dump_walk(t, 0, 0, 0, 0, cells, counts, refs, boxes, &nl, &nr);
+}
+
+/* ------------------------------------------------------------------ */
+/* Traversal (voxel_octree.cc:77-188) with work counters               */
+/* ------------------------------------------------------------------ */
+
+typedef struct {
+        uint64_t n_slab;      /* AABB slab tests                          */
+        uint64_t n_int;       /* interior nodes expanded (travorder calls) */
+        uint64_t n_leaf_all;  /* leaf visits incl. empty                   */
+        uint64_t n_leaf;      /* non-empty leaf visits                     */
+        uint64_t n_tri;       /* triangle tests                            */
+        uint64_t max_stack;
+} orc_counters;
+
+/* voxel_octree.cc:77-97: keys dot(d, centre-o); ascending, stable (libstdc++
+ * insertion-sorts 8 elements => ties keep ascending child index). */
+static void orc_travorder(const orc_tree* t, const orc_node* n, const float* ray,
+                          int ord[8])
+{
+        float key[8];
+        for (int i = 0; i < 8; ++i) {
+                const orc_node* c = &t->nodes[n->child[i]];
+                float s = 0.f;
+                for (int k = 0; k < 3; ++k) {
+                        float ctr = (c->mn[k] + c->mx[k]) * .5f;
+                        s += ray[3 + k] * (ctr - ray[k]);
+                }
+                key[i] = s;
+                ord[i] = i;
+        }
+        for (int i = 1; i < 8; ++i) { /* stable insertion sort on '<' */
+                int ci = ord[i];
+                float kv = key[ci];
+                int j = i;
+                while (j > 0 && kv < key[ord[j - 1]]) {
+                        ord[j] = ord[j - 1];
+                        --j;
+                }
+                ord[j] = ci;
+        }
+}
+
+/* voxel_octree.cc:438-460 Triangle::isect + :99-129 ray_march_isect. */
+static int orc_leaf_isect(const orc_tree* t, const orc_node* leaf, const float* ray,
+                          uint32_t* tri_out, float hit_out[3], float nrm_out[3],
+                          float* t_out, orc_counters* cn)
+{
+        int found = 0;
+        float best = 0.f;
+        for (uint32_t i = 0; i < leaf->nrefs; ++i) {
+                uint32_t ti = leaf->refs[i];
+                const float* p = t->tri + 9 * (size_t)ti;
+                double o[3] = { ray[0], ray[1], ray[2] };
+                double d[3] = { ray[3], ray[4], ray[5] };
+                double a[3] = { p[0], p[1], p[2] };
+                double b[3] = { p[3], p[4], p[5] };
+                double c[3] = { p[6], p[7], p[8] };
+                double dt = 0, du = 0, dv = 0;
+                if (cn)
+                        cn->n_tri++;
+                if (orc_raytri(o, d, a, b, c, &dt, &du, &dv) != 1)
+                        continue;
+                float hit[3];
+                float tf = (float)dt;
+                for (int k = 0; k < 3; ++k)
+                        hit[k] = ray[k] + tf * ray[3 + k];
+                /* depth = length(hit - o)  voxel_octree.cc:114 */
+                float s = 0.f;
+                for (int k = 0; k < 3; ++k) {
+                        float df = hit[k] - ray[k];
+                        s += df * df;
+                }
+                float depth = sqrtf(s);
+                /* std::min_element: first minimum wins (strict '<') */
+                if (!found || depth < best) {
+                        found = 1;
+                        best = depth;
+                        *tri_out = ti;
+                        *t_out = tf;
+                        memcpy(hit_out, hit, sizeof hit);
+                        float u = (float)du, v = (float)dv;
+                        u = u > 1.f ? 1.f : (u < 0.f ? 0.f : u);
+                        v = v > 1.f ? 1.f : (v < 0.f ? 0.f : v);
+                        float w = 1 - u - v;
+                        w = w > 1.f ? 1.f : (w < 0.f ? 0.f : w);
+                        const float* n = t->nrm + 9 * (size_t)ti;
+                        float nt[3];
+                        for (int k = 0; k < 3; ++k)
+                                nt[k] = (n[k] * w + n[3 + k] * u) + n[6 + k] * v;
+                        v3_normalize(nt);
+                        memcpy(nrm_out, nt, sizeof nt);
+                }
+        }
+        return found;
+}
+
+/* voxel_octree.cc:131-188 ray_march.  Returns 1 on hit and fills the hit
+ * record (cell xyz at level max_depth-1, triangle index, t, hit, normal). */
+int orc_ray_march(const orc_tree* t, const float ray[8], uint32_t cell[3],
+                  uint32_t* tri, float* tt, float hit[3], float nrm[3],
+                  orc_counters* cn)
+{
+        const orc_node* root = &t->nodes[0];
+        if (cn)
+                cn->n_slab++;
+        if (!orc_aabb_isect(root->mn, root->mx, ray))
+                return 0;
+        if (root->child[0] < 0) {
+                if (cn) {
+                        cn->n_leaf_all++;
+                        if (root->nrefs)
+                                cn->n_leaf++;
+                }
+                if (orc_leaf_isect(t, root, ray, tri, hit, nrm, tt, cn)) {
+                        cell[0] = cell[1] = cell[2] = 0;
+                        return 1;
+                }
+                return 0;
+        }
+        struct {
+                int32_t node;
+                int ord[8];
+                int cur;
+                uint32_t x, y, z;
+        } st[40];
+        int sp = 0;
+        st[0].node = 0;
+        st[0].cur = 0;
+        st[0].x = st[0].y = st[0].z = 0;
+        orc_travorder(t, root, ray, st[0].ord);
+        if (cn)
+                cn->n_int++;
+        sp = 1;
+        while (sp > 0) {
+                if (cn && (uint64_t)sp > cn->max_stack)
+                        cn->max_stack = (uint64_t)sp;
+                int top = sp - 1;
+                int ci = st[top].ord[st[top].cur++];
+                int32_t cidx = t->nodes[st[top].node].child[ci];
+                uint32_t cx = 2 * st[top].x + ((ci >> 2) & 1);
+                uint32_t cy = 2 * st[top].y + ((ci >> 1) & 1);
+                uint32_t cz = 2 * st[top].z + (ci & 1);
+                if (st[top].cur == 8)
+                        sp--; /* popped before the last child is processed */
+                const orc_node* c = &t->nodes[cidx];
+                if (cn)
+                        cn->n_slab++;
+                if (!orc_aabb_isect(c->mn, c->mx, ray))
+                        continue;
+                if (c->child[0] >= 0) {
+                        st[sp].node = cidx;
+                        st[sp].cur = 0;
+                        st[sp].x = cx;
+                        st[sp].y = cy;
+                        st[sp].z = cz;
+                        orc_travorder(t, c, ray, st[sp].ord);
+                        if (cn)
+                                cn->n_int++;
+                        sp++;
+                        continue;
+                }
+                if (cn) {
+                        cn->n_leaf_all++;
+                        if (c->nrefs)
+                                cn->n_leaf++;
+                }
+                if (orc_leaf_isect(t, c, ray, tri, hit, nrm, tt, cn)) {
+                        cell[0] = cx;
+                        cell[1] = cy;
+                        cell[2] = cz;
+                        return 1;
+                }
+        }
+        return 0;
+}
+
+/* Batch driver.  Outputs may be NULL except hit.  counters may be NULL. */
+void orc_trace_rays(const orc_tree* t, const float* rays, uint64_t R, uint8_t* hit,
+                    uint32_t* cell, uint32_t* tri, float* tt, float* pos, float* nrm,
+                    uint64_t* counters6)
+{
+        orc_counters cn;
+        memset(&cn, 0, sizeof cn);
+        for (uint64_t i = 0; i < R; ++i) {
+                uint32_t c[3] = { 0xffffffffu, 0xffffffffu, 0xffffffffu };
+                uint32_t ti = 0xffffffffu;
+                float t1 = 0.f, h[3] = { 0, 0, 0 }, n[3] = { 0, 0, 0 };
+                int r = orc_ray_march(t, rays + 8 * i, c, &ti, &t1, h, n,
+                                      counters6 ? &cn : NULL);
+                if (!r) {
+                        c[0] = c[1] = c[2] = 0xffffffffu;
+                        ti = 0xffffffffu;
+                        t1 = 0.f;
+                        memset(h, 0, sizeof h);
+                        memset(n, 0, sizeof n);
+                }
+                hit[i] = (uint8_t)r;
+                if (cell)
+                        memcpy(cell + 3 * i, c, sizeof c);
+                if (tri)
+                        tri[i] = ti;
+                if (tt)
+                        tt[i] = t1;
+                if (pos)
+                        memcpy(pos + 3 * i, h, sizeof h);
+                if (nrm)
+                        memcpy(nrm + 3 * i, n, sizeof n);
+        }
+        if (counters6) {
+                counters6[0] = cn.n_slab;
+                counters6[1] = cn.n_int;
+                counters6[2] = cn.n_leaf_all;
+                counters6[3] = cn.n_leaf;
+                counters6[4] = cn.n_tri;
+                counters6[5] = cn.max_stack;
+        }
+}
+
+/* Batch predicate entry points for the KATs. */
+void orc_tribox_batch(const float* centers, const float* halves, const float* tris,
+                      uint64_t n, uint8_t* out)
+{
+        for (uint64_t i = 0; i < n; ++i)
+                out[i] = (uint8_t)orc_tribox(centers + 3 * i, halves + 3 * i, tris + 9 * i);
+}
+
+void orc_tri_overlap_aabb_batch(const float* aabbs6, const float* tris, uint64_t n,
+                                uint8_t* out)
+{
+        for (uint64_t i = 0; i < n; ++i)
+                out[i] = (uint8_t)orc_tri_overlaps_aabb(aabbs6 + 6 * i, aabbs6 + 6 * i + 3,
+                                                        tris + 9 * i);
+}
+
+void orc_raytri_batch(const double* in, uint64_t n, uint8_t* res, double* tuv)
+{
+        for (uint64_t i = 0; i < n; ++i) {
+                const double* a = in + 15 * i;
+                double t = 0, u = 0, v = 0;
+                res[i] = (uint8_t)orc_raytri(a, a + 3, a + 6, a + 9, a + 12, &t, &u, &v);
+                tuv[3 * i] = t;
+                tuv[3 * i + 1] = u;
+                tuv[3 * i + 2] = v;
+        }
+}
+
+void orc_aabb_isect_batch(const float* aabbs6, const float* rays8, uint64_t n,
+                          uint8_t* out)
+{
+        for (uint64_t i = 0; i < n; ++i)
+                out[i] = (uint8_t)orc_aabb_isect(aabbs6 + 6 * i, aabbs6 + 6 * i + 3,
+                                                 rays8 + 8 * i);
+}
