@@ -1,0 +1,222 @@
+/* include/vrt.h -- C ABI of libvrt.so, the B200 (sm_100a) implementation of the
+ * sparse-voxel-octree hot path of jqly/VoxelRayTrace20190722.
+ *
+ * The reference has no FFI layer; its boundary for this path is the C++
+ * function surface below (paths relative to VoxelRayTrace20190722/).  Each
+ * entry point names the reference interface it replaces.  C++ adapters with
+ * the reference's exact signatures live in
+ * voxelraytrace20190722_b200/cpp/vrt_gi.{h,cc}; INTEGRATION.md shows how
+ * main.cc binds to them.
+ *
+ * Conventions
+ *   - every function returns VRT_OK (0) or a negative vrt_status; the message
+ *     of the last failure on the calling thread is vrt_last_error().  Nothing
+ *     in the library calls exit()/abort() (the reference does: voxel_octree.cc:329).
+ *   - handles (vrt_tree*) are allocated and freed by the library; every `out`
+ *     buffer is caller-allocated; input arrays are borrowed for the call only.
+ *   - functions without a suffix take HOST pointers and copy in/out inside the
+ *     call; functions ending in _dev take DEVICE pointers (current CUDA device)
+ *     and only enqueue work on the tree's stream + synchronise it.
+ *   - there is no CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with VRT_ERR_CUDA.
+ *   - triangle index == index into tri_xyz == OBJ face order
+ *     (voxel_octree.cc:334-368); it is the tie-break key of the reference.
+ *   - max_depth is the reference's 1-based depth (voxel_octree.cc:74):
+ *     leaves live at level max_depth-1, leaf grid = 2^(max_depth-1) per axis.
+ */
+#ifndef VRT_H
+#define VRT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* libvrt.so is built with -fvisibility=hidden; only this header is exported. */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define VRT_ABI_VERSION 1
+
+typedef enum vrt_status {
+        VRT_OK = 0,
+        VRT_ERR_ARG = -1,      /* bad argument (null pointer, depth out of range, ...) */
+        VRT_ERR_CUDA = -2,     /* CUDA runtime failure or no device                    */
+        VRT_ERR_NOMEM = -3,    /* device or host allocation failed                     */
+        VRT_ERR_CAPACITY = -4, /* key packing does not fit 64 bit (T, depth too large) */
+        VRT_ERR_STATE = -5     /* handle not built / wrong device                      */
+} vrt_status;
+
+#define VRT_MAX_DEPTH 17u      /* 1-based; 3*(max_depth-1) Morton bits + tri bits <= 64 */
+#define VRT_NO_TRI 0xffffffffu
+
+typedef struct vrt_tree vrt_tree;
+
+/* jql::Ray (graphics_math.h:1150-1167), 32 bytes, copied verbatim: d is NOT
+ * re-normalised by the library (the reference normalises in the Ray ctor; a
+ * caller that builds rays through vrt_gen_rays gets that for free). */
+typedef struct vrt_ray {
+        float o[3];
+        float d[3];
+        float tmin;
+        float tmax;
+} vrt_ray;
+
+/* Result of gi::ray_march (voxel_octree.h:87-89) for one ray.  48 bytes.
+ * (leaf_ptr, voxel_ptr, ISect) -> (cell, tri, pos/nrm); `t` is (float)dt of
+ * Triangle::isect (voxel_octree.cc:454). */
+typedef struct vrt_hit {
+        uint32_t hit;      /* 1 = ray_march returned true                        */
+        uint32_t tri;      /* index of *voxel_ptr in the input array, VRT_NO_TRI  */
+        uint32_t cell[3];  /* *leaf_ptr as cell coordinates at level max_depth-1  */
+        float t;
+        float pos[3];      /* ISect::hit                                          */
+        float nrm[3];      /* ISect::normal                                       */
+} vrt_hit;
+
+/* Compact per-ray record (16 bytes) -- the "hit record" SURVEY.md 8(d) counts. */
+typedef struct vrt_hit16 {
+        uint32_t leaf;     /* index into the Morton-sorted leaf array, VRT_NO_TRI on miss */
+        uint32_t tri;
+        float t;
+        uint32_t hit;
+} vrt_hit16;
+
+/* Camera as the reference constructs it: Camera(fov,eye,spot,up) camera.cc:65-75
+ * + Film(w,h,nx,ny) camera.h:24-29.  C is the column-major camera-to-world
+ * matrix C_ (private member of the reference's Camera); z is
+ * -(film_h/(2*tanf(fov/2))) (camera.cc:82,100) -- tanf stays on the host. */
+typedef struct vrt_camera {
+        float C[16];
+        float z;
+        float tmin, tmax;  /* Camera::near / Camera::far (camera.h:76-77): 0, FLT_MAX */
+        int32_t nx, ny;    /* film resolution                                         */
+        int32_t spp;       /* 1 = gen_rays1, 4 = gen_rays4                            */
+} vrt_camera;
+
+typedef struct vrt_tree_info {
+        uint32_t num_tris;
+        int32_t max_depth;
+        float root_aabb[6];    /* min xyz, max xyz (voxel_octree.cc:70-72)             */
+        uint64_t num_nodes;    /* non-empty nodes, all levels (interior + leaves)      */
+        uint64_t num_leaves;   /* non-empty leaves at level max_depth-1                */
+        uint64_t num_refs;     /* sum of leaf triangle-list lengths                    */
+        uint64_t level_offset[VRT_MAX_DEPTH + 1]; /* node index range of each level   */
+        uint64_t device_bytes; /* HBM held by the handle                               */
+        double build_ms;       /* device time of the last vrt_build (CUDA events)      */
+} vrt_tree_info;
+
+/* Host view of the flat octree (caller-allocated arrays, sizes from vrt_tree_info):
+ *   leaf_cell [num_leaves][3]  cell coordinates, Morton (= reference child) order
+ *   leaf_count[num_leaves]     triangles per leaf
+ *   leaf_refs [num_refs]       triangle indices, ascending inside each leaf
+ *   nodes     [num_nodes][2]   {child_mask | first_child<<?} see DESIGN.md; may be NULL
+ */
+typedef struct vrt_tree_view {
+        uint32_t* leaf_cell;
+        uint32_t* leaf_count;
+        uint32_t* leaf_refs;
+        uint32_t* nodes;
+} vrt_tree_view;
+
+/* ---- library ------------------------------------------------------------- */
+int vrt_abi_version(void);
+const char* vrt_last_error(void);
+/* number of CUDA devices visible; <0 on failure */
+int vrt_device_count(void);
+/* kernels launched by this process so far (bench.py's gpu_launches claim) */
+uint64_t vrt_launch_count(void);
+
+/* ---- build: replaces gi::ray_march_init (voxel_octree.h:85-86,
+ *      voxel_octree.cc:67-75) + Triangle ctor/get_aabb/is_overlap
+ *      (voxel_octree.cc:423-436,486-492) + triBoxOverlap (tribox2.cc:112) ----
+ * tri_nrm may be NULL (geometric normal cross(p1-p0,p2-p0) per triangle). */
+int vrt_build(const float* tri_xyz, const float* tri_nrm, uint32_t num_tris,
+              int max_depth, vrt_tree** out);
+int vrt_build_dev(const float* d_tri_xyz, const float* d_tri_nrm, uint32_t num_tris,
+                  int max_depth, vrt_tree** out);
+/* Re-run the build on the triangles already held by the handle (timing loops). */
+int vrt_rebuild(vrt_tree* tree, int max_depth);
+void vrt_tree_free(vrt_tree* tree);
+int vrt_tree_get_info(const vrt_tree* tree, vrt_tree_info* out);
+int vrt_tree_export(const vrt_tree* tree, vrt_tree_view* out);
+/* Build a handle from an externally produced leaf set (e.g. the oracle's tree):
+ * lets the ray kernel be checked independently of the voxelizer. */
+int vrt_tree_import(const float* tri_xyz, const float* tri_nrm, uint32_t num_tris,
+                    int max_depth, const float root_aabb[6], uint64_t num_leaves,
+                    const uint32_t* leaf_cell, const uint32_t* leaf_count,
+                    const uint32_t* leaf_refs, vrt_tree** out);
+/* Use `stream` (a cudaStream_t) for all work of this handle; NULL = default. */
+int vrt_tree_set_stream(vrt_tree* tree, void* stream);
+
+/* Raw device arrays of a built tree, for replication over NCCL:
+ * blob = one contiguous device allocation holding everything the ray kernel
+ * reads; a replica is created from a received copy with vrt_tree_from_blob_dev. */
+int vrt_tree_blob_dev(const vrt_tree* tree, const void** d_blob, uint64_t* bytes);
+int vrt_tree_from_blob_dev(const void* d_blob, uint64_t bytes, vrt_tree** out);
+
+/* ---- ray generation: replaces Camera::Camera + gen_rays1/gen_rays4
+ *      (camera.cc:65-112) ---------------------------------------------------- */
+/* cam10 = fov, eye[3], spot[3], up[3]; fills C, z, tmin/tmax (host arithmetic,
+ * identical to the reference ctor). */
+int vrt_camera_init(const float cam10[10], float film_h, int nx, int ny, int spp,
+                    vrt_camera* out);
+/* rays_out[(y1-y0)][(x1-x0)][spp] */
+int vrt_gen_rays(const vrt_camera* cam, int x0, int y0, int x1, int y1,
+                 vrt_ray* rays_out);
+
+/* ---- query: replaces gi::ray_march (voxel_octree.cc:131-188) and the
+ *      render_mt pixel loop (camera.h:41-68) --------------------------------- */
+int vrt_trace_rays(const vrt_tree* tree, const vrt_ray* rays, uint64_t num_rays,
+                   vrt_hit* out);
+int vrt_trace_rays_dev(const vrt_tree* tree, const vrt_ray* d_rays, uint64_t num_rays,
+                       vrt_hit* d_out);
+/* Ray generation fused into the traversal kernel; pixel rectangle [x0,x1)x[y0,y1);
+ * out[(y1-y0)][(x1-x0)][spp]. */
+int vrt_trace_camera(const vrt_tree* tree, const vrt_camera* cam, int x0, int y0,
+                     int x1, int y1, vrt_hit* out);
+int vrt_trace_camera_dev(const vrt_tree* tree, const vrt_camera* cam, int x0, int y0,
+                         int x1, int y1, vrt_hit* d_out);
+int vrt_trace_camera16_dev(const vrt_tree* tree, const vrt_camera* cam, int x0, int y0,
+                           int x1, int y1, vrt_hit16* d_out);
+
+/* Harness pixel: miss -> sky lerp of main.cc:18-20; hit ->
+ * kd*clamp(dot(normal,light),0,1); spp samples * (1/spp) accumulated in sample
+ * order (main.cc:119-122).  film_rgb[(y1-y0)][(x1-x0)][3] float. */
+typedef struct vrt_shade {
+        float light_dir[3]; /* normalised on the host, main.cc:72 */
+        float kd;
+} vrt_shade;
+int vrt_render_camera(const vrt_tree* tree, const vrt_camera* cam, const vrt_shade* sh,
+                      int x0, int y0, int x1, int y1, float* film_rgb);
+int vrt_render_camera_dev(const vrt_tree* tree, const vrt_camera* cam,
+                          const vrt_shade* sh, int x0, int y0, int x1, int y1,
+                          float* d_film_rgb);
+/* device time (ms, CUDA events on the tree's stream) of the last trace/render
+ * kernel launched through this handle */
+double vrt_last_kernel_ms(const vrt_tree* tree);
+
+/* ---- predicates (device KATs; each call launches a kernel) ---------------- */
+/* triBoxOverlap (tribox2.h:15): centers[n][3], halves[n][3], tris[n][3][3] */
+int vrt_tribox_batch(const float* centers, const float* halves, const float* tris,
+                     uint64_t n, uint8_t* out);
+/* Triangle::is_overlap (voxel_octree.cc:486-492): aabbs[n][6] */
+int vrt_tri_overlap_aabb_batch(const float* aabbs, const float* tris, uint64_t n,
+                               uint8_t* out);
+/* intersect_triangle3 (raytri.h:5-7): in[n][15]=orig,dir,v0,v1,v2; tuv[n][3] */
+int vrt_raytri_batch(const double* in, uint64_t n, uint8_t* result, double* tuv);
+/* AABB<Vec3>::isect(ray,nullptr) (graphics_math.h:1312-1332) */
+int vrt_aabb_isect_batch(const float* aabbs, const vrt_ray* rays, uint64_t n,
+                         uint8_t* out);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRT_H */

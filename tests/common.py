@@ -1,0 +1,90 @@
+"""Shared helpers for the parity tests (inputs, comparison, harness pixel)."""
+import numpy as np
+
+from voxelraytrace20190722_b200 import scenes
+
+RAD = np.pi / 180.0
+CAM_SPHERE = np.array([60 * RAD, 0, 1, 3, 0, 0, 0, 0, 1, 0], np.float32)
+CAM_MAIN = np.array([90 * RAD, 1, 1.3, -.2, 0, .4, 0, 0, 1, 0], np.float32)     # main.cc:112-115
+CAM_LIGHT = np.array([60 * RAD, 1, 10, 1, 0, 0, 0, 0, 1, 0], np.float32)        # main.cc:76-78
+
+
+def bits(a):
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.float32:
+        return a.view(np.uint32)
+    if a.dtype == np.float64:
+        return a.view(np.uint64)
+    return a
+
+
+def assert_bits_equal(a, b, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, f"{what}: shape {a.shape} vs {b.shape}"
+    ne = bits(a) != bits(b)
+    assert not ne.any(), f"{what}: {int(ne.sum())} of {ne.size} elements differ (first at {np.argwhere(ne)[0]})"
+
+
+def leaves_equal(a, b):
+    """(cells, counts, refs) triples, both in Morton order."""
+    for x, y, nm in zip(a, b, ("leaf cells", "leaf counts", "leaf refs")):
+        assert_bits_equal(x, y, nm)
+
+
+def compare_hits(gpu_hits, orc, what="", allow_mismatch=0.0):
+    """gpu_hits: structured HIT array; orc: oracle _HitArrays.  Bit-exact by default."""
+    n = len(gpu_hits)
+    bad = (gpu_hits["hit"] != orc.hit)
+    bad |= gpu_hits["tri"] != orc.tri
+    bad |= (gpu_hits["cell"] != orc.cell).any(axis=1)
+    frac = bad.sum() / max(n, 1)
+    assert frac <= allow_mismatch, f"{what}: {int(bad.sum())}/{n} rays differ in (hit, leaf cell, triangle)"
+    ok = ~bad
+    assert_bits_equal(gpu_hits["pos"][ok], orc.pos[ok], what + " ISect.hit")
+    assert_bits_equal(gpu_hits["nrm"][ok], orc.nrm[ok], what + " ISect.normal")
+    if getattr(orc, "t", None) is not None:
+        assert_bits_equal(gpu_hits["t"][ok], orc.t[ok], what + " t")
+    return int(bad.sum())
+
+
+def harness_film(rays, orc_hits, light, kd, spp):
+    """The harness pixel of SURVEY.md 8(d) evaluated on ORACLE hits with numpy float32
+    (sky: main.cc:18-20; samples added in order with weight 1/spp: main.cc:119-122)."""
+    f32 = np.float32
+    d = rays.reshape(-1, 8)[:, 3:6].astype(np.float32)
+    t = (0.5 * (d[:, 1].astype(np.float64) + 1.0)).astype(np.float32)
+    v1 = np.array([0.6, 0.8, 1.0], np.float32)
+    sky = (f32(1.0) + (v1[None, :] - f32(1.0)) * t[:, None]).astype(np.float32)
+    n = orc_hits.nrm.astype(np.float32)
+    L = np.asarray(light, np.float32)
+    dot = (f32(0) + n[:, 0] * L[0]).astype(np.float32)
+    dot = (dot + n[:, 1] * L[1]).astype(np.float32)
+    dot = (dot + n[:, 2] * L[2]).astype(np.float32)
+    dot = np.where(dot > 1, f32(1), np.where(dot < 0, f32(0), dot)).astype(np.float32)
+    c = (f32(kd) * dot).astype(np.float32)
+    col = np.where(orc_hits.hit[:, None].astype(bool), c[:, None].repeat(3, 1), sky).astype(np.float32)
+    w = f32(0.25) if spp == 4 else f32(1)
+    col = (col * w).astype(np.float32).reshape(-1, spp, 3)
+    acc = np.zeros((col.shape[0], 3), np.float32)
+    for s in range(spp):
+        acc = (acc + col[:, s]).astype(np.float32)
+    return acc
+
+
+def to_u8(film):
+    """Film::to_byte_array (camera.cc:25-47): v*255.9 -> uint8 cast."""
+    return np.clip(film.astype(np.float32) * np.float32(255.9), 0, 255).astype(np.uint8)
+
+
+def small_scenes():
+    """(name, tri, nrm, depth, cam10) cases that the oracle finishes in seconds."""
+    out = []
+    tri, nrm = scenes.uv_sphere(64, 32)
+    out.append(("sphere64_d6", tri, nrm, 6, CAM_SPHERE))
+    tri, nrm = scenes.uv_sphere()
+    out.append(("sphere256_d8", tri, nrm, 8, CAM_SPHERE))
+    tri, nrm = scenes.soup(20000, e=0.02)
+    out.append(("soup20k_d7", tri, nrm, 7, CAM_SPHERE))
+    tri, nrm = scenes.atrium(detail=0.35)
+    out.append(("atrium_d7", tri, nrm, 7, CAM_MAIN))
+    return out

@@ -1,0 +1,282 @@
+"""GPU parity tests: libvrt.so (through the C ABI) vs the CPU oracle.
+
+Bar (BASELINE.json north_star): leaf sets bit-exact, per-ray (hit, leaf cell,
+triangle) identical, ISect bit-exact, pixels within 1/255.  In practice every
+comparison below is exact.
+"""
+import numpy as np
+import pytest
+
+from tests.common import (CAM_LIGHT, CAM_MAIN, CAM_SPHERE, assert_bits_equal, compare_hits, harness_film,
+                          leaves_equal, small_scenes, to_u8)
+from voxelraytrace20190722_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+# ----------------------------------------------------------------------------
+# predicates
+# ----------------------------------------------------------------------------
+def _predicate_inputs(n, seed):
+    rng = np.random.default_rng(seed)
+    tris = rng.uniform(-1, 1, (n, 9)).astype(np.float32)
+    centers = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    halves = rng.uniform(0.01, 0.6, (n, 3)).astype(np.float32)
+    k = n // 8
+    # adversarial blocks: touching faces, axis-aligned triangles, degenerate triangles,
+    # triangle vertices exactly on box corners / planes, tiny and huge boxes
+    tris[:k, 0::3] = np.round(tris[:k, 0::3] * 4) / 4
+    centers[:k] = np.round(centers[:k] * 4) / 4
+    halves[:k] = 0.25
+    tris[k:2 * k, 3:6] = tris[k:2 * k, 0:3]  # degenerate (two equal vertices)
+    tris[2 * k:3 * k, 2::3] = tris[2 * k:3 * k, 2:3]  # axis-aligned (constant z)
+    c = centers[3 * k:4 * k]
+    h = halves[3 * k:4 * k]
+    tris[3 * k:4 * k, 0:3] = c + h  # vertex on a box corner
+    tris[4 * k:5 * k, 0] = (centers[4 * k:5 * k, 0] + halves[4 * k:5 * k, 0])  # vertex on the +x plane
+    halves[5 * k:6 * k] *= np.float32(1e-4)
+    halves[6 * k:7 * k] *= np.float32(50)
+    return centers, halves, tris
+
+
+def test_tribox_kat(gpu, port):
+    c, h, t = _predicate_inputs(400_000, 1)
+    got = gpu.tribox(c, h, t)
+    exp = port.tribox(c, h, t)
+    assert got.sum() > 1000 and (1 - got).sum() > 1000
+    assert_bits_equal(got, exp, "triBoxOverlap")
+
+
+def test_tri_overlap_aabb_kat(gpu, port):
+    c, h, t = _predicate_inputs(400_000, 2)
+    boxes = np.concatenate([c - h, c + h], axis=1).astype(np.float32)
+    assert_bits_equal(gpu.tri_overlap_aabb(boxes, t), port.tri_overlap_aabb(boxes, t), "Triangle::is_overlap")
+
+
+def test_raytri_kat(gpu, port):
+    rng = np.random.default_rng(3)
+    n = 400_000
+    a = rng.uniform(-1, 1, (n, 15)).astype(np.float32).astype(np.float64)
+    d = a[:, 3:6]
+    a[:, 3:6] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    k = n // 8
+    a[:k, 0:3] = a[:k, 6:9]                      # origin on a vertex
+    a[k:2 * k, 3:6] = a[k:2 * k, 9:12] - a[k:2 * k, 6:9]  # ray parallel to an edge
+    a[2 * k:3 * k, 12:15] = a[2 * k:3 * k, 9:12]          # degenerate triangle
+    a[3 * k:4 * k, 6:15] *= 1e-3                          # tiny triangles (|det| near 1e-6)
+    res, tuv = gpu.raytri(a)
+    eres, etuv = port.raytri(a)
+    assert res.sum() > 1000
+    assert_bits_equal(res, eres, "intersect_triangle3 result")
+    ok = res == 1
+    assert_bits_equal(tuv[ok], etuv[ok], "intersect_triangle3 t,u,v")
+
+
+def test_aabb_isect_kat(gpu, port):
+    rng = np.random.default_rng(4)
+    n = 400_000
+    lo = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    sz = rng.uniform(0.0, 1, (n, 3)).astype(np.float32)
+    boxes = np.concatenate([lo, lo + sz], axis=1).astype(np.float32)
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.uniform(-2, 2, (n, 3))
+    d = rng.normal(size=(n, 3))
+    rays[:, 3:6] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 6] = 0
+    rays[:, 7] = np.finfo(np.float32).max
+    k = n // 8
+    rays[:k, 3] = 0.0          # axis-parallel: the 0 -> FLT_MIN patch
+    rays[k:2 * k, 4] = -0.0
+    rays[2 * k:3 * k, 0:3] = boxes[2 * k:3 * k, 0:3]  # origin on the min corner
+    rays[3 * k:4 * k, 6] = 0.5  # tmin/tmax windows
+    rays[3 * k:4 * k, 7] = 1.5
+    got = gpu.aabb_isect(boxes, rays)
+    exp = port.aabb_isect(boxes, rays)
+    assert got.sum() > 1000 and (1 - got).sum() > 1000
+    assert_bits_equal(got, exp, "AABB::isect")
+
+
+# ----------------------------------------------------------------------------
+# ray generation
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize("cam10,nx,ny,spp", [(CAM_SPHERE, 192, 108, 1), (CAM_MAIN, 128, 128, 4),
+                                              (CAM_LIGHT, 97, 61, 4)])
+def test_gen_rays(gpu, port, cam10, nx, ny, spp):
+    cam = gpu.Camera(cam10[0], cam10[1:4], cam10[4:7], cam10[7:10], nx, ny, spp)
+    assert_bits_equal(cam.matrix, port.camera_matrix(cam10), "Camera C_")
+    got = cam.gen_rays().view(np.float32).reshape(-1, 8)
+    exp = port.gen_rays(cam10, 1.0, nx, ny, spp)
+    assert_bits_equal(got, exp, "gen_rays")
+    sub = cam.gen_rays((5, 7, 50, 33)).view(np.float32).reshape(-1, 8)
+    assert_bits_equal(sub, port.gen_rays(cam10, 1.0, nx, ny, spp, (5, 7, 50, 33)), "gen_rays rect")
+
+
+# ----------------------------------------------------------------------------
+# build + traversal on small scenes
+# ----------------------------------------------------------------------------
+@pytest.fixture(scope="module", params=small_scenes(), ids=lambda c: c[0])
+def case(request, port, gpu):
+    name, tri, nrm, depth, cam10 = request.param
+    orc = port.build(tri, nrm, depth)
+    tree = gpu.Octree.build(tri, nrm, depth)
+    yield dict(name=name, tri=tri, nrm=nrm, depth=depth, cam10=cam10, orc=orc, tree=tree)
+    tree.close()
+
+
+def test_build_leaf_sets(case):
+    info = case["tree"].info()
+    st = case["orc"].stats()
+    assert info["num_leaves"] == st["leaves"] and info["num_refs"] == st["refs"]
+    assert info["num_nodes"] <= st["nonempty_nodes"]
+    assert_bits_equal(info["root_aabb"], case["orc"].root_aabb(), "root AABB")
+    leaves_equal(case["tree"].leaves(), case["orc"].leaves())
+
+
+def test_node_array_consistency(case):
+    """Flat node array invariants: children contiguous, masks = popcount of children, leaves cover refs."""
+    tree = case["tree"]
+    info = tree.info()
+    cell, cnt, refs, nodes = tree.leaves(nodes=True)
+    L = info["max_depth"] - 1
+    off = info["level_offset"]
+    if info["num_nodes"] == 0:
+        return
+    assert off[1] - off[0] == 1 or L == 0
+    for l in range(L):
+        lv = nodes[off[l]:off[l + 1]]
+        pc = np.array([bin(int(m) & 0xff).count("1") for m in lv[:, 1]], np.int64)
+        assert (pc >= 1).all()
+        first = lv[:, 0].astype(np.int64)
+        assert first[0] == off[l + 1]
+        assert (first[1:] == first[:-1] + pc[:-1]).all()
+        assert first[-1] + pc[-1] == off[l + 2] if l + 2 <= L + 1 else True
+    lf = nodes[off[L]:off[L] + info["num_leaves"]]
+    assert (lf[:, 1] == cnt).all()
+    assert (np.cumsum(np.concatenate([[0], cnt[:-1]])) == lf[:, 0]).all()
+
+
+@pytest.mark.parametrize("spp", [1, 4])
+def test_trace_camera_vs_oracle(case, gpu, port, spp):
+    cam10 = case["cam10"]
+    nx, ny = 160, 96
+    cam = gpu.Camera(cam10[0], cam10[1:4], cam10[4:7], cam10[7:10], nx, ny, spp)
+    got = case["tree"].trace_camera(cam)
+    rays = port.gen_rays(cam10, 1.0, nx, ny, spp)
+    exp = case["orc"].trace(rays)
+    assert exp.hit.sum() > 0
+    bad = compare_hits(got, exp, case["name"])
+    assert bad == 0
+    # explicit-ray entry point gives the same records
+    got2 = case["tree"].trace_rays(rays)
+    assert got2.tobytes() == got.tobytes()
+
+
+def test_trace_on_imported_oracle_tree(case, gpu, port):
+    """Ray kernel on the ORACLE's leaf set (isolates traversal from voxelization)."""
+    cells, counts, refs = case["orc"].leaves()
+    tree = gpu.Octree.from_leaves(case["tri"], case["nrm"], case["depth"], case["orc"].root_aabb(), cells, counts, refs)
+    cam10 = case["cam10"]
+    cam = gpu.Camera(cam10[0], cam10[1:4], cam10[4:7], cam10[7:10], 96, 64, 1)
+    got = tree.trace_camera(cam)
+    exp = case["orc"].trace(port.gen_rays(cam10, 1.0, 96, 64, 1))
+    assert compare_hits(got, exp, case["name"] + " imported") == 0
+    leaves_equal(tree.leaves(), (cells, counts, refs))
+    tree.close()
+
+
+def test_render_film_vs_oracle(case, gpu, port):
+    cam10 = case["cam10"]
+    nx, ny, spp = 128, 72, 4
+    cam = gpu.Camera(cam10[0], cam10[1:4], cam10[4:7], cam10[7:10], nx, ny, spp)
+    film = case["tree"].render(cam, kd=0.8)
+    rays = port.gen_rays(cam10, 1.0, nx, ny, spp)
+    exp = harness_film(rays, case["orc"].trace(rays), gpu.default_light(), 0.8, spp).reshape(ny, nx, 3)
+    # tolerance of the north star: 1/255 after the reference's byte conversion
+    diff = np.abs(to_u8(film).astype(int) - to_u8(exp).astype(int))
+    assert diff.max() <= 1
+    assert_bits_equal(film, exp, "film (float)")
+
+
+def test_random_rays_inside_scene(case, gpu, port):
+    """Rays with arbitrary origins/directions (incl. axis-parallel and origins inside
+    the root box) -- the reference accepts hits behind the origin."""
+    rng = np.random.default_rng(7)
+    n = 20000
+    root = case["orc"].root_aabb()
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.uniform(root[:3] - 0.2, root[3:] + 0.2, (n, 3))
+    d = rng.normal(size=(n, 3))
+    d[: n // 10, 0] = 0.0
+    d[n // 10: n // 5, 1] = 0.0
+    rays[:, 3:6] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 7] = np.finfo(np.float32).max
+    got = case["tree"].trace_rays(rays)
+    exp = case["orc"].trace(rays)
+    assert compare_hits(got, exp, case["name"] + " random rays") == 0
+
+
+# ----------------------------------------------------------------------------
+# edge cases
+# ----------------------------------------------------------------------------
+def test_empty_scene(gpu):
+    tree = gpu.Octree.build(np.zeros((0, 3, 3), np.float32), None, 5)
+    info = tree.info()
+    assert info["num_leaves"] == 0 and info["num_nodes"] == 0
+    cam = gpu.Camera(CAM_SPHERE[0], CAM_SPHERE[1:4], CAM_SPHERE[4:7], CAM_SPHERE[7:10], 32, 16, 1)
+    assert tree.trace_camera(cam)["hit"].sum() == 0
+    tree.close()
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_shallow_depths(gpu, port, depth):
+    tri, nrm = scenes.uv_sphere(32, 16)
+    orc = port.build(tri, nrm, depth)
+    tree = gpu.Octree.build(tri, nrm, depth)
+    leaves_equal(tree.leaves(), orc.leaves())
+    cam = gpu.Camera(CAM_SPHERE[0], CAM_SPHERE[1:4], CAM_SPHERE[4:7], CAM_SPHERE[7:10], 64, 48, 1)
+    got = tree.trace_camera(cam)
+    exp = orc.trace(port.gen_rays(CAM_SPHERE, 1.0, 64, 48, 1))
+    assert compare_hits(got, exp, f"depth {depth}") == 0
+    tree.close()
+
+
+def test_single_triangle_and_degenerates(gpu, port):
+    tri = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0]],
+                    [[0, 0, 0], [0, 0, 0], [0, 0, 0]],       # point triangle
+                    [[0, 0, 0.5], [1, 1, 0.5], [2, 2, 0.5]],  # collinear
+                    [[0.25, 0.25, -1], [0.25, 0.25, 1], [0.3, 0.2, 0]]], np.float32)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (4, 3, 1))
+    for depth in (1, 4, 6):
+        orc = port.build(tri, nrm, depth)
+        tree = gpu.Octree.build(tri, nrm, depth)
+        leaves_equal(tree.leaves(), orc.leaves())
+        rays = port.gen_rays(CAM_SPHERE, 1.0, 64, 64, 4)
+        assert compare_hits(tree.trace_rays(rays), orc.trace(rays), "degenerates") == 0
+        tree.close()
+
+
+def test_bad_arguments(gpu):
+    tri, nrm = scenes.uv_sphere(16, 8)
+    with pytest.raises(gpu.VrtError):
+        gpu.Octree.build(tri, nrm, 0)
+    with pytest.raises(gpu.VrtError):
+        gpu.Octree.build(tri, nrm, 99)
+    tree = gpu.Octree.build(tri, nrm, 4)
+    cam = gpu.Camera(CAM_SPHERE[0], CAM_SPHERE[1:4], CAM_SPHERE[4:7], CAM_SPHERE[7:10], 32, 32, 1)
+    with pytest.raises(gpu.VrtError):
+        tree.trace_camera(cam, rect=(0, 0, 64, 32))  # outside the film (reference asserts, camera.cc:79)
+    tree.close()
+
+
+def test_rebuild_and_blob_replica(gpu, port):
+    tri, nrm = scenes.uv_sphere(64, 32)
+    tree = gpu.Octree.build(tri, nrm, 5)
+    tree.rebuild(7)
+    orc = port.build(tri, nrm, 7)
+    leaves_equal(tree.leaves(), orc.leaves())
+    ptr, nbytes = tree.blob_dev()
+    rep = gpu.Octree.from_blob_dev(ptr, nbytes)
+    cam = gpu.Camera(CAM_SPHERE[0], CAM_SPHERE[1:4], CAM_SPHERE[4:7], CAM_SPHERE[7:10], 64, 64, 4)
+    assert rep.trace_camera(cam).tobytes() == tree.trace_camera(cam).tobytes()
+    rep.close()
+    tree.close()

@@ -1,0 +1,331 @@
+"""ctypes binding of libvrt.so (include/vrt.h) -- the host-side mirror used by
+tests and bench.py.  Python is only plumbing here: every compute call lands in
+the CUDA library; if the library or a CUDA device is missing the calls raise
+:class:`VrtError` (there is no CPU fallback and no route into oracle/).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+VRT_MAX_DEPTH = 17
+VRT_NO_TRI = 0xFFFFFFFF
+
+
+class VrtError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libvrt error {code}: {msg}")
+        self.code = code
+
+
+class vrt_camera(C.Structure):
+    _fields_ = [("C", C.c_float * 16), ("z", C.c_float), ("tmin", C.c_float), ("tmax", C.c_float),
+                ("nx", C.c_int32), ("ny", C.c_int32), ("spp", C.c_int32)]
+
+
+class vrt_shade(C.Structure):
+    _fields_ = [("light_dir", C.c_float * 3), ("kd", C.c_float)]
+
+
+class vrt_tree_info(C.Structure):
+    _fields_ = [("num_tris", C.c_uint32), ("max_depth", C.c_int32), ("root_aabb", C.c_float * 6),
+                ("num_nodes", C.c_uint64), ("num_leaves", C.c_uint64), ("num_refs", C.c_uint64),
+                ("level_offset", C.c_uint64 * (VRT_MAX_DEPTH + 1)), ("device_bytes", C.c_uint64),
+                ("build_ms", C.c_double)]
+
+
+class vrt_tree_view(C.Structure):
+    _fields_ = [("leaf_cell", C.c_void_p), ("leaf_count", C.c_void_p), ("leaf_refs", C.c_void_p),
+                ("nodes", C.c_void_p)]
+
+
+HIT_DTYPE = np.dtype([("hit", "<u4"), ("tri", "<u4"), ("cell", "<u4", (3,)), ("t", "<f4"),
+                      ("pos", "<f4", (3,)), ("nrm", "<f4", (3,))])
+HIT16_DTYPE = np.dtype([("leaf", "<u4"), ("tri", "<u4"), ("t", "<f4"), ("hit", "<u4")])
+RAY_DTYPE = np.dtype([("o", "<f4", (3,)), ("d", "<f4", (3,)), ("tmin", "<f4"), ("tmax", "<f4")])
+assert HIT_DTYPE.itemsize == 48 and HIT16_DTYPE.itemsize == 16 and RAY_DTYPE.itemsize == 32
+
+# every symbol include/vrt.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "vrt_abi_version", "vrt_last_error", "vrt_device_count", "vrt_launch_count",
+    "vrt_build", "vrt_build_dev", "vrt_rebuild", "vrt_tree_free", "vrt_tree_get_info",
+    "vrt_tree_export", "vrt_tree_import", "vrt_tree_set_stream", "vrt_tree_blob_dev",
+    "vrt_tree_from_blob_dev", "vrt_camera_init", "vrt_gen_rays", "vrt_trace_rays",
+    "vrt_trace_rays_dev", "vrt_trace_camera", "vrt_trace_camera_dev", "vrt_trace_camera16_dev",
+    "vrt_render_camera", "vrt_render_camera_dev", "vrt_last_kernel_ms", "vrt_tribox_batch",
+    "vrt_tri_overlap_aabb_batch", "vrt_raytri_batch", "vrt_aabb_isect_batch",
+]
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """dlopen libvrt.so (building it in-tree with nvcc when stale and possible)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing and _build.is_stale():
+        try:
+            _build.build_native()
+        except Exception as e:  # keep a prebuilt .so if nvcc is unavailable
+            if not os.path.exists(path):
+                raise VrtError(-2, f"libvrt.so missing and cannot be built: {e}") from e
+    if not os.path.exists(path):
+        raise VrtError(-2, "libvrt.so missing (no CPU fallback exists)")
+    L = C.CDLL(path)
+    vp, u32, u64, i32, f32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_float
+    L.vrt_abi_version.restype = i32
+    L.vrt_last_error.restype = C.c_char_p
+    L.vrt_device_count.restype = i32
+    L.vrt_launch_count.restype = u64
+    L.vrt_build.argtypes = [vp, vp, u32, i32, C.POINTER(vp)]
+    L.vrt_build_dev.argtypes = [vp, vp, u32, i32, C.POINTER(vp)]
+    L.vrt_rebuild.argtypes = [vp, i32]
+    L.vrt_tree_free.argtypes = [vp]
+    L.vrt_tree_free.restype = None
+    L.vrt_tree_get_info.argtypes = [vp, C.POINTER(vrt_tree_info)]
+    L.vrt_tree_export.argtypes = [vp, C.POINTER(vrt_tree_view)]
+    L.vrt_tree_import.argtypes = [vp, vp, u32, i32, vp, u64, vp, vp, vp, C.POINTER(vp)]
+    L.vrt_tree_set_stream.argtypes = [vp, vp]
+    L.vrt_tree_blob_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    L.vrt_tree_from_blob_dev.argtypes = [vp, u64, C.POINTER(vp)]
+    L.vrt_camera_init.argtypes = [vp, f32, i32, i32, i32, C.POINTER(vrt_camera)]
+    L.vrt_gen_rays.argtypes = [C.POINTER(vrt_camera), i32, i32, i32, i32, vp]
+    L.vrt_trace_rays.argtypes = [vp, vp, u64, vp]
+    L.vrt_trace_rays_dev.argtypes = [vp, vp, u64, vp]
+    for name in ("vrt_trace_camera", "vrt_trace_camera_dev", "vrt_trace_camera16_dev"):
+        getattr(L, name).argtypes = [vp, C.POINTER(vrt_camera), i32, i32, i32, i32, vp]
+    for name in ("vrt_render_camera", "vrt_render_camera_dev"):
+        getattr(L, name).argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), i32, i32, i32, i32, vp]
+    L.vrt_last_kernel_ms.restype = C.c_double
+    L.vrt_last_kernel_ms.argtypes = [vp]
+    L.vrt_tribox_batch.argtypes = [vp, vp, vp, u64, vp]
+    L.vrt_tri_overlap_aabb_batch.argtypes = [vp, vp, u64, vp]
+    L.vrt_raytri_batch.argtypes = [vp, u64, vp, vp]
+    L.vrt_aabb_isect_batch.argtypes = [vp, vp, u64, vp]
+    for s in SYMBOLS:
+        f = getattr(L, s)
+        if f.restype is C.c_int and s not in ("vrt_abi_version", "vrt_device_count"):
+            pass
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise VrtError(rc, load().vrt_last_error().decode(errors="replace"))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+def device_count() -> int:
+    return int(load().vrt_device_count())
+
+
+def launch_count() -> int:
+    return int(load().vrt_launch_count())
+
+
+def default_light():
+    """normalize(Vec3{1,10,1}) with the reference's float arithmetic (main.cc:72)."""
+    v = np.array([1, 10, 1], np.float32)
+    s = np.float32(0)
+    for k in range(3):
+        s = np.float32(s + np.float32(v[k] * v[k]))
+    return (v / np.sqrt(s, dtype=np.float32)).astype(np.float32)
+
+
+class Camera:
+    """Mirror of the reference's ``Camera(fov, eye, spot, up)`` + ``Film(w,h,nx,ny)``
+    (camera.h:24-29,70-83)."""
+
+    def __init__(self, fov, eye, spot, up, nx, ny, spp=1, film_h=1.0):
+        self.cam10 = np.array([fov, *eye, *spot, *up], np.float32)
+        self.c = vrt_camera()
+        _check(load().vrt_camera_init(_ptr(self.cam10), float(film_h), int(nx), int(ny), int(spp), C.byref(self.c)))
+        self.nx, self.ny, self.spp, self.film_h = int(nx), int(ny), int(spp), float(film_h)
+
+    @property
+    def matrix(self):
+        return np.array(self.c.C[:], np.float32)
+
+    def gen_rays(self, rect=None):
+        """gen_rays1/gen_rays4 for every pixel of ``rect`` -> structured RAY array."""
+        x0, y0, x1, y1 = rect if rect else (0, 0, self.nx, self.ny)
+        out = np.zeros((y1 - y0) * (x1 - x0) * self.spp, RAY_DTYPE)
+        _check(load().vrt_gen_rays(C.byref(self.c), x0, y0, x1, y1, _ptr(out)))
+        return out
+
+
+class Octree:
+    """Owner of a ``vrt_tree*`` -- mirror of ``gi::VoxelOctree`` + ``ray_march_init``."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+
+    # ---- construction ------------------------------------------------------
+    @classmethod
+    def build(cls, tri_xyz, tri_nrm, max_depth):
+        """gi::ray_march_init(&root, voxels, max_depth) -- host arrays in."""
+        tri = _f32(tri_xyz, (-1, 9))
+        nrm = None if tri_nrm is None else _f32(tri_nrm, (-1, 9))
+        h = C.c_void_p()
+        _check(load().vrt_build(_ptr(tri), _ptr(nrm), tri.shape[0], int(max_depth), C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def build_dev(cls, d_tri_ptr, d_nrm_ptr, num_tris, max_depth):
+        h = C.c_void_p()
+        _check(load().vrt_build_dev(C.c_void_p(d_tri_ptr), C.c_void_p(d_nrm_ptr) if d_nrm_ptr else None,
+                                    int(num_tris), int(max_depth), C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_leaves(cls, tri_xyz, tri_nrm, max_depth, root_aabb, leaf_cell, leaf_count, leaf_refs):
+        tri = _f32(tri_xyz, (-1, 9))
+        nrm = None if tri_nrm is None else _f32(tri_nrm, (-1, 9))
+        root = _f32(root_aabb)
+        cell = np.ascontiguousarray(leaf_cell, np.uint32)
+        cnt = np.ascontiguousarray(leaf_count, np.uint32)
+        refs = np.ascontiguousarray(leaf_refs, np.uint32)
+        h = C.c_void_p()
+        _check(load().vrt_tree_import(_ptr(tri), _ptr(nrm), tri.shape[0], int(max_depth), _ptr(root), len(cnt),
+                                      _ptr(cell), _ptr(cnt), _ptr(refs), C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_blob_dev(cls, d_ptr, nbytes):
+        h = C.c_void_p()
+        _check(load().vrt_tree_from_blob_dev(C.c_void_p(d_ptr), int(nbytes), C.byref(h)))
+        return cls(h.value)
+
+    def rebuild(self, max_depth):
+        _check(load().vrt_rebuild(self._h, int(max_depth)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            load().vrt_tree_free(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(load().vrt_tree_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    # ---- inspection --------------------------------------------------------
+    def info(self):
+        i = vrt_tree_info()
+        _check(load().vrt_tree_get_info(self._h, C.byref(i)))
+        return dict(num_tris=i.num_tris, max_depth=i.max_depth, root_aabb=np.array(i.root_aabb[:], np.float32),
+                    num_nodes=int(i.num_nodes), num_leaves=int(i.num_leaves), num_refs=int(i.num_refs),
+                    level_offset=[int(v) for v in i.level_offset], device_bytes=int(i.device_bytes),
+                    build_ms=float(i.build_ms))
+
+    def leaves(self, nodes=False):
+        """(leaf_cell [L,3], leaf_count [L], leaf_refs [R]) in Morton order."""
+        i = self.info()
+        cell = np.zeros((i["num_leaves"], 3), np.uint32)
+        cnt = np.zeros(i["num_leaves"], np.uint32)
+        refs = np.zeros(i["num_refs"], np.uint32)
+        nd = np.zeros((i["num_nodes"], 2), np.uint32) if nodes else None
+        v = vrt_tree_view(_ptr(cell), _ptr(cnt), _ptr(refs), _ptr(nd))
+        _check(load().vrt_tree_export(self._h, C.byref(v)))
+        return (cell, cnt, refs, nd) if nodes else (cell, cnt, refs)
+
+    def blob_dev(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        _check(load().vrt_tree_blob_dev(self._h, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    @property
+    def last_kernel_ms(self):
+        return float(load().vrt_last_kernel_ms(self._h))
+
+    # ---- queries -----------------------------------------------------------
+    def trace_rays(self, rays):
+        """gi::ray_march for a batch of rays (structured RAY array or [R,8] float32)."""
+        rays = np.ascontiguousarray(rays)
+        if rays.dtype != RAY_DTYPE:
+            rays = np.ascontiguousarray(rays, np.float32).reshape(-1, 8).view(RAY_DTYPE).reshape(-1)
+        out = np.zeros(len(rays), HIT_DTYPE)
+        _check(load().vrt_trace_rays(self._h, _ptr(rays), len(rays), _ptr(out)))
+        return out
+
+    def trace_rays_dev(self, d_rays_ptr, n, d_out_ptr):
+        _check(load().vrt_trace_rays_dev(self._h, C.c_void_p(d_rays_ptr), int(n), C.c_void_p(d_out_ptr)))
+
+    def trace_camera(self, cam: Camera, rect=None):
+        """render_mt loop replaced by one launch: gen_rays + ray_march per pixel sample."""
+        x0, y0, x1, y1 = rect if rect else (0, 0, cam.nx, cam.ny)
+        out = np.zeros((y1 - y0) * (x1 - x0) * cam.spp, HIT_DTYPE)
+        _check(load().vrt_trace_camera(self._h, C.byref(cam.c), x0, y0, x1, y1, _ptr(out)))
+        return out
+
+    def trace_camera_dev(self, cam: Camera, d_out_ptr, rect=None, compact=False):
+        x0, y0, x1, y1 = rect if rect else (0, 0, cam.nx, cam.ny)
+        fn = load().vrt_trace_camera16_dev if compact else load().vrt_trace_camera_dev
+        _check(fn(self._h, C.byref(cam.c), x0, y0, x1, y1, C.c_void_p(d_out_ptr)))
+
+    def render(self, cam: Camera, light=None, kd=0.8, rect=None, out=None):
+        """Harness-shaded film (float RGB, [h,w,3]) through HOST buffers."""
+        x0, y0, x1, y1 = rect if rect else (0, 0, cam.nx, cam.ny)
+        sh = vrt_shade((C.c_float * 3)(*(default_light() if light is None else light)), float(kd))
+        if out is None:
+            out = np.zeros((y1 - y0, x1 - x0, 3), np.float32)
+        _check(load().vrt_render_camera(self._h, C.byref(cam.c), C.byref(sh), x0, y0, x1, y1, _ptr(out)))
+        return out
+
+    def render_dev(self, cam: Camera, d_film_ptr, light=None, kd=0.8, rect=None):
+        x0, y0, x1, y1 = rect if rect else (0, 0, cam.nx, cam.ny)
+        sh = vrt_shade((C.c_float * 3)(*(default_light() if light is None else light)), float(kd))
+        _check(load().vrt_render_camera_dev(self._h, C.byref(cam.c), C.byref(sh), x0, y0, x1, y1,
+                                            C.c_void_p(d_film_ptr)))
+
+
+# ---- predicates (device KATs) ------------------------------------------------
+def tribox(centers, halves, tris):
+    """triBoxOverlap(boxcenter, boxhalfsize, triverts) (tribox2.h:15), batched."""
+    c, h, t = _f32(centers, (-1, 3)), _f32(halves, (-1, 3)), _f32(tris, (-1, 9))
+    out = np.zeros(len(c), np.uint8)
+    _check(load().vrt_tribox_batch(_ptr(c), _ptr(h), _ptr(t), len(c), _ptr(out)))
+    return out
+
+
+def tri_overlap_aabb(aabbs, tris):
+    b, t = _f32(aabbs, (-1, 6)), _f32(tris, (-1, 9))
+    out = np.zeros(len(b), np.uint8)
+    _check(load().vrt_tri_overlap_aabb_batch(_ptr(b), _ptr(t), len(b), _ptr(out)))
+    return out
+
+
+def raytri(in15):
+    """intersect_triangle3(orig, dir, v0, v1, v2, &t, &u, &v) (raytri.h:5-7), batched."""
+    a = np.ascontiguousarray(in15, np.float64).reshape(-1, 15)
+    res = np.zeros(len(a), np.uint8)
+    tuv = np.zeros((len(a), 3), np.float64)
+    _check(load().vrt_raytri_batch(_ptr(a), len(a), _ptr(res), _ptr(tuv)))
+    return res, tuv
+
+
+def aabb_isect(aabbs, rays):
+    b = _f32(aabbs, (-1, 6))
+    r = np.ascontiguousarray(rays, np.float32).reshape(-1, 8)
+    out = np.zeros(len(b), np.uint8)
+    _check(load().vrt_aabb_isect_batch(_ptr(b), _ptr(r), len(b), _ptr(out)))
+    return out

@@ -1,0 +1,816 @@
+// vrt_api.cu -- the extern "C" boundary of libvrt.so (include/vrt.h): handle
+// management, error reporting, host<->device staging for the host-pointer entry
+// points, and the predicate KAT kernels.  No torch types, no CPU fallback.
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "vrt_exact.cuh"
+#include "vrt_internal.h"
+
+namespace vrt {
+
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{ 0 };
+
+void set_error(const char* fmt, ...)
+{
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        g_err = buf;
+}
+
+bool cuda_ok(cudaError_t e, const char* what)
+{
+        if (e == cudaSuccess)
+                return true;
+        set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+        cudaGetLastError();
+        return false;
+}
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int Scratch::reserve(size_t bytes)
+{
+        if (bytes <= cap && p)
+                return 0;
+        if (p) {
+                cudaFree(p);
+                p = nullptr;
+                cap = 0;
+        }
+        size_t want = std::max<size_t>(bytes, 256);
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+                cudaGetLastError();
+                p = nullptr;
+                set_error("cudaMalloc(%zu) failed", want);
+                return VRT_ERR_NOMEM;
+        }
+        cap = want;
+        return 0;
+}
+
+void Scratch::release()
+{
+        if (p)
+                cudaFree(p);
+        p = nullptr;
+        cap = 0;
+}
+
+int tree_alloc(vrt_tree** out)
+{
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+                cudaGetLastError();
+                set_error("no CUDA device available (libvrt has no CPU fallback)");
+                return VRT_ERR_CUDA;
+        }
+        vrt_tree* t = new (std::nothrow) vrt_tree();
+        if (!t)
+                return VRT_ERR_NOMEM;
+        if (!cuda_ok(cudaGetDevice(&t->device), "cudaGetDevice") ||
+            !cuda_ok(cudaMalloc(&t->d_counter, 256), "cudaMalloc(counter)") ||
+            !cuda_ok(cudaMallocHost(&t->h_counter, 256), "cudaMallocHost(counter)") ||
+            !cuda_ok(cudaMemset(t->d_counter, 0, 256), "cudaMemset(counter)") ||
+            !cuda_ok(cudaEventCreate(&t->ev0), "cudaEventCreate") ||
+            !cuda_ok(cudaEventCreate(&t->ev1), "cudaEventCreate")) {
+                vrt_tree_free(t);
+                return VRT_ERR_CUDA;
+        }
+        *out = t;
+        return VRT_OK;
+}
+
+void tree_bind_views(vrt_tree* t)
+{
+        const BlobHeader& h = t->hdr;
+        char* base = static_cast<char*>(t->blob);
+        TreeDev& d = t->dev;
+        d.nodes = reinterpret_cast<const uint2*>(base + h.off_nodes);
+        d.leaf_morton = reinterpret_cast<const unsigned long long*>(base + h.off_leaf_morton);
+        d.leaf_refs = reinterpret_cast<const uint32_t*>(base + h.off_leaf_refs);
+        d.tri4 = reinterpret_cast<const float4*>(base + h.off_tri4);
+        d.nrm = reinterpret_cast<const float*>(base + h.off_nrm);
+        for (int a = 0; a < 3; ++a) {
+                d.tab2[a] = reinterpret_cast<const float2*>(base + h.off_axis_tab) + a * h.axis_tab_stride;
+                d.tab4[a] = reinterpret_cast<const float4*>(d.tab2[a]);
+        }
+        d.num_nodes = (uint32_t)h.num_nodes;
+        d.num_leaves = (uint32_t)h.num_leaves;
+        d.L = h.max_depth - 1;
+}
+
+static int check_tree(const vrt_tree* t)
+{
+        if (!t) {
+                set_error("null tree handle");
+                return VRT_ERR_ARG;
+        }
+        if (!t->blob || t->hdr.magic != kBlobMagic) {
+                set_error("tree handle holds no built octree");
+                return VRT_ERR_STATE;
+        }
+        int dev = -1;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev != t->device) {
+                cudaGetLastError();
+                set_error("tree lives on device %d but the current device is %d", t->device, dev);
+                return VRT_ERR_STATE;
+        }
+        return VRT_OK;
+}
+
+static int upload_inputs(vrt_tree* t, const float* tri, const float* nrm, uint32_t T, bool from_device)
+{
+        const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        const size_t bytes = (size_t)std::max<uint32_t>(T, 1) * 36;
+        if (!cuda_ok(cudaMalloc(&t->d_tri_in, bytes), "cudaMalloc(tri)"))
+                return VRT_ERR_NOMEM;
+        if (T)
+                VRT_CUDA(cudaMemcpyAsync(t->d_tri_in, tri, (size_t)T * 36, kind, t->stream));
+        if (nrm) {
+                if (!cuda_ok(cudaMalloc(&t->d_nrm_in, bytes), "cudaMalloc(nrm)"))
+                        return VRT_ERR_NOMEM;
+                if (T)
+                        VRT_CUDA(cudaMemcpyAsync(t->d_nrm_in, nrm, (size_t)T * 36, kind, t->stream));
+        }
+        t->hdr.num_tris = T;
+        return VRT_OK;
+}
+
+static int build_common(const float* tri, const float* nrm, uint32_t T, int max_depth, bool dev, vrt_tree** out)
+{
+        if (!out || (T && !tri)) {
+                set_error("vrt_build: null argument");
+                return VRT_ERR_ARG;
+        }
+        *out = nullptr;
+        if (max_depth < 1 || max_depth > (int)VRT_MAX_DEPTH) {
+                set_error("vrt_build: max_depth %d out of range [1,%u]", max_depth, VRT_MAX_DEPTH);
+                return VRT_ERR_ARG;
+        }
+        vrt_tree* t = nullptr;
+        int rc = tree_alloc(&t);
+        if (rc)
+                return rc;
+        rc = upload_inputs(t, tri, nrm, T, dev);
+        if (!rc)
+                rc = build_tree(t, max_depth);
+        if (rc) {
+                vrt_tree_free(t);
+                return rc;
+        }
+        *out = t;
+        return VRT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// predicate KAT kernels
+// ---------------------------------------------------------------------------
+__global__ void k_tribox(const float* __restrict__ c, const float* __restrict__ h, const float* __restrict__ tri,
+                         uint64_t n, uint8_t* __restrict__ out)
+{
+        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n)
+                return;
+        float cc[3] = { c[3 * i], c[3 * i + 1], c[3 * i + 2] };
+        float hh[3] = { h[3 * i], h[3 * i + 1], h[3 * i + 2] };
+        const float* p = tri + 9 * i;
+        float v0[3] = { p[0], p[1], p[2] }, v1[3] = { p[3], p[4], p[5] }, v2[3] = { p[6], p[7], p[8] };
+        out[i] = tribox_overlap(cc, hh, v0, v1, v2) ? 1 : 0;
+}
+
+__global__ void k_tri_aabb(const float* __restrict__ box, const float* __restrict__ tri, uint64_t n,
+                           uint8_t* __restrict__ out)
+{
+        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n)
+                return;
+        float mn[3] = { box[6 * i], box[6 * i + 1], box[6 * i + 2] };
+        float mx[3] = { box[6 * i + 3], box[6 * i + 4], box[6 * i + 5] };
+        const float* p = tri + 9 * i;
+        float v0[3] = { p[0], p[1], p[2] }, v1[3] = { p[3], p[4], p[5] }, v2[3] = { p[6], p[7], p[8] };
+        out[i] = tri_overlaps_aabb(mn, mx, v0, v1, v2) ? 1 : 0;
+}
+
+__global__ void k_raytri(const double* __restrict__ in, uint64_t n, uint8_t* __restrict__ res,
+                         double* __restrict__ tuv)
+{
+        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n)
+                return;
+        const double* a = in + 15 * i;
+        double o[3] = { a[0], a[1], a[2] }, d[3] = { a[3], a[4], a[5] }, v0[3] = { a[6], a[7], a[8] },
+               v1[3] = { a[9], a[10], a[11] }, v2[3] = { a[12], a[13], a[14] };
+        double t = 0, u = 0, v = 0;
+        int r = ray_triangle3(o, d, v0, v1, v2, t, u, v);
+        res[i] = (uint8_t)r;
+        // on rejection the reference leaves *t untouched and *u/*v at their
+        // intermediate values; only report them for accepted hits
+        tuv[3 * i] = r ? t : 0.0;
+        tuv[3 * i + 1] = r ? u : 0.0;
+        tuv[3 * i + 2] = r ? v : 0.0;
+}
+
+__global__ void k_aabb_isect(const float* __restrict__ box, const vrt_ray* __restrict__ rays, uint64_t n,
+                             uint8_t* __restrict__ out)
+{
+        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n)
+                return;
+        float mn[3] = { box[6 * i], box[6 * i + 1], box[6 * i + 2] };
+        float mx[3] = { box[6 * i + 3], box[6 * i + 4], box[6 * i + 5] };
+        const vrt_ray r = rays[i];
+        float o[3] = { r.o[0], r.o[1], r.o[2] };
+        float dinv[3] = { slab_dinv(r.d[0]), slab_dinv(r.d[1]), slab_dinv(r.d[2]) };
+        out[i] = aabb_isect(mn, mx, o, dinv, r.tmin, r.tmax) ? 1 : 0;
+}
+
+__global__ void k_gen_rays(CameraParams cam, int x0, int y0, int x1, int y1, vrt_ray* __restrict__ out)
+{
+        const int W = x1 - x0;
+        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        uint64_t n = (uint64_t)W * (y1 - y0) * cam.spp;
+        if (i >= n)
+                return;
+        const int s = (int)(i % cam.spp);
+        const uint64_t pix = i / cam.spp;
+        const int px = x0 + (int)(pix % W), py = y0 + (int)(pix / W);
+        float o[3], d[3];
+        gen_ray(cam, px, py, s, o, d);
+        vrt_ray r;
+        r.o[0] = o[0]; r.o[1] = o[1]; r.o[2] = o[2];
+        r.d[0] = d[0]; r.d[1] = d[1]; r.d[2] = d[2];
+        r.tmin = cam.tmin;
+        r.tmax = cam.tmax;
+        out[i] = r;
+}
+
+// small RAII device buffer for the stateless batch entry points
+struct DevBuf {
+        void* p = nullptr;
+        ~DevBuf() { if (p) cudaFree(p); }
+        int alloc(size_t bytes)
+        {
+                if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) {
+                        cudaGetLastError();
+                        set_error("cudaMalloc(%zu) failed", bytes);
+                        p = nullptr;
+                        return VRT_ERR_NOMEM;
+                }
+                return 0;
+        }
+};
+
+static int need_device()
+{
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || n < 1) {
+                cudaGetLastError();
+                set_error("no CUDA device available (libvrt has no CPU fallback)");
+                return VRT_ERR_CUDA;
+        }
+        return VRT_OK;
+}
+
+static CameraParams to_params(const vrt_camera* c)
+{
+        CameraParams p;
+        for (int k = 0; k < 16; ++k)
+                p.C[k] = c->C[k];
+        p.z = c->z;
+        p.tmin = c->tmin;
+        p.tmax = c->tmax;
+        p.nx = c->nx;
+        p.ny = c->ny;
+        p.spp = c->spp;
+        return p;
+}
+
+static int check_camera(const vrt_camera* cam, int x0, int y0, int x1, int y1)
+{
+        if (!cam || (cam->spp != 1 && cam->spp != 4) || cam->nx < 1 || cam->ny < 1) {
+                set_error("bad camera (spp must be 1 or 4, nx/ny >= 1)");
+                return VRT_ERR_ARG;
+        }
+        // the reference asserts the pixel is inside the film (camera.cc:79,97)
+        if (x0 < 0 || y0 < 0 || x1 > cam->nx || y1 > cam->ny || x1 < x0 || y1 < y0) {
+                set_error("pixel rectangle [%d,%d)x[%d,%d) outside the %dx%d film", x0, x1, y0, y1, cam->nx, cam->ny);
+                return VRT_ERR_ARG;
+        }
+        return VRT_OK;
+}
+
+}  // namespace vrt
+
+using namespace vrt;
+
+uint64_t vrt_tree::scratch_bytes() const
+{
+        uint64_t b = keys_a.cap + keys_b.cap + tmp_a.cap + tmp_b.cap + tmp_c.cap + hist.cap + io_in.cap + io_out.cap;
+        for (unsigned l = 0; l <= VRT_MAX_DEPTH; ++l)
+                b += level_morton[l].cap + level_first[l].cap + level_mask[l].cap;
+        return b;
+}
+
+extern "C" {
+
+int vrt_abi_version(void) { return VRT_ABI_VERSION; }
+
+const char* vrt_last_error(void) { return g_err.c_str(); }
+
+int vrt_device_count(void)
+{
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("cudaGetDeviceCount failed");
+                return VRT_ERR_CUDA;
+        }
+        return n;
+}
+
+uint64_t vrt_launch_count(void) { return g_launches.load(); }
+
+int vrt_build(const float* tri_xyz, const float* tri_nrm, uint32_t num_tris, int max_depth, vrt_tree** out)
+{
+        return build_common(tri_xyz, tri_nrm, num_tris, max_depth, false, out);
+}
+
+int vrt_build_dev(const float* d_tri_xyz, const float* d_tri_nrm, uint32_t num_tris, int max_depth, vrt_tree** out)
+{
+        return build_common(d_tri_xyz, d_tri_nrm, num_tris, max_depth, true, out);
+}
+
+int vrt_rebuild(vrt_tree* tree, int max_depth)
+{
+        if (!tree || !tree->d_tri_in) {
+                set_error("vrt_rebuild: handle holds no input triangles");
+                return VRT_ERR_STATE;
+        }
+        if (max_depth < 1 || max_depth > (int)VRT_MAX_DEPTH) {
+                set_error("vrt_rebuild: max_depth %d out of range", max_depth);
+                return VRT_ERR_ARG;
+        }
+        return build_tree(tree, max_depth);
+}
+
+void vrt_tree_free(vrt_tree* t)
+{
+        if (!t)
+                return;
+        if (t->blob && t->own_blob)
+                cudaFree(t->blob);
+        if (t->d_tri_in)
+                cudaFree(t->d_tri_in);
+        if (t->d_nrm_in)
+                cudaFree(t->d_nrm_in);
+        t->keys_a.release();
+        t->keys_b.release();
+        t->tmp_a.release();
+        t->tmp_b.release();
+        t->tmp_c.release();
+        t->hist.release();
+        t->io_in.release();
+        t->io_out.release();
+        for (unsigned l = 0; l <= VRT_MAX_DEPTH; ++l) {
+                t->level_morton[l].release();
+                t->level_first[l].release();
+                t->level_mask[l].release();
+        }
+        if (t->d_counter)
+                cudaFree(t->d_counter);
+        if (t->h_counter)
+                cudaFreeHost(t->h_counter);
+        if (t->ev0)
+                cudaEventDestroy(t->ev0);
+        if (t->ev1)
+                cudaEventDestroy(t->ev1);
+        cudaGetLastError();
+        delete t;
+}
+
+int vrt_tree_get_info(const vrt_tree* t, vrt_tree_info* out)
+{
+        if (!out) {
+                set_error("null out");
+                return VRT_ERR_ARG;
+        }
+        int rc = check_tree(t);
+        if (rc)
+                return rc;
+        memset(out, 0, sizeof *out);
+        out->num_tris = t->hdr.num_tris;
+        out->max_depth = t->hdr.max_depth;
+        memcpy(out->root_aabb, t->hdr.root_aabb, 24);
+        out->num_nodes = t->hdr.num_nodes;
+        out->num_leaves = t->hdr.num_leaves;
+        out->num_refs = t->hdr.num_refs;
+        memcpy(out->level_offset, t->hdr.level_offset, sizeof out->level_offset);
+        out->device_bytes = t->blob_bytes + t->scratch_bytes() + (t->d_tri_in ? (uint64_t)t->hdr.num_tris * 36 : 0) +
+                            (t->d_nrm_in ? (uint64_t)t->hdr.num_tris * 36 : 0);
+        out->build_ms = t->build_ms;
+        return VRT_OK;
+}
+
+int vrt_tree_export(const vrt_tree* t, vrt_tree_view* out)
+{
+        if (!out) {
+                set_error("null out");
+                return VRT_ERR_ARG;
+        }
+        int rc = check_tree(t);
+        if (rc)
+                return rc;
+        const BlobHeader& h = t->hdr;
+        const char* base = static_cast<const char*>(t->blob);
+        VRT_CUDA(cudaStreamSynchronize(t->stream));
+        if (out->leaf_refs && h.num_refs)
+                VRT_CUDA(cudaMemcpy(out->leaf_refs, base + h.off_leaf_refs, h.num_refs * 4, cudaMemcpyDeviceToHost));
+        if (out->nodes && h.num_nodes)
+                VRT_CUDA(cudaMemcpy(out->nodes, base + h.off_nodes, h.num_nodes * 8, cudaMemcpyDeviceToHost));
+        if ((out->leaf_cell || out->leaf_count) && h.num_leaves) {
+                std::vector<unsigned long long> m(h.num_leaves);
+                std::vector<uint2> ln(h.num_leaves);
+                VRT_CUDA(cudaMemcpy(m.data(), base + h.off_leaf_morton, h.num_leaves * 8, cudaMemcpyDeviceToHost));
+                VRT_CUDA(cudaMemcpy(ln.data(), base + h.off_nodes + h.level_offset[h.max_depth - 1] * 8,
+                                    h.num_leaves * 8, cudaMemcpyDeviceToHost));
+                for (uint64_t i = 0; i < h.num_leaves; ++i) {
+                        if (out->leaf_cell) {
+                                // de-interleave: x bit2, y bit1, z bit0 of every 3-bit digit
+                                uint32_t x = 0, y = 0, z = 0;
+                                for (int l = 0; l < h.max_depth - 1; ++l) {
+                                        unsigned dgt = (unsigned)((m[i] >> (3 * l)) & 7ull);
+                                        x |= ((dgt >> 2) & 1u) << l;
+                                        y |= ((dgt >> 1) & 1u) << l;
+                                        z |= (dgt & 1u) << l;
+                                }
+                                out->leaf_cell[3 * i] = x;
+                                out->leaf_cell[3 * i + 1] = y;
+                                out->leaf_cell[3 * i + 2] = z;
+                        }
+                        if (out->leaf_count)
+                                out->leaf_count[i] = ln[i].y;
+                }
+        }
+        return VRT_OK;
+}
+
+int vrt_tree_import(const float* tri_xyz, const float* tri_nrm, uint32_t num_tris, int max_depth,
+                    const float root_aabb[6], uint64_t num_leaves, const uint32_t* leaf_cell,
+                    const uint32_t* leaf_count, const uint32_t* leaf_refs, vrt_tree** out)
+{
+        if (!out || (num_tris && !tri_xyz) || !root_aabb || (num_leaves && (!leaf_cell || !leaf_count || !leaf_refs))) {
+                set_error("vrt_tree_import: null argument");
+                return VRT_ERR_ARG;
+        }
+        *out = nullptr;
+        if (max_depth < 1 || max_depth > (int)VRT_MAX_DEPTH) {
+                set_error("vrt_tree_import: max_depth %d out of range", max_depth);
+                return VRT_ERR_ARG;
+        }
+        vrt_tree* t = nullptr;
+        int rc = tree_alloc(&t);
+        if (rc)
+                return rc;
+        rc = upload_inputs(t, tri_xyz, tri_nrm, num_tris, false);
+        if (!rc)
+                rc = import_leaves(t, max_depth, root_aabb, num_leaves, leaf_cell, leaf_count, leaf_refs);
+        if (rc) {
+                vrt_tree_free(t);
+                return rc;
+        }
+        *out = t;
+        return VRT_OK;
+}
+
+int vrt_tree_set_stream(vrt_tree* t, void* stream)
+{
+        if (!t) {
+                set_error("null tree handle");
+                return VRT_ERR_ARG;
+        }
+        t->stream = static_cast<cudaStream_t>(stream);
+        return VRT_OK;
+}
+
+int vrt_tree_blob_dev(const vrt_tree* t, const void** d_blob, uint64_t* bytes)
+{
+        int rc = check_tree(t);
+        if (rc)
+                return rc;
+        if (!d_blob || !bytes) {
+                set_error("null out");
+                return VRT_ERR_ARG;
+        }
+        *d_blob = t->blob;
+        *bytes = t->hdr.bytes;
+        return VRT_OK;
+}
+
+int vrt_tree_from_blob_dev(const void* d_blob, uint64_t bytes, vrt_tree** out)
+{
+        if (!d_blob || !out || bytes < kHeaderBytes) {
+                set_error("vrt_tree_from_blob_dev: bad argument");
+                return VRT_ERR_ARG;
+        }
+        *out = nullptr;
+        vrt_tree* t = nullptr;
+        int rc = tree_alloc(&t);
+        if (rc)
+                return rc;
+        BlobHeader h;
+        if (!cuda_ok(cudaMemcpy(&h, d_blob, sizeof h, cudaMemcpyDeviceToHost), "read blob header")) {
+                vrt_tree_free(t);
+                return VRT_ERR_CUDA;
+        }
+        if (h.magic != kBlobMagic || h.bytes > bytes || h.max_depth < 1 || h.max_depth > (int)VRT_MAX_DEPTH) {
+                set_error("not a vrt octree blob (magic/size mismatch)");
+                vrt_tree_free(t);
+                return VRT_ERR_ARG;
+        }
+        if (!cuda_ok(cudaMalloc(&t->blob, h.bytes), "cudaMalloc(blob)")) {
+                vrt_tree_free(t);
+                return VRT_ERR_NOMEM;
+        }
+        t->blob_bytes = h.bytes;
+        t->own_blob = true;
+        if (!cuda_ok(cudaMemcpy(t->blob, d_blob, h.bytes, cudaMemcpyDeviceToDevice), "copy blob")) {
+                vrt_tree_free(t);
+                return VRT_ERR_CUDA;
+        }
+        t->hdr = h;
+        tree_bind_views(t);
+        *out = t;
+        return VRT_OK;
+}
+
+// ---- camera -----------------------------------------------------------------
+// Host arithmetic identical to Camera::Camera (camera.cc:65-75): jql::normalize
+// = v / sqrtf(((0+x*x)+y*y)+z*z), jql::cross (graphics_math.h:588-592),
+// affine_transform (graphics_math.h:1002-1016).  Compiled with -ffp-contract=off.
+static void h_normalize(float v[3])
+{
+        float s = 0.f;
+        s += v[0] * v[0];
+        s += v[1] * v[1];
+        s += v[2] * v[2];
+        float l = sqrtf(s);
+        v[0] = v[0] / l;
+        v[1] = v[1] / l;
+        v[2] = v[2] / l;
+}
+
+static void h_cross(const float p[3], const float q[3], float o[3])
+{
+        o[0] = p[1] * q[2] - q[1] * p[2];
+        o[1] = p[2] * q[0] - q[2] * p[0];
+        o[2] = p[0] * q[1] - q[0] * p[1];
+}
+
+int vrt_camera_init(const float cam10[10], float film_h, int nx, int ny, int spp, vrt_camera* out)
+{
+        if (!cam10 || !out || (spp != 1 && spp != 4) || nx < 1 || ny < 1) {
+                set_error("vrt_camera_init: bad argument");
+                return VRT_ERR_ARG;
+        }
+        const float fov = cam10[0];
+        const float* eye = cam10 + 1;
+        const float* spot = cam10 + 4;
+        const float* up = cam10 + 7;
+        float f[3] = { spot[0] - eye[0], spot[1] - eye[1], spot[2] - eye[2] };
+        h_normalize(f);
+        float s[3], u[3];
+        h_cross(f, up, s);
+        h_normalize(s);
+        h_cross(s, f, u);
+        h_normalize(u);
+        memset(out, 0, sizeof *out);
+        for (int r = 0; r < 3; ++r) {
+                out->C[r] = s[r];
+                out->C[4 + r] = u[r];
+                out->C[8 + r] = -f[r];
+                out->C[12 + r] = eye[r];
+        }
+        out->C[15] = 1.f;
+        out->z = -(film_h / (2 * tanf(fov / 2)));  // camera.cc:82,100
+        out->tmin = 0.f;                           // camera.h:76
+        out->tmax = FLT_MAX;                       // camera.h:77
+        out->nx = nx;
+        out->ny = ny;
+        out->spp = spp;
+        return VRT_OK;
+}
+
+int vrt_gen_rays(const vrt_camera* cam, int x0, int y0, int x1, int y1, vrt_ray* rays_out)
+{
+        int rc = need_device();
+        if (rc)
+                return rc;
+        rc = check_camera(cam, x0, y0, x1, y1);
+        if (rc)
+                return rc;
+        const uint64_t n = (uint64_t)(x1 - x0) * (y1 - y0) * cam->spp;
+        if (!n)
+                return VRT_OK;
+        if (!rays_out) {
+                set_error("null rays_out");
+                return VRT_ERR_ARG;
+        }
+        DevBuf d;
+        if (d.alloc(n * sizeof(vrt_ray)))
+                return VRT_ERR_NOMEM;
+        k_gen_rays<<<(unsigned)((n + 255) / 256), 256>>>(to_params(cam), x0, y0, x1, y1, static_cast<vrt_ray*>(d.p));
+        count_launch();
+        VRT_CUDA(cudaGetLastError());
+        VRT_CUDA(cudaMemcpy(rays_out, d.p, n * sizeof(vrt_ray), cudaMemcpyDeviceToHost));
+        return VRT_OK;
+}
+
+// ---- trace ------------------------------------------------------------------
+int vrt_trace_rays_dev(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_hit* d_out)
+{
+        int rc = check_tree(t);
+        if (rc)
+                return rc;
+        if (n && (!d_rays || !d_out)) {
+                set_error("null ray/out pointer");
+                return VRT_ERR_ARG;
+        }
+        return launch_trace_rays(t, d_rays, n, d_out);
+}
+
+int vrt_trace_rays(const vrt_tree* tc, const vrt_ray* rays, uint64_t n, vrt_hit* out)
+{
+        int rc = check_tree(tc);
+        if (rc)
+                return rc;
+        if (!n)
+                return VRT_OK;
+        if (!rays || !out) {
+                set_error("null ray/out pointer");
+                return VRT_ERR_ARG;
+        }
+        vrt_tree* t = const_cast<vrt_tree*>(tc);
+        if (t->io_in.reserve(n * sizeof(vrt_ray)) || t->io_out.reserve(n * sizeof(vrt_hit)))
+                return VRT_ERR_NOMEM;
+        VRT_CUDA(cudaMemcpyAsync(t->io_in.p, rays, n * sizeof(vrt_ray), cudaMemcpyHostToDevice, t->stream));
+        rc = launch_trace_rays(t, t->io_in.as<vrt_ray>(), n, t->io_out.as<vrt_hit>());
+        if (rc)
+                return rc;
+        VRT_CUDA(cudaMemcpyAsync(out, t->io_out.p, n * sizeof(vrt_hit), cudaMemcpyDeviceToHost, t->stream));
+        VRT_CUDA(cudaStreamSynchronize(t->stream));
+        return VRT_OK;
+}
+
+static int trace_camera_common(const vrt_tree* tc, const vrt_camera* cam, const vrt_shade* sh, int x0, int y0, int x1,
+                               int y1, void* out, OutMode mode, bool dev)
+{
+        int rc = check_tree(tc);
+        if (rc)
+                return rc;
+        rc = check_camera(cam, x0, y0, x1, y1);
+        if (rc)
+                return rc;
+        const uint64_t npix = (uint64_t)(x1 - x0) * (y1 - y0);
+        if (!npix)
+                return VRT_OK;
+        if (!out || (mode == OUT_FILM && !sh)) {
+                set_error("null out/shade pointer");
+                return VRT_ERR_ARG;
+        }
+        if (dev)
+                return launch_trace_camera(tc, cam, sh, x0, y0, x1, y1, out, mode);
+        vrt_tree* t = const_cast<vrt_tree*>(tc);
+        const uint64_t bytes = mode == OUT_FILM ? npix * 12 : npix * cam->spp * (mode == OUT_HIT48 ? 48 : 16);
+        if (t->io_out.reserve(bytes))
+                return VRT_ERR_NOMEM;
+        rc = launch_trace_camera(t, cam, sh, x0, y0, x1, y1, t->io_out.p, mode);
+        if (rc)
+                return rc;
+        VRT_CUDA(cudaMemcpyAsync(out, t->io_out.p, bytes, cudaMemcpyDeviceToHost, t->stream));
+        VRT_CUDA(cudaStreamSynchronize(t->stream));
+        return VRT_OK;
+}
+
+int vrt_trace_camera(const vrt_tree* t, const vrt_camera* cam, int x0, int y0, int x1, int y1, vrt_hit* out)
+{
+        return trace_camera_common(t, cam, nullptr, x0, y0, x1, y1, out, OUT_HIT48, false);
+}
+int vrt_trace_camera_dev(const vrt_tree* t, const vrt_camera* cam, int x0, int y0, int x1, int y1, vrt_hit* d_out)
+{
+        return trace_camera_common(t, cam, nullptr, x0, y0, x1, y1, d_out, OUT_HIT48, true);
+}
+int vrt_trace_camera16_dev(const vrt_tree* t, const vrt_camera* cam, int x0, int y0, int x1, int y1, vrt_hit16* d_out)
+{
+        return trace_camera_common(t, cam, nullptr, x0, y0, x1, y1, d_out, OUT_HIT16, true);
+}
+int vrt_render_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, int x0, int y0, int x1, int y1,
+                      float* film_rgb)
+{
+        return trace_camera_common(t, cam, sh, x0, y0, x1, y1, film_rgb, OUT_FILM, false);
+}
+int vrt_render_camera_dev(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, int x0, int y0, int x1,
+                          int y1, float* d_film_rgb)
+{
+        return trace_camera_common(t, cam, sh, x0, y0, x1, y1, d_film_rgb, OUT_FILM, true);
+}
+
+double vrt_last_kernel_ms(const vrt_tree* t) { return t ? t->last_kernel_ms : 0.0; }
+
+// ---- predicates ---------------------------------------------------------------
+int vrt_tribox_batch(const float* centers, const float* halves, const float* tris, uint64_t n, uint8_t* out)
+{
+        int rc = need_device();
+        if (rc || !n)
+                return rc;
+        if (!centers || !halves || !tris || !out) {
+                set_error("null argument");
+                return VRT_ERR_ARG;
+        }
+        DevBuf c, h, t, o;
+        if (c.alloc(n * 12) || h.alloc(n * 12) || t.alloc(n * 36) || o.alloc(n))
+                return VRT_ERR_NOMEM;
+        VRT_CUDA(cudaMemcpy(c.p, centers, n * 12, cudaMemcpyHostToDevice));
+        VRT_CUDA(cudaMemcpy(h.p, halves, n * 12, cudaMemcpyHostToDevice));
+        VRT_CUDA(cudaMemcpy(t.p, tris, n * 36, cudaMemcpyHostToDevice));
+        k_tribox<<<(unsigned)((n + 255) / 256), 256>>>((float*)c.p, (float*)h.p, (float*)t.p, n, (uint8_t*)o.p);
+        count_launch();
+        VRT_CUDA(cudaGetLastError());
+        VRT_CUDA(cudaMemcpy(out, o.p, n, cudaMemcpyDeviceToHost));
+        return VRT_OK;
+}
+
+int vrt_tri_overlap_aabb_batch(const float* aabbs, const float* tris, uint64_t n, uint8_t* out)
+{
+        int rc = need_device();
+        if (rc || !n)
+                return rc;
+        if (!aabbs || !tris || !out) {
+                set_error("null argument");
+                return VRT_ERR_ARG;
+        }
+        DevBuf b, t, o;
+        if (b.alloc(n * 24) || t.alloc(n * 36) || o.alloc(n))
+                return VRT_ERR_NOMEM;
+        VRT_CUDA(cudaMemcpy(b.p, aabbs, n * 24, cudaMemcpyHostToDevice));
+        VRT_CUDA(cudaMemcpy(t.p, tris, n * 36, cudaMemcpyHostToDevice));
+        k_tri_aabb<<<(unsigned)((n + 255) / 256), 256>>>((float*)b.p, (float*)t.p, n, (uint8_t*)o.p);
+        count_launch();
+        VRT_CUDA(cudaGetLastError());
+        VRT_CUDA(cudaMemcpy(out, o.p, n, cudaMemcpyDeviceToHost));
+        return VRT_OK;
+}
+
+int vrt_raytri_batch(const double* in, uint64_t n, uint8_t* result, double* tuv)
+{
+        int rc = need_device();
+        if (rc || !n)
+                return rc;
+        if (!in || !result || !tuv) {
+                set_error("null argument");
+                return VRT_ERR_ARG;
+        }
+        DevBuf i, r, o;
+        if (i.alloc(n * 120) || r.alloc(n) || o.alloc(n * 24))
+                return VRT_ERR_NOMEM;
+        VRT_CUDA(cudaMemcpy(i.p, in, n * 120, cudaMemcpyHostToDevice));
+        k_raytri<<<(unsigned)((n + 255) / 256), 256>>>((double*)i.p, n, (uint8_t*)r.p, (double*)o.p);
+        count_launch();
+        VRT_CUDA(cudaGetLastError());
+        VRT_CUDA(cudaMemcpy(result, r.p, n, cudaMemcpyDeviceToHost));
+        VRT_CUDA(cudaMemcpy(tuv, o.p, n * 24, cudaMemcpyDeviceToHost));
+        return VRT_OK;
+}
+
+int vrt_aabb_isect_batch(const float* aabbs, const vrt_ray* rays, uint64_t n, uint8_t* out)
+{
+        int rc = need_device();
+        if (rc || !n)
+                return rc;
+        if (!aabbs || !rays || !out) {
+                set_error("null argument");
+                return VRT_ERR_ARG;
+        }
+        DevBuf b, r, o;
+        if (b.alloc(n * 24) || r.alloc(n * 32) || o.alloc(n))
+                return VRT_ERR_NOMEM;
+        VRT_CUDA(cudaMemcpy(b.p, aabbs, n * 24, cudaMemcpyHostToDevice));
+        VRT_CUDA(cudaMemcpy(r.p, rays, n * 32, cudaMemcpyHostToDevice));
+        k_aabb_isect<<<(unsigned)((n + 255) / 256), 256>>>((float*)b.p, (vrt_ray*)r.p, n, (uint8_t*)o.p);
+        count_launch();
+        VRT_CUDA(cudaGetLastError());
+        VRT_CUDA(cudaMemcpy(out, o.p, n, cudaMemcpyDeviceToHost));
+        return VRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,708 @@
+// vrt_build.cu -- GPU voxelization + sparse-octree construction.
+//
+// Replaces gi::ray_march_init / insert / split (voxel_octree.cc:27-75) and the
+// Triangle::is_overlap -> triBoxOverlap calls it makes (voxel_octree.cc:486-492,
+// tribox2.cc:112-186).  Semantics reproduced exactly:
+//   * root AABB = union of all triangle AABBs; child boxes by the reference's
+//     float recurrence, NOT a closed form (voxel_octree.cc:30-37);
+//   * a triangle reaches a leaf cell iff the SAT test passes for that cell AND
+//     for every ancestor including the root (hierarchical insert,
+//     voxel_octree.cc:43) -- hence a level-synchronous top-down expansion, which
+//     is exact by construction;
+//   * leaves hold triangle indices in ascending order.
+// Pipeline: root AABB reduction -> per-axis interval table -> root filter ->
+// L x expand (8 lanes per (triangle, cell) pair, one SAT test per lane, keys
+// Morton<<tb | tri appended through block-aggregated atomics) -> LSD radix sort
+// -> unique -> bottom-up parent derivation -> flat pointerless node array.
+#include <algorithm>
+#include <cfloat>
+#include <cstring>
+#include <vector>
+
+#include "vrt_exact.cuh"
+#include "vrt_internal.h"
+#include "vrt_prims.cuh"
+
+namespace vrt {
+
+// ---------------------------------------------------------------------------
+// Morton helpers: 3 bits per level, child digit c = (x<<2)|(y<<1)|z
+// (voxel_octree.cc:33: mask = (i&4, i&2, i&1) for (x,y,z)).
+// ---------------------------------------------------------------------------
+__host__ __device__ inline uint32_t compact1by2(unsigned long long v)
+{
+        v &= 0x1249249249249249ull;
+        v = (v ^ (v >> 2)) & 0x10c30c30c30c30c3ull;
+        v = (v ^ (v >> 4)) & 0x100f00f00f00f00full;
+        v = (v ^ (v >> 8)) & 0x001f0000ff0000ffull;
+        v = (v ^ (v >> 16)) & 0x001f00000000ffffull;
+        v = (v ^ (v >> 32)) & 0x00000000001fffffull;
+        return (uint32_t)v;
+}
+
+__host__ __device__ inline unsigned long long spread1by2(uint32_t x)
+{
+        unsigned long long v = x & 0x1fffffull;
+        v = (v | (v << 32)) & 0x001f00000000ffffull;
+        v = (v | (v << 16)) & 0x001f0000ff0000ffull;
+        v = (v | (v << 8)) & 0x100f00f00f00f00full;
+        v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+        v = (v | (v << 2)) & 0x1249249249249249ull;
+        return v;
+}
+
+__host__ __device__ inline unsigned long long morton_encode(uint32_t x, uint32_t y, uint32_t z)
+{
+        return (spread1by2(x) << 2) | (spread1by2(y) << 1) | spread1by2(z);
+}
+
+// ---------------------------------------------------------------------------
+// Root AABB: min/max over all vertices in index order, std::min/std::max
+// semantics (ties keep the EARLIEST element, which only matters for the sign
+// of a zero) -- graphics_math.h:1228-1266 via voxel_octree.cc:70-72,430.
+// ---------------------------------------------------------------------------
+struct MinMaxIdx {
+        float v;
+        uint32_t i;
+};
+__device__ __forceinline__ void mm_min(MinMaxIdx& a, float v, uint32_t i)
+{
+        if (v < a.v || (v == a.v && i < a.i)) {
+                a.v = v;
+                a.i = i;
+        }
+}
+__device__ __forceinline__ void mm_max(MinMaxIdx& a, float v, uint32_t i)
+{
+        if (a.v < v || (v == a.v && i < a.i)) {
+                a.v = v;
+                a.i = i;
+        }
+}
+
+// partial[block][12] as (value bits, index) pairs: 3 mins then 3 maxes
+__global__ void __launch_bounds__(256)
+k_aabb_partial(const float* __restrict__ tri, uint32_t num_verts, uint2* __restrict__ partial)
+{
+        MinMaxIdx mn[3], mx[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+                mn[k] = { FLT_MAX, 0xffffffffu };
+                mx[k] = { -FLT_MAX, 0xffffffffu };
+        }
+        for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < num_verts;
+             v += gridDim.x * blockDim.x) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                        float f = tri[3ull * v + k];
+                        mm_min(mn[k], f, v);
+                        mm_max(mx[k], f, v);
+                }
+        }
+        __shared__ MinMaxIdx sh[6][8];
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                        float ov = __shfl_down_sync(0xffffffffu, mn[k].v, o);
+                        uint32_t oi = __shfl_down_sync(0xffffffffu, mn[k].i, o);
+                        mm_min(mn[k], ov, oi);
+                        ov = __shfl_down_sync(0xffffffffu, mx[k].v, o);
+                        oi = __shfl_down_sync(0xffffffffu, mx[k].i, o);
+                        mm_max(mx[k], ov, oi);
+                }
+                if (lane == 0) {
+                        sh[k][w] = mn[k];
+                        sh[3 + k][w] = mx[k];
+                }
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) {
+                MinMaxIdx a = sh[threadIdx.x][0];
+                for (int i = 1; i < 8; ++i) {
+                        if (threadIdx.x < 3)
+                                mm_min(a, sh[threadIdx.x][i].v, sh[threadIdx.x][i].i);
+                        else
+                                mm_max(a, sh[threadIdx.x][i].v, sh[threadIdx.x][i].i);
+                }
+                partial[blockIdx.x * 6 + threadIdx.x] = make_uint2(__float_as_uint(a.v), a.i);
+        }
+}
+
+__global__ void k_aabb_final(const uint2* __restrict__ partial, int nblocks, float* __restrict__ out6)
+{
+        const int q = threadIdx.x;
+        if (q >= 6)
+                return;
+        MinMaxIdx a = { q < 3 ? FLT_MAX : -FLT_MAX, 0xffffffffu };
+        for (int b = 0; b < nblocks; ++b) {
+                uint2 p = partial[b * 6 + q];
+                if (q < 3)
+                        mm_min(a, __uint_as_float(p.x), p.y);
+                else
+                        mm_max(a, __uint_as_float(p.x), p.y);
+        }
+        out6[q] = a.v;
+}
+
+// ---------------------------------------------------------------------------
+// Per-axis interval table (float recurrence of split(), voxel_octree.cc:30-37):
+//   size = (max-min)/2 ; child b: min' = min + (float)b*size ; max' = min' + size
+// tab[a][(1<<l)+i] = (min,max) of cell i at level l.  One block, level by level.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_axis_table(const float* __restrict__ root6, float2* __restrict__ tab, uint64_t stride, int L)
+{
+        for (int a = threadIdx.x; a < 3; a += blockDim.x) {
+                tab[a * stride + 0] = make_float2(0.f, 0.f);
+                tab[a * stride + 1] = make_float2(root6[a], root6[3 + a]);
+        }
+        __syncthreads();
+        for (int l = 0; l < L; ++l) {
+                const uint32_t n = 1u << l;
+                for (uint32_t j = threadIdx.x; j < 3 * n; j += blockDim.x) {
+                        const uint32_t a = j / n, i = j - a * n;
+                        const float2 p = tab[a * stride + n + i];
+                        const float s = fdiv(fsub(p.y, p.x), 2.f);
+                        float2 c0, c1;
+                        c0.x = fadd(p.x, fmul(0.f, s));
+                        c0.y = fadd(c0.x, s);
+                        c1.x = fadd(p.x, fmul(1.f, s));
+                        c1.y = fadd(c1.x, s);
+                        tab[a * stride + 2 * n + 2 * i] = c0;
+                        tab[a * stride + 2 * n + 2 * i + 1] = c1;
+                }
+                __syncthreads();
+        }
+}
+
+// ---------------------------------------------------------------------------
+// Block-aggregated append: every thread contributes `flag`; returns the
+// output slot of this thread (valid when flag) -- one global atomic per block
+// call.  Must be called by all threads of the block.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_append(bool flag, uint32_t* counter)
+{
+        __shared__ uint32_t s_warp[32];
+        __shared__ uint32_t s_base;
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        const uint32_t bal = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0)
+                s_warp[w] = __popc(bal);
+        __syncthreads();
+        if (w == 0) {
+                uint32_t c = (lane < nw) ? s_warp[lane] : 0u;
+                uint32_t inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o)
+                                inc += t;
+                }
+                if (lane < nw)
+                        s_warp[lane] = inc - c;
+                if (lane == 31)
+                        s_base = inc ? atomicAdd(counter, inc) : 0u;
+        }
+        __syncthreads();
+        const uint32_t slot = s_base + s_warp[w] + __popc(bal & ((1u << lane) - 1u));
+        __syncthreads();
+        return slot;
+}
+
+// Level 0: triangles that overlap the root box (insert's first test at the
+// root, voxel_octree.cc:43).  key = tri (Morton code of the root is empty).
+__global__ void __launch_bounds__(256)
+k_root_filter(const float* __restrict__ tri, uint32_t T, const float* __restrict__ root6,
+              unsigned long long* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counter)
+{
+        const uint32_t rounds = (T + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+        for (uint32_t r = 0; r < rounds; ++r) {
+                const uint32_t t = (r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+                bool ov = false;
+                if (t < T) {
+                        const float* p = tri + 9ull * t;
+                        float v0[3] = { p[0], p[1], p[2] }, v1[3] = { p[3], p[4], p[5] },
+                              v2[3] = { p[6], p[7], p[8] };
+                        float mn[3] = { root6[0], root6[1], root6[2] };
+                        float mx[3] = { root6[3], root6[4], root6[5] };
+                        ov = tri_overlaps_aabb(mn, mx, v0, v1, v2);
+                }
+                const uint32_t slot = block_append(ov, counter);
+                if (ov && slot < cap)
+                        out[slot] = (unsigned long long)t;
+        }
+}
+
+// One level of the hierarchical insert: each surviving (triangle, cell) pair
+// tests the cell's 8 children (8 lanes per pair).  in/out keys = morton<<tb|tri.
+__global__ void __launch_bounds__(256)
+k_expand(const float* __restrict__ tri, const float2* __restrict__ tab, uint64_t stride,
+         const unsigned long long* __restrict__ in, uint32_t n_in, int level /* of the input cells */,
+         int tb, unsigned long long* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counter)
+{
+        const uint32_t pairs_per_block = blockDim.x >> 3;
+        const uint32_t rounds = (n_in + gridDim.x * pairs_per_block - 1) / (gridDim.x * pairs_per_block);
+        const uint32_t c = threadIdx.x & 7;
+        const unsigned long long tmask = (1ull << tb) - 1ull;
+        const uint32_t child_base = 2u << level;  // table offset of level+1
+        for (uint32_t r = 0; r < rounds; ++r) {
+                const uint32_t idx = (r * gridDim.x + blockIdx.x) * pairs_per_block + (threadIdx.x >> 3);
+                bool ov = false;
+                unsigned long long key_out = 0;
+                if (idx < n_in) {
+                        const unsigned long long key = in[idx];
+                        const uint32_t t = (uint32_t)(key & tmask);
+                        const unsigned long long m = key >> tb;
+                        const uint32_t cx = 2u * compact1by2(m >> 2) + ((c >> 2) & 1u);
+                        const uint32_t cy = 2u * compact1by2(m >> 1) + ((c >> 1) & 1u);
+                        const uint32_t cz = 2u * compact1by2(m) + (c & 1u);
+                        const float2 bx = tab[0 * stride + child_base + cx];
+                        const float2 by = tab[1 * stride + child_base + cy];
+                        const float2 bz = tab[2 * stride + child_base + cz];
+                        const float* p = tri + 9ull * t;
+                        float v0[3] = { p[0], p[1], p[2] }, v1[3] = { p[3], p[4], p[5] },
+                              v2[3] = { p[6], p[7], p[8] };
+                        float mn[3] = { bx.x, by.x, bz.x };
+                        float mx[3] = { bx.y, by.y, bz.y };
+                        ov = tri_overlaps_aabb(mn, mx, v0, v1, v2);
+                        key_out = (((m << 3) | c) << tb) | t;
+                }
+                const uint32_t slot = block_append(ov, counter);
+                if (ov && slot < cap)
+                        out[slot] = key_out;
+        }
+}
+
+// ---------------------------------------------------------------------------
+// After the sort: leaves, refs and the bottom-up parent derivation.
+// ---------------------------------------------------------------------------
+// flag[i] = 1 where a new code starts ; code(i) = keys[i] >> shift
+__global__ void k_head_flags(const unsigned long long* __restrict__ keys, uint64_t n, int shift,
+                             uint32_t* __restrict__ flag)
+{
+        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n)
+                return;
+        flag[i] = (i == 0 || (keys[i] >> shift) != (keys[i - 1] >> shift)) ? 1u : 0u;
+}
+
+// leaves from sorted keys: pos = exclusive scan of flags.
+__global__ void k_emit_leaves(const unsigned long long* __restrict__ keys, uint64_t n, int tb,
+                              const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos,
+                              unsigned long long* __restrict__ leaf_morton,
+                              uint32_t* __restrict__ leaf_start, uint32_t* __restrict__ refs)
+{
+        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n)
+                return;
+        const unsigned long long k = keys[i];
+        refs[i] = (uint32_t)(k & ((1ull << tb) - 1ull));
+        if (flag[i]) {
+                leaf_morton[pos[i]] = k >> tb;
+                leaf_start[pos[i]] = (uint32_t)i;
+        }
+}
+
+// parents of a sorted child-code list: flag where code>>3 changes.
+__global__ void k_parent_flags(const unsigned long long* __restrict__ child, uint64_t n,
+                               uint32_t* __restrict__ flag)
+{
+        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n)
+                return;
+        flag[i] = (i == 0 || (child[i] >> 3) != (child[i - 1] >> 3)) ? 1u : 0u;
+}
+
+__global__ void k_emit_parents(const unsigned long long* __restrict__ child, uint64_t n,
+                               const uint32_t* __restrict__ flag, const uint32_t* __restrict__ pos,
+                               unsigned long long* __restrict__ parent_morton,
+                               uint32_t* __restrict__ parent_first, uint32_t* __restrict__ parent_mask)
+{
+        uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n || !flag[i])
+                return;
+        const unsigned long long pm = child[i] >> 3;
+        uint32_t mask = 0;
+        for (uint64_t j = i; j < n && j < i + 8 && (child[j] >> 3) == pm; ++j)
+                mask |= 1u << (uint32_t)(child[j] & 7ull);
+        const uint32_t p = pos[i];
+        parent_morton[p] = pm;
+        parent_first[p] = (uint32_t)i;
+        parent_mask[p] = mask;
+}
+
+// final node array
+__global__ void k_write_interior(const uint32_t* __restrict__ first, const uint32_t* __restrict__ mask,
+                                 uint32_t n, uint32_t child_level_offset, uint2* __restrict__ nodes)
+{
+        uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < n)
+                nodes[i] = make_uint2(first[i] + child_level_offset, mask[i]);
+}
+
+__global__ void k_write_leaves(const uint32_t* __restrict__ start, uint32_t n, uint32_t num_refs,
+                               uint2* __restrict__ nodes)
+{
+        uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < n) {
+                uint32_t s = start[i];
+                uint32_t e = (i + 1 < n) ? start[i + 1] : num_refs;
+                nodes[i] = make_uint2(s, e - s);
+        }
+}
+
+// vertices -> float4 x3 ; normals normalised like the Triangle ctor
+// (voxel_octree.cc:426); NULL normals -> geometric normal cross(p1-p0,p2-p0).
+__global__ void k_pack_tris(const float* __restrict__ tri, const float* __restrict__ nrm_in, uint32_t T,
+                            float4* __restrict__ tri4, float* __restrict__ nrm_out)
+{
+        uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+        if (t >= T)
+                return;
+        const float* p = tri + 9ull * t;
+        float v[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+                v[k] = p[k];
+        tri4[3ull * t + 0] = make_float4(v[0], v[1], v[2], 0.f);
+        tri4[3ull * t + 1] = make_float4(v[3], v[4], v[5], 0.f);
+        tri4[3ull * t + 2] = make_float4(v[6], v[7], v[8], 0.f);
+        float n[9];
+        if (nrm_in) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                        n[k] = nrm_in[9ull * t + k];
+        } else {
+                // jql::cross(p1-p0, p2-p0) graphics_math.h:588-592
+                float a[3] = { fsub(v[3], v[0]), fsub(v[4], v[1]), fsub(v[5], v[2]) };
+                float b[3] = { fsub(v[6], v[0]), fsub(v[7], v[1]), fsub(v[8], v[2]) };
+                float g[3];
+                g[0] = fsub(fmul(a[1], b[2]), fmul(b[1], a[2]));
+                g[1] = fsub(fmul(a[2], b[0]), fmul(b[2], a[0]));
+                g[2] = fsub(fmul(a[0], b[1]), fmul(b[0], a[1]));
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                        n[k] = g[k % 3];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+                normalize3(n[3 * k], n[3 * k + 1], n[3 * k + 2]);
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+                nrm_out[9ull * t + k] = n[k];
+}
+
+// ---------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------
+static inline unsigned grid_for(uint64_t n, unsigned block)
+{
+        return (unsigned)std::max<uint64_t>(1, (n + block - 1) / block);
+}
+
+static int tri_bits_for(uint32_t T)
+{
+        int tb = 1;
+        while ((1ull << tb) < (unsigned long long)T)
+                ++tb;
+        return tb;
+}
+
+// Everything after the keys are known: sort (by Morton bits, or by the full key
+// when `sort_full`), leaves, bottom-up levels, blob assembly.
+static int finish_from_keys(vrt_tree* t, unsigned long long* keys, uint64_t n, int L, int tb,
+                            bool stable_input, const float* d_root6)
+{
+        cudaStream_t s = t->stream;
+        const uint32_t T = t->hdr.num_tris;
+        // --- sort -----------------------------------------------------------------
+        unsigned long long* sorted = keys;
+        if (n > 1) {
+                if (t->keys_b.reserve(n * 8))
+                        return VRT_ERR_NOMEM;
+                uint64_t he = sort_hist_elems(n);
+                if (t->hist.reserve(he * 4) || t->tmp_c.reserve(scan_scratch_elems(he) * 4))
+                        return VRT_ERR_NOMEM;
+                unsigned long long* other = (keys == t->keys_a.as<unsigned long long>())
+                                                    ? t->keys_b.as<unsigned long long>()
+                                                    : t->keys_a.as<unsigned long long>();
+                if (other == nullptr || other == keys) {
+                        other = t->keys_b.as<unsigned long long>();
+                }
+                int lo = stable_input ? tb : 0;
+                int hi = tb + 3 * L;
+                if (hi > lo)
+                        radix_sort_u64(keys, other, n, lo, hi, t->hist.as<uint32_t>(),
+                                       t->tmp_c.as<uint32_t>(), s, &sorted);
+        }
+        // --- leaves ---------------------------------------------------------------
+        uint64_t num_leaves = 0;
+        if (t->tmp_a.reserve((n + 1) * 4) || t->tmp_b.reserve((n + 1) * 4) ||
+            t->tmp_c.reserve(std::max<uint64_t>(scan_scratch_elems(n), 16) * 4))
+                return VRT_ERR_NOMEM;
+        uint32_t* flag = t->tmp_a.as<uint32_t>();
+        uint32_t* pos = t->tmp_b.as<uint32_t>();
+        Scratch refs_s;  // temporary refs until blob exists
+        if (n) {
+                k_head_flags<<<grid_for(n, 256), 256, 0, s>>>(sorted, n, tb, flag);
+                count_launch();
+                exclusive_scan_u32(flag, pos, n, t->tmp_c.as<uint32_t>(), s);
+                VRT_CUDA(cudaMemcpyAsync(&t->h_counter[0], pos + (n - 1), 4, cudaMemcpyDeviceToHost, s));
+                VRT_CUDA(cudaMemcpyAsync(&t->h_counter[1], flag + (n - 1), 4, cudaMemcpyDeviceToHost, s));
+                VRT_CUDA(cudaStreamSynchronize(s));
+                num_leaves = (uint64_t)t->h_counter[0] + t->h_counter[1];
+        }
+        if (num_leaves >= 0xfffffff0ull || n >= 0xfffffff0ull) {
+                set_error("octree too large for 32-bit node indices (%llu leaves, %llu refs)",
+                          (unsigned long long)num_leaves, (unsigned long long)n);
+                return VRT_ERR_CAPACITY;
+        }
+        // level arrays: morton (u64), first (u32), mask (u32).  Level L: first = ref start.
+        uint64_t level_n[VRT_MAX_DEPTH + 1] = { 0 };
+        level_n[L] = num_leaves;
+        if (t->level_morton[L].reserve(std::max<uint64_t>(num_leaves, 1) * 8) ||
+            t->level_first[L].reserve(std::max<uint64_t>(num_leaves, 1) * 4))
+                return VRT_ERR_NOMEM;
+        if (refs_s.reserve(std::max<uint64_t>(n, 1) * 4))
+                return VRT_ERR_NOMEM;
+        if (n) {
+                k_emit_leaves<<<grid_for(n, 256), 256, 0, s>>>(sorted, n, tb, flag, pos,
+                                                               t->level_morton[L].as<unsigned long long>(),
+                                                               t->level_first[L].as<uint32_t>(),
+                                                               refs_s.as<uint32_t>());
+                count_launch();
+        }
+        // --- bottom-up ------------------------------------------------------------
+        for (int l = L - 1; l >= 0; --l) {
+                const uint64_t nc = level_n[l + 1];
+                if (nc == 0) {
+                        level_n[l] = 0;
+                        continue;
+                }
+                const unsigned long long* child = t->level_morton[l + 1].as<unsigned long long>();
+                k_parent_flags<<<grid_for(nc, 256), 256, 0, s>>>(child, nc, flag);
+                count_launch();
+                exclusive_scan_u32(flag, pos, nc, t->tmp_c.as<uint32_t>(), s);
+                VRT_CUDA(cudaMemcpyAsync(&t->h_counter[0], pos + (nc - 1), 4, cudaMemcpyDeviceToHost, s));
+                VRT_CUDA(cudaMemcpyAsync(&t->h_counter[1], flag + (nc - 1), 4, cudaMemcpyDeviceToHost, s));
+                VRT_CUDA(cudaStreamSynchronize(s));
+                const uint64_t np = (uint64_t)t->h_counter[0] + t->h_counter[1];
+                level_n[l] = np;
+                if (t->level_morton[l].reserve(np * 8) || t->level_first[l].reserve(np * 4) ||
+                    t->level_mask[l].reserve(np * 4))
+                        return VRT_ERR_NOMEM;
+                k_emit_parents<<<grid_for(nc, 256), 256, 0, s>>>(child, nc, flag, pos,
+                                                                 t->level_morton[l].as<unsigned long long>(),
+                                                                 t->level_first[l].as<uint32_t>(),
+                                                                 t->level_mask[l].as<uint32_t>());
+                count_launch();
+        }
+        // --- blob -----------------------------------------------------------------
+        BlobHeader& h = t->hdr;
+        h.magic = kBlobMagic;
+        h.max_depth = L + 1;
+        h.num_leaves = num_leaves;
+        h.num_refs = n;
+        uint64_t off = 0;
+        for (int l = 0; l <= L; ++l) {
+                h.level_offset[l] = off;
+                off += level_n[l];
+        }
+        for (int l = L + 1; l <= (int)VRT_MAX_DEPTH; ++l)
+                h.level_offset[l] = off;
+        h.num_nodes = off;
+        if (h.num_nodes >= 0xfffffff0ull) {
+                set_error("octree too large for 32-bit node indices");
+                return VRT_ERR_CAPACITY;
+        }
+        h.axis_tab_stride = 2ull << L;
+        uint64_t b = kHeaderBytes;
+        h.off_nodes = b;
+        b = align256(b + std::max<uint64_t>(h.num_nodes, 1) * 8);
+        h.off_leaf_morton = b;
+        b = align256(b + std::max<uint64_t>(num_leaves, 1) * 8);
+        h.off_leaf_refs = b;
+        b = align256(b + std::max<uint64_t>(n, 1) * 4);
+        h.off_tri4 = b;
+        b = align256(b + std::max<uint64_t>(T, 1) * 48);
+        h.off_nrm = b;
+        b = align256(b + std::max<uint64_t>(T, 1) * 36);
+        h.off_axis_tab = b;
+        b = align256(b + 3 * h.axis_tab_stride * 8);
+        h.bytes = b;
+        if (t->blob && t->own_blob && t->blob_bytes < b) {
+                cudaFree(t->blob);
+                t->blob = nullptr;
+        }
+        if (!t->blob) {
+                if (cudaMalloc(&t->blob, b) != cudaSuccess) {
+                        cudaGetLastError();
+                        set_error("cudaMalloc(%llu) for the octree blob failed", (unsigned long long)b);
+                        return VRT_ERR_NOMEM;
+                }
+                t->blob_bytes = b;
+                t->own_blob = true;
+        }
+        char* base = static_cast<char*>(t->blob);
+        VRT_CUDA(cudaMemcpyAsync(h.root_aabb, d_root6, 24, cudaMemcpyDeviceToHost, s));
+        uint2* nodes = reinterpret_cast<uint2*>(base + h.off_nodes);
+        for (int l = 0; l < L; ++l) {
+                if (!level_n[l])
+                        continue;
+                k_write_interior<<<grid_for(level_n[l], 256), 256, 0, s>>>(
+                        t->level_first[l].as<uint32_t>(), t->level_mask[l].as<uint32_t>(),
+                        (uint32_t)level_n[l], (uint32_t)h.level_offset[l + 1], nodes + h.level_offset[l]);
+                count_launch();
+        }
+        if (num_leaves) {
+                k_write_leaves<<<grid_for(num_leaves, 256), 256, 0, s>>>(
+                        t->level_first[L].as<uint32_t>(), (uint32_t)num_leaves, (uint32_t)n,
+                        nodes + h.level_offset[L]);
+                count_launch();
+                VRT_CUDA(cudaMemcpyAsync(base + h.off_leaf_morton, t->level_morton[L].p, num_leaves * 8,
+                                         cudaMemcpyDeviceToDevice, s));
+                VRT_CUDA(cudaMemcpyAsync(base + h.off_leaf_refs, refs_s.p, n * 4, cudaMemcpyDeviceToDevice, s));
+        }
+        if (T) {
+                k_pack_tris<<<grid_for(T, 256), 256, 0, s>>>(t->d_tri_in, t->d_nrm_in, T,
+                                                             reinterpret_cast<float4*>(base + h.off_tri4),
+                                                             reinterpret_cast<float*>(base + h.off_nrm));
+                count_launch();
+        }
+        k_axis_table<<<1, 1024, 0, s>>>(d_root6, reinterpret_cast<float2*>(base + h.off_axis_tab),
+                                        h.axis_tab_stride, L);
+        count_launch();
+        VRT_CUDA(cudaStreamSynchronize(s));
+        VRT_CUDA(cudaMemcpyAsync(base, &h, sizeof h, cudaMemcpyHostToDevice, s));
+        VRT_CUDA(cudaStreamSynchronize(s));
+        refs_s.release();
+        tree_bind_views(t);
+        return VRT_OK;
+}
+
+int build_tree(vrt_tree* t, int max_depth)
+{
+        cudaStream_t s = t->stream;
+        const uint32_t T = t->hdr.num_tris;
+        const int L = max_depth - 1;
+        const int tb = tri_bits_for(T);
+        if (3 * L + tb > 64) {
+                set_error("key does not fit 64 bit: 3*(max_depth-1)=%d Morton bits + %d triangle bits", 3 * L, tb);
+                return VRT_ERR_CAPACITY;
+        }
+        VRT_CUDA(cudaEventRecord(t->ev0, s));
+        // root AABB + axis table (scratch copy; the blob gets its own at assembly)
+        const int nb = 296;
+        if (t->tmp_a.reserve(std::max<uint64_t>((uint64_t)nb * 6 * 8 + 64, 4096)))
+                return VRT_ERR_NOMEM;
+        float* d_root6 = reinterpret_cast<float*>(t->d_counter + 8);
+        k_aabb_partial<<<nb, 256, 0, s>>>(t->d_tri_in, 3u * T, t->tmp_a.as<uint2>());
+        k_aabb_final<<<1, 32, 0, s>>>(t->tmp_a.as<uint2>(), nb, d_root6);
+        count_launch(2);
+        const uint64_t stride = 2ull << L;
+        Scratch tab_s;
+        if (tab_s.reserve(3 * stride * 8))
+                return VRT_ERR_NOMEM;
+        k_axis_table<<<1, 1024, 0, s>>>(d_root6, tab_s.as<float2>(), stride, L);
+        count_launch();
+        // level 0
+        if (t->keys_a.reserve(std::max<uint64_t>(T, 1) * 8))
+                return VRT_ERR_NOMEM;
+        VRT_CUDA(cudaMemsetAsync(t->d_counter, 0, 32, s));
+        if (T) {
+                k_root_filter<<<std::min<unsigned>(grid_for(T, 256), 148 * 8), 256, 0, s>>>(
+                        t->d_tri_in, T, d_root6, t->keys_a.as<unsigned long long>(), T, t->d_counter);
+                count_launch();
+        }
+        VRT_CUDA(cudaMemcpyAsync(t->h_counter, t->d_counter, 4, cudaMemcpyDeviceToHost, s));
+        VRT_CUDA(cudaStreamSynchronize(s));
+        uint64_t n = t->h_counter[0];
+        Scratch* cur = &t->keys_a;
+        Scratch* nxt = &t->keys_b;
+        for (int l = 0; l < L && n; ++l) {
+                // capacity guess: surfaces grow ~4x per level; retry on overflow
+                uint64_t cap = std::max<uint64_t>(n * 5, 1u << 16);
+                cap = std::min<uint64_t>(cap, n * 8);
+                for (;;) {
+                        if (nxt->cap < cap * 8 && nxt->reserve(cap * 8))
+                                return VRT_ERR_NOMEM;
+                        cap = nxt->cap / 8;
+                        if (cap > 0xffffffffull)
+                                cap = 0xffffffffull;
+                        VRT_CUDA(cudaMemsetAsync(t->d_counter, 0, 4, s));
+                        const uint64_t pairs_per_block = 32;
+                        unsigned grid = (unsigned)std::min<uint64_t>((n + pairs_per_block - 1) / pairs_per_block,
+                                                                     148ull * 16);
+                        k_expand<<<grid, 256, 0, s>>>(t->d_tri_in, tab_s.as<float2>(), stride,
+                                                      cur->as<unsigned long long>(), (uint32_t)n, l, tb,
+                                                      nxt->as<unsigned long long>(), (uint32_t)cap, t->d_counter);
+                        count_launch();
+                        VRT_CUDA(cudaMemcpyAsync(t->h_counter, t->d_counter, 4, cudaMemcpyDeviceToHost, s));
+                        VRT_CUDA(cudaStreamSynchronize(s));
+                        const uint64_t produced = t->h_counter[0];
+                        if (produced <= cap) {
+                                n = produced;
+                                break;
+                        }
+                        cap = produced;  // exact size known now: redo this level once
+                }
+                std::swap(cur, nxt);
+                if (n >= 0xfffffff0ull) {
+                        set_error("more than 2^32 (triangle, cell) pairs at level %d", l + 1);
+                        return VRT_ERR_CAPACITY;
+                }
+        }
+        // keys live in *cur; make sure finish_from_keys ping-pongs with the other one
+        if (cur != &t->keys_a)
+                std::swap(t->keys_a, t->keys_b);
+        int rc = finish_from_keys(t, t->keys_a.as<unsigned long long>(), n, L, tb, /*stable_input=*/false, d_root6);
+        tab_s.release();
+        if (rc)
+                return rc;
+        VRT_CUDA(cudaEventRecord(t->ev1, s));
+        VRT_CUDA(cudaEventSynchronize(t->ev1));
+        float ms = 0;
+        VRT_CUDA(cudaEventElapsedTime(&ms, t->ev0, t->ev1));
+        t->build_ms = ms;
+        return VRT_OK;
+}
+
+int import_leaves(vrt_tree* t, int max_depth, const float root_aabb[6], uint64_t num_leaves,
+                  const uint32_t* leaf_cell, const uint32_t* leaf_count, const uint32_t* leaf_refs)
+{
+        const int L = max_depth - 1;
+        const uint32_t T = t->hdr.num_tris;
+        const int tb = tri_bits_for(T);
+        if (3 * L + tb > 64) {
+                set_error("key does not fit 64 bit");
+                return VRT_ERR_CAPACITY;
+        }
+        uint64_t n = 0;
+        for (uint64_t i = 0; i < num_leaves; ++i)
+                n += leaf_count[i];
+        std::vector<unsigned long long> keys(n);
+        uint64_t k = 0;
+        for (uint64_t i = 0; i < num_leaves; ++i) {
+                unsigned long long m = morton_encode(leaf_cell[3 * i], leaf_cell[3 * i + 1], leaf_cell[3 * i + 2]);
+                for (uint32_t j = 0; j < leaf_count[i]; ++j, ++k) {
+                        if (leaf_refs[k] >= T) {
+                                set_error("leaf_refs[%llu]=%u out of range", (unsigned long long)k, leaf_refs[k]);
+                                return VRT_ERR_ARG;
+                        }
+                        keys[k] = (m << tb) | leaf_refs[k];
+                }
+        }
+        if (t->keys_a.reserve(std::max<uint64_t>(n, 1) * 8))
+                return VRT_ERR_NOMEM;
+        cudaStream_t s = t->stream;
+        if (n)
+                VRT_CUDA(cudaMemcpyAsync(t->keys_a.p, keys.data(), n * 8, cudaMemcpyHostToDevice, s));
+        float* d_root6 = reinterpret_cast<float*>(t->d_counter + 8);
+        VRT_CUDA(cudaMemcpyAsync(d_root6, root_aabb, 24, cudaMemcpyHostToDevice, s));
+        VRT_CUDA(cudaStreamSynchronize(s));
+        return finish_from_keys(t, t->keys_a.as<unsigned long long>(), n, L, tb, false, d_root6);
+}
+
+}  // namespace vrt

@@ -1,0 +1,335 @@
+// vrt_exact.cuh -- bit-exact device restatements of the reference's scalar
+// arithmetic on the hot path.  Everything here must evaluate exactly like the
+// reference compiled for x86-64 WITHOUT fused multiply-add
+// (VoxelRayTrace20190722.vcxproj:91-120: MSVC /O2 /fp:precise, no /arch), so
+//   * every multiply and add is a separately rounded IEEE-754 operation: we use
+//     the __f*_rn / __d*_rn intrinsics, which nvcc never contracts into FMA (the
+//     translation units are ALSO compiled with -fmad=false as a second guard);
+//   * division and sqrt are the IEEE-correct variants (__fdiv_rn, __fsqrt_rn);
+//   * denormals are kept (no -ftz), min/max follow std::min/std::max, and
+//     first-extremum tie rules follow std::min_element/std::max_element.
+// Reference file:line citations are relative to VoxelRayTrace20190722/.
+#pragma once
+
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace vrt {
+
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+
+// std::min(a,b) = (b<a)?b:a ; std::max(a,b) = (a<b)?b:a  (differs from fminf/fmaxf
+// only for NaN operands and for the sign of equal zeros).
+__device__ __forceinline__ float std_min(float a, float b) { return (b < a) ? b : a; }
+__device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b : a; }
+
+// jql::dot for Vec3 (graphics_math.h:532-549): value_sum starts at 0 and adds
+// the element products left to right.
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz)
+{
+        float s = fadd(0.f, fmul(ax, bx));
+        s = fadd(s, fmul(ay, by));
+        s = fadd(s, fmul(az, bz));
+        return s;
+}
+
+// jql::normalize (graphics_math.h:576-586): v / sqrtf(dot(v,v)), true division.
+__device__ __forceinline__ void normalize3(float& x, float& y, float& z)
+{
+        float l = __fsqrt_rn(dot3(x, y, z, x, y, z));
+        x = fdiv(x, l);
+        y = fdiv(y, l);
+        z = fdiv(z, l);
+}
+
+// jql::clamp (graphics_math.h:905-909)
+__device__ __forceinline__ float clampf(float s, float lo, float hi)
+{
+        return s > hi ? hi : (s < lo ? lo : s);
+}
+
+// ---------------------------------------------------------------------------
+// triBoxOverlap (tribox2.cc:112-186) incl. planeBoxOverlap (tribox2.cc:42-63).
+// c = box centre, h = box half size, v* = triangle vertices.
+// The reference evaluates the 13 axes in a fixed order and returns at the first
+// separating one; the result is the conjunction of 13 independent predicates,
+// so evaluating the cheap box-axis tests first does not change it.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool axis_sep(float pa, float pb, float rad)
+{
+        // if(pa<pb){min=pa;max=pb;}else{min=pb;max=pa;} if(min>rad||max<-rad) return 0;
+        float mn = (pa < pb) ? pa : pb;
+        float mx = (pa < pb) ? pb : pa;
+        return (mn > rad) || (mx < -rad);
+}
+
+__device__ __forceinline__ bool tribox_overlap(const float c[3], const float h[3],
+                                               const float t0[3], const float t1[3],
+                                               const float t2[3])
+{
+        float v0[3], v1[3], v2[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+                v0[k] = fsub(t0[k], c[k]);
+                v1[k] = fsub(t1[k], c[k]);
+                v2[k] = fsub(t2[k], c[k]);
+        }
+        // box axes (tribox2.cc:166-176), strict inequalities
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+                float mn = v0[k], mx = v0[k];
+                if (v1[k] < mn) mn = v1[k];
+                if (v1[k] > mx) mx = v1[k];
+                if (v2[k] < mn) mn = v2[k];
+                if (v2[k] > mx) mx = v2[k];
+                if (mn > h[k] || mx < -h[k])
+                        return false;
+        }
+        float e0[3], e1[3], e2[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+                e0[k] = fsub(v1[k], v0[k]);
+                e1[k] = fsub(v2[k], v1[k]);
+                e2[k] = fsub(v0[k], v2[k]);
+        }
+        float fx, fy, fz;
+        // edge 0: AXISTEST_X01, Y02, Z12 (tribox2.cc:139-144)
+        fx = fabsf(e0[0]); fy = fabsf(e0[1]); fz = fabsf(e0[2]);
+        if (axis_sep(fsub(fmul(e0[2], v0[1]), fmul(e0[1], v0[2])),
+                     fsub(fmul(e0[2], v2[1]), fmul(e0[1], v2[2])),
+                     fadd(fmul(fz, h[1]), fmul(fy, h[2])))) return false;
+        if (axis_sep(fadd(fmul(-e0[2], v0[0]), fmul(e0[0], v0[2])),
+                     fadd(fmul(-e0[2], v2[0]), fmul(e0[0], v2[2])),
+                     fadd(fmul(fz, h[0]), fmul(fx, h[2])))) return false;
+        if (axis_sep(fsub(fmul(e0[1], v2[0]), fmul(e0[0], v2[1])),
+                     fsub(fmul(e0[1], v1[0]), fmul(e0[0], v1[1])),
+                     fadd(fmul(fy, h[0]), fmul(fx, h[1])))) return false;
+        // edge 1: X01, Y02, Z0 (tribox2.cc:146-151)
+        fx = fabsf(e1[0]); fy = fabsf(e1[1]); fz = fabsf(e1[2]);
+        if (axis_sep(fsub(fmul(e1[2], v0[1]), fmul(e1[1], v0[2])),
+                     fsub(fmul(e1[2], v2[1]), fmul(e1[1], v2[2])),
+                     fadd(fmul(fz, h[1]), fmul(fy, h[2])))) return false;
+        if (axis_sep(fadd(fmul(-e1[2], v0[0]), fmul(e1[0], v0[2])),
+                     fadd(fmul(-e1[2], v2[0]), fmul(e1[0], v2[2])),
+                     fadd(fmul(fz, h[0]), fmul(fx, h[2])))) return false;
+        if (axis_sep(fsub(fmul(e1[1], v0[0]), fmul(e1[0], v0[1])),
+                     fsub(fmul(e1[1], v1[0]), fmul(e1[0], v1[1])),
+                     fadd(fmul(fy, h[0]), fmul(fx, h[1])))) return false;
+        // edge 2: X2, Y1, Z12 (tribox2.cc:153-158)
+        fx = fabsf(e2[0]); fy = fabsf(e2[1]); fz = fabsf(e2[2]);
+        if (axis_sep(fsub(fmul(e2[2], v0[1]), fmul(e2[1], v0[2])),
+                     fsub(fmul(e2[2], v1[1]), fmul(e2[1], v1[2])),
+                     fadd(fmul(fz, h[1]), fmul(fy, h[2])))) return false;
+        if (axis_sep(fadd(fmul(-e2[2], v0[0]), fmul(e2[0], v0[2])),
+                     fadd(fmul(-e2[2], v1[0]), fmul(e2[0], v1[2])),
+                     fadd(fmul(fz, h[0]), fmul(fx, h[2])))) return false;
+        if (axis_sep(fsub(fmul(e2[1], v2[0]), fmul(e2[0], v2[1])),
+                     fsub(fmul(e2[1], v1[0]), fmul(e2[0], v1[1])),
+                     fadd(fmul(fy, h[0]), fmul(fx, h[1])))) return false;
+        // plane (tribox2.cc:181-183 + 42-63)
+        float n[3];
+        n[0] = fsub(fmul(e0[1], e1[2]), fmul(e0[2], e1[1]));
+        n[1] = fsub(fmul(e0[2], e1[0]), fmul(e0[0], e1[2]));
+        n[2] = fsub(fmul(e0[0], e1[1]), fmul(e0[1], e1[0]));
+        float d = -fadd(fadd(fmul(n[0], v0[0]), fmul(n[1], v0[1])), fmul(n[2], v0[2]));
+        float lo[3], hi[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+                if (n[q] > 0.0f) {
+                        lo[q] = -h[q];
+                        hi[q] = h[q];
+                } else {
+                        lo[q] = h[q];
+                        hi[q] = -h[q];
+                }
+        }
+        float dmin = fadd(fadd(fadd(fmul(n[0], lo[0]), fmul(n[1], lo[1])), fmul(n[2], lo[2])), d);
+        if (dmin > 0.0f)
+                return false;
+        float dmax = fadd(fadd(fadd(fmul(n[0], hi[0]), fmul(n[1], hi[1])), fmul(n[2], hi[2])), d);
+        return dmax >= 0.0f;
+}
+
+// Triangle::is_overlap (voxel_octree.cc:486-492): centre=(min+max)*.5f
+// (graphics_math.h:1252-1255), half=(max-min)/2.f.
+__device__ __forceinline__ bool tri_overlaps_aabb(const float mn[3], const float mx[3],
+                                                  const float t0[3], const float t1[3],
+                                                  const float t2[3])
+{
+        float c[3], h[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+                c[k] = fmul(fadd(mn[k], mx[k]), .5f);
+                h[k] = fdiv(fsub(mx[k], mn[k]), 2.f);
+        }
+        return tribox_overlap(c, h, t0, t1, t2);
+}
+
+// ---------------------------------------------------------------------------
+// intersect_triangle3 (raytri.cc:197-249): double, two-sided, EPSILON 1e-6
+// (raytri.cc:9), inv_det computed before the sign branch, no test on t.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double ddot3(const double a[3], const double b[3])
+{
+        return dadd(dadd(dmul(a[0], b[0]), dmul(a[1], b[1])), dmul(a[2], b[2]));
+}
+
+__device__ __forceinline__ void dcross(double o[3], const double a[3], const double b[3])
+{
+        o[0] = dsub(dmul(a[1], b[2]), dmul(a[2], b[1]));
+        o[1] = dsub(dmul(a[2], b[0]), dmul(a[0], b[2]));
+        o[2] = dsub(dmul(a[0], b[1]), dmul(a[1], b[0]));
+}
+
+__device__ __forceinline__ int ray_triangle3(const double o[3], const double dir[3],
+                                             const double a[3], const double b[3],
+                                             const double c[3], double& t, double& u,
+                                             double& v)
+{
+        const double eps = 0.000001;
+        double e1[3], e2[3], tv[3], pv[3], qv[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+                e1[k] = dsub(b[k], a[k]);
+                e2[k] = dsub(c[k], a[k]);
+        }
+        dcross(pv, dir, e2);
+        double det = ddot3(e1, pv);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+                tv[k] = dsub(o[k], a[k]);
+        if (det > eps) {
+                u = ddot3(tv, pv);
+                if (u < 0.0 || u > det)
+                        return 0;
+                dcross(qv, tv, e1);
+                v = ddot3(dir, qv);
+                if (v < 0.0 || dadd(u, v) > det)
+                        return 0;
+        } else if (det < -eps) {
+                u = ddot3(tv, pv);
+                if (u > 0.0 || u < det)
+                        return 0;
+                dcross(qv, tv, e1);
+                v = ddot3(dir, qv);
+                if (v > 0.0 || dadd(u, v) < det)
+                        return 0;
+        } else {
+                return 0;
+        }
+        double inv = __ddiv_rn(1.0, det);
+        t = dmul(ddot3(e2, qv), inv);
+        u = dmul(u, inv);
+        v = dmul(v, inv);
+        return 1;
+}
+
+// ---------------------------------------------------------------------------
+// AABB<Vec3>::isect(ray, nullptr) (graphics_math.h:1312-1332)
+// ---------------------------------------------------------------------------
+// d with every 0.f (incl. -0.f) replaced by FLT_MIN, then 1.f/d (true division).
+__device__ __forceinline__ float slab_dinv(float d)
+{
+        float dd = (d == 0.f) ? FLT_MIN : d;
+        return fdiv(1.f, dd);
+}
+
+// *std::max_element over 3 values: first maximum, '<' only.
+__device__ __forceinline__ float max_element3(float a, float b, float c)
+{
+        float m = a;
+        if (m < b) m = b;
+        if (m < c) m = c;
+        return m;
+}
+__device__ __forceinline__ float min_element3(float a, float b, float c)
+{
+        float m = a;
+        if (b < m) m = b;
+        if (c < m) m = c;
+        return m;
+}
+
+__device__ __forceinline__ bool slab_accept(float t0, float t1, float tmin, float tmax)
+{
+        if (t0 > t1)
+                return false;
+        return (t0 >= tmin && t0 <= tmax) || (t1 >= tmin && t1 <= tmax);
+}
+
+__device__ __forceinline__ bool aabb_isect(const float mn[3], const float mx[3],
+                                           const float o[3], const float dinv[3],
+                                           float tmin, float tmax)
+{
+        float lo[3], hi[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+                float a = fmul(fsub(mn[k], o[k]), dinv[k]);
+                float b = fmul(fsub(mx[k], o[k]), dinv[k]);
+                lo[k] = std_min(a, b);
+                hi[k] = std_max(a, b);
+        }
+        float t0 = max_element3(lo[0], lo[1], lo[2]);
+        float t1 = min_element3(hi[0], hi[1], hi[2]);
+        return slab_accept(t0, t1, tmin, tmax);
+}
+
+// ---------------------------------------------------------------------------
+// Camera::gen_rays1/gen_rays4 (camera.cc:77-112) for sample s of pixel (px,py)
+// ---------------------------------------------------------------------------
+struct CameraParams {
+        float C[16];
+        float z;
+        float tmin, tmax;
+        int nx, ny, spp;
+};
+
+__device__ __forceinline__ void gen_ray(const CameraParams& cam, int px, int py, int s,
+                                        float o[3], float d[3])
+{
+        // samples: gen_rays1 {4,4}/8 ; gen_rays4 {1,5},{3,1},{7,3},{5,7} /8
+        float sx, sy;
+        if (cam.spp == 4) {
+                sx = (s == 0) ? 0.125f : (s == 1) ? 0.375f : (s == 2) ? 0.875f : 0.625f;
+                sy = (s == 0) ? 0.625f : (s == 1) ? 0.125f : (s == 2) ? 0.375f : 0.875f;
+        } else {
+                sx = 0.5f;
+                sy = 0.5f;
+        }
+        const float x = (float)(px - cam.nx / 2);
+        const float y = (float)((cam.ny - 1 - py) - cam.ny / 2);
+        const float x_ = fdiv(fadd(x, sx), (float)cam.nx);
+        const float y_ = fdiv(fadd(y, sy), (float)cam.ny);
+        // point_transform(C,{0,0,0}) / vector_transform(C,{x_,y_,z})
+        // graphics_math.h:1063-1077 via dot(Mat4,Vec4) :552-562
+        float o4[4], d4[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+                float a = fadd(0.f, fmul(cam.C[r], 0.f));
+                a = fadd(a, fmul(cam.C[4 + r], 0.f));
+                a = fadd(a, fmul(cam.C[8 + r], 0.f));
+                a = fadd(a, fmul(cam.C[12 + r], 1.f));
+                o4[r] = a;
+                float b = fadd(0.f, fmul(cam.C[r], x_));
+                b = fadd(b, fmul(cam.C[4 + r], y_));
+                b = fadd(b, fmul(cam.C[8 + r], cam.z));
+                b = fadd(b, fmul(cam.C[12 + r], 0.f));
+                d4[r] = b;
+        }
+        o[0] = fdiv(o4[0], o4[3]);
+        o[1] = fdiv(o4[1], o4[3]);
+        o[2] = fdiv(o4[2], o4[3]);
+        d[0] = d4[0];
+        d[1] = d4[1];
+        d[2] = d4[2];
+        normalize3(d[0], d[1], d[2]);  // Ray ctor graphics_math.h:1159-1166
+}
+
+}  // namespace vrt

@@ -1,0 +1,137 @@
+// vrt_internal.h -- handle layout, HBM blob layout and helpers shared by the
+// translation units of libvrt.so.  Not part of the public ABI.
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <cuda_runtime.h>
+
+#include "../../include/vrt.h"
+
+namespace vrt {
+
+// ---------------------------------------------------------------------------
+// HBM layout ("blob"): ONE contiguous device allocation holding everything the
+// ray kernel reads, so that a replica is a single ncclBroadcast.  All section
+// offsets are 256-byte aligned byte offsets from the start of the blob.
+//
+//   header      BlobHeader (512 B)
+//   nodes       uint2[num_nodes], BFS order: level 0 (root) first, each level
+//               sorted by Morton code, children of one node contiguous.
+//                 interior (level < L): .x = index of first non-empty child,
+//                                       .y = 8-bit child mask (bit c = child c
+//                                            non-empty; c: x bit2, y bit1, z bit0)
+//                 leaf     (level == L): .x = first triangle ref, .y = ref count
+//   leaf_morton uint64[num_leaves]  Morton code of leaf i (3 bits per level)
+//   leaf_refs   uint32[num_refs]    triangle indices, ascending per leaf
+//   tri4        float4[3*num_tris]  vertices padded to 16 B (v0,_)(v1,_)(v2,_)
+//   nrm         float[9*num_tris]   per-vertex normals, normalised like the
+//                                   Triangle ctor (voxel_octree.cc:426)
+//   axis_tab    float2[3][2^(L+1)]  per-axis cell bounds: entry (1<<l)+i of
+//               axis a = (min,max) of cell i at level l along a, produced by the
+//               reference's float recurrence (voxel_octree.cc:30-37).  Boxes are
+//               products of three 1-D intervals, so this table IS the set of all
+//               node AABBs ("pointerless and box-less" node array).
+// ---------------------------------------------------------------------------
+struct BlobHeader {
+        uint64_t magic;
+        uint64_t bytes;
+        uint32_t num_tris;
+        int32_t max_depth;  // reference's 1-based depth; L = max_depth-1
+        float root_aabb[6];
+        uint64_t num_nodes;
+        uint64_t num_leaves;
+        uint64_t num_refs;
+        uint64_t level_offset[VRT_MAX_DEPTH + 1];
+        uint64_t off_nodes;
+        uint64_t off_leaf_morton;
+        uint64_t off_leaf_refs;
+        uint64_t off_tri4;
+        uint64_t off_nrm;
+        uint64_t off_axis_tab;
+        uint64_t axis_tab_stride;  // float2 entries per axis = 2^(L+1)
+};
+static_assert(sizeof(BlobHeader) <= 512, "header grew");
+constexpr uint64_t kBlobMagic = 0x3142305452565856ull;  // "VXVRT0B1"
+constexpr uint64_t kHeaderBytes = 512;
+
+inline uint64_t align256(uint64_t x) { return (x + 255ull) & ~255ull; }
+
+// Device-side view handed to kernels by value.
+struct TreeDev {
+        const uint2* nodes;
+        const unsigned long long* leaf_morton;
+        const uint32_t* leaf_refs;
+        const float4* tri4;
+        const float* nrm;
+        const float4* tab4[3];  // axis table viewed as float4: entry (1<<l)+x =
+                                // (lo.min, lo.max, hi.min, hi.max) of the two
+                                // children of cell x at level l
+        const float2* tab2[3];
+        uint32_t num_nodes;
+        uint32_t num_leaves;
+        int L;  // leaf level = max_depth-1
+};
+
+void set_error(const char* fmt, ...);
+bool cuda_ok(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+
+#define VRT_CUDA(expr)                                  \
+        do {                                            \
+                if (!::vrt::cuda_ok((expr), #expr))     \
+                        return VRT_ERR_CUDA;            \
+        } while (0)
+
+// Growable device scratch buffer (kept across rebuilds so timing loops do not
+// hit cudaMalloc).
+struct Scratch {
+        void* p = nullptr;
+        size_t cap = 0;
+        int reserve(size_t bytes);
+        void release();
+        template <class T>
+        T* as() const { return static_cast<T*>(p); }
+};
+
+}  // namespace vrt
+
+struct vrt_tree {
+        int device = 0;
+        cudaStream_t stream = nullptr;
+        bool own_blob = true;
+        void* blob = nullptr;  // device
+        uint64_t blob_bytes = 0;
+        vrt::BlobHeader hdr{};  // host copy
+        vrt::TreeDev dev{};
+        // inputs kept for vrt_rebuild
+        float* d_tri_in = nullptr;  // [T][9] as given
+        float* d_nrm_in = nullptr;  // [T][9] as given, or null
+        // build scratch
+        vrt::Scratch keys_a, keys_b, tmp_a, tmp_b, tmp_c, hist, level_morton[VRT_MAX_DEPTH + 1],
+            level_first[VRT_MAX_DEPTH + 1], level_mask[VRT_MAX_DEPTH + 1];
+        uint32_t* d_counter = nullptr;  // small device counter block
+        uint32_t* h_counter = nullptr;  // pinned mirror
+        // trace scratch (host-pointer entry points)
+        vrt::Scratch io_in, io_out;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        double build_ms = 0;
+        mutable double last_kernel_ms = 0;
+        uint64_t scratch_bytes() const;
+};
+
+namespace vrt {
+int tree_alloc(vrt_tree** out);
+void tree_bind_views(vrt_tree* t);
+// build pipeline (vrt_build.cu)
+int build_tree(vrt_tree* t, int max_depth);
+int import_leaves(vrt_tree* t, int max_depth, const float root_aabb[6], uint64_t num_leaves,
+                  const uint32_t* leaf_cell, const uint32_t* leaf_count,
+                  const uint32_t* leaf_refs);
+// trace (vrt_trace.cu)
+enum OutMode { OUT_HIT48 = 0, OUT_HIT16 = 1, OUT_FILM = 2 };
+int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_hit* d_out);
+int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, int x0,
+                        int y0, int x1, int y1, void* d_out, OutMode mode);
+}  // namespace vrt

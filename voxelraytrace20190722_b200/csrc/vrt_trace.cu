@@ -1,0 +1,524 @@
+// vrt_trace.cu -- octree traversal + leaf triangle hits + fused ray generation.
+//
+// Replaces gi::ray_march / travorder / ray_march_isect (voxel_octree.cc:77-188),
+// Triangle::isect -> intersect_triangle3 (voxel_octree.cc:438-460,
+// raytri.cc:197-249), AABB<Vec3>::isect (graphics_math.h:1312-1332),
+// Camera::gen_rays1/4 (camera.cc:77-112) and the render_mt pixel loop
+// (camera.h:41-68).
+//
+// Reference semantics kept:
+//   1. children are visited in ascending dot(d, centre-o), ties by child index
+//      (libstdc++ insertion sort of 8 items is stable);
+//   2. a child is entered only if its slab test passes; empty children can never
+//      produce a hit and are dropped up front (child mask);
+//   3. the first leaf (in that order) with ANY accepted triangle ends the ray;
+//      inside the leaf the smallest float length(hit-o) wins, first index on ties;
+//      no t>0 / tmin / tmax test on triangle hits, hit not clipped to the leaf;
+//   4. slab and key arithmetic are FMA-free and use the reference's operation
+//      order; child boxes come from the recurrence table (vrt_internal.h).
+//
+// Work decomposition: one ray per thread, 32 rays of one warp form an 8x4 pixel
+// tile (spp=1) or a 4x2 pixel tile x 4 samples (spp=4); warps pull tiles from an
+// atomic queue (persistent threads).  The traversal stack (one 12-byte record
+// per level) lives in shared memory, indexed [level][thread] -> conflict free.
+#include <algorithm>
+#include <cfloat>
+
+#include "vrt_exact.cuh"
+#include "vrt_internal.h"
+
+namespace vrt {
+
+constexpr int kTraceThreads = 128;
+constexpr int kMaxLevels = VRT_MAX_DEPTH;  // stack records per thread
+
+struct TraceParams {
+        TreeDev tree;
+        CameraParams cam;
+        int x0, y0, x1, y1;  // pixel rectangle (camera modes)
+        const vrt_ray* rays;  // explicit-ray mode
+        unsigned long long num_rays;
+        void* out;
+        uint32_t* queue;  // tile counter
+        uint32_t num_tiles;
+        float light[3];
+        float kd;
+        float root[6];
+};
+
+struct HitState {
+        uint32_t tri;
+        uint32_t leaf;  // global node index of the leaf
+        uint32_t cx, cy, cz;
+        float t, u, v;
+        bool hit;
+};
+
+// Triangle::isect + ray_march_isect for one leaf (voxel_octree.cc:99-129,438-460).
+__device__ __forceinline__ bool leaf_isect(const TreeDev& tr, uint32_t leaf_node, const float o[3],
+                                           const float d[3], HitState& hs)
+{
+        const uint2 rec = __ldg(&tr.nodes[leaf_node]);
+        const double od[3] = { (double)o[0], (double)o[1], (double)o[2] };
+        const double dd[3] = { (double)d[0], (double)d[1], (double)d[2] };
+        bool found = false;
+        float best = 0.f;
+        for (uint32_t i = 0; i < rec.y; ++i) {
+                const uint32_t ti = __ldg(&tr.leaf_refs[rec.x + i]);
+                const float4 a4 = __ldg(&tr.tri4[3ull * ti + 0]);
+                const float4 b4 = __ldg(&tr.tri4[3ull * ti + 1]);
+                const float4 c4 = __ldg(&tr.tri4[3ull * ti + 2]);
+                const double a[3] = { (double)a4.x, (double)a4.y, (double)a4.z };
+                const double b[3] = { (double)b4.x, (double)b4.y, (double)b4.z };
+                const double c[3] = { (double)c4.x, (double)c4.y, (double)c4.z };
+                double dt, du, dv;
+                if (ray_triangle3(od, dd, a, b, c, dt, du, dv) != 1)
+                        continue;
+                // hit = o + (float)dt * d ; depth = length(hit - o)   voxel_octree.cc:454,114
+                const float tf = __double2float_rn(dt);
+                const float hx = fadd(o[0], fmul(tf, d[0]));
+                const float hy = fadd(o[1], fmul(tf, d[1]));
+                const float hz = fadd(o[2], fmul(tf, d[2]));
+                const float ex = fsub(hx, o[0]), ey = fsub(hy, o[1]), ez = fsub(hz, o[2]);
+                const float depth = __fsqrt_rn(dot3(ex, ey, ez, ex, ey, ez));
+                if (!found || depth < best) {  // std::min_element: first minimum
+                        found = true;
+                        best = depth;
+                        hs.tri = ti;
+                        hs.t = tf;
+                        hs.u = __double2float_rn(du);
+                        hs.v = __double2float_rn(dv);
+                }
+        }
+        return found;
+}
+
+// ISect of the winning triangle (voxel_octree.cc:449-454).
+__device__ __forceinline__ void finish_isect(const TreeDev& tr, const HitState& hs, const float o[3],
+                                             const float d[3], float pos[3], float nrm[3])
+{
+        const float u = clampf(hs.u, 0.f, 1.f);
+        const float v = clampf(hs.v, 0.f, 1.f);
+        const float w = clampf(fsub(fsub(1.f, u), v), 0.f, 1.f);
+        const float* n = tr.nrm + 9ull * hs.tri;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+                nrm[k] = fadd(fadd(fmul(__ldg(n + k), w), fmul(__ldg(n + 3 + k), u)), fmul(__ldg(n + 6 + k), v));
+        normalize3(nrm[0], nrm[1], nrm[2]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+                pos[k] = fadd(o[k], fmul(hs.t, d[k]));
+}
+
+// One ray through the octree.  s_first/s_meta/s_list: shared stack columns of
+// this thread (stride = blockDim.x).
+__device__ __forceinline__ void trace_one(const TreeDev& tr, const float root[6], const float o[3],
+                                          const float d[3], float tmin, float tmax, uint32_t* s_first,
+                                          uint32_t* s_meta, uint32_t* s_list, HitState& hs)
+{
+        hs.hit = false;
+        hs.tri = VRT_NO_TRI;
+        hs.leaf = VRT_NO_TRI;
+        hs.cx = hs.cy = hs.cz = 0xffffffffu;
+        hs.t = hs.u = hs.v = 0.f;
+        if (tr.num_nodes == 0)
+                return;
+        float dinv[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+                dinv[k] = slab_dinv(d[k]);
+        {
+                const float mn[3] = { root[0], root[1], root[2] };
+                const float mx[3] = { root[3], root[4], root[5] };
+                if (!aabb_isect(mn, mx, o, dinv, tmin, tmax))  // voxel_octree.cc:134
+                        return;
+        }
+        const int L = tr.L;
+        if (L == 0) {  // root is the only leaf (voxel_octree.cc:137-144)
+                if (leaf_isect(tr, 0, o, d, hs)) {
+                        hs.hit = true;
+                        hs.leaf = 0;
+                        hs.cx = hs.cy = hs.cz = 0;
+                }
+                return;
+        }
+        const int stride = blockDim.x;
+        int level = 0;           // level of the node whose children are being iterated
+        uint32_t x = 0, y = 0, z = 0;
+        uint32_t node = 0;       // node to expand
+        uint32_t first = 0, mask = 0, list = 0, cnt = 0;
+        bool need_expand = true;
+        for (;;) {
+                if (need_expand) {
+                        // ---- expand `node` at (level; x,y,z): order + slab-test its 8 children ----
+                        const uint2 rec = __ldg(&tr.nodes[node]);
+                        first = rec.x;
+                        mask = rec.y & 0xffu;
+                        const uint32_t ti = (1u << level) + 0u;
+                        const float4 bx = __ldg(&tr.tab4[0][ti + x]);
+                        const float4 by = __ldg(&tr.tab4[1][ti + y]);
+                        const float4 bz = __ldg(&tr.tab4[2][ti + z]);
+                        // per axis, per half (lo/hi child): slab interval and centre key term
+                        float smin[3][2], smax[3][2], kterm[3][2];
+                        const float4 bb[3] = { bx, by, bz };
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                                const float mnv[2] = { bb[a].x, bb[a].z };
+                                const float mxv[2] = { bb[a].y, bb[a].w };
+#pragma unroll
+                                for (int hsel = 0; hsel < 2; ++hsel) {
+                                        const float t_a = fmul(fsub(mnv[hsel], o[a]), dinv[a]);
+                                        const float t_b = fmul(fsub(mxv[hsel], o[a]), dinv[a]);
+                                        smin[a][hsel] = std_min(t_a, t_b);
+                                        smax[a][hsel] = std_max(t_a, t_b);
+                                        // travorder key term: d * (centre - o), centre=(min+max)*.5f
+                                        const float ctr = fmul(fadd(mnv[hsel], mxv[hsel]), .5f);
+                                        kterm[a][hsel] = fmul(d[a], fsub(ctr, o[a]));
+                                }
+                        }
+                        float key[8];
+                        uint32_t valid = 0;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                                const int hx = (c >> 2) & 1, hy = (c >> 1) & 1, hz = c & 1;
+                                const float t0 = max_element3(smin[0][hx], smin[1][hy], smin[2][hz]);
+                                const float t1 = min_element3(smax[0][hx], smax[1][hy], smax[2][hz]);
+                                if (((mask >> c) & 1u) && slab_accept(t0, t1, tmin, tmax))
+                                        valid |= 1u << c;
+                                key[c] = fadd(fadd(fadd(0.f, kterm[0][hx]), kterm[1][hy]), kterm[2][hz]);
+                        }
+                        // stable rank of every valid child among the valid children
+                        uint32_t rank[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                                rank[c] = 0;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                                for (int j = i + 1; j < 8; ++j) {
+                                        const bool j_first = key[j] < key[i];  // else i (lower index) first
+                                        rank[i] += (j_first && ((valid >> j) & 1u)) ? 1u : 0u;
+                                        rank[j] += (!j_first && ((valid >> i) & 1u)) ? 1u : 0u;
+                                }
+                        }
+                        list = 0;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                                if ((valid >> c) & 1u)
+                                        list |= (uint32_t)c << (3u * rank[c]);
+                        cnt = __popc(valid);
+                        need_expand = false;
+                }
+                if (cnt == 0) {
+                        if (level == 0)
+                                return;  // miss
+                        --level;
+                        x >>= 1;
+                        y >>= 1;
+                        z >>= 1;
+                        first = s_first[level * stride];
+                        const uint32_t m = s_meta[level * stride];
+                        mask = m & 0xffu;
+                        cnt = m >> 8;
+                        list = s_list[level * stride];
+                        continue;
+                }
+                const uint32_t c = list & 7u;
+                list >>= 3;
+                --cnt;
+                const uint32_t child = first + __popc(mask & ((1u << c) - 1u));
+                const uint32_t cx = 2u * x + ((c >> 2) & 1u);
+                const uint32_t cy = 2u * y + ((c >> 1) & 1u);
+                const uint32_t cz = 2u * z + (c & 1u);
+                if (level + 1 == L) {
+                        if (leaf_isect(tr, child, o, d, hs)) {
+                                hs.hit = true;
+                                hs.leaf = child;
+                                hs.cx = cx;
+                                hs.cy = cy;
+                                hs.cz = cz;
+                                return;
+                        }
+                } else {
+                        s_first[level * stride] = first;
+                        s_meta[level * stride] = mask | (cnt << 8);
+                        s_list[level * stride] = list;
+                        ++level;
+                        x = cx;
+                        y = cy;
+                        z = cz;
+                        node = child;
+                        need_expand = true;
+                }
+        }
+}
+
+__device__ __forceinline__ void store_hit48(vrt_hit* out, const TreeDev& tr, const HitState& hs,
+                                            const float o[3], const float d[3])
+{
+        float pos[3] = { 0.f, 0.f, 0.f }, nrm[3] = { 0.f, 0.f, 0.f };
+        if (hs.hit)
+                finish_isect(tr, hs, o, d, pos, nrm);
+        float4* q = reinterpret_cast<float4*>(out);
+        q[0] = make_float4(__uint_as_float(hs.hit ? 1u : 0u), __uint_as_float(hs.tri), __uint_as_float(hs.cx),
+                           __uint_as_float(hs.cy));
+        q[1] = make_float4(__uint_as_float(hs.cz), hs.hit ? hs.t : 0.f, pos[0], pos[1]);
+        q[2] = make_float4(pos[2], nrm[0], nrm[1], nrm[2]);
+}
+
+// Harness pixel (main.cc:18-20 for the sky).
+__device__ __forceinline__ void shade(const TraceParams& p, const HitState& hs, const float o[3],
+                                      const float d[3], float rgb[3])
+{
+        if (!hs.hit) {
+                // float t = 0.5 * (ray.d.y + 1.0)  -- double arithmetic, then lerp in float
+                const float t = __double2float_rn(dmul(0.5, dadd((double)d[1], 1.0)));
+                const float v1[3] = { 0.6f, 0.8f, 1.0f };
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                        rgb[k] = fadd(1.0f, fmul(fsub(v1[k], 1.0f), t));
+                return;
+        }
+        float pos[3], nrm[3];
+        finish_isect(p.tree, hs, o, d, pos, nrm);
+        const float nl = clampf(dot3(nrm[0], nrm[1], nrm[2], p.light[0], p.light[1], p.light[2]), 0.f, 1.f);
+        const float c = fmul(p.kd, nl);
+        rgb[0] = rgb[1] = rgb[2] = c;
+}
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTraceThreads)
+k_trace_rays(TraceParams p)
+{
+        extern __shared__ uint32_t s_stack[];
+        uint32_t* s_first = s_stack + threadIdx.x;
+        uint32_t* s_meta = s_first + kMaxLevels * blockDim.x;
+        uint32_t* s_list = s_meta + kMaxLevels * blockDim.x;
+        const unsigned long long nwarp_items = (p.num_rays + 31ull) / 32ull;
+        const int lane = threadIdx.x & 31;
+        for (;;) {
+                uint32_t tile = 0;
+                if (lane == 0)
+                        tile = atomicAdd(p.queue, 1u);
+                tile = __shfl_sync(0xffffffffu, tile, 0);
+                if (tile >= nwarp_items)
+                        break;
+                const unsigned long long r = (unsigned long long)tile * 32ull + lane;
+                if (r < p.num_rays) {
+                        const float4* rp = reinterpret_cast<const float4*>(p.rays + r);
+                        const float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                        const float o[3] = { r0.x, r0.y, r0.z };
+                        const float d[3] = { r0.w, r1.x, r1.y };
+                        HitState hs;
+                        trace_one(p.tree, p.root, o, d, r1.z, r1.w, s_first, s_meta, s_list, hs);
+                        store_hit48(static_cast<vrt_hit*>(p.out) + r, p.tree, hs, o, d);
+                }
+                __syncwarp();
+        }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kTraceThreads)
+k_trace_camera(TraceParams p)
+{
+        extern __shared__ uint32_t s_stack[];
+        uint32_t* s_first = s_stack + threadIdx.x;
+        uint32_t* s_meta = s_first + kMaxLevels * blockDim.x;
+        uint32_t* s_list = s_meta + kMaxLevels * blockDim.x;
+        const int lane = threadIdx.x & 31;
+        const int W = p.x1 - p.x0, H = p.y1 - p.y0;
+        const int spp = p.cam.spp;
+        // warp tile: 8x4 pixels (spp 1) or 4x2 pixels x 4 samples (spp 4)
+        const int tw = (spp == 4) ? 4 : 8, th = (spp == 4) ? 2 : 4;
+        const int tiles_x = (W + tw - 1) / tw;
+        for (;;) {
+                uint32_t tile = 0;
+                if (lane == 0)
+                        tile = atomicAdd(p.queue, 1u);
+                tile = __shfl_sync(0xffffffffu, tile, 0);
+                if (tile >= p.num_tiles)
+                        break;
+                const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+                int s, lx, ly;
+                if (spp == 4) {
+                        s = lane & 3;
+                        lx = (lane >> 2) & 3;
+                        ly = lane >> 4;
+                } else {
+                        s = 0;
+                        lx = lane & 7;
+                        ly = lane >> 3;
+                }
+                const int px = p.x0 + tx * tw + lx, py = p.y0 + ty * th + ly;
+                const bool active = (px < p.x1) && (py < p.y1);
+                float o[3] = { 0, 0, 0 }, d[3] = { 0, 0, 1 };
+                HitState hs;
+                hs.hit = false;
+                if (active) {
+                        gen_ray(p.cam, px, py, s, o, d);
+                        trace_one(p.tree, p.root, o, d, p.cam.tmin, p.cam.tmax, s_first, s_meta, s_list, hs);
+                }
+                const unsigned long long pix = (unsigned long long)(py - p.y0) * W + (px - p.x0);
+                if (MODE == OUT_HIT48) {
+                        if (active)
+                                store_hit48(static_cast<vrt_hit*>(p.out) + pix * spp + s, p.tree, hs, o, d);
+                } else if (MODE == OUT_HIT16) {
+                        if (active) {
+                                uint4 q;
+                                q.x = hs.hit ? (hs.leaf - p.tree.num_nodes + p.tree.num_leaves) : VRT_NO_TRI;
+                                q.y = hs.tri;
+                                q.z = __float_as_uint(hs.hit ? hs.t : 0.f);
+                                q.w = hs.hit ? 1u : 0u;
+                                reinterpret_cast<uint4*>(p.out)[pix * spp + s] = q;
+                        }
+                } else {
+                        float rgb[3] = { 0, 0, 0 };
+                        if (active)
+                                shade(p, hs, o, d, rgb);
+                        // film->add(px,py, c * (1/spp)) in sample order (main.cc:119-122)
+                        const float wgt = (spp == 4) ? .25f : 1.f;
+                        float acc[3];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                                const float c = fmul(rgb[k], wgt);
+                                if (spp == 4) {
+                                        const float c1 = __shfl_down_sync(0xffffffffu, c, 1);
+                                        const float c2 = __shfl_down_sync(0xffffffffu, c, 2);
+                                        const float c3 = __shfl_down_sync(0xffffffffu, c, 3);
+                                        acc[k] = fadd(fadd(fadd(fadd(0.f, c), c1), c2), c3);
+                                } else {
+                                        acc[k] = fadd(0.f, c);
+                                }
+                        }
+                        if (active && s == 0) {
+                                float* f = static_cast<float*>(p.out) + pix * 3ull;
+                                f[0] = acc[0];
+                                f[1] = acc[1];
+                                f[2] = acc[2];
+                        }
+                }
+                __syncwarp();
+        }
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+static int g_sm_count = 0;
+
+static int persistent_grid(const void* kernel, size_t smem)
+{
+        if (!g_sm_count) {
+                int dev = 0;
+                cudaGetDevice(&dev);
+                cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+                if (g_sm_count <= 0)
+                        g_sm_count = 148;
+        }
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceThreads, smem) != cudaSuccess ||
+            per_sm < 1) {
+                cudaGetLastError();
+                per_sm = 4;
+        }
+        return g_sm_count * per_sm;
+}
+
+static void fill_common(const vrt_tree* t, TraceParams& p)
+{
+        p.tree = t->dev;
+        for (int k = 0; k < 6; ++k)
+                p.root[k] = t->hdr.root_aabb[k];
+        p.queue = t->d_counter + 16;
+}
+
+int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_hit* d_out)
+{
+        if (n == 0)
+                return VRT_OK;
+        if ((n + 31) / 32 >= 0xffffffffull) {
+                set_error("too many rays for one launch");
+                return VRT_ERR_ARG;
+        }
+        TraceParams p{};
+        fill_common(t, p);
+        p.rays = d_rays;
+        p.num_rays = n;
+        p.out = d_out;
+        const size_t smem = (size_t)3 * kMaxLevels * kTraceThreads * sizeof(uint32_t);
+        VRT_CUDA(cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const uint64_t warps = (n + 31) / 32;
+        int grid = persistent_grid((const void*)k_trace_rays, smem);
+        grid = (int)std::min<uint64_t>((uint64_t)grid, (warps + 3) / 4);
+        VRT_CUDA(cudaMemsetAsync(p.queue, 0, 4, t->stream));
+        VRT_CUDA(cudaEventRecord(t->ev0, t->stream));
+        k_trace_rays<<<grid, kTraceThreads, smem, t->stream>>>(p);
+        count_launch();
+        VRT_CUDA(cudaGetLastError());
+        VRT_CUDA(cudaEventRecord(t->ev1, t->stream));
+        VRT_CUDA(cudaEventSynchronize(t->ev1));
+        float ms = 0;
+        VRT_CUDA(cudaEventElapsedTime(&ms, t->ev0, t->ev1));
+        t->last_kernel_ms = ms;
+        return VRT_OK;
+}
+
+int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, int x0, int y0,
+                        int x1, int y1, void* d_out, OutMode mode)
+{
+        if (x1 <= x0 || y1 <= y0)
+                return VRT_OK;
+        TraceParams p{};
+        fill_common(t, p);
+        for (int k = 0; k < 16; ++k)
+                p.cam.C[k] = cam->C[k];
+        p.cam.z = cam->z;
+        p.cam.tmin = cam->tmin;
+        p.cam.tmax = cam->tmax;
+        p.cam.nx = cam->nx;
+        p.cam.ny = cam->ny;
+        p.cam.spp = cam->spp;
+        p.x0 = x0;
+        p.y0 = y0;
+        p.x1 = x1;
+        p.y1 = y1;
+        p.out = d_out;
+        if (sh) {
+                p.light[0] = sh->light_dir[0];
+                p.light[1] = sh->light_dir[1];
+                p.light[2] = sh->light_dir[2];
+                p.kd = sh->kd;
+        }
+        const int tw = (cam->spp == 4) ? 4 : 8, th = (cam->spp == 4) ? 2 : 4;
+        const uint64_t tiles = (uint64_t)((x1 - x0 + tw - 1) / tw) * (uint64_t)((y1 - y0 + th - 1) / th);
+        if (tiles >= 0xffffffffull) {
+                set_error("too many tiles for one launch");
+                return VRT_ERR_ARG;
+        }
+        p.num_tiles = (uint32_t)tiles;
+        const size_t smem = (size_t)3 * kMaxLevels * kTraceThreads * sizeof(uint32_t);
+        const void* kern = nullptr;
+        switch (mode) {
+        case OUT_HIT48: kern = (const void*)k_trace_camera<OUT_HIT48>; break;
+        case OUT_HIT16: kern = (const void*)k_trace_camera<OUT_HIT16>; break;
+        default: kern = (const void*)k_trace_camera<OUT_FILM>; break;
+        }
+        VRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int grid = persistent_grid(kern, smem);
+        grid = (int)std::min<uint64_t>((uint64_t)grid, (tiles + 3) / 4);
+        VRT_CUDA(cudaMemsetAsync(p.queue, 0, 4, t->stream));
+        VRT_CUDA(cudaEventRecord(t->ev0, t->stream));
+        void* args[] = { &p };
+        VRT_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(kTraceThreads), args, smem, t->stream));
+        count_launch();
+        VRT_CUDA(cudaEventRecord(t->ev1, t->stream));
+        VRT_CUDA(cudaEventSynchronize(t->ev1));
+        float ms = 0;
+        VRT_CUDA(cudaEventElapsedTime(&ms, t->ev0, t->ev1));
+        t->last_kernel_ms = ms;
+        return VRT_OK;
+}
+
+}  // namespace vrt
