@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the octree hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): the "Sponza 1024^3 @4K" configuration of BASELINE.json
+on the procedural atrium stand-in (sponza.obj is absent from the reference checkout,
+SURVEY.md 0): 266,156 triangles voxelized at max_depth 11 (1024^3 leaf grid), main.cc's
+final camera (main.cc:112-115), 3840x2160 film, gen_rays4 -> 33,177,600 primary rays
+per step.  A step = one frame = one launch of the persistent ray kernel per GPU.
+
+  value     Mrays/s with everything resident in HBM (hit16 records written to HBM;
+            N>1: rows sharded in 8-row bands, frame gathered to rank 0 inside the step)
+  e2e       Mrays/s through the host-buffer C-ABI call vrt_render_camera: camera in,
+            shaded float film copied back to pinned host memory inside the timed region
+  roofline  algorithmic bytes per ray (8*N_int + 8*N_leaf + 40*N_tri + 16,
+            N_* counted on the same frame) * rays / kernel time, against the measured HBM
+            copy bandwidth of MEASURED_PEAKS.json
+  build     voxelization + octree build throughput (Mtris/s), device-timed and end to end
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref) on the host cores: ray_march_init
+            (1 thread by construction) and render_mt (thread pool) on a bounded sample
+
+--impl reference times the reference's own CPU implementation on the same workload
+(bounded sample per step) and prints the same JSON shape with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+RAD = np.pi / 180.0
+WORKLOADS = {
+    # name: (scene, scene kwargs, max_depth, cam10, nx, ny, spp)
+    "atrium1024_4k_spp4": ("atrium", {}, 11, [90 * RAD, 1, 1.3, -.2, 0, .4, 0, 0, 1, 0], 3840, 2160, 4),
+    "atrium1024_4k_spp1": ("atrium", {}, 11, [90 * RAD, 1, 1.3, -.2, 0, .4, 0, 0, 1, 0], 3840, 2160, 1),
+    "sphere256_1080p_spp1": ("sphere", {}, 9, [60 * RAD, 0, 1, 3, 0, 0, 0, 0, 1, 0], 1920, 1080, 1),
+    "atrium32_1k_spp4": ("atrium", {}, 6, [90 * RAD, 1, 1.3, -.2, 0, .4, 0, 0, 1, 0], 1024, 1024, 4),
+}
+DEFAULT_WORKLOAD = "atrium1024_4k_spp4"
+CPU_SAMPLE = (640, 360)  # film used for the bounded CPU sample (same scene, camera, spp)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            c = [x.strip() for x in r.split(",")]
+            if len(c) < 8:
+                continue
+            try:
+                sm.append(float(c[0]))
+                mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scene(wl):
+    from voxelraytrace20190722_b200 import scenes
+    scene, kw, depth, cam10, nx, ny, spp = WORKLOADS[wl]
+    tri, nrm = scenes.make_scene(scene, **kw)
+    return tri, nrm, depth, np.asarray(cam10, np.float32), nx, ny, spp
+
+
+# ----------------------------------------------------------------------------
+# reference arm / cpu baseline (oracle/_ref = the unmodified reference)
+# ----------------------------------------------------------------------------
+def cpu_reference(tri, nrm, depth, cam10, spp, steps, warmup, sample=CPU_SAMPLE):
+    from oracle.bindings import Ref
+    ref = Ref()
+    scene = ref.scene(tri, nrm)
+    build_s = scene.build(depth)
+    nx, ny = sample
+    times, rays = [], 0
+    for i in range(warmup + steps):
+        sec, rays, _ = scene.render_mt(cam10, 1.0, nx, ny, spp, outputs=False)
+        if i >= warmup:
+            times.append(sec)
+    cores = ref.hardware_concurrency()
+    return dict(build_s=build_s, mtris=len(tri) / build_s / 1e6, ms_per_step=1e3 * float(np.mean(times)),
+                mrays=rays / float(np.mean(times)) / 1e6, rays=rays, cores=cores,
+                sample=f"same scene/camera/spp at {nx}x{ny} ({rays} rays per step) through render_mt + gen_rays{spp} + "
+                       f"gi::ray_march on {min(cores, 64)} pool threads; octree built once by gi::ray_march_init "
+                       f"(1 thread, {build_s:.1f} s, {len(tri) / build_s / 1e6:.4f} Mtris/s)")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    tri, nrm, depth, cam10, nx, ny, spp = make_scene(args.workload)
+    r = cpu_reference(tri, nrm, depth, cam10, spp, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "Mrays/s octree traversal", "value": r["mrays"], "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": workload_config(args.workload, len(tri), args.gpus),
+        "cpu_baseline": {"value": r["mrays"], "unit": "Mrays/s", "cores": r["cores"], "kind": "reference",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["mrays"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "build": {"mtris_per_s": r["mtris"], "seconds": r["build_s"], "threads": 1},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(wl, ntris, gpus):
+    scene, kw, depth, cam10, nx, ny, spp = WORKLOADS[wl]
+    return {"workload": wl,
+            "scene": f"{scene} ({ntris} tris" + ("; procedural Sponza stand-in, sponza.obj absent from the reference checkout)"
+                                                  if scene == "atrium" else ")"),
+            "max_depth": depth, "leaf_grid": f"{2 ** (depth - 1)}^3", "film": f"{nx}x{ny}", "spp": spp,
+            "rays_per_step": nx * ny * spp, "camera": "main.cc:112-115" if scene == "atrium" else "SURVEY 8d config 2",
+            "sharding": f"8-row bands round-robin over {gpus} GPU(s), replicated octree, frame gathered to rank 0",
+            "l2": "inputs larger than L2: octree blob > 126 MB and every step writes 16 B/ray of fresh hit records"}
+
+
+# ----------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from voxelraytrace20190722_b200 import capi, dist as vdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (libvrt has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as td
+        td.init_process_group("nccl", device_id=dev)
+    capi.load()
+
+    tri, nrm, depth, cam10, nx, ny, spp = make_scene(args.workload)
+    T = len(tri)
+    rays_per_step = nx * ny * spp
+    launches0 = capi.launch_count()
+
+    # ---- build on rank 0 (end to end: host triangles -> octree in HBM), replicate ----
+    build = {}
+    tree = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        tree = capi.Octree.build(tri, nrm, depth)
+        build["e2e_s"] = time.perf_counter() - t0
+        ms = []
+        for _ in range(args.build_reps + 1):
+            tree.rebuild(depth)
+            ms.append(tree.info()["build_ms"])
+        build["ms"] = float(np.mean(ms[1:])) if len(ms) > 1 else ms[0]
+    if world > 1:
+        tree = vdist.replicate_octree(tree, dev)
+    info = tree.info()
+    cam = capi.Camera(cam10[0], cam10[1:4], cam10[4:7], cam10[7:10], nx, ny, spp)
+    stream = torch.cuda.current_stream(dev)
+    tree.set_stream(stream.cuda_stream)
+
+    rows = vdist.max_band_rows(ny, world)  # padded to the largest shard so the gather is uniform
+    hits = torch.empty((rows, nx * spp * 4), dtype=torch.int32, device=dev)  # hit16 records, 16 B each
+
+    def step():
+        tree.trace_bands16_dev(cam, hits.data_ptr(), vdist.BAND_H, rank, world)
+        if world > 1:
+            return vdist.gather_rows(hits, ny)
+        return hits
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            td.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = capi.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+        kernel_ms.append(tree.last_kernel_ms)
+    e1.record(stream)
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = capi.launch_count() - l0
+    total_ms = e0.elapsed_time(e1)
+    t = torch.tensor([total_ms, float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    total_ms, kern_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    value = rays_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: host-buffer C-ABI call, film copied back to pinned host memory every step ----
+    if world == 1:
+        film_host = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory()
+        film_np = film_host.numpy()
+        tree.set_stream(0)
+        for _ in range(max(1, args.warmup // 2)):
+            tree.render(cam, out=film_np)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            tree.render(cam, out=film_np)
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        d2h = film_np.nbytes
+    else:
+        film = torch.empty((rows, nx, 3), dtype=torch.float32, device=dev)
+        film_host = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
+
+        def e2e_step():
+            tree.render_bands_dev(cam, film.data_ptr(), vdist.BAND_H, rank, world)
+            full = vdist.gather_rows(film, ny)
+            if rank == 0:
+                film_host.copy_(full, non_blocking=True)
+                torch.cuda.synchronize(dev)
+
+        for _ in range(max(1, args.warmup // 2)):
+            e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        sync_all()
+        tt = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=dev)
+        td.all_reduce(tt, op=td.ReduceOp.MAX)
+        e2e_ms = float(tt[0])
+        d2h = ny * nx * 12
+    e2e_value = rays_per_step / (e2e_ms * 1e-3) / 1e6
+
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return 0
+
+    # ---- roofline: algorithmic bytes of the reference algorithm on this very frame ----
+    tree.set_stream(0)
+    cnt = tree.count_camera(cam)
+    n_int, n_leaf, n_tri = (cnt[k] / cnt["rays"] for k in ("n_int", "n_leaf", "n_tri"))
+    b_ray = 8 * n_int + 8 * n_leaf + 40 * n_tri + 16
+    peaks, peak_src = measured_peaks()
+    rays_per_launch = rays_per_step / world
+    achieved = b_ray * rays_per_launch / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
+                "kernel": "k_trace_camera<HIT16>", "kernel_ms": kern_ms, "bytes_per_ray": b_ray,
+                "n_int": n_int, "n_leaf": n_leaf, "n_tri": n_tri, "hit_fraction": cnt["hits"] / cnt["rays"]}
+
+    # ---- build metric ----
+    b_tri = None
+    rho = info["num_refs"] / max(T, 1)
+    nu = info["num_nodes"] / max(T, 1)
+    b_tri = 36 + 12 * rho + 8 * nu
+    build_out = {"mtris_per_s": T / (build["ms"] * 1e-3) / 1e6, "ms": build["ms"],
+                 "e2e_mtris_per_s": T / build["e2e_s"] / 1e6, "e2e_s_first_call": build["e2e_s"],
+                 "h2d_bytes": int(tri.nbytes + nrm.nbytes), "bytes_per_tri": b_tri,
+                 "roofline_frac": b_tri * T / (build["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                 "leaves": info["num_leaves"], "nodes": info["num_nodes"], "refs": info["num_refs"]}
+
+    # ---- cpu baseline (rank 0, N=1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = cpu_reference(tri, nrm, depth, cam10, spp, steps=1, warmup=0)
+            cpu = {"value": r["mrays"], "unit": "Mrays/s", "cores": r["cores"], "kind": "reference",
+                   "sample": r["sample"], "build_mtris_per_s": r["mtris"], "build_seconds": r["build_s"]}
+        except Exception as e:  # oracle/_ref missing on this box
+            cpu = {"value": None, "unit": "Mrays/s", "cores": None, "kind": "reference",
+                   "sample": f"unavailable: {e}"}
+
+    line = {
+        "metric": "Mrays/s octree traversal", "value": value, "unit": "Mrays/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+        "config": workload_config(args.workload, T, world),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 92, "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_ms, "call": "vrt_render_camera (camera struct in, shaded float film out to pinned host)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "build": build_out,
+        "octree": {"device_bytes": info["device_bytes"], "nodes": info["num_nodes"], "leaves": info["num_leaves"]},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--build-reps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -195,6 +195,26 @@ int vrt_render_camera(const vrt_tree* tree, const vrt_camera* cam, const vrt_sha
 int vrt_render_camera_dev(const vrt_tree* tree, const vrt_camera* cam,
                           const vrt_shade* sh, int x0, int y0, int x1, int y1,
                           float* d_film_rgb);
+/* Row-interleaved shard of the film for multi-GPU runs (replaces the
+ * static 8x8 tile split of render_mt, camera.h:45-55): the film is cut into bands
+ * of band_h rows; the call renders bands band_first, band_first+band_stride, ...
+ * over the full film width and writes them compactly, out[local_row][nx][...]
+ * with vrt_band_rows() local rows. */
+typedef struct vrt_bands {
+        int32_t band_h;
+        int32_t band_first;
+        int32_t band_stride;
+} vrt_bands;
+int vrt_band_rows(const vrt_camera* cam, const vrt_bands* bands);
+int vrt_render_bands_dev(const vrt_tree* tree, const vrt_camera* cam, const vrt_shade* sh,
+                         const vrt_bands* bands, float* d_film_rgb);
+int vrt_trace_bands16_dev(const vrt_tree* tree, const vrt_camera* cam,
+                          const vrt_bands* bands, vrt_hit16* d_out);
+/* Work counters of the reference algorithm for a camera frame:
+ * counts[0..4] = rays traced, interior nodes expanded (travorder calls), non-empty
+ * leaves visited, triangle tests, hits.  Host pointer out. */
+int vrt_count_camera(const vrt_tree* tree, const vrt_camera* cam, int x0, int y0, int x1,
+                     int y1, uint64_t counts[5]);
 /* device time (ms, CUDA events on the tree's stream) of the last trace/render
  * kernel launched through this handle */
 double vrt_last_kernel_ms(const vrt_tree* tree);

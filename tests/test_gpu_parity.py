@@ -280,3 +280,22 @@ def test_rebuild_and_blob_replica(gpu, port):
     assert rep.trace_camera(cam).tobytes() == tree.trace_camera(cam).tobytes()
     rep.close()
     tree.close()
+
+
+def test_work_counters_match_oracle(case, gpu, port):
+    """The counting kernel (feeds bench.py's algorithmic bytes per ray) reproduces the
+    instrumented oracle: interior expansions, non-empty leaf visits, triangle tests."""
+    cam10 = case["cam10"]
+    nx, ny, spp = 96, 64, 4
+    cam = gpu.Camera(cam10[0], cam10[1:4], cam10[4:7], cam10[7:10], nx, ny, spp)
+    got = case["tree"].count_camera(cam)
+    exp = case["orc"].trace(port.gen_rays(cam10, 1.0, nx, ny, spp), counters=True)
+    assert got["rays"] == nx * ny * spp
+    assert got["hits"] == int(exp.hit.sum())
+    assert got["n_leaf"] == exp.counters["n_leaf"]
+    assert got["n_tri"] == exp.counters["n_tri"]
+    # the reference also expands interior nodes whose subtree holds no triangle (a
+    # triangle that passed the parent's SAT test but none of the children's); the flat
+    # array prunes them, so the GPU count can only be smaller, and only marginally
+    assert got["n_int"] <= exp.counters["n_int"]
+    assert got["n_int"] >= 0.999 * exp.counters["n_int"]

@@ -31,6 +31,10 @@ class vrt_shade(C.Structure):
     _fields_ = [("light_dir", C.c_float * 3), ("kd", C.c_float)]
 
 
+class vrt_bands(C.Structure):
+    _fields_ = [("band_h", C.c_int32), ("band_first", C.c_int32), ("band_stride", C.c_int32)]
+
+
 class vrt_tree_info(C.Structure):
     _fields_ = [("num_tris", C.c_uint32), ("max_depth", C.c_int32), ("root_aabb", C.c_float * 6),
                 ("num_nodes", C.c_uint64), ("num_leaves", C.c_uint64), ("num_refs", C.c_uint64),
@@ -56,7 +60,8 @@ SYMBOLS = [
     "vrt_tree_export", "vrt_tree_import", "vrt_tree_set_stream", "vrt_tree_blob_dev",
     "vrt_tree_from_blob_dev", "vrt_camera_init", "vrt_gen_rays", "vrt_trace_rays",
     "vrt_trace_rays_dev", "vrt_trace_camera", "vrt_trace_camera_dev", "vrt_trace_camera16_dev",
-    "vrt_render_camera", "vrt_render_camera_dev", "vrt_last_kernel_ms", "vrt_tribox_batch",
+    "vrt_render_camera", "vrt_render_camera_dev", "vrt_band_rows", "vrt_render_bands_dev",
+    "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_last_kernel_ms", "vrt_tribox_batch",
     "vrt_tri_overlap_aabb_batch", "vrt_raytri_batch", "vrt_aabb_isect_batch",
 ]
 
@@ -106,6 +111,10 @@ def load(build_if_missing: bool = True):
         getattr(L, name).argtypes = [vp, C.POINTER(vrt_camera), i32, i32, i32, i32, vp]
     for name in ("vrt_render_camera", "vrt_render_camera_dev"):
         getattr(L, name).argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), i32, i32, i32, i32, vp]
+    L.vrt_band_rows.argtypes = [C.POINTER(vrt_camera), C.POINTER(vrt_bands)]
+    L.vrt_render_bands_dev.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), C.POINTER(vrt_bands), vp]
+    L.vrt_trace_bands16_dev.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_bands), vp]
+    L.vrt_count_camera.argtypes = [vp, C.POINTER(vrt_camera), i32, i32, i32, i32, vp]
     L.vrt_last_kernel_ms.restype = C.c_double
     L.vrt_last_kernel_ms.argtypes = [vp]
     L.vrt_tribox_batch.argtypes = [vp, vp, vp, u64, vp]
@@ -291,11 +300,36 @@ class Octree:
         _check(load().vrt_render_camera(self._h, C.byref(cam.c), C.byref(sh), x0, y0, x1, y1, _ptr(out)))
         return out
 
+    def render_bands_dev(self, cam: Camera, d_film_ptr, band_h, band_first, band_stride, light=None, kd=0.8):
+        """Rank `band_first` of `band_stride` in a row-interleaved multi-GPU frame."""
+        sh = vrt_shade((C.c_float * 3)(*(default_light() if light is None else light)), float(kd))
+        b = vrt_bands(int(band_h), int(band_first), int(band_stride))
+        _check(load().vrt_render_bands_dev(self._h, C.byref(cam.c), C.byref(sh), C.byref(b), C.c_void_p(d_film_ptr)))
+
+    def trace_bands16_dev(self, cam: Camera, d_out_ptr, band_h, band_first, band_stride):
+        b = vrt_bands(int(band_h), int(band_first), int(band_stride))
+        _check(load().vrt_trace_bands16_dev(self._h, C.byref(cam.c), C.byref(b), C.c_void_p(d_out_ptr)))
+
+    def count_camera(self, cam: Camera, rect=None):
+        """Work counters of the reference algorithm over a frame."""
+        x0, y0, x1, y1 = rect if rect else (0, 0, cam.nx, cam.ny)
+        c = np.zeros(5, np.uint64)
+        _check(load().vrt_count_camera(self._h, C.byref(cam.c), x0, y0, x1, y1, _ptr(c)))
+        return dict(rays=int(c[0]), n_int=int(c[1]), n_leaf=int(c[2]), n_tri=int(c[3]), hits=int(c[4]))
+
     def render_dev(self, cam: Camera, d_film_ptr, light=None, kd=0.8, rect=None):
         x0, y0, x1, y1 = rect if rect else (0, 0, cam.nx, cam.ny)
         sh = vrt_shade((C.c_float * 3)(*(default_light() if light is None else light)), float(kd))
         _check(load().vrt_render_camera_dev(self._h, C.byref(cam.c), C.byref(sh), x0, y0, x1, y1,
                                             C.c_void_p(d_film_ptr)))
+
+
+def band_rows(cam: Camera, band_h, band_first, band_stride) -> int:
+    b = vrt_bands(int(band_h), int(band_first), int(band_stride))
+    r = load().vrt_band_rows(C.byref(cam.c), C.byref(b))
+    if r < 0:
+        _check(r)
+    return int(r)
 
 
 # ---- predicates (device KATs) ------------------------------------------------

@@ -725,6 +725,79 @@ int vrt_render_camera_dev(const vrt_tree* t, const vrt_camera* cam, const vrt_sh
         return trace_camera_common(t, cam, sh, x0, y0, x1, y1, d_film_rgb, OUT_FILM, true);
 }
 
+int vrt_count_camera(const vrt_tree* tc, const vrt_camera* cam, int x0, int y0, int x1, int y1, uint64_t counts[5])
+{
+        int rc = check_tree(tc);
+        if (rc)
+                return rc;
+        rc = check_camera(cam, x0, y0, x1, y1);
+        if (rc)
+                return rc;
+        if (!counts) {
+                set_error("null counts");
+                return VRT_ERR_ARG;
+        }
+        vrt_tree* t = const_cast<vrt_tree*>(tc);
+        if (t->io_out.reserve(64))
+                return VRT_ERR_NOMEM;
+        VRT_CUDA(cudaMemsetAsync(t->io_out.p, 0, 64, t->stream));
+        memset(counts, 0, 5 * sizeof(uint64_t));
+        if (x1 > x0 && y1 > y0) {
+                rc = launch_trace_camera(t, cam, nullptr, x0, y0, x1, y1, t->io_out.p, OUT_COUNT);
+                if (rc)
+                        return rc;
+        }
+        VRT_CUDA(cudaMemcpyAsync(counts, t->io_out.p, 40, cudaMemcpyDeviceToHost, t->stream));
+        VRT_CUDA(cudaStreamSynchronize(t->stream));
+        return VRT_OK;
+}
+
+int vrt_band_rows(const vrt_camera* cam, const vrt_bands* b)
+{
+        if (!cam || !b || b->band_h < 1 || b->band_stride < 1 || b->band_first < 0) {
+                set_error("bad band description");
+                return VRT_ERR_ARG;
+        }
+        long rows = 0;
+        for (long k = b->band_first; k * b->band_h < cam->ny; k += b->band_stride)
+                rows += std::min<long>(b->band_h, cam->ny - k * b->band_h);
+        return (int)rows;
+}
+
+static int bands_common(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, const vrt_bands* b, void* d_out,
+                        OutMode mode)
+{
+        int rc = check_tree(t);
+        if (rc)
+                return rc;
+        rc = check_camera(cam, 0, 0, cam ? cam->nx : 0, cam ? cam->ny : 0);
+        if (rc)
+                return rc;
+        const int rows = vrt_band_rows(cam, b);
+        if (rows < 0)
+                return rows;
+        if (rows == 0)
+                return VRT_OK;
+        if (!d_out || (mode == OUT_FILM && !sh)) {
+                set_error("null out/shade pointer");
+                return VRT_ERR_ARG;
+        }
+        const int y0 = b->band_first * b->band_h;
+        return launch_trace_camera(t, cam, sh, 0, y0, cam->nx, y0 + rows, d_out, mode, b->band_h,
+                                   b->band_stride * b->band_h);
+}
+
+int vrt_render_bands_dev(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, const vrt_bands* b,
+                         float* d_film_rgb)
+{
+        return bands_common(t, cam, sh, b, d_film_rgb, OUT_FILM);
+}
+
+int vrt_trace_bands16_dev(const vrt_tree* t, const vrt_camera* cam, const vrt_bands* b, vrt_hit16* d_out)
+{
+        return bands_common(t, cam, nullptr, b, d_out, OUT_HIT16);
+}
+
 double vrt_last_kernel_ms(const vrt_tree* t) { return t ? t->last_kernel_ms : 0.0; }
 
 // ---- predicates ---------------------------------------------------------------

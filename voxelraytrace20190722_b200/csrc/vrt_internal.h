@@ -130,8 +130,11 @@ int import_leaves(vrt_tree* t, int max_depth, const float root_aabb[6], uint64_t
                   const uint32_t* leaf_cell, const uint32_t* leaf_count,
                   const uint32_t* leaf_refs);
 // trace (vrt_trace.cu)
-enum OutMode { OUT_HIT48 = 0, OUT_HIT16 = 1, OUT_FILM = 2 };
+enum OutMode { OUT_HIT48 = 0, OUT_HIT16 = 1, OUT_FILM = 2, OUT_COUNT = 3 };
 int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_hit* d_out);
+// band_h > 0: rows [y0,y1) are LOCAL rows of a banded shard; local row r maps to film row
+// y0_film + (r / band_h) * band_pitch + r % band_h (y0 then carries y0_film, y1 = y0 + local rows).
 int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, int x0,
-                        int y0, int x1, int y1, void* d_out, OutMode mode);
+                        int y0, int x1, int y1, void* d_out, OutMode mode, int band_h = 0,
+                        int band_pitch = 0);
 }  // namespace vrt

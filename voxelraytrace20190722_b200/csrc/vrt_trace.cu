@@ -35,7 +35,8 @@ constexpr int kMaxLevels = VRT_MAX_DEPTH;  // stack records per thread
 struct TraceParams {
         TreeDev tree;
         CameraParams cam;
-        int x0, y0, x1, y1;  // pixel rectangle (camera modes)
+        int x0, y0, x1, y1;  // pixel rectangle (camera modes); y range is LOCAL rows when banded
+        int band_h, band_pitch;  // local row r -> film row y0 + (r/band_h)*band_pitch + r%band_h
         const vrt_ray* rays;  // explicit-ray mode
         unsigned long long num_rays;
         void* out;
@@ -54,11 +55,22 @@ struct HitState {
         bool hit;
 };
 
+// Per-ray work counters of the reference algorithm: interior nodes
+// expanded (travorder calls), non-empty leaves visited, triangle tests.
+struct WorkCount {
+        uint32_t n_int, n_leaf, n_tri;
+};
+
 // Triangle::isect + ray_march_isect for one leaf (voxel_octree.cc:99-129,438-460).
+template <bool COUNT>
 __device__ __forceinline__ bool leaf_isect(const TreeDev& tr, uint32_t leaf_node, const float o[3],
-                                           const float d[3], HitState& hs)
+                                           const float d[3], HitState& hs, WorkCount& wc)
 {
         const uint2 rec = __ldg(&tr.nodes[leaf_node]);
+        if (COUNT) {
+                wc.n_leaf += 1;
+                wc.n_tri += rec.y;
+        }
         const double od[3] = { (double)o[0], (double)o[1], (double)o[2] };
         const double dd[3] = { (double)d[0], (double)d[1], (double)d[2] };
         bool found = false;
@@ -112,9 +124,10 @@ __device__ __forceinline__ void finish_isect(const TreeDev& tr, const HitState& 
 
 // One ray through the octree.  s_first/s_meta/s_list: shared stack columns of
 // this thread (stride = blockDim.x).
+template <bool COUNT>
 __device__ __forceinline__ void trace_one(const TreeDev& tr, const float root[6], const float o[3],
                                           const float d[3], float tmin, float tmax, uint32_t* s_first,
-                                          uint32_t* s_meta, uint32_t* s_list, HitState& hs)
+                                          uint32_t* s_meta, uint32_t* s_list, HitState& hs, WorkCount& wc)
 {
         hs.hit = false;
         hs.tri = VRT_NO_TRI;
@@ -135,7 +148,7 @@ __device__ __forceinline__ void trace_one(const TreeDev& tr, const float root[6]
         }
         const int L = tr.L;
         if (L == 0) {  // root is the only leaf (voxel_octree.cc:137-144)
-                if (leaf_isect(tr, 0, o, d, hs)) {
+                if (leaf_isect<COUNT>(tr, 0, o, d, hs, wc)) {
                         hs.hit = true;
                         hs.leaf = 0;
                         hs.cx = hs.cy = hs.cz = 0;
@@ -152,6 +165,8 @@ __device__ __forceinline__ void trace_one(const TreeDev& tr, const float root[6]
                 if (need_expand) {
                         // ---- expand `node` at (level; x,y,z): order + slab-test its 8 children ----
                         const uint2 rec = __ldg(&tr.nodes[node]);
+                        if (COUNT)
+                                wc.n_int += 1;
                         first = rec.x;
                         mask = rec.y & 0xffu;
                         const uint32_t ti = (1u << level) + 0u;
@@ -231,7 +246,7 @@ __device__ __forceinline__ void trace_one(const TreeDev& tr, const float root[6]
                 const uint32_t cy = 2u * y + ((c >> 1) & 1u);
                 const uint32_t cz = 2u * z + (c & 1u);
                 if (level + 1 == L) {
-                        if (leaf_isect(tr, child, o, d, hs)) {
+                        if (leaf_isect<COUNT>(tr, child, o, d, hs, wc)) {
                                 hs.hit = true;
                                 hs.leaf = child;
                                 hs.cx = cx;
@@ -312,7 +327,8 @@ k_trace_rays(TraceParams p)
                         const float o[3] = { r0.x, r0.y, r0.z };
                         const float d[3] = { r0.w, r1.x, r1.y };
                         HitState hs;
-                        trace_one(p.tree, p.root, o, d, r1.z, r1.w, s_first, s_meta, s_list, hs);
+                        WorkCount wc;
+                        trace_one<false>(p.tree, p.root, o, d, r1.z, r1.w, s_first, s_meta, s_list, hs, wc);
                         store_hit48(static_cast<vrt_hit*>(p.out) + r, p.tree, hs, o, d);
                 }
                 __syncwarp();
@@ -351,19 +367,35 @@ k_trace_camera(TraceParams p)
                         lx = lane & 7;
                         ly = lane >> 3;
                 }
-                const int px = p.x0 + tx * tw + lx, py = p.y0 + ty * th + ly;
-                const bool active = (px < p.x1) && (py < p.y1);
+                const int px = p.x0 + tx * tw + lx;
+                const int ry = ty * th + ly;  // local row
+                const int py = p.y0 + (ry / p.band_h) * p.band_pitch + (ry % p.band_h);
+                const bool active = (px < p.x1) && (ry < H);
                 float o[3] = { 0, 0, 0 }, d[3] = { 0, 0, 1 };
                 HitState hs;
                 hs.hit = false;
+                WorkCount wc = { 0, 0, 0 };
                 if (active) {
                         gen_ray(p.cam, px, py, s, o, d);
-                        trace_one(p.tree, p.root, o, d, p.cam.tmin, p.cam.tmax, s_first, s_meta, s_list, hs);
+                        trace_one<MODE == OUT_COUNT>(p.tree, p.root, o, d, p.cam.tmin, p.cam.tmax, s_first, s_meta,
+                                                     s_list, hs, wc);
                 }
-                const unsigned long long pix = (unsigned long long)(py - p.y0) * W + (px - p.x0);
+                const unsigned long long pix = (unsigned long long)ry * W + (px - p.x0);
                 if (MODE == OUT_HIT48) {
                         if (active)
                                 store_hit48(static_cast<vrt_hit*>(p.out) + pix * spp + s, p.tree, hs, o, d);
+                } else if (MODE == OUT_COUNT) {
+                        // out = uint64[5]: rays, n_int, n_leaf, n_tri, hits
+                        unsigned long long v[5] = { active ? 1ull : 0ull, wc.n_int, wc.n_leaf, wc.n_tri,
+                                                    (active && hs.hit) ? 1ull : 0ull };
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+#pragma unroll
+                                for (int o2 = 16; o2 > 0; o2 >>= 1)
+                                        v[k] += __shfl_down_sync(0xffffffffu, v[k], o2);
+                                if (lane == 0)
+                                        atomicAdd(static_cast<unsigned long long*>(p.out) + k, v[k]);
+                        }
                 } else if (MODE == OUT_HIT16) {
                         if (active) {
                                 uint4 q;
@@ -466,7 +498,7 @@ int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_
 }
 
 int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, int x0, int y0,
-                        int x1, int y1, void* d_out, OutMode mode)
+                        int x1, int y1, void* d_out, OutMode mode, int band_h, int band_pitch)
 {
         if (x1 <= x0 || y1 <= y0)
                 return VRT_OK;
@@ -484,6 +516,8 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         p.y0 = y0;
         p.x1 = x1;
         p.y1 = y1;
+        p.band_h = band_h > 0 ? band_h : (y1 - y0);
+        p.band_pitch = band_h > 0 ? band_pitch : 0;
         p.out = d_out;
         if (sh) {
                 p.light[0] = sh->light_dir[0];
@@ -503,6 +537,7 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         switch (mode) {
         case OUT_HIT48: kern = (const void*)k_trace_camera<OUT_HIT48>; break;
         case OUT_HIT16: kern = (const void*)k_trace_camera<OUT_HIT16>; break;
+        case OUT_COUNT: kern = (const void*)k_trace_camera<OUT_COUNT>; break;
         default: kern = (const void*)k_trace_camera<OUT_FILM>; break;
         }
         VRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
