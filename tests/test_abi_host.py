@@ -1,0 +1,107 @@
+"""CPU: the C-ABI library loads and exports every symbol include/vrt.h declares; host-side
+logic (camera ctor mirror, scene generators, band sharding) is correct.  No compute calls."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests.common import CAM_LIGHT, CAM_MAIN, CAM_SPHERE, assert_bits_equal
+from voxelraytrace20190722_b200 import build as vbuild
+from voxelraytrace20190722_b200 import capi, scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "vrt.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vrt_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = vbuild.build_native()
+    L = ctypes.CDLL(lib)
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    missing = [s for s in declared if not hasattr(L, s)]
+    assert not missing, missing
+    assert sorted(capi.SYMBOLS) == declared
+    assert L.vrt_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(capi.vrt_camera) == 16 * 4 + 3 * 4 + 3 * 4
+    assert ctypes.sizeof(capi.vrt_shade) == 16
+    assert ctypes.sizeof(capi.vrt_bands) == 12
+    assert capi.HIT_DTYPE.itemsize == 48 and capi.RAY_DTYPE.itemsize == 32
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without CUDA every compute entry point must fail loudly."""
+    capi.load()
+    if capi.device_count() > 0:
+        pytest.skip("CUDA device present")
+    tri, nrm = scenes.uv_sphere(8, 4)
+    with pytest.raises(capi.VrtError):
+        capi.Octree.build(tri, nrm, 3)
+    with pytest.raises(capi.VrtError):
+        capi.tribox(np.zeros((1, 3)), np.ones((1, 3)), np.zeros((1, 9)))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "voxelraytrace20190722_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
+                txt = open(os.path.join(dp, fn), errors="replace").read()
+                assert "from oracle" not in txt and "import oracle" not in txt and "libvrt_oracle" not in txt \
+                    and "libvrt_ref" not in txt, fn
+
+
+@pytest.mark.parametrize("cam10", [CAM_SPHERE, CAM_MAIN, CAM_LIGHT])
+def test_camera_ctor_host_mirror(port, cam10):
+    """vrt_camera_init is host arithmetic (no GPU needed): identical to Camera::Camera."""
+    cam = capi.Camera(cam10[0], cam10[1:4], cam10[4:7], cam10[7:10], 64, 48, 4)
+    assert_bits_equal(cam.matrix, port.camera_matrix(cam10), "C_")
+    assert_bits_equal(np.float32(cam.c.z), port.camera_z(cam10[0], 1.0), "z")
+    assert cam.c.tmin == 0.0 and cam.c.tmax == np.finfo(np.float32).max
+
+
+def test_scene_generators_are_deterministic():
+    a, an = scenes.uv_sphere()
+    assert a.shape == (65024, 3, 3) and a.dtype == np.float32
+    b, _ = scenes.uv_sphere()
+    assert a.tobytes() == b.tobytes()
+    s1, _ = scenes.soup(5000)
+    s2, _ = scenes.soup(5000)
+    assert s1.tobytes() == s2.tobytes()
+    assert np.abs(s1).max(axis=(0, 1))[0] < 1.01
+    t, n = scenes.atrium(detail=0.2)
+    assert np.isfinite(t).all() and np.isfinite(n).all() and (np.abs(n).sum(axis=2) > 0).all()
+
+
+def test_pcg_matches_scalar_definition():
+    def pcg(seed, n):
+        s, out = seed, []
+        for _ in range(n):
+            s = (s * 6364136223846793005 + 1442695040888963407) & (2 ** 64 - 1)
+            x = ((s ^ (s >> 18)) >> 27) & 0xffffffff
+            r = s >> 59
+            out.append(((x >> r) | (x << ((-r) & 31))) & 0xffffffff)
+        return out
+    assert list(scenes.pcg32_stream(0xc01dbeefdeadbead, 5000)) == pcg(0xc01dbeefdeadbead, 5000)
+
+
+@pytest.mark.parametrize("ny,world", [(2160, 1), (2160, 2), (2160, 4), (2160, 8), (1080, 8), (37, 3)])
+def test_band_partition_covers_film(ny, world):
+    torch = pytest.importorskip("torch")
+    from voxelraytrace20190722_b200 import dist as vdist
+    rows = [vdist.band_rows(ny, r, world) for r in range(world)]
+    assert sum(rows) == ny and max(rows) == vdist.max_band_rows(ny, world)
+    perm = vdist.band_row_index(ny, world)
+    assert sorted(perm.tolist()) == list(range(ny))
+    cam = capi.Camera(CAM_MAIN[0], CAM_MAIN[1:4], CAM_MAIN[4:7], CAM_MAIN[7:10], 64, ny, 1)
+    for r in range(world):
+        assert capi.band_rows(cam, vdist.BAND_H, r, world) == rows[r]

@@ -1,0 +1,61 @@
+"""CPU, world_size 2, gloo: the N>1 host logic (row-band sharding, uniform gather,
+film re-ordering) without any GPU."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.multiprocessing as mp  # noqa: E402
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ny, nx, ok):
+    import torch.distributed as td
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from voxelraytrace20190722_b200 import dist as vdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    # each rank "renders" its bands: pixel value = film row index * 1000 + column
+    rows = vdist.band_rows(ny, rank, world)
+    local = torch.zeros((vdist.max_band_rows(ny, world), nx), dtype=torch.float32)
+    r = 0
+    k = rank
+    while k * vdist.BAND_H < ny:
+        for y in range(k * vdist.BAND_H, min((k + 1) * vdist.BAND_H, ny)):
+            local[r] = y * 1000 + torch.arange(nx)
+            r += 1
+        k += world
+    assert r == rows
+    full = vdist.gather_rows(local, ny)
+    if rank == 0:
+        exp = torch.arange(ny, dtype=torch.float32)[:, None] * 1000 + torch.arange(nx)[None, :]
+        ok.value = int(torch.equal(full, exp))
+    else:
+        assert full is None
+    td.barrier()
+    td.destroy_process_group()
+
+
+@pytest.mark.parametrize("ny", [64, 37, 2160])
+def test_banded_gather_world2(ny):
+    ctx = mp.get_context("spawn")
+    ok = ctx.Value("i", 0)
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ny, 16, ok)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ok.value == 1

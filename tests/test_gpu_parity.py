@@ -299,3 +299,24 @@ def test_work_counters_match_oracle(case, gpu, port):
     # array prunes them, so the GPU count can only be smaller, and only marginally
     assert got["n_int"] <= exp.counters["n_int"]
     assert got["n_int"] >= 0.999 * exp.counters["n_int"]
+
+
+def test_untame_rays_take_exact_path(case, gpu, port):
+    """Rays the FMNMX fast path must not handle (denormal direction components, huge
+    origins): the exact restatement is used and still matches the oracle."""
+    rng = np.random.default_rng(11)
+    n = 6000
+    root = case["orc"].root_aabb()
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rng.uniform(root[:3] - 0.1, root[3:] + 0.1, (n, 3))
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 3:6] = d
+    rays[: n // 3, 3] = np.float32(1e-41)           # denormal, non-zero
+    rays[n // 3: n // 2, 4] = np.float32(-3e-40)
+    rays[n // 2: 2 * n // 3, 0] = np.float32(3e19)  # origin far outside the tame range
+    rays[2 * n // 3:, 3:6] *= np.float32(1e-30)      # tiny but normal directions (tame)
+    rays[:, 7] = np.finfo(np.float32).max
+    got = case["tree"].trace_rays(rays)
+    exp = case["orc"].trace(rays)
+    assert compare_hits(got, exp, case["name"] + " untame rays") == 0

@@ -1,0 +1,51 @@
+"""CPU: the C restatement (oracle/vrt_oracle.c) against the golden vectors generated from
+the UNMODIFIED reference (tests/golden/make_golden.py).  This is what pins the oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from tests.common import assert_bits_equal
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_predicates_golden(port):
+    z = np.load(os.path.join(G, "predicates.npz"))
+    assert_bits_equal(port.tribox(z["centers"], z["halves"], z["tris"]), z["tribox"], "triBoxOverlap")
+    assert_bits_equal(port.tri_overlap_aabb(z["boxes"], z["tris"]), z["tri_overlap_aabb"], "is_overlap")
+    res, tuv = port.raytri(z["raytri_in"])
+    assert_bits_equal(res, z["raytri_res"], "intersect_triangle3")
+    tuv[res == 0] = 0
+    assert_bits_equal(tuv, z["raytri_tuv"], "t,u,v")
+    assert_bits_equal(port.aabb_isect(z["boxes"], z["slab_rays"]), z["slab"], "AABB::isect")
+    assert 100 < z["tribox"].sum() < len(z["tribox"]) - 100
+    assert z["raytri_res"].sum() > 50 and z["slab"].sum() > 100
+
+
+def test_camera_golden(port):
+    z = np.load(os.path.join(G, "camera.npz"))
+    for name in ("sphere", "main", "light"):
+        cam10 = z[name + "_cam10"]
+        nx, ny, spp = (int(v) for v in z[name + "_dims"])
+        assert_bits_equal(port.camera_matrix(cam10), z[name + "_C"], name + " C_")
+        assert_bits_equal(port.gen_rays(cam10, 1.0, nx, ny, spp), z[name + "_rays"], name + " rays")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(G, "scene_*.npz"))), ids=os.path.basename)
+def test_scene_golden(port, path):
+    z = np.load(path)
+    tree = port.build(z["tri"], z["nrm"], int(z["depth"]))
+    assert_bits_equal(tree.root_aabb(), z["root_aabb"], "root AABB")
+    cells, counts, refs, boxes = tree.leaves(boxes=True)
+    assert_bits_equal(cells, z["leaf_cell"], "leaf cells")
+    assert_bits_equal(counts, z["leaf_count"], "leaf counts")
+    assert_bits_equal(refs, z["leaf_refs"], "leaf refs")
+    assert_bits_equal(boxes, z["leaf_boxes"], "leaf boxes (split recurrence)")
+    h = tree.trace(z["rays"])
+    assert_bits_equal(h.hit, z["hit"], "hit")
+    assert_bits_equal(h.cell, z["hit_cell"], "leaf")
+    assert_bits_equal(h.tri, z["hit_tri"], "triangle")
+    assert_bits_equal(h.pos, z["hit_pos"], "ISect.hit")
+    assert_bits_equal(h.nrm, z["hit_nrm"], "ISect.normal")

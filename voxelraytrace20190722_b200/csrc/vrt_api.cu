@@ -108,6 +108,12 @@ void tree_bind_views(vrt_tree* t)
         d.num_nodes = (uint32_t)h.num_nodes;
         d.num_leaves = (uint32_t)h.num_leaves;
         d.L = h.max_depth - 1;
+        d.tame = 1;
+        for (int a = 0; a < 3; ++a) {
+                const float mn = h.root_aabb[a], mx = h.root_aabb[3 + a];
+                if (!(mn <= mx) || !(fabsf(mn) <= 1e18f) || !(fabsf(mx) <= 1e18f))
+                        d.tame = 0;
+        }
 }
 
 static int check_tree(const vrt_tree* t)

@@ -72,6 +72,7 @@ struct TreeDev {
         uint32_t num_nodes;
         uint32_t num_leaves;
         int L;  // leaf level = max_depth-1
+        int tame;  // root box valid and |coords| <= 1e18: the FMNMX fast path is exact
 };
 
 void set_error(const char* fmt, ...);

@@ -122,20 +122,15 @@ __device__ __forceinline__ void finish_isect(const TreeDev& tr, const HitState& 
                 pos[k] = fadd(o[k], fmul(hs.t, d[k]));
 }
 
-// One ray through the octree.  s_first/s_meta/s_list: shared stack columns of
-// this thread (stride = blockDim.x).
+// EXACT path: one ray through the octree with every min/max/first-extremum rule of
+// the reference restated literally (NaN/Inf/denormal-safe).  Only rays that fail the
+// `ray_is_tame` test below take it, so it is kept out of line.
+// s_first/s_meta/s_list: shared stack columns of this thread (stride = blockDim.x).
 template <bool COUNT>
-__device__ __forceinline__ void trace_one(const TreeDev& tr, const float root[6], const float o[3],
-                                          const float d[3], float tmin, float tmax, uint32_t* s_first,
-                                          uint32_t* s_meta, uint32_t* s_list, HitState& hs, WorkCount& wc)
+__device__ __noinline__ void trace_one_exact(const TreeDev& tr, const float* root, const float* o,
+                                             const float* d, float tmin, float tmax, uint32_t* s_first,
+                                             uint32_t* s_meta, uint32_t* s_list, HitState& hs, WorkCount& wc)
 {
-        hs.hit = false;
-        hs.tri = VRT_NO_TRI;
-        hs.leaf = VRT_NO_TRI;
-        hs.cx = hs.cy = hs.cz = 0xffffffffu;
-        hs.t = hs.u = hs.v = 0.f;
-        if (tr.num_nodes == 0)
-                return;
         float dinv[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k)
@@ -266,6 +261,186 @@ __device__ __forceinline__ void trace_one(const TreeDev& tr, const float root[6]
                         need_expand = true;
                 }
         }
+}
+
+// ---------------------------------------------------------------------------
+// FAST path (taken by every ray with finite, moderately sized origin/direction whose
+// direction components are zero or normal floats).  For such rays no NaN can appear in
+// the slab or key arithmetic -- (plane-o) is finite and 1/d' is finite and non-zero --
+// so std::min/std::max/min_element/max_element coincide with FMNMX up to the sign of a
+// zero, which none of the comparisons below can observe.  Same operations, same order,
+// same roundings as the exact path; only the instruction selection differs:
+//   * hi.min of a child pair is bitwise lo.max (both are min+size in the recurrence), so
+//     3 planes per axis instead of 4;
+//   * invalid children get key=+inf and the stable order is kept as eight packed 4-bit
+//     ranks (start 0x76543210 = index order; every pair (i<j) with key[j]<key[i] moves
+//     one rank from j to i) -- 28 compares + 28 predicated adds, no list is built;
+//   * the next child is found by a zero-nibble search on the packed ranks; only levels
+//     that still have unvisited children are pushed on the (shared-memory) return stack.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool ray_is_tame(const TreeDev& tr, const float o[3], const float d[3])
+{
+        bool ok = tr.tame != 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+                const float ad = fabsf(d[k]);
+                ok = ok && (fabsf(o[k]) <= 1e18f) && (ad <= 1e18f) && (ad == 0.f || ad >= FLT_MIN);
+        }
+        return ok;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float root[6], const float o[3],
+                                               const float d[3], float tmin, float tmax, uint32_t* s_first,
+                                               uint32_t* s_meta, uint32_t* s_rank, HitState& hs, WorkCount& wc)
+{
+        float dinv[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+                dinv[k] = slab_dinv(d[k]);
+        {
+                const float mn[3] = { root[0], root[1], root[2] };
+                const float mx[3] = { root[3], root[4], root[5] };
+                if (!aabb_isect(mn, mx, o, dinv, tmin, tmax))  // voxel_octree.cc:134
+                        return;
+        }
+        const int L = tr.L;
+        if (L == 0) {  // root is the only leaf (voxel_octree.cc:137-144)
+                if (leaf_isect<COUNT>(tr, 0, o, d, hs, wc)) {
+                        hs.hit = true;
+                        hs.leaf = 0;
+                        hs.cx = hs.cy = hs.cz = 0;
+                }
+                return;
+        }
+        const int stride = blockDim.x;
+        const float inf = __int_as_float(0x7f800000);
+        int level = 0, sp = 0;
+        uint32_t x = 0, y = 0, z = 0, node = 0;
+        uint32_t first, mask, ranks, k, cnt;
+        for (;;) {
+                // ---- expand `node` (level; x,y,z) -------------------------------------------
+                {
+                        const uint2 rec = __ldg(&tr.nodes[node]);
+                        if (COUNT)
+                                wc.n_int += 1;
+                        first = rec.x;
+                        mask = rec.y;
+                        const uint32_t ti = 1u << level;
+                        const float4 bb[3] = { __ldg(&tr.tab4[0][ti + x]), __ldg(&tr.tab4[1][ti + y]),
+                                               __ldg(&tr.tab4[2][ti + z]) };
+                        float smin[3][2], smax[3][2], kt[3][2];
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                                const float p0 = bb[a].x, p1 = bb[a].y, p2 = bb[a].w;
+                                const float tA = fmul(fsub(p0, o[a]), dinv[a]);
+                                const float tB = fmul(fsub(p1, o[a]), dinv[a]);
+                                const float tC = fmul(fsub(p2, o[a]), dinv[a]);
+                                smin[a][0] = fminf(tA, tB);
+                                smax[a][0] = fmaxf(tA, tB);
+                                smin[a][1] = fminf(tB, tC);
+                                smax[a][1] = fmaxf(tB, tC);
+                                kt[a][0] = fmul(d[a], fsub(fmul(fadd(p0, p1), .5f), o[a]));
+                                kt[a][1] = fmul(d[a], fsub(fmul(fadd(p1, p2), .5f), o[a]));
+                        }
+                        float t0xy[4], t1xy[4], kxy[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                                t0xy[q] = fmaxf(smin[0][q >> 1], smin[1][q & 1]);
+                                t1xy[q] = fminf(smax[0][q >> 1], smax[1][q & 1]);
+                                kxy[q] = fadd(kt[0][q >> 1], kt[1][q & 1]);
+                        }
+                        float key[8];
+                        cnt = 0;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                                const float t0 = fmaxf(t0xy[c >> 1], smin[2][c & 1]);
+                                const float t1 = fminf(t1xy[c >> 1], smax[2][c & 1]);
+                                const bool ok = ((mask >> c) & 1u) && slab_accept(t0, t1, tmin, tmax);
+                                key[c] = ok ? fadd(kxy[c >> 1], kt[2][c & 1]) : inf;
+                                cnt += ok ? 1u : 0u;
+                        }
+                        ranks = 0x76543210u;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                                for (int j = i + 1; j < 8; ++j)
+                                        if (key[j] < key[i])
+                                                ranks += (1u << (4 * i)) - (1u << (4 * j));
+                        }
+                        k = 0;
+                }
+                // ---- visit children in order until we descend, hit, or run out -----------------
+                for (;;) {
+                        if (k == cnt) {
+                                if (sp == 0)
+                                        return;  // miss
+                                --sp;
+                                first = s_first[sp * stride];
+                                const uint32_t m = s_meta[sp * stride];
+                                ranks = s_rank[sp * stride];
+                                mask = m & 0xffu;
+                                k = (m >> 8) & 0xfu;
+                                cnt = (m >> 12) & 0xfu;
+                                const int nl = (int)(m >> 16);
+                                x >>= (level - nl);
+                                y >>= (level - nl);
+                                z >>= (level - nl);
+                                level = nl;
+                                continue;
+                        }
+                        // child whose rank nibble equals k
+                        const uint32_t tq = ranks ^ (k * 0x11111111u);
+                        const uint32_t zq = (tq - 0x11111111u) & ~tq & 0x88888888u;
+                        const uint32_t c = (uint32_t)(__ffs((int)zq) - 1) >> 2;
+                        ++k;
+                        const uint32_t child = first + __popc(mask & ((1u << c) - 1u));
+                        const uint32_t cx = 2u * x + ((c >> 2) & 1u);
+                        const uint32_t cy = 2u * y + ((c >> 1) & 1u);
+                        const uint32_t cz = 2u * z + (c & 1u);
+                        if (level + 1 == L) {
+                                if (leaf_isect<COUNT>(tr, child, o, d, hs, wc)) {
+                                        hs.hit = true;
+                                        hs.leaf = child;
+                                        hs.cx = cx;
+                                        hs.cy = cy;
+                                        hs.cz = cz;
+                                        return;
+                                }
+                                continue;
+                        }
+                        if (k < cnt) {  // remember this level only if it has children left
+                                s_first[sp * stride] = first;
+                                s_meta[sp * stride] = mask | (k << 8) | (cnt << 12) | ((uint32_t)level << 16);
+                                s_rank[sp * stride] = ranks;
+                                ++sp;
+                        }
+                        ++level;
+                        x = cx;
+                        y = cy;
+                        z = cz;
+                        node = child;
+                        break;
+                }
+        }
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void trace_one(const TreeDev& tr, const float root[6], const float o[3],
+                                          const float d[3], float tmin, float tmax, uint32_t* s_first,
+                                          uint32_t* s_meta, uint32_t* s_list, HitState& hs, WorkCount& wc)
+{
+        hs.hit = false;
+        hs.tri = VRT_NO_TRI;
+        hs.leaf = VRT_NO_TRI;
+        hs.cx = hs.cy = hs.cz = 0xffffffffu;
+        hs.t = hs.u = hs.v = 0.f;
+        if (tr.num_nodes == 0)
+                return;
+        if (ray_is_tame(tr, o, d))
+                trace_one_fast<COUNT>(tr, root, o, d, tmin, tmax, s_first, s_meta, s_list, hs, wc);
+        else
+                trace_one_exact<COUNT>(tr, root, o, d, tmin, tmax, s_first, s_meta, s_list, hs, wc);
 }
 
 __device__ __forceinline__ void store_hit48(vrt_hit* out, const TreeDev& tr, const HitState& hs,
