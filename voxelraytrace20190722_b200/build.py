@@ -13,7 +13,7 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-LIB = os.path.join(PKG, "libvrt.so")
+LIB = os.path.join(PKG, "libvrt%s.so" % os.environ.get("VRT_LIB_SUFFIX", ""))
 SOURCES = ["vrt_api.cu", "vrt_build.cu", "vrt_trace.cu"]
 HEADERS = ["vrt_exact.cuh", "vrt_internal.h", "vrt_prims.cuh", os.path.join("..", "..", "include", "vrt.h")]
 
@@ -50,8 +50,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     procs = []
     os.makedirs(os.path.join(PKG, "build"), exist_ok=True)
     for s in SOURCES:
-        o = os.path.join(PKG, "build", s.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
+        o = os.path.join(PKG, "build", s.replace(".cu", "%s.o" % os.environ.get("VRT_LIB_SUFFIX", "")))
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("VRT_EXTRA_NVCC", "").split(), "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     log = []

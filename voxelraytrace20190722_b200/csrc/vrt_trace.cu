@@ -29,7 +29,13 @@
 
 namespace vrt {
 
-constexpr int kTraceThreads = 128;
+#ifndef VRT_TRACE_THREADS
+#define VRT_TRACE_THREADS 128
+#endif
+#ifndef VRT_TRACE_MIN_BLOCKS
+#define VRT_TRACE_MIN_BLOCKS 6  // k_trace_rays (48-byte records)
+#endif
+constexpr int kTraceThreads = VRT_TRACE_THREADS;
 constexpr int kMaxLevels = VRT_MAX_DEPTH;  // stack records per thread
 
 struct TraceParams {
@@ -271,7 +277,7 @@ __device__ __noinline__ void trace_one_exact(const TreeDev& tr, const float* roo
 // zero, which none of the comparisons below can observe.  Same operations, same order,
 // same roundings as the exact path; only the instruction selection differs:
 //   * hi.min of a child pair is bitwise lo.max (both are min+size in the recurrence), so
-//     3 planes per axis instead of 4;
+//     3 planes per axis instead of 4; FMNMX3 per child; branch-free slab verdicts;
 //   * invalid children get key=+inf and the stable order is kept as eight packed 4-bit
 //     ranks (start 0x76543210 = index order; every pair (i<j) with key[j]<key[i] moves
 //     one rank from j to i) -- 28 compares + 28 predicated adds, no list is built;
@@ -287,6 +293,19 @@ __device__ __forceinline__ bool ray_is_tame(const TreeDev& tr, const float o[3],
                 ok = ok && (fabsf(o[k]) <= 1e18f) && (ad <= 1e18f) && (ad == 0.f || ad >= FLT_MIN);
         }
         return ok;
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+        float r;
+        asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+        return r;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c)
+{
+        float r;
+        asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+        return r;
 }
 
 template <bool COUNT>
@@ -343,30 +362,31 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 kt[a][0] = fmul(d[a], fsub(fmul(fadd(p0, p1), .5f), o[a]));
                                 kt[a][1] = fmul(d[a], fsub(fmul(fadd(p1, p2), .5f), o[a]));
                         }
-                        float t0xy[4], t1xy[4], kxy[4];
+                        float kxy[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                                t0xy[q] = fmaxf(smin[0][q >> 1], smin[1][q & 1]);
-                                t1xy[q] = fminf(smax[0][q >> 1], smax[1][q & 1]);
+                        for (int q = 0; q < 4; ++q)
                                 kxy[q] = fadd(kt[0][q >> 1], kt[1][q & 1]);
-                        }
                         float key[8];
                         cnt = 0;
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                                const float t0 = fmaxf(t0xy[c >> 1], smin[2][c & 1]);
-                                const float t1 = fminf(t1xy[c >> 1], smax[2][c & 1]);
-                                const bool ok = ((mask >> c) & 1u) && slab_accept(t0, t1, tmin, tmax);
-                                key[c] = ok ? fadd(kxy[c >> 1], kt[2][c & 1]) : inf;
-                                cnt += ok ? 1u : 0u;
+                                const float t0 = fmax3(smin[0][c >> 2], smin[1][(c >> 1) & 1], smin[2][c & 1]);
+                                const float t1 = fmin3(smax[0][c >> 2], smax[1][(c >> 1) & 1], smax[2][c & 1]);
+                                // short-circuit on purpose: ~78 % of the children are empty or have
+                                // t0 > t1, and skipping their window test + key add is cheaper than
+                                // evaluating everything branch-free (measured: 12.2 vs 14.2 ms/frame)
+                                key[c] = inf;
+                                if (((mask >> c) & 1u) && slab_accept(t0, t1, tmin, tmax)) {
+                                        key[c] = fadd(kxy[c >> 1], kt[2][c & 1]);
+                                        cnt += 1u;
+                                }
                         }
                         ranks = 0x76543210u;
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
 #pragma unroll
                                 for (int j = i + 1; j < 8; ++j)
-                                        if (key[j] < key[i])
-                                                ranks += (1u << (4 * i)) - (1u << (4 * j));
+                                        ranks += (key[j] < key[i]) ? ((1u << (4 * i)) - (1u << (4 * j))) : 0u;
                         }
                         k = 0;
                 }
@@ -479,7 +499,7 @@ __device__ __forceinline__ void shade(const TraceParams& p, const HitState& hs, 
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTraceThreads)
+__global__ void __launch_bounds__(kTraceThreads, VRT_TRACE_MIN_BLOCKS)
 k_trace_rays(TraceParams p)
 {
         extern __shared__ uint32_t s_stack[];
@@ -510,8 +530,10 @@ k_trace_rays(TraceParams p)
         }
 }
 
+// 64 registers (8 CTAs/SM) is fastest for the compact outputs; the modes that also
+// evaluate the ISect/normal/shading tail spill at 64 and run best at 80 (6 CTAs/SM).
 template <int MODE>
-__global__ void __launch_bounds__(kTraceThreads)
+__global__ void __launch_bounds__(kTraceThreads, (MODE == OUT_HIT16 || MODE == OUT_COUNT) ? 8 : 6)
 k_trace_camera(TraceParams p)
 {
         extern __shared__ uint32_t s_stack[];
