@@ -322,7 +322,8 @@ using namespace vrt;
 
 uint64_t vrt_tree::scratch_bytes() const
 {
-        uint64_t b = keys_a.cap + keys_b.cap + tmp_a.cap + tmp_b.cap + tmp_c.cap + hist.cap + io_in.cap + io_out.cap;
+        uint64_t b = keys_a.cap + keys_b.cap + tmp_a.cap + tmp_b.cap + tmp_c.cap + hist.cap + refs_s.cap + tab_s.cap +
+                     io_in.cap + io_out.cap;
         for (unsigned l = 0; l <= VRT_MAX_DEPTH; ++l)
                 b += level_morton[l].cap + level_first[l].cap + level_mask[l].cap;
         return b;
@@ -386,6 +387,8 @@ void vrt_tree_free(vrt_tree* t)
         t->tmp_b.release();
         t->tmp_c.release();
         t->hist.release();
+        t->refs_s.release();
+        t->tab_s.release();
         t->io_in.release();
         t->io_out.release();
         for (unsigned l = 0; l <= VRT_MAX_DEPTH; ++l) {

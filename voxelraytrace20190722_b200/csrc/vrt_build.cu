@@ -444,7 +444,7 @@ static int finish_from_keys(vrt_tree* t, unsigned long long* keys, uint64_t n, i
                 return VRT_ERR_NOMEM;
         uint32_t* flag = t->tmp_a.as<uint32_t>();
         uint32_t* pos = t->tmp_b.as<uint32_t>();
-        Scratch refs_s;  // temporary refs until blob exists
+        Scratch& refs_s = t->refs_s;  // refs until the blob exists (kept across rebuilds)
         if (n) {
                 k_head_flags<<<grid_for(n, 256), 256, 0, s>>>(sorted, n, tb, flag);
                 count_launch();
@@ -577,7 +577,6 @@ static int finish_from_keys(vrt_tree* t, unsigned long long* keys, uint64_t n, i
         VRT_CUDA(cudaStreamSynchronize(s));
         VRT_CUDA(cudaMemcpyAsync(base, &h, sizeof h, cudaMemcpyHostToDevice, s));
         VRT_CUDA(cudaStreamSynchronize(s));
-        refs_s.release();
         tree_bind_views(t);
         return VRT_OK;
 }
@@ -602,7 +601,7 @@ int build_tree(vrt_tree* t, int max_depth)
         k_aabb_final<<<1, 32, 0, s>>>(t->tmp_a.as<uint2>(), nb, d_root6);
         count_launch(2);
         const uint64_t stride = 2ull << L;
-        Scratch tab_s;
+        Scratch& tab_s = t->tab_s;
         if (tab_s.reserve(3 * stride * 8))
                 return VRT_ERR_NOMEM;
         k_axis_table<<<1, 1024, 0, s>>>(d_root6, tab_s.as<float2>(), stride, L);
@@ -658,7 +657,6 @@ int build_tree(vrt_tree* t, int max_depth)
         if (cur != &t->keys_a)
                 std::swap(t->keys_a, t->keys_b);
         int rc = finish_from_keys(t, t->keys_a.as<unsigned long long>(), n, L, tb, /*stable_input=*/false, d_root6);
-        tab_s.release();
         if (rc)
                 return rc;
         VRT_CUDA(cudaEventRecord(t->ev1, s));

@@ -110,7 +110,7 @@ struct vrt_tree {
         float* d_tri_in = nullptr;  // [T][9] as given
         float* d_nrm_in = nullptr;  // [T][9] as given, or null
         // build scratch
-        vrt::Scratch keys_a, keys_b, tmp_a, tmp_b, tmp_c, hist, level_morton[VRT_MAX_DEPTH + 1],
+        vrt::Scratch keys_a, keys_b, tmp_a, tmp_b, tmp_c, hist, refs_s, tab_s, level_morton[VRT_MAX_DEPTH + 1],
             level_first[VRT_MAX_DEPTH + 1], level_mask[VRT_MAX_DEPTH + 1];
         uint32_t* d_counter = nullptr;  // small device counter block
         uint32_t* h_counter = nullptr;  // pinned mirror
