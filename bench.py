@@ -9,8 +9,10 @@ SURVEY.md 0): 266,156 triangles voxelized at max_depth 11 (1024^3 leaf grid), ma
 final camera (main.cc:112-115), 3840x2160 film, gen_rays4 -> 33,177,600 primary rays
 per step.  A step = one frame = one launch of the persistent ray kernel per GPU.
 
-  value     Mrays/s with everything resident in HBM (hit16 records written to HBM;
-            N>1: rows sharded in 8-row bands, frame gathered to rank 0 inside the step)
+  value     Mrays/s with everything resident in HBM: per step every rank traces its 8-row
+            bands and writes 16-byte hit records + the shaded film bands to HBM; N>1: the film
+            bands are gathered to rank 0 (NCCL, double-buffered under the next frame's kernel)
+            and re-ordered into the frame inside the timed region
   e2e       Mrays/s through the host-buffer C-ABI call vrt_render_camera: camera in,
             shaded float film copied back to pinned host memory inside the timed region
   roofline  algorithmic bytes per ray (8*N_int + 8*N_leaf + 40*N_tri + 16,
@@ -167,7 +169,7 @@ def workload_config(wl, ntris, gpus):
             "max_depth": depth, "leaf_grid": f"{2 ** (depth - 1)}^3", "film": f"{nx}x{ny}", "spp": spp,
             "rays_per_step": nx * ny * spp, "camera": "main.cc:112-115" if scene == "atrium" else "SURVEY 8d config 2",
             "sharding": f"8-row bands round-robin over {gpus} GPU(s), replicated octree, frame gathered to rank 0",
-            "l2": "inputs larger than L2: octree blob > 126 MB and every step writes 16 B/ray of fresh hit records"}
+            "l2": "inputs larger than L2: octree blob > 126 MB and every step writes 16 B/ray of hit records + 12 B/pixel of film"}
 
 
 # ----------------------------------------------------------------------------
@@ -213,14 +215,32 @@ def run_ours(args):
     stream = torch.cuda.current_stream(dev)
     tree.set_stream(stream.cuda_stream)
 
+    # One step = one frame: this rank's 8-row bands through the ray kernel, which writes the
+    # compact per-ray hit records (kept sharded in HBM) AND the shaded film bands; for N>1 the
+    # film bands are gathered to rank 0 (double-buffered, asynchronous: the gather of frame k
+    # overlaps the kernel of frame k+1) and re-ordered into the frame.
     rows = vdist.max_band_rows(ny, world)  # padded to the largest shard so the gather is uniform
-    hits = torch.empty((rows, nx * spp * 4), dtype=torch.int32, device=dev)  # hit16 records, 16 B each
+    hits = [torch.empty((rows, nx * spp * 4), dtype=torch.int32, device=dev) for _ in range(2)]
+    if world > 1:
+        fg = vdist.FrameGather(ny, nx, 3, torch.float32, dev)
+        films = None
+    else:
+        fg = None
+        films = [torch.empty((rows, nx, 3), dtype=torch.float32, device=dev) for _ in range(2)]
 
-    def step():
-        tree.trace_bands16_dev(cam, hits.data_ptr(), vdist.BAND_H, rank, world)
-        if world > 1:
-            return vdist.gather_rows(hits, ny)
-        return hits
+    def step(i):
+        k = i & 1
+        film = fg.buffer(k) if fg else films[k]
+        tree.frame_bands_dev(cam, hits[k].data_ptr(), film.data_ptr(), vdist.BAND_H, rank, world)
+        if fg:
+            if i > 0:
+                fg.assemble(k ^ 1)  # frame i-1 (its gather ran under this frame's kernel)
+            fg.gather_async(k)
+
+    def drain(i_last):
+        if fg:
+            fg.assemble(i_last & 1)
+            fg.finish()
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -228,25 +248,25 @@ def run_ours(args):
             td.barrier()
             torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        step()
+    for i in range(args.warmup):
+        step(i)
+    drain(args.warmup - 1)
     sync_all()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     l0 = capi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
     e0.record(stream)
-    for _ in range(args.steps):
-        step()
-        kernel_ms.append(tree.last_kernel_ms)
+    for i in range(args.steps):
+        step(i)
+    drain(args.steps - 1)
     e1.record(stream)
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
     launches = capi.launch_count() - l0
     total_ms = e0.elapsed_time(e1)
-    t = torch.tensor([total_ms, float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, tree.mean_kernel_ms(min(args.steps, 64))], dtype=torch.float64, device=dev)
     if world > 1:
         td.all_reduce(t, op=td.ReduceOp.MAX)
     total_ms, kern_ms = float(t[0]), float(t[1])
@@ -266,15 +286,15 @@ def run_ours(args):
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         d2h = film_np.nbytes
     else:
-        film = torch.empty((rows, nx, 3), dtype=torch.float32, device=dev)
         film_host = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
 
         def e2e_step():
-            tree.render_bands_dev(cam, film.data_ptr(), vdist.BAND_H, rank, world)
-            full = vdist.gather_rows(film, ny)
+            tree.render_bands_dev(cam, fg.buffer(0).data_ptr(), vdist.BAND_H, rank, world)
+            fg.gather_async(0)
+            full = fg.assemble(0)
             if rank == 0:
                 film_host.copy_(full, non_blocking=True)
-                torch.cuda.synchronize(dev)
+            torch.cuda.synchronize(dev)
 
         for _ in range(max(1, args.warmup // 2)):
             e2e_step()
@@ -312,7 +332,7 @@ def run_ours(args):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                "kernel": "k_trace_camera<HIT16>", "kernel_ms": kern_ms, "bytes_per_ray": b_ray,
+                "kernel": "k_trace_camera<HIT16_FILM>", "kernel_ms": kern_ms, "bytes_per_ray": b_ray,
                 "n_int": n_int, "n_leaf": n_leaf, "n_tri": n_tri, "hit_fraction": cnt["hits"] / cnt["rays"]}
 
     # ---- build metric ----

@@ -14,9 +14,10 @@
  *     in the library calls exit()/abort() (the reference does: voxel_octree.cc:329).
  *   - handles (vrt_tree*) are allocated and freed by the library; every `out`
  *     buffer is caller-allocated; input arrays are borrowed for the call only.
- *   - functions without a suffix take HOST pointers and copy in/out inside the
- *     call; functions ending in _dev take DEVICE pointers (current CUDA device)
- *     and only enqueue work on the tree's stream + synchronise it.
+ *   - functions without a suffix take HOST pointers, copy in/out inside the call
+ *     and return when the result is in the caller's buffer; functions ending in
+ *     _dev take DEVICE pointers (current CUDA device) and only ENQUEUE work on the
+ *     tree's stream (vrt_tree_sync / vrt_last_kernel_ms wait for it).
  *   - there is no CPU fallback: without a usable CUDA device every compute
  *     entry point fails with VRT_ERR_CUDA.
  *   - triangle index == index into tri_xyz == OBJ face order
@@ -215,9 +216,20 @@ int vrt_trace_bands16_dev(const vrt_tree* tree, const vrt_camera* cam,
  * leaves visited, triangle tests, hits.  Host pointer out. */
 int vrt_count_camera(const vrt_tree* tree, const vrt_camera* cam, int x0, int y0, int x1,
                      int y1, uint64_t counts[5]);
-/* device time (ms, CUDA events on the tree's stream) of the last trace/render
- * kernel launched through this handle */
+/* One frame step of the multi-GPU render loop: this rank's bands, writing BOTH the
+ * compact per-ray hit records (kept sharded in this GPU's HBM) and the shaded film
+ * bands (the piece the framebuffer gather collects).  d_hits[local_row][nx][spp],
+ * d_film_rgb[local_row][nx][3]. */
+int vrt_frame_bands_dev(const vrt_tree* tree, const vrt_camera* cam, const vrt_shade* sh,
+                        const vrt_bands* bands, vrt_hit16* d_hits, float* d_film_rgb);
+/* _dev launches are asynchronous with respect to the host: they return once the work is
+ * enqueued on the tree's stream.  vrt_tree_sync waits for it. */
+int vrt_tree_sync(const vrt_tree* tree);
+/* device time (ms, CUDA events on the tree's stream) of the last trace/render kernel
+ * launched through this handle, and the mean over the last n launches (n <= 64); both
+ * wait for those launches to finish. */
 double vrt_last_kernel_ms(const vrt_tree* tree);
+double vrt_mean_kernel_ms(const vrt_tree* tree, int last_n);
 
 /* ---- predicates (device KATs; each call launches a kernel) ---------------- */
 /* triBoxOverlap (tribox2.h:15): centers[n][3], halves[n][3], tris[n][3][3] */

@@ -99,7 +99,7 @@ def test_band_partition_covers_film(ny, world):
     torch = pytest.importorskip("torch")
     from voxelraytrace20190722_b200 import dist as vdist
     rows = [vdist.band_rows(ny, r, world) for r in range(world)]
-    assert sum(rows) == ny and max(rows) == vdist.max_band_rows(ny, world)
+    assert sum(rows) == ny and max(rows) <= vdist.max_band_rows(ny, world) < max(rows) + vdist.BAND_H
     perm = vdist.band_row_index(ny, world)
     assert sorted(perm.tolist()) == list(range(ny))
     cam = capi.Camera(CAM_MAIN[0], CAM_MAIN[1:4], CAM_MAIN[4:7], CAM_MAIN[7:10], 64, ny, 1)

@@ -38,11 +38,30 @@ def _worker(rank, world, port, ny, nx, ok):
         k += world
     assert r == rows
     full = vdist.gather_rows(local, ny)
+    good = True
     if rank == 0:
         exp = torch.arange(ny, dtype=torch.float32)[:, None] * 1000 + torch.arange(nx)[None, :]
-        ok.value = int(torch.equal(full, exp))
+        good = torch.equal(full, exp)
     else:
         assert full is None
+    # the double-buffered asynchronous form used by bench.py: three frames, frame f scaled by f+1
+    fg = vdist.FrameGather(ny, nx, 1, torch.float32, torch.device("cpu"))
+    frames = []
+    for f in range(3):
+        k = f & 1
+        fg.buffer(k).copy_((local * (f + 1)).unsqueeze(-1))
+        if f > 0:
+            fr = fg.assemble(k ^ 1)
+            if rank == 0:
+                frames.append(fr.clone())
+        fg.gather_async(k)
+    fr = fg.assemble(2 & 1 ^ 1 ^ 1)
+    if rank == 0:
+        frames.append(fr.clone())
+        for f, fr in enumerate(frames):
+            good = good and torch.equal(fr[..., 0], exp * (f + 1))
+        ok.value = int(good and len(frames) == 3)
+    fg.finish()
     td.barrier()
     td.destroy_process_group()
 

@@ -61,7 +61,8 @@ SYMBOLS = [
     "vrt_tree_from_blob_dev", "vrt_camera_init", "vrt_gen_rays", "vrt_trace_rays",
     "vrt_trace_rays_dev", "vrt_trace_camera", "vrt_trace_camera_dev", "vrt_trace_camera16_dev",
     "vrt_render_camera", "vrt_render_camera_dev", "vrt_band_rows", "vrt_render_bands_dev",
-    "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_last_kernel_ms", "vrt_tribox_batch",
+    "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_tree_sync",
+    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_tribox_batch",
     "vrt_tri_overlap_aabb_batch", "vrt_raytri_batch", "vrt_aabb_isect_batch",
 ]
 
@@ -115,6 +116,10 @@ def load(build_if_missing: bool = True):
     L.vrt_render_bands_dev.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), C.POINTER(vrt_bands), vp]
     L.vrt_trace_bands16_dev.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_bands), vp]
     L.vrt_count_camera.argtypes = [vp, C.POINTER(vrt_camera), i32, i32, i32, i32, vp]
+    L.vrt_frame_bands_dev.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), C.POINTER(vrt_bands), vp, vp]
+    L.vrt_tree_sync.argtypes = [vp]
+    L.vrt_mean_kernel_ms.restype = C.c_double
+    L.vrt_mean_kernel_ms.argtypes = [vp, i32]
     L.vrt_last_kernel_ms.restype = C.c_double
     L.vrt_last_kernel_ms.argtypes = [vp]
     L.vrt_tribox_batch.argtypes = [vp, vp, vp, u64, vp]
@@ -305,6 +310,20 @@ class Octree:
         sh = vrt_shade((C.c_float * 3)(*(default_light() if light is None else light)), float(kd))
         b = vrt_bands(int(band_h), int(band_first), int(band_stride))
         _check(load().vrt_render_bands_dev(self._h, C.byref(cam.c), C.byref(sh), C.byref(b), C.c_void_p(d_film_ptr)))
+
+    def frame_bands_dev(self, cam: Camera, d_hits_ptr, d_film_ptr, band_h, band_first, band_stride, light=None,
+                        kd=0.8):
+        """One frame step of rank `band_first` of `band_stride`: hit16 records + film bands (async)."""
+        sh = vrt_shade((C.c_float * 3)(*(default_light() if light is None else light)), float(kd))
+        b = vrt_bands(int(band_h), int(band_first), int(band_stride))
+        _check(load().vrt_frame_bands_dev(self._h, C.byref(cam.c), C.byref(sh), C.byref(b), C.c_void_p(d_hits_ptr),
+                                          C.c_void_p(d_film_ptr)))
+
+    def sync(self):
+        _check(load().vrt_tree_sync(self._h))
+
+    def mean_kernel_ms(self, last_n):
+        return float(load().vrt_mean_kernel_ms(self._h, int(last_n)))
 
     def trace_bands16_dev(self, cam: Camera, d_out_ptr, band_h, band_first, band_stride):
         b = vrt_bands(int(band_h), int(band_first), int(band_stride))

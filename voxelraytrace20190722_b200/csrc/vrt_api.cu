@@ -87,6 +87,12 @@ int tree_alloc(vrt_tree** out)
                 vrt_tree_free(t);
                 return VRT_ERR_CUDA;
         }
+        for (int i = 0; i < vrt_tree::kEvRing; ++i)
+                if (!cuda_ok(cudaEventCreate(&t->ring0[i]), "cudaEventCreate") ||
+                    !cuda_ok(cudaEventCreate(&t->ring1[i]), "cudaEventCreate")) {
+                        vrt_tree_free(t);
+                        return VRT_ERR_CUDA;
+                }
         *out = t;
         return VRT_OK;
 }
@@ -404,6 +410,12 @@ void vrt_tree_free(vrt_tree* t)
                 cudaEventDestroy(t->ev0);
         if (t->ev1)
                 cudaEventDestroy(t->ev1);
+        for (int i = 0; i < vrt_tree::kEvRing; ++i) {
+                if (t->ring0[i])
+                        cudaEventDestroy(t->ring0[i]);
+                if (t->ring1[i])
+                        cudaEventDestroy(t->ring1[i]);
+        }
         cudaGetLastError();
         delete t;
 }
@@ -807,7 +819,54 @@ int vrt_trace_bands16_dev(const vrt_tree* t, const vrt_camera* cam, const vrt_ba
         return bands_common(t, cam, nullptr, b, d_out, OUT_HIT16);
 }
 
-double vrt_last_kernel_ms(const vrt_tree* t) { return t ? t->last_kernel_ms : 0.0; }
+double vrt_last_kernel_ms(const vrt_tree* t)
+{
+        double ms = 0;
+        if (t)
+                trace_ms_mean(t, 1, &ms);
+        return ms;
+}
+
+double vrt_mean_kernel_ms(const vrt_tree* t, int last_n)
+{
+        double ms = 0;
+        if (t)
+                trace_ms_mean(t, last_n, &ms);
+        return ms;
+}
+
+int vrt_tree_sync(const vrt_tree* t)
+{
+        if (!t) {
+                set_error("null tree handle");
+                return VRT_ERR_ARG;
+        }
+        VRT_CUDA(cudaStreamSynchronize(t->stream));
+        return VRT_OK;
+}
+
+int vrt_frame_bands_dev(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, const vrt_bands* b,
+                        vrt_hit16* d_hits, float* d_film_rgb)
+{
+        int rc = check_tree(t);
+        if (rc)
+                return rc;
+        rc = check_camera(cam, 0, 0, cam ? cam->nx : 0, cam ? cam->ny : 0);
+        if (rc)
+                return rc;
+        const int rows = vrt_band_rows(cam, b);
+        if (rows < 0)
+                return rows;
+        if (rows == 0)
+                return VRT_OK;
+        if (!d_hits || !d_film_rgb || !sh) {
+                set_error("null out/shade pointer");
+                return VRT_ERR_ARG;
+        }
+        const int y0 = b->band_first * b->band_h;
+        return launch_trace_camera(t, cam, sh, 0, y0, cam->nx, y0 + rows, d_hits, OUT_HIT16_FILM, b->band_h,
+                                   b->band_stride * b->band_h, d_film_rgb);
+}
 
 // ---- predicates ---------------------------------------------------------------
 int vrt_tribox_batch(const float* centers, const float* halves, const float* tris, uint64_t n, uint8_t* out)

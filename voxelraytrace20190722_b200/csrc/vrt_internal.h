@@ -116,7 +116,11 @@ struct vrt_tree {
         uint32_t* h_counter = nullptr;  // pinned mirror
         // trace scratch (host-pointer entry points)
         vrt::Scratch io_in, io_out;
-        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // build timing
+        // trace launches are asynchronous: each one records a (start, stop) pair in this ring
+        static constexpr int kEvRing = 64;
+        cudaEvent_t ring0[kEvRing] = {}, ring1[kEvRing] = {};
+        mutable uint64_t n_trace_launches = 0;
         double build_ms = 0;
         mutable double last_kernel_ms = 0;
         uint64_t scratch_bytes() const;
@@ -131,11 +135,13 @@ int import_leaves(vrt_tree* t, int max_depth, const float root_aabb[6], uint64_t
                   const uint32_t* leaf_cell, const uint32_t* leaf_count,
                   const uint32_t* leaf_refs);
 // trace (vrt_trace.cu)
-enum OutMode { OUT_HIT48 = 0, OUT_HIT16 = 1, OUT_FILM = 2, OUT_COUNT = 3 };
+enum OutMode { OUT_HIT48 = 0, OUT_HIT16 = 1, OUT_FILM = 2, OUT_COUNT = 3, OUT_HIT16_FILM = 4 };
 int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_hit* d_out);
 // band_h > 0: rows [y0,y1) are LOCAL rows of a banded shard; local row r maps to film row
 // y0_film + (r / band_h) * band_pitch + r % band_h (y0 then carries y0_film, y1 = y0 + local rows).
 int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, int x0,
                         int y0, int x1, int y1, void* d_out, OutMode mode, int band_h = 0,
-                        int band_pitch = 0);
+                        int band_pitch = 0, void* d_out2 = nullptr);
+// mean device time (ms) of the last n trace launches (waits for them)
+int trace_ms_mean(const vrt_tree* t, int last_n, double* ms);
 }  // namespace vrt

@@ -46,6 +46,7 @@ struct TraceParams {
         const vrt_ray* rays;  // explicit-ray mode
         unsigned long long num_rays;
         void* out;
+        void* out2;  // film when MODE == OUT_HIT16_FILM
         uint32_t* queue;  // tile counter
         uint32_t num_tiles;
         float light[3];
@@ -533,7 +534,7 @@ k_trace_rays(TraceParams p)
 // 64 registers (8 CTAs/SM) is fastest for the compact outputs; the modes that also
 // evaluate the ISect/normal/shading tail spill at 64 and run best at 80 (6 CTAs/SM).
 template <int MODE>
-__global__ void __launch_bounds__(kTraceThreads, (MODE == OUT_HIT16 || MODE == OUT_COUNT) ? 8 : 6)
+__global__ void __launch_bounds__(kTraceThreads, (MODE == OUT_HIT16 || MODE == OUT_COUNT) ? 8 : 6)  // see launch-bounds note
 k_trace_camera(TraceParams p)
 {
         extern __shared__ uint32_t s_stack[];
@@ -593,7 +594,7 @@ k_trace_camera(TraceParams p)
                                 if (lane == 0)
                                         atomicAdd(static_cast<unsigned long long*>(p.out) + k, v[k]);
                         }
-                } else if (MODE == OUT_HIT16) {
+                } else if (MODE == OUT_HIT16) {  // (OUT_HIT16_FILM handled below)
                         if (active) {
                                 uint4 q;
                                 q.x = hs.hit ? (hs.leaf - p.tree.num_nodes + p.tree.num_leaves) : VRT_NO_TRI;
@@ -603,6 +604,14 @@ k_trace_camera(TraceParams p)
                                 reinterpret_cast<uint4*>(p.out)[pix * spp + s] = q;
                         }
                 } else {
+                        if (MODE == OUT_HIT16_FILM && active) {
+                                uint4 q;
+                                q.x = hs.hit ? (hs.leaf - p.tree.num_nodes + p.tree.num_leaves) : VRT_NO_TRI;
+                                q.y = hs.tri;
+                                q.z = __float_as_uint(hs.hit ? hs.t : 0.f);
+                                q.w = hs.hit ? 1u : 0u;
+                                reinterpret_cast<uint4*>(p.out)[pix * spp + s] = q;
+                        }
                         float rgb[3] = { 0, 0, 0 };
                         if (active)
                                 shade(p, hs, o, d, rgb);
@@ -622,7 +631,7 @@ k_trace_camera(TraceParams p)
                                 }
                         }
                         if (active && s == 0) {
-                                float* f = static_cast<float*>(p.out) + pix * 3ull;
+                                float* f = static_cast<float*>(MODE == OUT_HIT16_FILM ? p.out2 : p.out) + pix * 3ull;
                                 f[0] = acc[0];
                                 f[1] = acc[1];
                                 f[2] = acc[2];
@@ -682,20 +691,18 @@ int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_
         int grid = persistent_grid((const void*)k_trace_rays, smem);
         grid = (int)std::min<uint64_t>((uint64_t)grid, (warps + 3) / 4);
         VRT_CUDA(cudaMemsetAsync(p.queue, 0, 4, t->stream));
-        VRT_CUDA(cudaEventRecord(t->ev0, t->stream));
+        const int slot = (int)(t->n_trace_launches % vrt_tree::kEvRing);
+        VRT_CUDA(cudaEventRecord(t->ring0[slot], t->stream));
         k_trace_rays<<<grid, kTraceThreads, smem, t->stream>>>(p);
         count_launch();
         VRT_CUDA(cudaGetLastError());
-        VRT_CUDA(cudaEventRecord(t->ev1, t->stream));
-        VRT_CUDA(cudaEventSynchronize(t->ev1));
-        float ms = 0;
-        VRT_CUDA(cudaEventElapsedTime(&ms, t->ev0, t->ev1));
-        t->last_kernel_ms = ms;
+        VRT_CUDA(cudaEventRecord(t->ring1[slot], t->stream));
+        t->n_trace_launches++;
         return VRT_OK;
 }
 
 int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, int x0, int y0,
-                        int x1, int y1, void* d_out, OutMode mode, int band_h, int band_pitch)
+                        int x1, int y1, void* d_out, OutMode mode, int band_h, int band_pitch, void* d_out2)
 {
         if (x1 <= x0 || y1 <= y0)
                 return VRT_OK;
@@ -716,6 +723,7 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         p.band_h = band_h > 0 ? band_h : (y1 - y0);
         p.band_pitch = band_h > 0 ? band_pitch : 0;
         p.out = d_out;
+        p.out2 = d_out2;
         if (sh) {
                 p.light[0] = sh->light_dir[0];
                 p.light[1] = sh->light_dir[1];
@@ -735,21 +743,39 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         case OUT_HIT48: kern = (const void*)k_trace_camera<OUT_HIT48>; break;
         case OUT_HIT16: kern = (const void*)k_trace_camera<OUT_HIT16>; break;
         case OUT_COUNT: kern = (const void*)k_trace_camera<OUT_COUNT>; break;
+        case OUT_HIT16_FILM: kern = (const void*)k_trace_camera<OUT_HIT16_FILM>; break;
         default: kern = (const void*)k_trace_camera<OUT_FILM>; break;
         }
         VRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = persistent_grid(kern, smem);
         grid = (int)std::min<uint64_t>((uint64_t)grid, (tiles + 3) / 4);
         VRT_CUDA(cudaMemsetAsync(p.queue, 0, 4, t->stream));
-        VRT_CUDA(cudaEventRecord(t->ev0, t->stream));
+        const int slot = (int)(t->n_trace_launches % vrt_tree::kEvRing);
+        VRT_CUDA(cudaEventRecord(t->ring0[slot], t->stream));
         void* args[] = { &p };
         VRT_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(kTraceThreads), args, smem, t->stream));
         count_launch();
-        VRT_CUDA(cudaEventRecord(t->ev1, t->stream));
-        VRT_CUDA(cudaEventSynchronize(t->ev1));
-        float ms = 0;
-        VRT_CUDA(cudaEventElapsedTime(&ms, t->ev0, t->ev1));
-        t->last_kernel_ms = ms;
+        VRT_CUDA(cudaEventRecord(t->ring1[slot], t->stream));
+        t->n_trace_launches++;
+        return VRT_OK;
+}
+
+int trace_ms_mean(const vrt_tree* t, int last_n, double* ms)
+{
+        *ms = 0;
+        const uint64_t n = t->n_trace_launches;
+        if (n == 0)
+                return VRT_OK;
+        const int cnt = (int)std::min<uint64_t>({ (uint64_t)std::max(last_n, 1), n, (uint64_t)vrt_tree::kEvRing });
+        double sum = 0;
+        for (int i = 0; i < cnt; ++i) {
+                const int slot = (int)((n - 1 - i) % vrt_tree::kEvRing);
+                VRT_CUDA(cudaEventSynchronize(t->ring1[slot]));
+                float e = 0;
+                VRT_CUDA(cudaEventElapsedTime(&e, t->ring0[slot], t->ring1[slot]));
+                sum += e;
+        }
+        *ms = sum / cnt;
         return VRT_OK;
 }
 

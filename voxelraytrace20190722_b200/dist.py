@@ -75,37 +75,82 @@ def replicate_octree(tree: capi.Octree | None, device, src: int = 0) -> capi.Oct
 
 
 def max_band_rows(ny: int, world: int, band_h: int = BAND_H) -> int:
-    """Rows of the largest shard (rank 0); every rank's buffer is padded to this so that
-    the gather moves equal-sized pieces."""
-    return band_rows(ny, 0, world, band_h)
+    """Rows of every rank's (padded) buffer: a whole number of bands, enough for the largest
+    shard, so that the gather moves equal-sized pieces and the band-major landing buffer
+    can be re-ordered with one strided copy."""
+    num_bands = (ny + band_h - 1) // band_h
+    return ((num_bands + world - 1) // world) * band_h
+
+
+class FrameGather:
+    """Framebuffer assembly on rank `dst` (the ncclGather of SURVEY.md 8e), double-buffered
+    and asynchronous so that the gather of frame k overlaps the ray kernel of frame k+1.
+
+    Every rank owns two [max_band_rows, nx, C] film buffers; rank `dst` owns two
+    [world, max_band_rows, nx, C] landing buffers the NCCL receives write into directly
+    (no staging copy) and one [ny, nx, C] film-ordered frame.
+    """
+
+    def __init__(self, ny, nx, channels, dtype, device, band_h: int = BAND_H, dst: int = 0):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world, self.rank, self.dst = dist.get_world_size(), dist.get_rank(), dst
+        self.ny, self.nx, self.band_h = ny, nx, band_h
+        self.rows_max = max_band_rows(ny, self.world, band_h)
+        self.local = [torch.empty((self.rows_max, nx, channels), dtype=dtype, device=device) for _ in range(2)]
+        self.work = [None, None]
+        if self.rank == dst:
+            self.landing = [torch.empty((self.world, self.rows_max, nx, channels), dtype=dtype, device=device)
+                            for _ in range(2)]
+            self.frame = torch.empty((ny, nx, channels), dtype=dtype, device=device)
+        else:
+            self.landing, self.frame = [None, None], None
+
+    def buffer(self, k):
+        """Film buffer of slot k (waits, on the stream, for the gather that last read it)."""
+        if self.work[k] is not None:
+            self.work[k].wait()
+            self.work[k] = None
+        return self.local[k]
+
+    def gather_async(self, k):
+        lst = list(self.landing[k].unbind(0)) if self.rank == self.dst else None
+        self.work[k] = self.dist.gather(self.local[k], lst, dst=self.dst, async_op=True)
+
+    def assemble(self, k):
+        """Band-major landing buffer -> film-ordered frame (rank dst only; one strided copy)."""
+        if self.work[k] is not None:
+            self.work[k].wait()
+            self.work[k] = None
+        if self.rank != self.dst:
+            return None
+        nb = self.rows_max // self.band_h
+        g = self.landing[k].view(self.world, nb, self.band_h, -1).permute(1, 0, 2, 3)
+        self.frame.view(self.ny, -1).copy_(g.reshape(nb * self.world * self.band_h, -1)[: self.ny])
+        return self.frame
+
+    def finish(self):
+        for k in range(2):
+            if self.work[k] is not None:
+                self.work[k].wait()
+                self.work[k] = None
 
 
 def gather_rows(local: torch.Tensor, ny: int, band_h: int = BAND_H, dst: int = 0):
-    """Assemble the frame on rank `dst`.  `local` is this rank's [max_band_rows, ...]
-    tensor (rows beyond the rank's own count are padding).  Returns the film-ordered
-    [ny, ...] tensor on `dst`, None elsewhere."""
+    """Synchronous one-shot form of FrameGather (tests): `local` is this rank's padded
+    [max_band_rows, ...] tensor; returns the film-ordered [ny, ...] tensor on `dst`."""
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(), dist.get_rank()
+    rows_max = local.shape[0]
     if rank == dst:
-        parts = [torch.empty_like(local) for _ in range(world)]
+        landing = torch.empty((world,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+        parts = list(landing.unbind(0))
     else:
-        parts = None
+        landing, parts = None, None
     dist.gather(local, parts, dst=dst)
     if rank != dst:
         return None
-    cat = torch.cat([parts[r][:band_rows(ny, r, world, band_h)] for r in range(world)], dim=0)
-    out = torch.empty_like(cat)
-    perm = _perm_cache(ny, world, band_h, local.device)
-    out[perm] = cat
-    return out
-
-
-_PERMS: dict = {}
-
-
-def _perm_cache(ny, world, band_h, device):
-    key = (ny, world, band_h, str(device))
-    if key not in _PERMS:
-        _PERMS[key] = torch.as_tensor(band_row_index(ny, world, band_h), device=device)
-    return _PERMS[key]
+    nb = rows_max // band_h
+    g = landing.view(world, nb, band_h, -1).permute(1, 0, 2, 3).reshape(nb * world * band_h, -1)[:ny]
+    return g.reshape((ny,) + tuple(local.shape[1:])).contiguous()
