@@ -168,7 +168,7 @@ def workload_config(wl, ntris, gpus):
                                                   if scene == "atrium" else ")"),
             "max_depth": depth, "leaf_grid": f"{2 ** (depth - 1)}^3", "film": f"{nx}x{ny}", "spp": spp,
             "rays_per_step": nx * ny * spp, "camera": "main.cc:112-115" if scene == "atrium" else "SURVEY 8d config 2",
-            "sharding": f"8-row bands round-robin over {gpus} GPU(s), replicated octree, frame gathered to rank 0",
+            "sharding": f"8-row bands round-robin over {gpus} GPU(s), replicated octree (one NCCL broadcast), frame assembled on rank 0",
             "l2": "inputs larger than L2: octree blob > 126 MB and every step writes 16 B/ray of hit records + 12 B/pixel of film"}
 
 
@@ -216,31 +216,42 @@ def run_ours(args):
     tree.set_stream(stream.cuda_stream)
 
     # One step = one frame: this rank's 8-row bands through the ray kernel, which writes the
-    # compact per-ray hit records (kept sharded in HBM) AND the shaded film bands; for N>1 the
-    # film bands are gathered to rank 0 (double-buffered, asynchronous: the gather of frame k
-    # overlaps the kernel of frame k+1) and re-ordered into the frame.
+    # compact per-ray hit records (kept sharded in HBM) AND the shaded pixels.  Framebuffer
+    # assembly on rank 0 is fused into the kernel (default, --assemble peer): the pixels are
+    # stored straight into rank 0's double-buffered frame over NVLink (CUDA-IPC mapped), so
+    # there is no collective and no re-order pass.  --assemble gather uses the NCCL gather
+    # (double-buffered, asynchronous) + one re-order copy instead.
     rows = vdist.max_band_rows(ny, world)  # padded to the largest shard so the gather is uniform
     hits = [torch.empty((rows, nx * spp * 4), dtype=torch.int32, device=dev) for _ in range(2)]
-    if world > 1:
-        fg = vdist.FrameGather(ny, nx, 3, torch.float32, dev)
-        films = None
-    else:
-        fg = None
-        films = [torch.empty((rows, nx, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+    use_gather = (args.assemble == "gather") and world > 1
+    fg = vdist.FrameGather(ny, nx, 3, torch.float32, dev) if use_gather else None
+    pf = None if use_gather else vdist.PeerFrame(ny, nx, dev)
+    # two streams, alternating per frame: the head of frame k+1 fills the SMs that the tail of
+    # frame k (a few long rays) leaves idle.  (Not with NCCL in the loop: its kernels cannot
+    # become resident while two persistent grids own every SM.)
+    S = [torch.cuda.Stream(dev)]
+    S.append(S[0] if use_gather else torch.cuda.Stream(dev))
 
     def step(i):
         k = i & 1
-        film = fg.buffer(k) if fg else films[k]
-        tree.frame_bands_dev(cam, hits[k].data_ptr(), film.data_ptr(), vdist.BAND_H, rank, world)
-        if fg:
-            if i > 0:
-                fg.assemble(k ^ 1)  # frame i-1 (its gather ran under this frame's kernel)
-            fg.gather_async(k)
+        with torch.cuda.stream(S[k]):
+            tree.set_stream(S[k].cuda_stream)
+            if use_gather:
+                film = fg.buffer(k)
+                tree.frame_bands_dev(cam, hits[k].data_ptr(), film.data_ptr(), vdist.BAND_H, rank, world)
+                if i > 0:
+                    fg.assemble(k ^ 1)  # frame i-1 (its gather ran under this frame's kernel)
+                fg.gather_async(k)
+            else:
+                tree.frame_bands_dev(cam, hits[k].data_ptr(), pf.ptr(k), vdist.BAND_H, rank, world, full_frame=True)
 
     def drain(i_last):
-        if fg:
-            fg.assemble(i_last & 1)
-            fg.finish()
+        if use_gather:
+            with torch.cuda.stream(S[0]):
+                fg.assemble(i_last & 1)
+                fg.finish()
+        stream.wait_stream(S[0])
+        stream.wait_stream(S[1])
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -258,6 +269,8 @@ def run_ours(args):
     l0 = capi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    S[0].wait_stream(stream)
+    S[1].wait_stream(stream)
     for i in range(args.steps):
         step(i)
     drain(args.steps - 1)
@@ -268,9 +281,18 @@ def run_ours(args):
     total_ms = e0.elapsed_time(e1)
     t = torch.tensor([total_ms, tree.mean_kernel_ms(min(args.steps, 64))], dtype=torch.float64, device=dev)
     if world > 1:
+        if os.environ.get("VRT_BENCH_DEBUG"):
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            td.all_gather(allt, t)
+            if rank == 0:
+                sys.stderr.write("per-rank [total_ms, kernel_ms]: " + str([[round(float(v), 3) for v in a] for a in allt]) + "\n")
         td.all_reduce(t, op=td.ReduceOp.MAX)
-    total_ms, kern_ms = float(t[0]), float(t[1])
+    total_ms, kern_ms_events = float(t[0]), float(t[1])
     ms_per_step = total_ms / args.steps
+    # launches of consecutive frames overlap (two streams), so a launch's own event pair also
+    # spans the time it waits behind its predecessor; the average launch duration over the
+    # timed region is the CUDA-event time of the region / launches
+    kern_ms = ms_per_step
     value = rays_per_step / (ms_per_step * 1e-3) / 1e6
 
     # ---- e2e: host-buffer C-ABI call, film copied back to pinned host memory every step ----
@@ -288,10 +310,18 @@ def run_ours(args):
     else:
         film_host = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
 
+        tree.set_stream(stream.cuda_stream)
+
         def e2e_step():
-            tree.render_bands_dev(cam, fg.buffer(0).data_ptr(), vdist.BAND_H, rank, world)
-            fg.gather_async(0)
-            full = fg.assemble(0)
+            if use_gather:
+                tree.render_bands_dev(cam, fg.buffer(0).data_ptr(), vdist.BAND_H, rank, world)
+                fg.gather_async(0)
+                full = fg.assemble(0)
+            else:
+                tree.frame_bands_dev(cam, hits[0].data_ptr(), pf.ptr(0), vdist.BAND_H, rank, world, full_frame=True)
+                torch.cuda.synchronize(dev)
+                td.barrier()  # every rank's pixels have landed in rank 0's frame
+                full = pf.frame(0)
             if rank == 0:
                 film_host.copy_(full, non_blocking=True)
             torch.cuda.synchronize(dev)
@@ -308,6 +338,17 @@ def run_ours(args):
         e2e_ms = float(tt[0])
         d2h = ny * nx * 12
     e2e_value = rays_per_step / (e2e_ms * 1e-3) / 1e6
+
+    # ---- N-GPU frame == 1-GPU frame, bytewise (outside every timed region) ----
+    frame_check = None
+    if rank == 0:
+        tree.set_stream(0)
+        ref_film = torch.empty((ny, nx, 3), dtype=torch.float32, device=dev)
+        tree.render_dev(cam, ref_film.data_ptr())
+        tree.sync()
+        got = fg.frame if use_gather else pf.frame(0)
+        frame_check = bool(torch.equal(got.view(torch.int32), ref_film.view(torch.int32)))
+        del ref_film
 
     if rank != 0:
         if world > 1:
@@ -332,7 +373,7 @@ def run_ours(args):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                "kernel": "k_trace_camera<HIT16_FILM>", "kernel_ms": kern_ms, "bytes_per_ray": b_ray,
+                "kernel": "k_trace_camera<HIT16_FILM>", "kernel_ms": kern_ms, "kernel_ms_event_pairs": kern_ms_events, "bytes_per_ray": b_ray,
                 "n_int": n_int, "n_leaf": n_leaf, "n_tri": n_tri, "hit_fraction": cnt["hits"] / cnt["rays"]}
 
     # ---- build metric ----
@@ -370,6 +411,9 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "build": build_out,
         "octree": {"device_bytes": info["device_bytes"], "nodes": info["num_nodes"], "leaves": info["num_leaves"]},
+        "frame_check": {"n_gpu_frame_equals_1_gpu_frame_bytewise": frame_check},
+        "assemble": ("nccl gather + re-order copy" if use_gather else
+                     "fused: peer stores into rank 0's IPC-mapped frame over NVLink" if world > 1 else "local frame"),
     }
     print(json.dumps(line))
     if world > 1:
@@ -385,6 +429,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--build-reps", type=int, default=3)
+    ap.add_argument("--assemble", default="peer", choices=["peer", "gather"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

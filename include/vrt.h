@@ -222,6 +222,20 @@ int vrt_count_camera(const vrt_tree* tree, const vrt_camera* cam, int x0, int y0
  * d_film_rgb[local_row][nx][3]. */
 int vrt_frame_bands_dev(const vrt_tree* tree, const vrt_camera* cam, const vrt_shade* sh,
                         const vrt_bands* bands, vrt_hit16* d_hits, float* d_film_rgb);
+/* Same step with the framebuffer assembly FUSED into the ray kernel (SURVEY.md 5/8e,
+ * the alternative to gather): d_frame_rgb is the FULL [ny][nx][3] frame, normally rank
+ * 0's buffer mapped into this process with vrt_ipc_open, and the kernel stores every
+ * finished pixel straight to its final place over NVLink (peer stores; no NCCL, no
+ * staging, no re-order pass).  On rank 0 / a single GPU it is just a local pointer. */
+int vrt_frame_bands_peer_dev(const vrt_tree* tree, const vrt_camera* cam, const vrt_shade* sh,
+                             const vrt_bands* bands, vrt_hit16* d_hits, float* d_frame_rgb);
+/* Plain device memory that can be shared between the processes of one node
+ * (cudaMalloc + CUDA IPC): export a 64-byte handle on the owner, open it on the peers. */
+int vrt_dev_alloc(uint64_t bytes, void** d_ptr);
+int vrt_dev_free(void* d_ptr);
+int vrt_ipc_export(const void* d_ptr, uint8_t handle[64]);
+int vrt_ipc_open(const uint8_t handle[64], void** d_ptr);
+int vrt_ipc_close(void* d_ptr);
 /* _dev launches are asynchronous with respect to the host: they return once the work is
  * enqueued on the tree's stream.  vrt_tree_sync waits for it. */
 int vrt_tree_sync(const vrt_tree* tree);

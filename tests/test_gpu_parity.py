@@ -320,3 +320,40 @@ def test_untame_rays_take_exact_path(case, gpu, port):
     got = case["tree"].trace_rays(rays)
     exp = case["orc"].trace(rays)
     assert compare_hits(got, exp, case["name"] + " untame rays") == 0
+
+
+def test_frame_step_hits_and_film_match_separate_modes(case, gpu):
+    """vrt_frame_bands(_peer)_dev (the bench step: hit16 records + film in one launch, film
+    addressed by band or by final film row) agrees with the single-purpose entry points."""
+    torch = pytest.importorskip("torch")
+    from voxelraytrace20190722_b200 import dist as vdist
+    cam10 = case["cam10"]
+    nx, ny, spp = 136, 52, 4  # not multiples of the tile / band sizes
+    cam = gpu.Camera(cam10[0], cam10[1:4], cam10[4:7], cam10[7:10], nx, ny, spp)
+    tree = case["tree"]
+    film_ref = tree.render(cam)
+    hits_ref = tree.trace_camera(cam)
+    for world in (1, 3):
+        full = torch.zeros((ny, nx, 3), dtype=torch.float32, device="cuda")
+        parts = []
+        for rank in range(world):
+            rows = vdist.max_band_rows(ny, world)
+            h16 = torch.zeros((rows, nx * spp, 4), dtype=torch.int32, device="cuda")
+            film = torch.zeros((rows, nx, 3), dtype=torch.float32, device="cuda")
+            tree.frame_bands_dev(cam, h16.data_ptr(), film.data_ptr(), vdist.BAND_H, rank, world)
+            tree.frame_bands_dev(cam, h16.data_ptr(), full.data_ptr(), vdist.BAND_H, rank, world, full_frame=True)
+            tree.sync()
+            parts.append((h16.cpu().numpy(), film.cpu().numpy()))
+        assert np.array_equal(full.cpu().numpy().view(np.uint32), film_ref.view(np.uint32))
+        perm = vdist.band_row_index(ny, world)
+        film_cat = np.concatenate([p[1][:vdist.band_rows(ny, r, world)] for r, p in enumerate(parts)])
+        hit_cat = np.concatenate([p[0][:vdist.band_rows(ny, r, world)] for r, p in enumerate(parts)])
+        film_out = np.empty_like(film_cat)
+        film_out[perm] = film_cat
+        hit_out = np.empty_like(hit_cat)
+        hit_out[perm] = hit_cat
+        assert np.array_equal(film_out.view(np.uint32), film_ref.view(np.uint32))
+        h = hit_out.reshape(-1, 4)
+        assert np.array_equal(h[:, 3].astype(np.uint32), hits_ref["hit"])
+        assert np.array_equal(h[:, 1].view(np.uint32), hits_ref["tri"])
+        assert np.array_equal(h[:, 2].view(np.float32).view(np.uint32), hits_ref["t"].view(np.uint32))

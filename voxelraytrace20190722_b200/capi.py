@@ -61,7 +61,8 @@ SYMBOLS = [
     "vrt_tree_from_blob_dev", "vrt_camera_init", "vrt_gen_rays", "vrt_trace_rays",
     "vrt_trace_rays_dev", "vrt_trace_camera", "vrt_trace_camera_dev", "vrt_trace_camera16_dev",
     "vrt_render_camera", "vrt_render_camera_dev", "vrt_band_rows", "vrt_render_bands_dev",
-    "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_tree_sync",
+    "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_frame_bands_peer_dev",
+    "vrt_dev_alloc", "vrt_dev_free", "vrt_ipc_export", "vrt_ipc_open", "vrt_ipc_close", "vrt_tree_sync",
     "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_tribox_batch",
     "vrt_tri_overlap_aabb_batch", "vrt_raytri_batch", "vrt_aabb_isect_batch",
 ]
@@ -117,6 +118,12 @@ def load(build_if_missing: bool = True):
     L.vrt_trace_bands16_dev.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_bands), vp]
     L.vrt_count_camera.argtypes = [vp, C.POINTER(vrt_camera), i32, i32, i32, i32, vp]
     L.vrt_frame_bands_dev.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), C.POINTER(vrt_bands), vp, vp]
+    L.vrt_frame_bands_peer_dev.argtypes = L.vrt_frame_bands_dev.argtypes
+    L.vrt_dev_alloc.argtypes = [u64, C.POINTER(vp)]
+    L.vrt_dev_free.argtypes = [vp]
+    L.vrt_ipc_export.argtypes = [vp, vp]
+    L.vrt_ipc_open.argtypes = [vp, C.POINTER(vp)]
+    L.vrt_ipc_close.argtypes = [vp]
     L.vrt_tree_sync.argtypes = [vp]
     L.vrt_mean_kernel_ms.restype = C.c_double
     L.vrt_mean_kernel_ms.argtypes = [vp, i32]
@@ -312,12 +319,14 @@ class Octree:
         _check(load().vrt_render_bands_dev(self._h, C.byref(cam.c), C.byref(sh), C.byref(b), C.c_void_p(d_film_ptr)))
 
     def frame_bands_dev(self, cam: Camera, d_hits_ptr, d_film_ptr, band_h, band_first, band_stride, light=None,
-                        kd=0.8):
-        """One frame step of rank `band_first` of `band_stride`: hit16 records + film bands (async)."""
+                        kd=0.8, full_frame=False):
+        """One frame step of rank `band_first` of `band_stride`: hit16 records + film (async).
+        full_frame=True: d_film_ptr is the whole [ny][nx][3] frame (possibly peer-mapped from
+        rank 0) and pixels are stored at their final place."""
         sh = vrt_shade((C.c_float * 3)(*(default_light() if light is None else light)), float(kd))
         b = vrt_bands(int(band_h), int(band_first), int(band_stride))
-        _check(load().vrt_frame_bands_dev(self._h, C.byref(cam.c), C.byref(sh), C.byref(b), C.c_void_p(d_hits_ptr),
-                                          C.c_void_p(d_film_ptr)))
+        fn = load().vrt_frame_bands_peer_dev if full_frame else load().vrt_frame_bands_dev
+        _check(fn(self._h, C.byref(cam.c), C.byref(sh), C.byref(b), C.c_void_p(d_hits_ptr), C.c_void_p(d_film_ptr)))
 
     def sync(self):
         _check(load().vrt_tree_sync(self._h))
@@ -341,6 +350,33 @@ class Octree:
         sh = vrt_shade((C.c_float * 3)(*(default_light() if light is None else light)), float(kd))
         _check(load().vrt_render_camera_dev(self._h, C.byref(cam.c), C.byref(sh), x0, y0, x1, y1,
                                             C.c_void_p(d_film_ptr)))
+
+
+def dev_alloc(nbytes: int) -> int:
+    p = C.c_void_p()
+    _check(load().vrt_dev_alloc(int(nbytes), C.byref(p)))
+    return p.value
+
+
+def dev_free(ptr: int):
+    _check(load().vrt_dev_free(C.c_void_p(ptr)))
+
+
+def ipc_export(ptr: int) -> bytes:
+    h = (C.c_uint8 * 64)()
+    _check(load().vrt_ipc_export(C.c_void_p(ptr), h))
+    return bytes(h)
+
+
+def ipc_open(handle: bytes) -> int:
+    h = (C.c_uint8 * 64).from_buffer_copy(handle)
+    p = C.c_void_p()
+    _check(load().vrt_ipc_open(h, C.byref(p)))
+    return p.value
+
+
+def ipc_close(ptr: int):
+    _check(load().vrt_ipc_close(C.c_void_p(ptr)))
 
 
 def band_rows(cam: Camera, band_h, band_first, band_stride) -> int:

@@ -845,8 +845,8 @@ int vrt_tree_sync(const vrt_tree* t)
         return VRT_OK;
 }
 
-int vrt_frame_bands_dev(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, const vrt_bands* b,
-                        vrt_hit16* d_hits, float* d_film_rgb)
+static int frame_common(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, const vrt_bands* b,
+                        vrt_hit16* d_hits, float* d_film_rgb, int film_full)
 {
         int rc = check_tree(t);
         if (rc)
@@ -865,7 +865,70 @@ int vrt_frame_bands_dev(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         }
         const int y0 = b->band_first * b->band_h;
         return launch_trace_camera(t, cam, sh, 0, y0, cam->nx, y0 + rows, d_hits, OUT_HIT16_FILM, b->band_h,
-                                   b->band_stride * b->band_h, d_film_rgb);
+                                   b->band_stride * b->band_h, d_film_rgb, film_full);
+}
+
+int vrt_frame_bands_dev(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, const vrt_bands* b,
+                        vrt_hit16* d_hits, float* d_film_rgb)
+{
+        return frame_common(t, cam, sh, b, d_hits, d_film_rgb, 0);
+}
+
+int vrt_frame_bands_peer_dev(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, const vrt_bands* b,
+                             vrt_hit16* d_hits, float* d_frame_rgb)
+{
+        return frame_common(t, cam, sh, b, d_hits, d_frame_rgb, 1);
+}
+
+int vrt_dev_alloc(uint64_t bytes, void** d_ptr)
+{
+        if (!d_ptr || !bytes) {
+                set_error("vrt_dev_alloc: bad argument");
+                return VRT_ERR_ARG;
+        }
+        if (cudaMalloc(d_ptr, bytes) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("cudaMalloc(%llu) failed", (unsigned long long)bytes);
+                return VRT_ERR_NOMEM;
+        }
+        return VRT_OK;
+}
+
+int vrt_dev_free(void* d_ptr)
+{
+        VRT_CUDA(cudaFree(d_ptr));
+        return VRT_OK;
+}
+
+int vrt_ipc_export(const void* d_ptr, uint8_t handle[64])
+{
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+        if (!d_ptr || !handle) {
+                set_error("vrt_ipc_export: null argument");
+                return VRT_ERR_ARG;
+        }
+        cudaIpcMemHandle_t h;
+        VRT_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+        memcpy(handle, &h, 64);
+        return VRT_OK;
+}
+
+int vrt_ipc_open(const uint8_t handle[64], void** d_ptr)
+{
+        if (!d_ptr || !handle) {
+                set_error("vrt_ipc_open: null argument");
+                return VRT_ERR_ARG;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handle, 64);
+        VRT_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        return VRT_OK;
+}
+
+int vrt_ipc_close(void* d_ptr)
+{
+        VRT_CUDA(cudaIpcCloseMemHandle(d_ptr));
+        return VRT_OK;
 }
 
 // ---- predicates ---------------------------------------------------------------

@@ -141,7 +141,7 @@ int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_
 // y0_film + (r / band_h) * band_pitch + r % band_h (y0 then carries y0_film, y1 = y0 + local rows).
 int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, int x0,
                         int y0, int x1, int y1, void* d_out, OutMode mode, int band_h = 0,
-                        int band_pitch = 0, void* d_out2 = nullptr);
+                        int band_pitch = 0, void* d_out2 = nullptr, int film_full = 0);
 // mean device time (ms) of the last n trace launches (waits for them)
 int trace_ms_mean(const vrt_tree* t, int last_n, double* ms);
 }  // namespace vrt

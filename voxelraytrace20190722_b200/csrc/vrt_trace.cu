@@ -47,6 +47,7 @@ struct TraceParams {
         unsigned long long num_rays;
         void* out;
         void* out2;  // film when MODE == OUT_HIT16_FILM
+        int film_full;  // out2 is the full [ny][nx][3] frame (peer-mapped): address by film row
         uint32_t* queue;  // tile counter
         uint32_t num_tiles;
         float light[3];
@@ -632,6 +633,9 @@ k_trace_camera(TraceParams p)
                         }
                         if (active && s == 0) {
                                 float* f = static_cast<float*>(MODE == OUT_HIT16_FILM ? p.out2 : p.out) + pix * 3ull;
+                                if (MODE == OUT_HIT16_FILM && p.film_full)
+                                        f = static_cast<float*>(p.out2) +
+                                            ((unsigned long long)py * p.cam.nx + px) * 3ull;
                                 f[0] = acc[0];
                                 f[1] = acc[1];
                                 f[2] = acc[2];
@@ -669,7 +673,9 @@ static void fill_common(const vrt_tree* t, TraceParams& p)
         p.tree = t->dev;
         for (int k = 0; k < 6; ++k)
                 p.root[k] = t->hdr.root_aabb[k];
-        p.queue = t->d_counter + 16;
+        // one work-queue counter per in-flight launch (launches on alternating streams may
+        // overlap): 8 slots
+        p.queue = t->d_counter + 16 + 2 * (t->n_trace_launches % 8);
 }
 
 int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_hit* d_out)
@@ -702,7 +708,7 @@ int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_
 }
 
 int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, int x0, int y0,
-                        int x1, int y1, void* d_out, OutMode mode, int band_h, int band_pitch, void* d_out2)
+                        int x1, int y1, void* d_out, OutMode mode, int band_h, int band_pitch, void* d_out2, int film_full)
 {
         if (x1 <= x0 || y1 <= y0)
                 return VRT_OK;
@@ -724,6 +730,7 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         p.band_pitch = band_h > 0 ? band_pitch : 0;
         p.out = d_out;
         p.out2 = d_out2;
+        p.film_full = film_full;
         if (sh) {
                 p.light[0] = sh->light_dir[0];
                 p.light[1] = sh->light_dir[1];

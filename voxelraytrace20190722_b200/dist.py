@@ -82,6 +82,55 @@ def max_band_rows(ny: int, world: int, band_h: int = BAND_H) -> int:
     return ((num_bands + world - 1) // world) * band_h
 
 
+class PeerFrame:
+    """Framebuffer assembly FUSED into the ray kernel: rank `dst` owns `nbuf` full
+    [ny, nx, 3] float frames in plain device memory, shares them with the other ranks of
+    the node through CUDA IPC, and every rank's ray kernel stores its finished pixels
+    straight to their final place over NVLink (vrt_frame_bands_peer_dev).  No collective,
+    no staging buffer, no re-order pass; frame k lives in buffer k % nbuf and is complete
+    once every rank's stream has passed launch k (bench.py: barrier at the end of the
+    timed region; the e2e loop: stream sync + barrier per frame)."""
+
+    def __init__(self, ny, nx, device, nbuf: int = 2, dst: int = 0):
+        import torch.distributed as dist
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.dst, self.ny, self.nx, self.nbuf, self.device = dst, ny, nx, nbuf, device
+        self.nbytes = ny * nx * 3 * 4
+        handles = torch.zeros((nbuf, 64), dtype=torch.uint8, device=device)
+        self.owned, self.ptrs = [], []
+        if self.rank == dst:
+            for _ in range(nbuf):
+                p = capi.dev_alloc(self.nbytes)
+                self.owned.append(p)
+                self.ptrs.append(p)
+            if self.world > 1:
+                handles.copy_(torch.tensor([list(capi.ipc_export(p)) for p in self.owned], dtype=torch.uint8))
+        if self.world > 1:
+            dist.broadcast(handles, dst)
+            if self.rank != dst:
+                hb = handles.cpu().numpy()
+                self.ptrs = [capi.ipc_open(bytes(hb[i].tobytes())) for i in range(nbuf)]
+
+    def ptr(self, k: int) -> int:
+        return self.ptrs[k % self.nbuf]
+
+    def frame(self, k: int):
+        """[ny, nx, 3] float32 view of frame buffer k (rank dst only)."""
+        if self.rank != self.dst:
+            return None
+        return view_device_bytes(self.ptrs[k % self.nbuf], self.nbytes, self.device).view(torch.float32).view(
+            self.ny, self.nx, 3)
+
+    def close(self):
+        if self.rank != self.dst:
+            for p in self.ptrs:
+                capi.ipc_close(p)
+        for p in self.owned:
+            capi.dev_free(p)
+        self.ptrs, self.owned = [], []
+
+
 class FrameGather:
     """Framebuffer assembly on rank `dst` (the ncclGather of SURVEY.md 8e), double-buffered
     and asynchronous so that the gather of frame k overlaps the ray kernel of frame k+1.
