@@ -236,6 +236,9 @@ int vrt_dev_free(void* d_ptr);
 int vrt_ipc_export(const void* d_ptr, uint8_t handle[64]);
 int vrt_ipc_open(const uint8_t handle[64], void** d_ptr);
 int vrt_ipc_close(void* d_ptr);
+/* Test hook: how many node expansions of this process took the general (>4 candidate
+ * children) ordering path of the ray kernel. */
+uint64_t vrt_debug_general_order_calls(void);
 /* _dev launches are asynchronous with respect to the host: they return once the work is
  * enqueued on the tree's stream.  vrt_tree_sync waits for it. */
 int vrt_tree_sync(const vrt_tree* tree);

@@ -357,3 +357,41 @@ def test_frame_step_hits_and_film_match_separate_modes(case, gpu):
         assert np.array_equal(h[:, 3].astype(np.uint32), hits_ref["hit"])
         assert np.array_equal(h[:, 1].view(np.uint32), hits_ref["tri"])
         assert np.array_equal(h[:, 2].view(np.float32).view(np.uint32), hits_ref["t"].view(np.uint32))
+
+
+def test_rays_through_cell_edges_and_corners(gpu, port):
+    """Rays that run exactly inside shared faces / through shared edges and corners pass
+    the slab test of more than four children of a node (closed-interval test): the ray
+    kernel's >4-candidate ordering path must agree with the oracle too."""
+    tri, nrm = scenes.soup(60000, e=0.04)  # dense: nearly every cell is occupied
+    depth = 5
+    orc = port.build(tri, nrm, depth)
+    tree = gpu.Octree.build(tri, nrm, depth)
+    root = orc.root_aabb()
+    ctr = ((root[:3] + root[3:]) * np.float32(0.5)).astype(np.float32)
+    dirs = []
+    for a in (-1, 0, 1):
+        for b in (-1, 0, 1):
+            for c in (-1, 0, 1):
+                if (a, b, c) != (0, 0, 0):
+                    dirs.append((a, b, c))
+    dirs = np.array(dirs, np.float64)
+    rays = []
+    for dv in dirs:
+        dn = (dv / np.linalg.norm(dv)).astype(np.float32)
+        for start in (ctr, ctr - np.float32(3.0) * dn, root[:3], root[3:]):
+            rays.append(np.concatenate([start, dn, [0.0, np.finfo(np.float32).max]]))
+    # also start on the mid-planes of deeper levels
+    size = (root[3:] - root[:3]).astype(np.float32)
+    for k in (0.25, 0.75, 0.375):
+        p = (root[:3] + size * np.float32(k)).astype(np.float32)
+        for dv in dirs[:13]:
+            dn = (dv / np.linalg.norm(dv)).astype(np.float32)
+            rays.append(np.concatenate([p, dn, [0.0, np.finfo(np.float32).max]]))
+    rays = np.array(rays, np.float32)
+    before = gpu.debug_general_order_calls()
+    got = tree.trace_rays(rays)
+    exp = orc.trace(rays)
+    assert compare_hits(got, exp, "edge/corner rays") == 0
+    assert gpu.debug_general_order_calls() > before, "the >4-candidate path was not exercised"
+    tree.close()

@@ -63,7 +63,7 @@ SYMBOLS = [
     "vrt_render_camera", "vrt_render_camera_dev", "vrt_band_rows", "vrt_render_bands_dev",
     "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_frame_bands_peer_dev",
     "vrt_dev_alloc", "vrt_dev_free", "vrt_ipc_export", "vrt_ipc_open", "vrt_ipc_close", "vrt_tree_sync",
-    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_tribox_batch",
+    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_tribox_batch",
     "vrt_tri_overlap_aabb_batch", "vrt_raytri_batch", "vrt_aabb_isect_batch",
 ]
 
@@ -124,6 +124,7 @@ def load(build_if_missing: bool = True):
     L.vrt_ipc_export.argtypes = [vp, vp]
     L.vrt_ipc_open.argtypes = [vp, C.POINTER(vp)]
     L.vrt_ipc_close.argtypes = [vp]
+    L.vrt_debug_general_order_calls.restype = u64
     L.vrt_tree_sync.argtypes = [vp]
     L.vrt_mean_kernel_ms.restype = C.c_double
     L.vrt_mean_kernel_ms.argtypes = [vp, i32]
@@ -350,6 +351,10 @@ class Octree:
         sh = vrt_shade((C.c_float * 3)(*(default_light() if light is None else light)), float(kd))
         _check(load().vrt_render_camera_dev(self._h, C.byref(cam.c), C.byref(sh), x0, y0, x1, y1,
                                             C.c_void_p(d_film_ptr)))
+
+
+def debug_general_order_calls() -> int:
+    return int(load().vrt_debug_general_order_calls())
 
 
 def dev_alloc(nbytes: int) -> int:

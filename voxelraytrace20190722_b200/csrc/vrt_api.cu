@@ -835,6 +835,13 @@ double vrt_mean_kernel_ms(const vrt_tree* t, int last_n)
         return ms;
 }
 
+uint64_t vrt_debug_general_order_calls(void)
+{
+        unsigned long long n = 0;
+        general_order_calls(&n);
+        return n;
+}
+
 int vrt_tree_sync(const vrt_tree* t)
 {
         if (!t) {

@@ -144,4 +144,5 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
                         int band_pitch = 0, void* d_out2 = nullptr, int film_full = 0);
 // mean device time (ms) of the last n trace launches (waits for them)
 int trace_ms_mean(const vrt_tree* t, int last_n, double* ms);
+int general_order_calls(unsigned long long* out);
 }  // namespace vrt

@@ -280,11 +280,12 @@ __device__ __noinline__ void trace_one_exact(const TreeDev& tr, const float* roo
 // same roundings as the exact path; only the instruction selection differs:
 //   * hi.min of a child pair is bitwise lo.max (both are min+size in the recurrence), so
 //     3 planes per axis instead of 4; FMNMX3 per child; branch-free slab verdicts;
-//   * invalid children get key=+inf and the stable order is kept as eight packed 4-bit
-//     ranks (start 0x76543210 = index order; every pair (i<j) with key[j]<key[i] moves
-//     one rank from j to i) -- 28 compares + 28 predicated adds, no list is built;
-//   * the next child is found by a zero-nibble search on the packed ranks; only levels
-//     that still have unvisited children are pushed on the (shared-memory) return stack.
+//   * children that pass the slab test (22 % on average) are inserted into a 4-slot
+//     list kept sorted by key (stable), packed into 3-bit ids; the rare 5th candidate
+//     falls back to a general packed-rank ordering of all 8 (order_children_general);
+//   * packed FADD2/FMUL2 for the per-axis plane and centre arithmetic;
+//   * only levels that still have unvisited children are pushed on the (shared-memory)
+//     return stack.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ bool ray_is_tame(const TreeDev& tr, const float o[3], const float d[3])
 {
@@ -310,10 +311,76 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
         return r;
 }
 
+// Packed FP32x2 arithmetic (sm_100+ FADD2/FMUL2): two independently rounded IEEE
+// operations per issued instruction.  ptxas contracts a packed mul feeding a packed
+// add/sub into FFMA2 even with explicit .rn and --fmad=false (observed with CUDA 12.9),
+// so these helpers are ONLY used where the consumer of a product is not an add/sub:
+// sub->mul and add->mul chains.  The SASS of the expansion block is checked for FFMA2.
+__device__ __forceinline__ float2 sub2s(float ax, float ay, float b)
+{
+        float2 r;
+        asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%4}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(ax), "f"(ay), "f"(b));
+        return r;
+}
+__device__ __forceinline__ float2 add2(float ax, float ay, float bx, float by)
+{
+        float2 r;
+        asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(ax), "f"(ay), "f"(bx), "f"(by));
+        return r;
+}
+__device__ __forceinline__ float2 mul2s(float2 a, float b)
+{
+        float2 r;
+        asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%4}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+            : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b));
+        return r;
+}
+
+// General ordering of a node's children (any number of valid children): the packed-rank
+// method.  Only reached when more than four children of one node pass the slab test
+// (a ray through shared faces/edges); kept out of line.  Returns the visiting order as a
+// list of 3-bit child ids (lowest bits first) and the count.
+__device__ unsigned long long g_general_calls = 0;  // how often the >4-candidate path ran (tests)
+
+__device__ __noinline__ uint32_t order_children_general(const float* smin6, const float* smax6, const float* kt6,
+                                                        uint32_t mask, float tmin, float tmax, uint32_t* cnt_out)
+{
+        const float inf = __int_as_float(0x7f800000);
+        atomicAdd(&g_general_calls, 1ull);
+        float key[8];
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+                const int hx = c >> 2, hy = (c >> 1) & 1, hz = c & 1;
+                const float t0 = fmaxf(fmaxf(smin6[hx], smin6[2 + hy]), smin6[4 + hz]);
+                const float t1 = fminf(fminf(smax6[hx], smax6[2 + hy]), smax6[4 + hz]);
+                key[c] = inf;
+                if (((mask >> c) & 1u) && slab_accept(t0, t1, tmin, tmax)) {
+                        key[c] = fadd(fadd(kt6[hx], kt6[2 + hy]), kt6[4 + hz]);
+                        cnt += 1u;
+                }
+        }
+        uint32_t ranks = 0x76543210u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                for (int j = i + 1; j < 8; ++j)
+                        ranks += (key[j] < key[i]) ? ((1u << (4 * i)) - (1u << (4 * j))) : 0u;
+        }
+        uint32_t list = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+                list |= (uint32_t)c << (3u * ((ranks >> (4 * c)) & 15u));  // invalid ones land behind the valid ones
+        *cnt_out = cnt;
+        return list;
+}
+
 template <bool COUNT>
 __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float root[6], const float o[3],
                                                const float d[3], float tmin, float tmax, uint32_t* s_first,
-                                               uint32_t* s_meta, uint32_t* s_rank, HitState& hs, WorkCount& wc)
+                                               uint32_t* s_meta, uint32_t* s_list, HitState& hs, WorkCount& wc)
 {
         float dinv[3];
 #pragma unroll
@@ -338,7 +405,7 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
         const float inf = __int_as_float(0x7f800000);
         int level = 0, sp = 0;
         uint32_t x = 0, y = 0, z = 0, node = 0;
-        uint32_t first, mask, ranks, k, cnt;
+        uint32_t first, mask, list, cnt;
         for (;;) {
                 // ---- expand `node` (level; x,y,z) -------------------------------------------
                 {
@@ -353,69 +420,76 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                         float smin[3][2], smax[3][2], kt[3][2];
 #pragma unroll
                         for (int a = 0; a < 3; ++a) {
-                                const float p0 = bb[a].x, p1 = bb[a].y, p2 = bb[a].w;
-                                const float tA = fmul(fsub(p0, o[a]), dinv[a]);
-                                const float tB = fmul(fsub(p1, o[a]), dinv[a]);
-                                const float tC = fmul(fsub(p2, o[a]), dinv[a]);
-                                smin[a][0] = fminf(tA, tB);
-                                smax[a][0] = fmaxf(tA, tB);
-                                smin[a][1] = fminf(tB, tC);
-                                smax[a][1] = fmaxf(tB, tC);
-                                kt[a][0] = fmul(d[a], fsub(fmul(fadd(p0, p1), .5f), o[a]));
-                                kt[a][1] = fmul(d[a], fsub(fmul(fadd(p1, p2), .5f), o[a]));
+                                // b = (p0, p1, p1, p2): lo child [p0,p1], hi child [p1,p2]
+                                const float2 t01 = mul2s(sub2s(bb[a].x, bb[a].y, o[a]), dinv[a]);  // (p-o)*dinv
+                                const float2 t12 = mul2s(sub2s(bb[a].z, bb[a].w, o[a]), dinv[a]);
+                                smin[a][0] = fminf(t01.x, t01.y);
+                                smax[a][0] = fmaxf(t01.x, t01.y);
+                                smin[a][1] = fminf(t12.x, t12.y);
+                                smax[a][1] = fmaxf(t12.x, t12.y);
+                                // travorder key terms d*((min+max)*.5f - o); the subtraction stays scalar
+                                // so that it cannot be contracted with the *.5f
+                                const float2 h = mul2s(add2(bb[a].x, bb[a].y, bb[a].z, bb[a].w), .5f);
+                                kt[a][0] = fmul(d[a], fsub(h.x, o[a]));
+                                kt[a][1] = fmul(d[a], fsub(h.y, o[a]));
                         }
                         float kxy[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
                                 kxy[q] = fadd(kt[0][q >> 1], kt[1][q & 1]);
-                        float key[8];
+                        // candidates are inserted into a 4-slot list sorted by key; a later child
+                        // (higher index) goes behind equal keys -- the stable order of the
+                        // reference's insertion sort.  A line meets at most 4 of the 8 octants,
+                        // so a 5th candidate is rare and handled by the general method.
+                        float sk0 = inf, sk1 = inf, sk2 = inf, sk3 = inf;
+                        uint32_t si0 = 0, si1 = 0, si2 = 0, si3 = 0;
                         cnt = 0;
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                                 const float t0 = fmax3(smin[0][c >> 2], smin[1][(c >> 1) & 1], smin[2][c & 1]);
                                 const float t1 = fmin3(smax[0][c >> 2], smax[1][(c >> 1) & 1], smax[2][c & 1]);
-                                // short-circuit on purpose: ~78 % of the children are empty or have
-                                // t0 > t1, and skipping their window test + key add is cheaper than
-                                // evaluating everything branch-free (measured: 12.2 vs 14.2 ms/frame)
-                                key[c] = inf;
                                 if (((mask >> c) & 1u) && slab_accept(t0, t1, tmin, tmax)) {
-                                        key[c] = fadd(kxy[c >> 1], kt[2][c & 1]);
+                                        float ck = fadd(kxy[c >> 1], kt[2][c & 1]);
+                                        uint32_t ci = c;
                                         cnt += 1u;
+                                        bool p;
+                                        float tk;
+                                        uint32_t tiq;
+                                        p = ck < sk0; tk = sk0; tiq = si0; sk0 = p ? ck : sk0; si0 = p ? ci : si0; ck = p ? tk : ck; ci = p ? tiq : ci;
+                                        p = ck < sk1; tk = sk1; tiq = si1; sk1 = p ? ck : sk1; si1 = p ? ci : si1; ck = p ? tk : ck; ci = p ? tiq : ci;
+                                        p = ck < sk2; tk = sk2; tiq = si2; sk2 = p ? ck : sk2; si2 = p ? ci : si2; ck = p ? tk : ck; ci = p ? tiq : ci;
+                                        p = ck < sk3; sk3 = p ? ck : sk3; si3 = p ? ci : si3;
                                 }
                         }
-                        ranks = 0x76543210u;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-#pragma unroll
-                                for (int j = i + 1; j < 8; ++j)
-                                        ranks += (key[j] < key[i]) ? ((1u << (4 * i)) - (1u << (4 * j))) : 0u;
+                        list = si0 | (si1 << 3) | (si2 << 6) | (si3 << 9);
+                        if (cnt > 4u) {
+                                const float a_min[6] = { smin[0][0], smin[0][1], smin[1][0], smin[1][1], smin[2][0], smin[2][1] };
+                                const float a_max[6] = { smax[0][0], smax[0][1], smax[1][0], smax[1][1], smax[2][0], smax[2][1] };
+                                const float a_kt[6] = { kt[0][0], kt[0][1], kt[1][0], kt[1][1], kt[2][0], kt[2][1] };
+                                list = order_children_general(a_min, a_max, a_kt, mask, tmin, tmax, &cnt);
                         }
-                        k = 0;
                 }
                 // ---- visit children in order until we descend, hit, or run out -----------------
                 for (;;) {
-                        if (k == cnt) {
+                        if (cnt == 0) {
                                 if (sp == 0)
                                         return;  // miss
                                 --sp;
                                 first = s_first[sp * stride];
                                 const uint32_t m = s_meta[sp * stride];
-                                ranks = s_rank[sp * stride];
+                                list = s_list[sp * stride];
                                 mask = m & 0xffu;
-                                k = (m >> 8) & 0xfu;
-                                cnt = (m >> 12) & 0xfu;
-                                const int nl = (int)(m >> 16);
+                                cnt = (m >> 8) & 0xfu;
+                                const int nl = (int)(m >> 12);
                                 x >>= (level - nl);
                                 y >>= (level - nl);
                                 z >>= (level - nl);
                                 level = nl;
                                 continue;
                         }
-                        // child whose rank nibble equals k
-                        const uint32_t tq = ranks ^ (k * 0x11111111u);
-                        const uint32_t zq = (tq - 0x11111111u) & ~tq & 0x88888888u;
-                        const uint32_t c = (uint32_t)(__ffs((int)zq) - 1) >> 2;
-                        ++k;
+                        const uint32_t c = list & 7u;
+                        list >>= 3;
+                        --cnt;
                         const uint32_t child = first + __popc(mask & ((1u << c) - 1u));
                         const uint32_t cx = 2u * x + ((c >> 2) & 1u);
                         const uint32_t cy = 2u * y + ((c >> 1) & 1u);
@@ -431,10 +505,10 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 }
                                 continue;
                         }
-                        if (k < cnt) {  // remember this level only if it has children left
+                        if (cnt != 0u) {  // remember this level only if it has children left
                                 s_first[sp * stride] = first;
-                                s_meta[sp * stride] = mask | (k << 8) | (cnt << 12) | ((uint32_t)level << 16);
-                                s_rank[sp * stride] = ranks;
+                                s_meta[sp * stride] = mask | (cnt << 8) | ((uint32_t)level << 12);
+                                s_list[sp * stride] = list;
                                 ++sp;
                         }
                         ++level;
@@ -764,6 +838,13 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         count_launch();
         VRT_CUDA(cudaEventRecord(t->ring1[slot], t->stream));
         t->n_trace_launches++;
+        return VRT_OK;
+}
+
+int general_order_calls(unsigned long long* out)
+{
+        VRT_CUDA(cudaDeviceSynchronize());
+        VRT_CUDA(cudaMemcpyFromSymbol(out, g_general_calls, sizeof(unsigned long long)));
         return VRT_OK;
 }
 
