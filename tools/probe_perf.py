@@ -17,11 +17,13 @@ for D in depths:
         cam = capi.Camera(CAM_MAIN[0], CAM_MAIN[1:4], CAM_MAIN[4:7], CAM_MAIN[7:10], nx, ny, spp)
         out = torch.empty(nx * ny * spp * 16, dtype=torch.uint8, device='cuda')
         film = torch.empty(nx * ny * 3, dtype=torch.float32, device='cuda')
-        for mode in ("hit16", "film"):
+        frame = torch.empty(nx * ny * 3, dtype=torch.float32, device='cuda')
+        for mode in ("hit16", "film", "frame"):
             ts = []
             for i in range(6):
                 if mode == "hit16": tree.trace_camera_dev(cam, out.data_ptr(), compact=True)
-                else: tree.render_dev(cam, film.data_ptr())
+                elif mode == "film": tree.render_dev(cam, film.data_ptr())
+                else: tree.frame_bands_dev(cam, out.data_ptr(), frame.data_ptr(), 8, 0, 1, full_frame=True)
                 ts.append(tree.last_kernel_ms)
             R = nx * ny * spp
             print(f"  {nx}x{ny}x{spp} {mode}: ms {min(ts):.3f} (max {max(ts):.3f}) -> {R/min(ts)/1e3:.1f} Mrays/s", flush=True)

@@ -466,7 +466,9 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 const float a_min[6] = { smin[0][0], smin[0][1], smin[1][0], smin[1][1], smin[2][0], smin[2][1] };
                                 const float a_max[6] = { smax[0][0], smax[0][1], smax[1][0], smax[1][1], smax[2][0], smax[2][1] };
                                 const float a_kt[6] = { kt[0][0], kt[0][1], kt[1][0], kt[1][1], kt[2][0], kt[2][1] };
-                                list = order_children_general(a_min, a_max, a_kt, mask, tmin, tmax, &cnt);
+                                uint32_t cnt_general = 0;  // (keeps `cnt` itself in a register)
+                                list = order_children_general(a_min, a_max, a_kt, mask, tmin, tmax, &cnt_general);
+                                cnt = cnt_general;
                         }
                 }
                 // ---- visit children in order until we descend, hit, or run out -----------------
@@ -609,7 +611,10 @@ k_trace_rays(TraceParams p)
 // 64 registers (8 CTAs/SM) is fastest for the compact outputs; the modes that also
 // evaluate the ISect/normal/shading tail spill at 64 and run best at 80 (6 CTAs/SM).
 template <int MODE>
-__global__ void __launch_bounds__(kTraceThreads, (MODE == OUT_HIT16 || MODE == OUT_COUNT) ? 8 : 6)  // see launch-bounds note
+#ifndef VRT_FILM_MIN_BLOCKS
+#define VRT_FILM_MIN_BLOCKS 7
+#endif
+__global__ void __launch_bounds__(kTraceThreads, (MODE == OUT_HIT16 || MODE == OUT_COUNT) ? 8 : VRT_FILM_MIN_BLOCKS)
 k_trace_camera(TraceParams p)
 {
         extern __shared__ uint32_t s_stack[];
