@@ -48,7 +48,12 @@ WORKLOADS = {
     "atrium1024_4k_spp1": ("atrium", {}, 11, [90 * RAD, 1, 1.3, -.2, 0, .4, 0, 0, 1, 0], 3840, 2160, 1),
     "sphere256_1080p_spp1": ("sphere", {}, 9, [60 * RAD, 0, 1, 3, 0, 0, 0, 0, 1, 0], 1920, 1080, 1),
     "atrium32_1k_spp4": ("atrium", {}, 6, [90 * RAD, 1, 1.3, -.2, 0, .4, 0, 0, 1, 0], 1024, 1024, 4),
+    # BASELINE config 5: 2048^3, 8K, 64-frame camera orbit, primary + one shadow ray per hit
+    "atrium2048_8k_orbit_shadow": ("atrium", {}, 12, [90 * RAD, 1, 1.3, -.2, 0, .4, 0, 0, 1, 0], 7680, 4320, 4),
 }
+# per-workload extras: camera orbit (eye(k) = c + (r cos 2 pi k/n, h, r sin 2 pi k/n) looking at c) and shadow rays
+EXTRAS = {"atrium2048_8k_orbit_shadow": {"orbit": 64, "orbit_c": (0.0, 0.4, 0.0), "orbit_r": 0.9, "orbit_h": 0.6,
+                                          "shadow_eps": 1e-3}}
 DEFAULT_WORKLOAD = "atrium1024_4k_spp4"
 CPU_SAMPLE = (640, 360)  # film used for the bounded CPU sample (same scene, camera, spp)
 
@@ -167,7 +172,10 @@ def workload_config(wl, ntris, gpus):
             "scene": f"{scene} ({ntris} tris" + ("; procedural Sponza stand-in, sponza.obj absent from the reference checkout)"
                                                   if scene == "atrium" else ")"),
             "max_depth": depth, "leaf_grid": f"{2 ** (depth - 1)}^3", "film": f"{nx}x{ny}", "spp": spp,
-            "rays_per_step": nx * ny * spp, "camera": "main.cc:112-115" if scene == "atrium" else "SURVEY 8d config 2",
+            "rays_per_step": nx * ny * spp,
+            "camera": ("64-frame orbit (SURVEY 8d config 5), one frame per step; value counts primary rays, every hit "
+                       "also traces one shadow ray in the same launch" if wl in EXTRAS else
+                       "main.cc:112-115" if scene == "atrium" else "SURVEY 8d config 2"),
             "sharding": f"8-row bands round-robin over {gpus} GPU(s), replicated octree (one NCCL broadcast), frame assembled on rank 0",
             "l2": "inputs larger than L2: octree blob > 126 MB and every step writes 16 B/ray of hit records + 12 B/pixel of film"}
 
@@ -211,7 +219,18 @@ def run_ours(args):
     if world > 1:
         tree = vdist.replicate_octree(tree, dev)
     info = tree.info()
-    cam = capi.Camera(cam10[0], cam10[1:4], cam10[4:7], cam10[7:10], nx, ny, spp)
+    extra = EXTRAS.get(args.workload, {})
+    shadow_eps = extra.get("shadow_eps")
+    if extra.get("orbit"):
+        n_orb, c, r, h = extra["orbit"], np.asarray(extra["orbit_c"]), extra["orbit_r"], extra["orbit_h"]
+        cams = []
+        for k in range(n_orb):
+            a = 2 * np.pi * k / n_orb
+            eye = c + np.array([r * np.cos(a), h, r * np.sin(a)])
+            cams.append(capi.Camera(cam10[0], eye.astype(np.float32), c.astype(np.float32), (0, 1, 0), nx, ny, spp))
+    else:
+        cams = [capi.Camera(cam10[0], cam10[1:4], cam10[4:7], cam10[7:10], nx, ny, spp)]
+    cam = cams[0]
     stream = torch.cuda.current_stream(dev)
     tree.set_stream(stream.cuda_stream)
 
@@ -238,12 +257,14 @@ def run_ours(args):
             tree.set_stream(S[k].cuda_stream)
             if use_gather:
                 film = fg.buffer(k)
-                tree.frame_bands_dev(cam, hits[k].data_ptr(), film.data_ptr(), vdist.BAND_H, rank, world)
+                tree.frame_bands_dev(cams[i % len(cams)], hits[k].data_ptr(), film.data_ptr(), vdist.BAND_H, rank, world,
+                                     shadow_eps=shadow_eps)
                 if i > 0:
                     fg.assemble(k ^ 1)  # frame i-1 (its gather ran under this frame's kernel)
                 fg.gather_async(k)
             else:
-                tree.frame_bands_dev(cam, hits[k].data_ptr(), pf.ptr(k), vdist.BAND_H, rank, world, full_frame=True)
+                tree.frame_bands_dev(cams[i % len(cams)], hits[k].data_ptr(), pf.ptr(k), vdist.BAND_H, rank, world,
+                                     full_frame=True, shadow_eps=shadow_eps)
 
     def drain(i_last):
         if use_gather:
@@ -301,10 +322,10 @@ def run_ours(args):
         film_np = film_host.numpy()
         tree.set_stream(0)
         for _ in range(max(1, args.warmup // 2)):
-            tree.render(cam, out=film_np)
+            tree.render(cam, out=film_np, shadow_eps=shadow_eps)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            tree.render(cam, out=film_np)
+            tree.render(cam, out=film_np, shadow_eps=shadow_eps)
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
         d2h = film_np.nbytes
     else:
@@ -314,11 +335,12 @@ def run_ours(args):
 
         def e2e_step():
             if use_gather:
-                tree.render_bands_dev(cam, fg.buffer(0).data_ptr(), vdist.BAND_H, rank, world)
+                tree.render_bands_dev(cam, fg.buffer(0).data_ptr(), vdist.BAND_H, rank, world, shadow_eps=shadow_eps)
                 fg.gather_async(0)
                 full = fg.assemble(0)
             else:
-                tree.frame_bands_dev(cam, hits[0].data_ptr(), pf.ptr(0), vdist.BAND_H, rank, world, full_frame=True)
+                tree.frame_bands_dev(cam, hits[0].data_ptr(), pf.ptr(0), vdist.BAND_H, rank, world, full_frame=True,
+                                     shadow_eps=shadow_eps)
                 torch.cuda.synchronize(dev)
                 td.barrier()  # every rank's pixels have landed in rank 0's frame
                 full = pf.frame(0)
@@ -344,7 +366,7 @@ def run_ours(args):
     if rank == 0:
         tree.set_stream(0)
         ref_film = torch.empty((ny, nx, 3), dtype=torch.float32, device=dev)
-        tree.render_dev(cam, ref_film.data_ptr())
+        tree.render_dev(cam, ref_film.data_ptr(), shadow_eps=shadow_eps)
         tree.sync()
         got = fg.frame if use_gather else pf.frame(0)
         frame_check = bool(torch.equal(got.view(torch.int32), ref_film.view(torch.int32)))

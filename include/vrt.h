@@ -190,6 +190,9 @@ int vrt_trace_camera16_dev(const vrt_tree* tree, const vrt_camera* cam, int x0, 
 typedef struct vrt_shade {
         float light_dir[3]; /* normalised on the host, main.cc:72 */
         float kd;
+        float shadow_eps;   /* shadow ray origin = hit + shadow_eps * normal              */
+        int32_t shadow;     /* 1: one shadow ray per hit toward light_dir (config 5 of
+                               BASELINE.json; harness-defined, same ray_march semantics) */
 } vrt_shade;
 int vrt_render_camera(const vrt_tree* tree, const vrt_camera* cam, const vrt_shade* sh,
                       int x0, int y0, int x1, int y1, float* film_rgb);

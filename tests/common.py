@@ -47,7 +47,18 @@ def compare_hits(gpu_hits, orc, what="", allow_mismatch=0.0):
     return int(bad.sum())
 
 
-def harness_film(rays, orc_hits, light, kd, spp):
+def shadow_rays(orc_hits, light, eps):
+    """Harness shadow rays (config 5): origin = hit + eps*normal (float32 ops), direction = light."""
+    f32 = np.float32
+    o = (orc_hits.pos + (f32(eps) * orc_hits.nrm).astype(np.float32)).astype(np.float32)
+    r = np.zeros((len(o), 8), np.float32)
+    r[:, 0:3] = o
+    r[:, 3:6] = np.asarray(light, np.float32)
+    r[:, 7] = np.finfo(np.float32).max
+    return r
+
+
+def harness_film(rays, orc_hits, light, kd, spp, visibility=None):
     """The harness pixel of SURVEY.md 8(d) evaluated on ORACLE hits with numpy float32
     (sky: main.cc:18-20; samples added in order with weight 1/spp: main.cc:119-122)."""
     f32 = np.float32
@@ -62,6 +73,8 @@ def harness_film(rays, orc_hits, light, kd, spp):
     dot = (dot + n[:, 2] * L[2]).astype(np.float32)
     dot = np.where(dot > 1, f32(1), np.where(dot < 0, f32(0), dot)).astype(np.float32)
     c = (f32(kd) * dot).astype(np.float32)
+    if visibility is not None:
+        c = (c * visibility.astype(np.float32)).astype(np.float32)
     col = np.where(orc_hits.hit[:, None].astype(bool), c[:, None].repeat(3, 1), sky).astype(np.float32)
     w = f32(0.25) if spp == 4 else f32(1)
     col = (col * w).astype(np.float32).reshape(-1, spp, 3)

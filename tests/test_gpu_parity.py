@@ -395,3 +395,21 @@ def test_rays_through_cell_edges_and_corners(gpu, port):
     assert compare_hits(got, exp, "edge/corner rays") == 0
     assert gpu.debug_general_order_calls() > before, "the >4-candidate path was not exercised"
     tree.close()
+
+
+def test_shadow_rays_vs_oracle(case, gpu, port):
+    """Config 5's harness shading: primary hit + one shadow ray per hit (a second
+    ray_march query from hit + eps*normal toward the light), fused in the kernel."""
+    from tests.common import shadow_rays
+    cam10 = case["cam10"]
+    nx, ny, spp, eps = 96, 56, 4, 1e-3
+    cam = gpu.Camera(cam10[0], cam10[1:4], cam10[4:7], cam10[7:10], nx, ny, spp)
+    light = gpu.default_light()
+    film = case["tree"].render(cam, kd=0.8, shadow_eps=eps)
+    rays = port.gen_rays(cam10, 1.0, nx, ny, spp)
+    prim = case["orc"].trace(rays)
+    sh = case["orc"].trace(shadow_rays(prim, light, eps))
+    vis = np.where(prim.hit.astype(bool), 1 - sh.hit, 1)
+    exp = harness_film(rays, prim, light, 0.8, spp, visibility=vis).reshape(ny, nx, 3)
+    assert_bits_equal(film, exp, "film with shadow rays")
+    assert (vis[prim.hit.astype(bool)] == 0).sum() > 0, "no occluded hit in this view"

@@ -28,7 +28,7 @@ class vrt_camera(C.Structure):
 
 
 class vrt_shade(C.Structure):
-    _fields_ = [("light_dir", C.c_float * 3), ("kd", C.c_float)]
+    _fields_ = [("light_dir", C.c_float * 3), ("kd", C.c_float), ("shadow_eps", C.c_float), ("shadow", C.c_int32)]
 
 
 class vrt_bands(C.Structure):
@@ -154,6 +154,12 @@ def _ptr(a):
 def _f32(a, shape=None):
     a = np.ascontiguousarray(a, np.float32)
     return a if shape is None else a.reshape(shape)
+
+
+def _shade(light, kd, shadow_eps):
+    """vrt_shade: light direction (default main.cc:72), kd, optional shadow rays (eps > 0)."""
+    return vrt_shade((C.c_float * 3)(*(default_light() if light is None else light)), float(kd),
+                     float(shadow_eps or 0.0), 1 if shadow_eps else 0)
 
 
 def device_count() -> int:
@@ -304,27 +310,28 @@ class Octree:
         fn = load().vrt_trace_camera16_dev if compact else load().vrt_trace_camera_dev
         _check(fn(self._h, C.byref(cam.c), x0, y0, x1, y1, C.c_void_p(d_out_ptr)))
 
-    def render(self, cam: Camera, light=None, kd=0.8, rect=None, out=None):
+    def render(self, cam: Camera, light=None, kd=0.8, rect=None, out=None, shadow_eps=None):
         """Harness-shaded film (float RGB, [h,w,3]) through HOST buffers."""
         x0, y0, x1, y1 = rect if rect else (0, 0, cam.nx, cam.ny)
-        sh = vrt_shade((C.c_float * 3)(*(default_light() if light is None else light)), float(kd))
+        sh = _shade(light, kd, shadow_eps)
         if out is None:
             out = np.zeros((y1 - y0, x1 - x0, 3), np.float32)
         _check(load().vrt_render_camera(self._h, C.byref(cam.c), C.byref(sh), x0, y0, x1, y1, _ptr(out)))
         return out
 
-    def render_bands_dev(self, cam: Camera, d_film_ptr, band_h, band_first, band_stride, light=None, kd=0.8):
+    def render_bands_dev(self, cam: Camera, d_film_ptr, band_h, band_first, band_stride, light=None, kd=0.8,
+                         shadow_eps=None):
         """Rank `band_first` of `band_stride` in a row-interleaved multi-GPU frame."""
-        sh = vrt_shade((C.c_float * 3)(*(default_light() if light is None else light)), float(kd))
+        sh = _shade(light, kd, shadow_eps)
         b = vrt_bands(int(band_h), int(band_first), int(band_stride))
         _check(load().vrt_render_bands_dev(self._h, C.byref(cam.c), C.byref(sh), C.byref(b), C.c_void_p(d_film_ptr)))
 
     def frame_bands_dev(self, cam: Camera, d_hits_ptr, d_film_ptr, band_h, band_first, band_stride, light=None,
-                        kd=0.8, full_frame=False):
+                        kd=0.8, full_frame=False, shadow_eps=None):
         """One frame step of rank `band_first` of `band_stride`: hit16 records + film (async).
         full_frame=True: d_film_ptr is the whole [ny][nx][3] frame (possibly peer-mapped from
         rank 0) and pixels are stored at their final place."""
-        sh = vrt_shade((C.c_float * 3)(*(default_light() if light is None else light)), float(kd))
+        sh = _shade(light, kd, shadow_eps)
         b = vrt_bands(int(band_h), int(band_first), int(band_stride))
         fn = load().vrt_frame_bands_peer_dev if full_frame else load().vrt_frame_bands_dev
         _check(fn(self._h, C.byref(cam.c), C.byref(sh), C.byref(b), C.c_void_p(d_hits_ptr), C.c_void_p(d_film_ptr)))
@@ -346,9 +353,9 @@ class Octree:
         _check(load().vrt_count_camera(self._h, C.byref(cam.c), x0, y0, x1, y1, _ptr(c)))
         return dict(rays=int(c[0]), n_int=int(c[1]), n_leaf=int(c[2]), n_tri=int(c[3]), hits=int(c[4]))
 
-    def render_dev(self, cam: Camera, d_film_ptr, light=None, kd=0.8, rect=None):
+    def render_dev(self, cam: Camera, d_film_ptr, light=None, kd=0.8, rect=None, shadow_eps=None):
         x0, y0, x1, y1 = rect if rect else (0, 0, cam.nx, cam.ny)
-        sh = vrt_shade((C.c_float * 3)(*(default_light() if light is None else light)), float(kd))
+        sh = _shade(light, kd, shadow_eps)
         _check(load().vrt_render_camera_dev(self._h, C.byref(cam.c), C.byref(sh), x0, y0, x1, y1,
                                             C.c_void_p(d_film_ptr)))
 

@@ -267,7 +267,7 @@ void render_gpu(Film* film, Camera& cam, gi::VoxelOctree* root, int spp, const j
         if (!root || !root->gpu)
                 throw std::runtime_error("render_gpu: octree not initialised (call ray_march_init)");
         const vrt_camera c = cam.native(*film, spp);
-        vrt_shade sh{ { light_dir.x, light_dir.y, light_dir.z }, kd };
+        vrt_shade sh{ { light_dir.x, light_dir.y, light_dir.z }, kd, 0.f, 0 };
         check(vrt_render_camera(root->gpu->tree, &c, &sh, 0, 0, film->nx, film->ny, &film->data()->x), "render_gpu");
         if (hits) {
                 hits->resize((size_t)film->nx * film->ny * spp);

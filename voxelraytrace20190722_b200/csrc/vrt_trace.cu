@@ -52,6 +52,8 @@ struct TraceParams {
         uint32_t num_tiles;
         float light[3];
         float kd;
+        float shadow_eps;
+        int shadow;  // harness shadow ray per hit (BASELINE config 5)
         float root[6];
 };
 
@@ -554,9 +556,15 @@ __device__ __forceinline__ void store_hit48(vrt_hit* out, const TreeDev& tr, con
         q[2] = make_float4(pos[2], nrm[0], nrm[1], nrm[2]);
 }
 
-// Harness pixel (main.cc:18-20 for the sky).
+// Harness pixel (main.cc:18-20 for the sky): miss -> sky lerp; hit ->
+// kd * clamp(dot(normal, light), 0, 1) * visibility.  With p.shadow the visibility is a
+// second ray_march-semantics query from hit + eps*normal toward the light (config 5 of
+// BASELINE.json; harness-defined -- the reference itself has no shadow rays); it runs in
+// the same kernel, reusing the thread's traversal stack.
+template <bool COUNT>
 __device__ __forceinline__ void shade(const TraceParams& p, const HitState& hs, const float o[3],
-                                      const float d[3], float rgb[3])
+                                      const float d[3], uint32_t* s_first, uint32_t* s_meta, uint32_t* s_list,
+                                      WorkCount& wc, float rgb[3])
 {
         if (!hs.hit) {
                 // float t = 0.5 * (ray.d.y + 1.0)  -- double arithmetic, then lerp in float
@@ -570,7 +578,15 @@ __device__ __forceinline__ void shade(const TraceParams& p, const HitState& hs, 
         float pos[3], nrm[3];
         finish_isect(p.tree, hs, o, d, pos, nrm);
         const float nl = clampf(dot3(nrm[0], nrm[1], nrm[2], p.light[0], p.light[1], p.light[2]), 0.f, 1.f);
-        const float c = fmul(p.kd, nl);
+        float c = fmul(p.kd, nl);
+        if (p.shadow) {
+                const float so[3] = { fadd(pos[0], fmul(p.shadow_eps, nrm[0])), fadd(pos[1], fmul(p.shadow_eps, nrm[1])),
+                                      fadd(pos[2], fmul(p.shadow_eps, nrm[2])) };
+                const float sd[3] = { p.light[0], p.light[1], p.light[2] };
+                HitState sh;
+                trace_one<COUNT>(p.tree, p.root, so, sd, 0.f, FLT_MAX, s_first, s_meta, s_list, sh, wc);
+                c = fmul(c, sh.hit ? 0.f : 1.f);
+        }
         rgb[0] = rgb[1] = rgb[2] = c;
 }
 
@@ -694,7 +710,7 @@ k_trace_camera(TraceParams p)
                         }
                         float rgb[3] = { 0, 0, 0 };
                         if (active)
-                                shade(p, hs, o, d, rgb);
+                                shade<MODE == OUT_COUNT>(p, hs, o, d, s_first, s_meta, s_list, wc, rgb);
                         // film->add(px,py, c * (1/spp)) in sample order (main.cc:119-122)
                         const float wgt = (spp == 4) ? .25f : 1.f;
                         float acc[3];
@@ -815,6 +831,8 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
                 p.light[1] = sh->light_dir[1];
                 p.light[2] = sh->light_dir[2];
                 p.kd = sh->kd;
+                p.shadow = sh->shadow;
+                p.shadow_eps = sh->shadow_eps;
         }
         const int tw = (cam->spp == 4) ? 4 : 8, th = (cam->spp == 4) ? 2 : 4;
         const uint64_t tiles = (uint64_t)((x1 - x0 + tw - 1) / tw) * (uint64_t)((y1 - y0 + th - 1) / th);
