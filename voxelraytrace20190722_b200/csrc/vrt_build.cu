@@ -11,9 +11,10 @@
 //     is exact by construction;
 //   * leaves hold triangle indices in ascending order.
 // Pipeline: root AABB reduction -> per-axis interval table -> root filter ->
-// L x expand (8 lanes per (triangle, cell) pair, one SAT test per lane, keys
-// Morton<<tb | tri appended through block-aggregated atomics) -> LSD radix sort
-// -> unique -> bottom-up parent derivation -> flat pointerless node array.
+// L x expand (8 lanes per (triangle, cell) pair, one SAT test per lane; mask pass,
+// scan, emit pass: deterministic, no atomics; keys Morton<<tb | tri stay sorted by
+// (triangle, Morton)) -> stable LSD radix sort on the Morton bits -> unique ->
+// bottom-up parent derivation -> flat pointerless node array.
 #include <algorithm>
 #include <cfloat>
 #include <cstring>
@@ -178,79 +179,107 @@ k_axis_table(const float* __restrict__ root6, float2* __restrict__ tab, uint64_t
 }
 
 // ---------------------------------------------------------------------------
-// Block-aggregated append: every thread contributes `flag`; returns the
-// output slot of this thread (valid when flag) -- one global atomic per block
-// call.  Must be called by all threads of the block.
+// Hierarchical voxelization, one level per step, in two deterministic passes:
+//   mask pass : 8 lanes per (triangle, cell) pair, lane c runs the SAT test against
+//               child c; the 8 verdicts are stored as one mask byte per pair and the
+//               survivors are counted per block (no atomics);
+//   (exclusive scan of the block counts)
+//   emit pass : every pair writes its surviving children, in child order, at its exact
+//               position.
+// The output order is (input order, child index).  The level-0 frontier is in triangle
+// order, so by induction every frontier is sorted by (triangle, Morton code) -- which lets
+// the final sort run on the Morton bits only (stable LSD passes keep the triangle order
+// inside a leaf = the reference's insertion order).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t block_append(bool flag, uint32_t* counter)
+constexpr int kPairsPerBlock = 256;
+
+__device__ __forceinline__ uint32_t block_sum_256(uint32_t v)
 {
-        __shared__ uint32_t s_warp[32];
-        __shared__ uint32_t s_base;
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-        const uint32_t bal = __ballot_sync(0xffffffffu, flag);
-        if (lane == 0)
-                s_warp[w] = __popc(bal);
-        __syncthreads();
-        if (w == 0) {
-                uint32_t c = (lane < nw) ? s_warp[lane] : 0u;
-                uint32_t inc = c;
+        __shared__ uint32_t s_w[8];
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= o)
-                                inc += t;
-                }
-                if (lane < nw)
-                        s_warp[lane] = inc - c;
-                if (lane == 31)
-                        s_base = inc ? atomicAdd(counter, inc) : 0u;
-        }
+        for (int o = 16; o > 0; o >>= 1)
+                v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0)
+                s_w[threadIdx.x >> 5] = v;
         __syncthreads();
-        const uint32_t slot = s_base + s_warp[w] + __popc(bal & ((1u << lane) - 1u));
+        uint32_t tot = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+                tot += s_w[i];
         __syncthreads();
-        return slot;
+        return tot;
 }
 
-// Level 0: triangles that overlap the root box (insert's first test at the
-// root, voxel_octree.cc:43).  key = tri (Morton code of the root is empty).
-__global__ void __launch_bounds__(256)
-k_root_filter(const float* __restrict__ tri, uint32_t T, const float* __restrict__ root6,
-              unsigned long long* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counter)
+// exclusive prefix of v over the 256 threads of the block
+__device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v)
 {
-        const uint32_t rounds = (T + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
-        for (uint32_t r = 0; r < rounds; ++r) {
-                const uint32_t t = (r * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
-                bool ov = false;
-                if (t < T) {
-                        const float* p = tri + 9ull * t;
-                        float v0[3] = { p[0], p[1], p[2] }, v1[3] = { p[3], p[4], p[5] },
-                              v2[3] = { p[6], p[7], p[8] };
-                        float mn[3] = { root6[0], root6[1], root6[2] };
-                        float mx[3] = { root6[3], root6[4], root6[5] };
-                        ov = tri_overlaps_aabb(mn, mx, v0, v1, v2);
-                }
-                const uint32_t slot = block_append(ov, counter);
-                if (ov && slot < cap)
-                        out[slot] = (unsigned long long)t;
+        __shared__ uint32_t s_w[8];
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o)
+                        inc += t;
         }
+        if (lane == 31)
+                s_w[w] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+                woff += (i < w) ? s_w[i] : 0u;
+        __syncthreads();
+        return woff + inc - v;
 }
 
-// One level of the hierarchical insert: each surviving (triangle, cell) pair
-// tests the cell's 8 children (8 lanes per pair).  in/out keys = morton<<tb|tri.
+// Level 0: triangles that overlap the root box (insert's first test at the root,
+// voxel_octree.cc:43).  One thread per triangle.
 __global__ void __launch_bounds__(256)
-k_expand(const float* __restrict__ tri, const float2* __restrict__ tab, uint64_t stride,
-         const unsigned long long* __restrict__ in, uint32_t n_in, int level /* of the input cells */,
-         int tb, unsigned long long* __restrict__ out, uint32_t cap, uint32_t* __restrict__ counter)
+k_root_mask(const float* __restrict__ tri, uint32_t T, const float* __restrict__ root6,
+            uint8_t* __restrict__ masks, uint32_t* __restrict__ block_counts)
 {
-        const uint32_t pairs_per_block = blockDim.x >> 3;
-        const uint32_t rounds = (n_in + gridDim.x * pairs_per_block - 1) / (gridDim.x * pairs_per_block);
+        const uint32_t t = blockIdx.x * kPairsPerBlock + threadIdx.x;
+        bool ov = false;
+        if (t < T) {
+                const float* p = tri + 9ull * t;
+                float v0[3] = { p[0], p[1], p[2] }, v1[3] = { p[3], p[4], p[5] }, v2[3] = { p[6], p[7], p[8] };
+                float mn[3] = { root6[0], root6[1], root6[2] };
+                float mx[3] = { root6[3], root6[4], root6[5] };
+                ov = tri_overlaps_aabb(mn, mx, v0, v1, v2);
+                masks[t] = ov ? 1 : 0;
+        }
+        const uint32_t tot = block_sum_256(ov ? 1u : 0u);
+        if (threadIdx.x == 0)
+                block_counts[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(256)
+k_root_emit(uint32_t T, const uint8_t* __restrict__ masks, const uint32_t* __restrict__ block_offs,
+            unsigned long long* __restrict__ out)
+{
+        const uint32_t t = blockIdx.x * kPairsPerBlock + threadIdx.x;
+        const uint32_t m = (t < T) ? masks[t] : 0u;
+        const uint32_t off = block_excl_scan_256(m);
+        if (m)
+                out[block_offs[blockIdx.x] + off] = (unsigned long long)t;  // Morton code of the root is empty
+}
+
+// One level of the hierarchical insert, mask pass.  in keys = morton<<tb | tri.
+__global__ void __launch_bounds__(256)
+k_expand_mask(const float* __restrict__ tri, const float2* __restrict__ tab, uint64_t stride,
+              const unsigned long long* __restrict__ in, uint32_t n_in, int level /* of the input cells */,
+              int tb, uint8_t* __restrict__ masks, uint32_t* __restrict__ block_counts)
+{
         const uint32_t c = threadIdx.x & 7;
+        const uint32_t lane = threadIdx.x & 31;
         const unsigned long long tmask = (1ull << tb) - 1ull;
         const uint32_t child_base = 2u << level;  // table offset of level+1
-        for (uint32_t r = 0; r < rounds; ++r) {
-                const uint32_t idx = (r * gridDim.x + blockIdx.x) * pairs_per_block + (threadIdx.x >> 3);
+        uint32_t cnt = 0;
+#pragma unroll 1
+        for (int it = 0; it < kPairsPerBlock / 32; ++it) {
+                const uint32_t idx = blockIdx.x * kPairsPerBlock + it * 32 + (threadIdx.x >> 3);
                 bool ov = false;
-                unsigned long long key_out = 0;
                 if (idx < n_in) {
                         const unsigned long long key = in[idx];
                         const uint32_t t = (uint32_t)(key & tmask);
@@ -262,16 +291,41 @@ k_expand(const float* __restrict__ tri, const float2* __restrict__ tab, uint64_t
                         const float2 by = tab[1 * stride + child_base + cy];
                         const float2 bz = tab[2 * stride + child_base + cz];
                         const float* p = tri + 9ull * t;
-                        float v0[3] = { p[0], p[1], p[2] }, v1[3] = { p[3], p[4], p[5] },
-                              v2[3] = { p[6], p[7], p[8] };
+                        float v0[3] = { p[0], p[1], p[2] }, v1[3] = { p[3], p[4], p[5] }, v2[3] = { p[6], p[7], p[8] };
                         float mn[3] = { bx.x, by.x, bz.x };
                         float mx[3] = { bx.y, by.y, bz.y };
                         ov = tri_overlaps_aabb(mn, mx, v0, v1, v2);
-                        key_out = (((m << 3) | c) << tb) | t;
                 }
-                const uint32_t slot = block_append(ov, counter);
-                if (ov && slot < cap)
-                        out[slot] = key_out;
+                const uint32_t bal = __ballot_sync(0xffffffffu, ov);
+                if (c == 0 && idx < n_in)
+                        masks[idx] = (uint8_t)((bal >> (lane & 24u)) & 0xffu);
+                cnt += ov ? 1u : 0u;
+        }
+        const uint32_t tot = block_sum_256(cnt);
+        if (threadIdx.x == 0)
+                block_counts[blockIdx.x] = tot;
+}
+
+// Emit pass: thread t handles pair blockIdx*256+t and writes its surviving children.
+__global__ void __launch_bounds__(256)
+k_expand_emit(const unsigned long long* __restrict__ in, uint32_t n_in, int tb,
+              const uint8_t* __restrict__ masks, const uint32_t* __restrict__ block_offs,
+              unsigned long long* __restrict__ out)
+{
+        const uint32_t idx = blockIdx.x * kPairsPerBlock + threadIdx.x;
+        uint32_t m = 0;
+        unsigned long long key = 0;
+        if (idx < n_in) {
+                m = masks[idx];
+                key = in[idx];
+        }
+        uint32_t pos = block_offs[blockIdx.x] + block_excl_scan_256(__popc(m));
+        const unsigned long long t = key & ((1ull << tb) - 1ull);
+        const unsigned long long mo = (key >> tb) << 3;
+        while (m) {
+                const uint32_t c = __ffs((int)m) - 1;
+                m &= m - 1u;
+                out[pos++] = ((mo | c) << tb) | t;
         }
 }
 
@@ -609,54 +663,58 @@ int build_tree(vrt_tree* t, int max_depth)
         // level 0
         if (t->keys_a.reserve(std::max<uint64_t>(T, 1) * 8))
                 return VRT_ERR_NOMEM;
-        VRT_CUDA(cudaMemsetAsync(t->d_counter, 0, 32, s));
+        uint64_t n = 0;
         if (T) {
-                k_root_filter<<<std::min<unsigned>(grid_for(T, 256), 148 * 8), 256, 0, s>>>(
-                        t->d_tri_in, T, d_root6, t->keys_a.as<unsigned long long>(), T, t->d_counter);
+                const uint32_t nblk = (T + kPairsPerBlock - 1) / kPairsPerBlock;
+                if (t->tmp_b.reserve(T) || t->hist.reserve((nblk + 1ull) * 4) ||
+                    t->tmp_c.reserve(scan_scratch_elems(nblk + 1ull) * 4))
+                        return VRT_ERR_NOMEM;
+                uint32_t* bc = t->hist.as<uint32_t>();
+                VRT_CUDA(cudaMemsetAsync(bc + nblk, 0, 4, s));
+                k_root_mask<<<nblk, 256, 0, s>>>(t->d_tri_in, T, d_root6, t->tmp_b.as<uint8_t>(), bc);
                 count_launch();
+                exclusive_scan_u32(bc, bc, nblk + 1ull, t->tmp_c.as<uint32_t>(), s);
+                k_root_emit<<<nblk, 256, 0, s>>>(T, t->tmp_b.as<uint8_t>(), bc, t->keys_a.as<unsigned long long>());
+                count_launch();
+                VRT_CUDA(cudaMemcpyAsync(t->h_counter, bc + nblk, 4, cudaMemcpyDeviceToHost, s));
+                VRT_CUDA(cudaStreamSynchronize(s));
+                n = t->h_counter[0];
         }
-        VRT_CUDA(cudaMemcpyAsync(t->h_counter, t->d_counter, 4, cudaMemcpyDeviceToHost, s));
-        VRT_CUDA(cudaStreamSynchronize(s));
-        uint64_t n = t->h_counter[0];
         Scratch* cur = &t->keys_a;
         Scratch* nxt = &t->keys_b;
         for (int l = 0; l < L && n; ++l) {
-                // capacity guess: surfaces grow ~4x per level; retry on overflow
-                uint64_t cap = std::max<uint64_t>(n * 5, 1u << 16);
-                cap = std::min<uint64_t>(cap, n * 8);
-                for (;;) {
-                        if (nxt->cap < cap * 8 && nxt->reserve(cap * 8))
-                                return VRT_ERR_NOMEM;
-                        cap = nxt->cap / 8;
-                        if (cap > 0xffffffffull)
-                                cap = 0xffffffffull;
-                        VRT_CUDA(cudaMemsetAsync(t->d_counter, 0, 4, s));
-                        const uint64_t pairs_per_block = 32;
-                        unsigned grid = (unsigned)std::min<uint64_t>((n + pairs_per_block - 1) / pairs_per_block,
-                                                                     148ull * 16);
-                        k_expand<<<grid, 256, 0, s>>>(t->d_tri_in, tab_s.as<float2>(), stride,
-                                                      cur->as<unsigned long long>(), (uint32_t)n, l, tb,
-                                                      nxt->as<unsigned long long>(), (uint32_t)cap, t->d_counter);
-                        count_launch();
-                        VRT_CUDA(cudaMemcpyAsync(t->h_counter, t->d_counter, 4, cudaMemcpyDeviceToHost, s));
-                        VRT_CUDA(cudaStreamSynchronize(s));
-                        const uint64_t produced = t->h_counter[0];
-                        if (produced <= cap) {
-                                n = produced;
-                                break;
-                        }
-                        cap = produced;  // exact size known now: redo this level once
-                }
-                std::swap(cur, nxt);
-                if (n >= 0xfffffff0ull) {
+                const uint32_t nblk = (uint32_t)((n + kPairsPerBlock - 1) / kPairsPerBlock);
+                if (t->tmp_b.reserve(n) || t->hist.reserve((nblk + 1ull) * 4) ||
+                    t->tmp_c.reserve(scan_scratch_elems(nblk + 1ull) * 4))
+                        return VRT_ERR_NOMEM;
+                uint32_t* bc = t->hist.as<uint32_t>();
+                VRT_CUDA(cudaMemsetAsync(bc + nblk, 0, 4, s));
+                k_expand_mask<<<nblk, 256, 0, s>>>(t->d_tri_in, tab_s.as<float2>(), stride,
+                                                   cur->as<unsigned long long>(), (uint32_t)n, l, tb,
+                                                   t->tmp_b.as<uint8_t>(), bc);
+                count_launch();
+                exclusive_scan_u32(bc, bc, nblk + 1ull, t->tmp_c.as<uint32_t>(), s);
+                VRT_CUDA(cudaMemcpyAsync(t->h_counter, bc + nblk, 4, cudaMemcpyDeviceToHost, s));
+                VRT_CUDA(cudaStreamSynchronize(s));
+                const uint64_t produced = t->h_counter[0];
+                if (produced >= 0xfffffff0ull) {
                         set_error("more than 2^32 (triangle, cell) pairs at level %d", l + 1);
                         return VRT_ERR_CAPACITY;
                 }
+                if (nxt->reserve(std::max<uint64_t>(produced, 1) * 8))
+                        return VRT_ERR_NOMEM;
+                if (produced) {
+                        k_expand_emit<<<nblk, 256, 0, s>>>(cur->as<unsigned long long>(), (uint32_t)n, tb,
+                                                           t->tmp_b.as<uint8_t>(), bc, nxt->as<unsigned long long>());
+                        count_launch();
+                }
+                n = produced;
+                std::swap(cur, nxt);
         }
         // keys live in *cur; make sure finish_from_keys ping-pongs with the other one
         if (cur != &t->keys_a)
                 std::swap(t->keys_a, t->keys_b);
-        int rc = finish_from_keys(t, t->keys_a.as<unsigned long long>(), n, L, tb, /*stable_input=*/false, d_root6);
+        int rc = finish_from_keys(t, t->keys_a.as<unsigned long long>(), n, L, tb, /*stable_input=*/true, d_root6);
         if (rc)
                 return rc;
         VRT_CUDA(cudaEventRecord(t->ev1, s));
