@@ -133,18 +133,29 @@ k_aabb_partial(const float* __restrict__ tri, uint32_t num_verts, uint2* __restr
 
 __global__ void k_aabb_final(const uint2* __restrict__ partial, int nblocks, float* __restrict__ out6)
 {
-        const int q = threadIdx.x;
+        // warp q reduces quantity q (3 mins, 3 maxes) over the block partials
+        const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
         if (q >= 6)
                 return;
         MinMaxIdx a = { q < 3 ? FLT_MAX : -FLT_MAX, 0xffffffffu };
-        for (int b = 0; b < nblocks; ++b) {
+        for (int b = lane; b < nblocks; b += 32) {
                 uint2 p = partial[b * 6 + q];
                 if (q < 3)
                         mm_min(a, __uint_as_float(p.x), p.y);
                 else
                         mm_max(a, __uint_as_float(p.x), p.y);
         }
-        out6[q] = a.v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+                float ov = __shfl_down_sync(0xffffffffu, a.v, o);
+                uint32_t oi = __shfl_down_sync(0xffffffffu, a.i, o);
+                if (q < 3)
+                        mm_min(a, ov, oi);
+                else
+                        mm_max(a, ov, oi);
+        }
+        if (lane == 0)
+                out6[q] = a.v;
 }
 
 // ---------------------------------------------------------------------------
@@ -652,7 +663,7 @@ int build_tree(vrt_tree* t, int max_depth)
                 return VRT_ERR_NOMEM;
         float* d_root6 = reinterpret_cast<float*>(t->d_counter + 8);
         k_aabb_partial<<<nb, 256, 0, s>>>(t->d_tri_in, 3u * T, t->tmp_a.as<uint2>());
-        k_aabb_final<<<1, 32, 0, s>>>(t->tmp_a.as<uint2>(), nb, d_root6);
+        k_aabb_final<<<1, 192, 0, s>>>(t->tmp_a.as<uint2>(), nb, d_root6);
         count_launch(2);
         const uint64_t stride = 2ull << L;
         Scratch& tab_s = t->tab_s;

@@ -60,7 +60,8 @@ __device__ __forceinline__ float clampf(float s, float lo, float hi)
 // c = box centre, h = box half size, v* = triangle vertices.
 // The reference evaluates the 13 axes in a fixed order and returns at the first
 // separating one; the result is the conjunction of 13 independent predicates,
-// so evaluating the cheap box-axis tests first does not change it.
+// so evaluating them cheapest-and-most-selective first (3 box axes, the plane,
+// then the 9 edge axes) does not change it.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ bool axis_sep(float pa, float pb, float rad)
 {
@@ -99,6 +100,29 @@ __device__ __forceinline__ bool tribox_overlap(const float c[3], const float h[3
                 e1[k] = fsub(v2[k], v1[k]);
                 e2[k] = fsub(v0[k], v2[k]);
         }
+        // plane (tribox2.cc:181-183 + 42-63)
+        float n[3];
+        n[0] = fsub(fmul(e0[1], e1[2]), fmul(e0[2], e1[1]));
+        n[1] = fsub(fmul(e0[2], e1[0]), fmul(e0[0], e1[2]));
+        n[2] = fsub(fmul(e0[0], e1[1]), fmul(e0[1], e1[0]));
+        float d = -fadd(fadd(fmul(n[0], v0[0]), fmul(n[1], v0[1])), fmul(n[2], v0[2]));
+        float lo[3], hi[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+                if (n[q] > 0.0f) {
+                        lo[q] = -h[q];
+                        hi[q] = h[q];
+                } else {
+                        lo[q] = h[q];
+                        hi[q] = -h[q];
+                }
+        }
+        float dmin = fadd(fadd(fadd(fmul(n[0], lo[0]), fmul(n[1], lo[1])), fmul(n[2], lo[2])), d);
+        if (dmin > 0.0f)
+                return false;
+        float dmax = fadd(fadd(fadd(fmul(n[0], hi[0]), fmul(n[1], hi[1])), fmul(n[2], hi[2])), d);
+        if (!(dmax >= 0.0f))
+                return false;
         float fx, fy, fz;
         // edge 0: AXISTEST_X01, Y02, Z12 (tribox2.cc:139-144)
         fx = fabsf(e0[0]); fy = fabsf(e0[1]); fz = fabsf(e0[2]);
@@ -133,28 +157,7 @@ __device__ __forceinline__ bool tribox_overlap(const float c[3], const float h[3
         if (axis_sep(fsub(fmul(e2[1], v2[0]), fmul(e2[0], v2[1])),
                      fsub(fmul(e2[1], v1[0]), fmul(e2[0], v1[1])),
                      fadd(fmul(fy, h[0]), fmul(fx, h[1])))) return false;
-        // plane (tribox2.cc:181-183 + 42-63)
-        float n[3];
-        n[0] = fsub(fmul(e0[1], e1[2]), fmul(e0[2], e1[1]));
-        n[1] = fsub(fmul(e0[2], e1[0]), fmul(e0[0], e1[2]));
-        n[2] = fsub(fmul(e0[0], e1[1]), fmul(e0[1], e1[0]));
-        float d = -fadd(fadd(fmul(n[0], v0[0]), fmul(n[1], v0[1])), fmul(n[2], v0[2]));
-        float lo[3], hi[3];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-                if (n[q] > 0.0f) {
-                        lo[q] = -h[q];
-                        hi[q] = h[q];
-                } else {
-                        lo[q] = h[q];
-                        hi[q] = -h[q];
-                }
-        }
-        float dmin = fadd(fadd(fadd(fmul(n[0], lo[0]), fmul(n[1], lo[1])), fmul(n[2], lo[2])), d);
-        if (dmin > 0.0f)
-                return false;
-        float dmax = fadd(fadd(fadd(fmul(n[0], hi[0]), fmul(n[1], hi[1])), fmul(n[2], hi[2])), d);
-        return dmax >= 0.0f;
+        return true;
 }
 
 // Triangle::is_overlap (voxel_octree.cc:486-492): centre=(min+max)*.5f
