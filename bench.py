@@ -78,7 +78,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -87,7 +87,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark(self, name):
+        self.marks = getattr(self, "marks", {})
+        self.marks[name] = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -100,7 +104,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        marks = getattr(self, "marks", {})
+        windows = [(marks[a], marks[b]) for a, b in (("t0", "t1"), ("e0", "e1")) if a in marks and b in marks]
+        for ts, r in self.rows:
+            if windows and not any(lo <= ts <= hi + 0.06 for lo, hi in windows):
+                continue  # only samples taken while a timed region (value loop, e2e loop) was running
             c = [x.strip() for x in r.split(",")]
             if len(c) < 8:
                 continue
@@ -198,6 +206,9 @@ def run_ours(args):
         import torch.distributed as td
         td.init_process_group("nccl", device_id=dev)
     capi.load()
+    sampler = ClockSampler(local)  # runs for the whole job; only samples inside the timed regions are kept
+    if rank == 0:
+        sampler.start()
 
     tri, nrm, depth, cam10, nx, ny, spp = make_scene(args.workload)
     T = len(tri)
@@ -208,8 +219,9 @@ def run_ours(args):
     build = {}
     tree = None
     if rank == 0:
+        capi.Octree.build(tri[:1024], nrm[:1024], 4).close()  # CUDA context + module load, outside the timing
         t0 = time.perf_counter()
-        tree = capi.Octree.build(tri, nrm, depth)
+        tree = capi.Octree.build(tri, nrm, depth)  # host triangles in -> octree resident in HBM (fresh handle)
         build["e2e_s"] = time.perf_counter() - t0
         ms = []
         for _ in range(args.build_reps + 1):
@@ -284,9 +296,7 @@ def run_ours(args):
         step(i)
     drain(args.warmup - 1)
     sync_all()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.mark("t0")
     l0 = capi.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -297,7 +307,7 @@ def run_ours(args):
     drain(args.steps - 1)
     e1.record(stream)
     sync_all()
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.mark("t1")
     launches = capi.launch_count() - l0
     total_ms = e0.elapsed_time(e1)
     t = torch.tensor([total_ms, tree.mean_kernel_ms(min(args.steps, 64))], dtype=torch.float64, device=dev)
@@ -318,15 +328,29 @@ def run_ours(args):
 
     # ---- e2e: host-buffer C-ABI call, film copied back to pinned host memory every step ----
     if world == 1:
-        film_host = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory()
-        film_np = film_host.numpy()
+        # frame loop through the host-buffer C ABI: vrt_render_camera_async enqueues the frame and
+        # its device->host copy (pinned film, alternating between two host buffers); the copy of
+        # frame k overlaps the kernel of frame k+1; every frame's film is in host memory when the
+        # timed region ends (vrt_tree_sync)
+        film_hosts = [torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+        film_nps = [f.numpy() for f in film_hosts]
+        film_np = film_nps[0]
         tree.set_stream(0)
-        for _ in range(max(1, args.warmup // 2)):
-            tree.render(cam, out=film_np, shadow_eps=shadow_eps)
+        for i in range(max(2, args.warmup // 2)):
+            tree.render_async(cams[i % len(cams)], film_nps[i & 1], shadow_eps=shadow_eps)
+        tree.sync()
+        sampler.mark("e0")
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            tree.render(cam, out=film_np, shadow_eps=shadow_eps)
+        for i in range(args.steps):
+            tree.render_async(cams[i % len(cams)], film_nps[i & 1], shadow_eps=shadow_eps)
+        tree.sync()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        sampler.mark("e1")
+        # the synchronous single-frame call, for reference
+        t0 = time.perf_counter()
+        for _ in range(min(args.steps, 5)):
+            tree.render(cam, out=film_np, shadow_eps=shadow_eps)
+        e2e_sync_ms = (time.perf_counter() - t0) * 1e3 / min(args.steps, 5)
         d2h = film_np.nbytes
     else:
         film_host = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
@@ -351,15 +375,18 @@ def run_ours(args):
         for _ in range(max(1, args.warmup // 2)):
             e2e_step()
         sync_all()
+        sampler.mark("e0")
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
         sync_all()
+        sampler.mark("e1")
         tt = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=dev)
         td.all_reduce(tt, op=td.ReduceOp.MAX)
         e2e_ms = float(tt[0])
         d2h = ny * nx * 12
     e2e_value = rays_per_step / (e2e_ms * 1e-3) / 1e6
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- N-GPU frame == 1-GPU frame, bytewise (outside every timed region) ----
     frame_check = None
@@ -404,7 +431,7 @@ def run_ours(args):
     nu = info["num_nodes"] / max(T, 1)
     b_tri = 36 + 12 * rho + 8 * nu
     build_out = {"mtris_per_s": T / (build["ms"] * 1e-3) / 1e6, "ms": build["ms"],
-                 "e2e_mtris_per_s": T / build["e2e_s"] / 1e6, "e2e_s_first_call": build["e2e_s"],
+                 "e2e_mtris_per_s": T / build["e2e_s"] / 1e6, "e2e_s": build["e2e_s"],
                  "h2d_bytes": int(tri.nbytes + nrm.nbytes), "bytes_per_tri": b_tri,
                  "roofline_frac": b_tri * T / (build["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
                  "leaves": info["num_leaves"], "nodes": info["num_nodes"], "refs": info["num_refs"]}
@@ -427,7 +454,11 @@ def run_ours(args):
         "config": workload_config(args.workload, T, world),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 92, "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_ms, "call": "vrt_render_camera (camera struct in, shaded float film out to pinned host)"},
+                "ms_per_step": e2e_ms,
+                "call": ("vrt_render_camera_async per frame + vrt_tree_sync (camera struct in, shaded float film out to pinned "
+                         "host; frame k's copy overlaps frame k+1's kernel)" if world == 1 else
+                         "vrt_frame_bands_peer_dev per rank + barrier + film copied to pinned host on rank 0, per frame"),
+                "sync_single_frame_ms": e2e_sync_ms if world == 1 else None},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -199,6 +199,13 @@ int vrt_render_camera(const vrt_tree* tree, const vrt_camera* cam, const vrt_sha
 int vrt_render_camera_dev(const vrt_tree* tree, const vrt_camera* cam,
                           const vrt_shade* sh, int x0, int y0, int x1, int y1,
                           float* d_film_rgb);
+/* Frame-sequence form of vrt_render_camera: returns once the frame is ENQUEUED; the
+ * kernel of the next frame overlaps this frame's device->host copy (two device films, a
+ * copy stream).  film_rgb should be pinned host memory and must stay valid until
+ * vrt_tree_sync() returns; alternate between (at least) two host buffers. */
+int vrt_render_camera_async(const vrt_tree* tree, const vrt_camera* cam,
+                            const vrt_shade* sh, int x0, int y0, int x1, int y1,
+                            float* film_rgb);
 /* Row-interleaved shard of the film for multi-GPU runs (replaces the
  * static 8x8 tile split of render_mt, camera.h:45-55): the film is cut into bands
  * of band_h rows; the call renders bands band_first, band_first+band_stride, ...

@@ -413,3 +413,21 @@ def test_shadow_rays_vs_oracle(case, gpu, port):
     exp = harness_film(rays, prim, light, 0.8, spp, visibility=vis).reshape(ny, nx, 3)
     assert_bits_equal(film, exp, "film with shadow rays")
     assert (vis[prim.hit.astype(bool)] == 0).sum() > 0, "no occluded hit in this view"
+
+
+def test_render_async_pipeline_matches_sync(case, gpu):
+    """vrt_render_camera_async (frame k's host copy overlapping frame k+1's kernel) delivers the
+    same films as the synchronous call, for several frames in flight."""
+    torch = pytest.importorskip("torch")
+    cam10 = case["cam10"]
+    nx, ny, spp = 120, 68, 4
+    cams = [gpu.Camera(cam10[0], cam10[1:4] + np.float32(0.01 * k), cam10[4:7], cam10[7:10], nx, ny, spp)
+            for k in range(5)]
+    tree = case["tree"]
+    expect = [tree.render(c) for c in cams]
+    bufs = [torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory() for _ in range(len(cams))]
+    for c, b in zip(cams, bufs):
+        tree.render_async(c, b.numpy())
+    tree.sync()
+    for e, b in zip(expect, bufs):
+        assert np.array_equal(e.view(np.uint32), b.numpy().view(np.uint32))

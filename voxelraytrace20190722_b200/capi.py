@@ -60,7 +60,7 @@ SYMBOLS = [
     "vrt_tree_export", "vrt_tree_import", "vrt_tree_set_stream", "vrt_tree_blob_dev",
     "vrt_tree_from_blob_dev", "vrt_camera_init", "vrt_gen_rays", "vrt_trace_rays",
     "vrt_trace_rays_dev", "vrt_trace_camera", "vrt_trace_camera_dev", "vrt_trace_camera16_dev",
-    "vrt_render_camera", "vrt_render_camera_dev", "vrt_band_rows", "vrt_render_bands_dev",
+    "vrt_render_camera", "vrt_render_camera_dev", "vrt_render_camera_async", "vrt_band_rows", "vrt_render_bands_dev",
     "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_frame_bands_peer_dev",
     "vrt_dev_alloc", "vrt_dev_free", "vrt_ipc_export", "vrt_ipc_open", "vrt_ipc_close", "vrt_tree_sync",
     "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_tribox_batch",
@@ -111,7 +111,7 @@ def load(build_if_missing: bool = True):
     L.vrt_trace_rays_dev.argtypes = [vp, vp, u64, vp]
     for name in ("vrt_trace_camera", "vrt_trace_camera_dev", "vrt_trace_camera16_dev"):
         getattr(L, name).argtypes = [vp, C.POINTER(vrt_camera), i32, i32, i32, i32, vp]
-    for name in ("vrt_render_camera", "vrt_render_camera_dev"):
+    for name in ("vrt_render_camera", "vrt_render_camera_dev", "vrt_render_camera_async"):
         getattr(L, name).argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), i32, i32, i32, i32, vp]
     L.vrt_band_rows.argtypes = [C.POINTER(vrt_camera), C.POINTER(vrt_bands)]
     L.vrt_render_bands_dev.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), C.POINTER(vrt_bands), vp]
@@ -352,6 +352,13 @@ class Octree:
         c = np.zeros(5, np.uint64)
         _check(load().vrt_count_camera(self._h, C.byref(cam.c), x0, y0, x1, y1, _ptr(c)))
         return dict(rays=int(c[0]), n_int=int(c[1]), n_leaf=int(c[2]), n_tri=int(c[3]), hits=int(c[4]))
+
+    def render_async(self, cam: Camera, out, light=None, kd=0.8, rect=None, shadow_eps=None):
+        """Pipelined frame loop: enqueue one frame whose film lands in the (pinned) host array
+        `out`; call sync() before reading.  Alternate between two host arrays."""
+        x0, y0, x1, y1 = rect if rect else (0, 0, cam.nx, cam.ny)
+        sh = _shade(light, kd, shadow_eps)
+        _check(load().vrt_render_camera_async(self._h, C.byref(cam.c), C.byref(sh), x0, y0, x1, y1, _ptr(out)))
 
     def render_dev(self, cam: Camera, d_film_ptr, light=None, kd=0.8, rect=None, shadow_eps=None):
         x0, y0, x1, y1 = rect if rect else (0, 0, cam.nx, cam.ny)

@@ -397,6 +397,16 @@ void vrt_tree_free(vrt_tree* t)
         t->tab_s.release();
         t->io_in.release();
         t->io_out.release();
+        t->film_dev[0].release();
+        t->film_dev[1].release();
+        if (t->copy_stream)
+                cudaStreamDestroy(t->copy_stream);
+        for (int i = 0; i < 2; ++i) {
+                if (t->film_ready[i])
+                        cudaEventDestroy(t->film_ready[i]);
+                if (t->film_copied[i])
+                        cudaEventDestroy(t->film_copied[i]);
+        }
         for (unsigned l = 0; l <= VRT_MAX_DEPTH; ++l) {
                 t->level_morton[l].release();
                 t->level_first[l].release();
@@ -720,6 +730,51 @@ static int trace_camera_common(const vrt_tree* tc, const vrt_camera* cam, const 
                 return rc;
         VRT_CUDA(cudaMemcpyAsync(out, t->io_out.p, bytes, cudaMemcpyDeviceToHost, t->stream));
         VRT_CUDA(cudaStreamSynchronize(t->stream));
+        return VRT_OK;
+}
+
+// Pipelined frame loop: the kernel of frame k+1 runs while frame k's film crosses PCIe.
+int vrt_render_camera_async(const vrt_tree* tc, const vrt_camera* cam, const vrt_shade* sh, int x0, int y0, int x1,
+                            int y1, float* film_rgb)
+{
+        int rc = check_tree(tc);
+        if (rc)
+                return rc;
+        rc = check_camera(cam, x0, y0, x1, y1);
+        if (rc)
+                return rc;
+        const uint64_t npix = (uint64_t)(x1 - x0) * (y1 - y0);
+        if (!npix)
+                return VRT_OK;
+        if (!film_rgb || !sh) {
+                set_error("null out/shade pointer");
+                return VRT_ERR_ARG;
+        }
+        vrt_tree* t = const_cast<vrt_tree*>(tc);
+        if (!t->copy_stream) {
+                VRT_CUDA(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+                for (int i = 0; i < 2; ++i) {
+                        VRT_CUDA(cudaEventCreateWithFlags(&t->film_ready[i], cudaEventDisableTiming));
+                        VRT_CUDA(cudaEventCreateWithFlags(&t->film_copied[i], cudaEventDisableTiming));
+                }
+        }
+        const int k = (int)(t->n_async_frames & 1);
+        const uint64_t bytes = npix * 12;
+        if (t->film_dev[k].cap < bytes) {
+                VRT_CUDA(cudaStreamSynchronize(t->copy_stream));  // nothing may still read the old buffer
+                if (t->film_dev[k].reserve(bytes))
+                        return VRT_ERR_NOMEM;
+        }
+        if (t->n_async_frames >= 2)  // the copy that last read this device film must be done
+                VRT_CUDA(cudaStreamWaitEvent(t->stream, t->film_copied[k], 0));
+        rc = launch_trace_camera(t, cam, sh, x0, y0, x1, y1, t->film_dev[k].p, OUT_FILM);
+        if (rc)
+                return rc;
+        VRT_CUDA(cudaEventRecord(t->film_ready[k], t->stream));
+        VRT_CUDA(cudaStreamWaitEvent(t->copy_stream, t->film_ready[k], 0));
+        VRT_CUDA(cudaMemcpyAsync(film_rgb, t->film_dev[k].p, bytes, cudaMemcpyDeviceToHost, t->copy_stream));
+        VRT_CUDA(cudaEventRecord(t->film_copied[k], t->copy_stream));
+        t->n_async_frames++;
         return VRT_OK;
 }
 

@@ -116,6 +116,11 @@ struct vrt_tree {
         uint32_t* h_counter = nullptr;  // pinned mirror
         // trace scratch (host-pointer entry points)
         vrt::Scratch io_in, io_out;
+        // pipelined host-film path (vrt_render_camera_async): two device films, a copy stream
+        vrt::Scratch film_dev[2];
+        cudaStream_t copy_stream = nullptr;
+        cudaEvent_t film_ready[2] = {}, film_copied[2] = {};
+        mutable uint64_t n_async_frames = 0;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // build timing
         // trace launches are asynchronous: each one records a (start, stop) pair in this ring
         static constexpr int kEvRing = 64;
