@@ -159,6 +159,11 @@ int vrt_tree_set_stream(vrt_tree* tree, void* stream);
 int vrt_tree_blob_dev(const vrt_tree* tree, const void** d_blob, uint64_t* bytes);
 int vrt_tree_from_blob_dev(const void* d_blob, uint64_t bytes, vrt_tree** out);
 
+/* Checkpoint of a built octree (the reference rebuilds its tree on every run;
+ * the flat blob IS a serialisable format): the whole device blob, byte for byte. */
+int vrt_tree_save(const vrt_tree* tree, const char* path);
+int vrt_tree_load(const char* path, vrt_tree** out);
+
 /* ---- ray generation: replaces Camera::Camera + gen_rays1/gen_rays4
  *      (camera.cc:65-112) ---------------------------------------------------- */
 /* cam10 = fov, eye[3], spot[3], up[3]; fills C, z, tmin/tmax (host arithmetic,

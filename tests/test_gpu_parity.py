@@ -282,6 +282,32 @@ def test_rebuild_and_blob_replica(gpu, port):
     tree.close()
 
 
+def test_octree_checkpoint_roundtrip(gpu, tmp_path):
+    """vrt_tree_save / vrt_tree_load: the flat blob is the checkpoint format; a loaded tree
+    traces identically without a rebuild, and a corrupt file is refused."""
+    tri, nrm = scenes.uv_sphere(64, 32)
+    tree = gpu.Octree.build(tri, nrm, 7)
+    path = str(tmp_path / "sphere.vrt")
+    tree.save(path)
+    rep = gpu.Octree.load(path)
+    assert rep.info()["num_nodes"] == tree.info()["num_nodes"]
+    leaves_equal(rep.leaves(), tree.leaves())
+    cam = gpu.Camera(CAM_SPHERE[0], CAM_SPHERE[1:4], CAM_SPHERE[4:7], CAM_SPHERE[7:10], 64, 64, 4)
+    assert rep.trace_camera(cam).tobytes() == tree.trace_camera(cam).tobytes()
+    rep.close()
+    tree.close()
+    bad = str(tmp_path / "bad.vrt")
+    with open(path, "rb") as f:
+        data = bytearray(f.read())
+    data[0] ^= 0xFF
+    with open(bad, "wb") as f:
+        f.write(data)
+    with pytest.raises(gpu.VrtError):
+        gpu.Octree.load(bad)
+    with pytest.raises(gpu.VrtError):
+        gpu.Octree.load(str(tmp_path / "missing.vrt"))
+
+
 def test_work_counters_match_oracle(case, gpu, port):
     """The counting kernel (feeds bench.py's algorithmic bytes per ray) reproduces the
     instrumented oracle: interior expansions, non-empty leaf visits, triangle tests."""

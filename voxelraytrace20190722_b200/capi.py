@@ -58,7 +58,7 @@ SYMBOLS = [
     "vrt_abi_version", "vrt_last_error", "vrt_device_count", "vrt_launch_count",
     "vrt_build", "vrt_build_dev", "vrt_rebuild", "vrt_tree_free", "vrt_tree_get_info",
     "vrt_tree_export", "vrt_tree_import", "vrt_tree_set_stream", "vrt_tree_blob_dev",
-    "vrt_tree_from_blob_dev", "vrt_camera_init", "vrt_gen_rays", "vrt_trace_rays",
+    "vrt_tree_from_blob_dev", "vrt_tree_save", "vrt_tree_load", "vrt_camera_init", "vrt_gen_rays", "vrt_trace_rays",
     "vrt_trace_rays_dev", "vrt_trace_camera", "vrt_trace_camera_dev", "vrt_trace_camera16_dev",
     "vrt_render_camera", "vrt_render_camera_dev", "vrt_render_camera_async", "vrt_band_rows", "vrt_render_bands_dev",
     "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_frame_bands_peer_dev",
@@ -105,6 +105,8 @@ def load(build_if_missing: bool = True):
     L.vrt_tree_set_stream.argtypes = [vp, vp]
     L.vrt_tree_blob_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.vrt_tree_from_blob_dev.argtypes = [vp, u64, C.POINTER(vp)]
+    L.vrt_tree_save.argtypes = [vp, C.c_char_p]
+    L.vrt_tree_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.vrt_camera_init.argtypes = [vp, f32, i32, i32, i32, C.POINTER(vrt_camera)]
     L.vrt_gen_rays.argtypes = [C.POINTER(vrt_camera), i32, i32, i32, i32, vp]
     L.vrt_trace_rays.argtypes = [vp, vp, u64, vp]
@@ -242,6 +244,16 @@ class Octree:
         h = C.c_void_p()
         _check(load().vrt_tree_from_blob_dev(C.c_void_p(d_ptr), int(nbytes), C.byref(h)))
         return cls(h.value)
+
+    @classmethod
+    def load(cls, path):
+        """Octree checkpoint written by :meth:`save` -> a usable handle (no rebuild)."""
+        h = C.c_void_p()
+        _check(load().vrt_tree_load(os.fsencode(path), C.byref(h)))
+        return cls(h.value)
+
+    def save(self, path):
+        _check(load().vrt_tree_save(self._h, os.fsencode(path)))
 
     def rebuild(self, max_depth):
         _check(load().vrt_rebuild(self._h, int(max_depth)))

@@ -585,6 +585,71 @@ int vrt_tree_from_blob_dev(const void* d_blob, uint64_t bytes, vrt_tree** out)
         return VRT_OK;
 }
 
+int vrt_tree_save(const vrt_tree* t, const char* path)
+{
+        int rc = check_tree(t);
+        if (rc)
+                return rc;
+        if (!path) {
+                set_error("null path");
+                return VRT_ERR_ARG;
+        }
+        std::vector<char> host(t->hdr.bytes);
+        VRT_CUDA(cudaStreamSynchronize(t->stream));
+        VRT_CUDA(cudaMemcpy(host.data(), t->blob, t->hdr.bytes, cudaMemcpyDeviceToHost));
+        FILE* f = fopen(path, "wb");
+        if (!f) {
+                set_error("cannot open %s for writing", path);
+                return VRT_ERR_ARG;
+        }
+        const size_t w = fwrite(host.data(), 1, host.size(), f);
+        fclose(f);
+        if (w != host.size()) {
+                set_error("short write to %s", path);
+                return VRT_ERR_ARG;
+        }
+        return VRT_OK;
+}
+
+int vrt_tree_load(const char* path, vrt_tree** out)
+{
+        if (!path || !out) {
+                set_error("null argument");
+                return VRT_ERR_ARG;
+        }
+        *out = nullptr;
+        FILE* f = fopen(path, "rb");
+        if (!f) {
+                set_error("cannot open %s", path);
+                return VRT_ERR_ARG;
+        }
+        fseek(f, 0, SEEK_END);
+        const long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        if (sz < (long)kHeaderBytes) {
+                fclose(f);
+                set_error("%s is not a vrt octree checkpoint", path);
+                return VRT_ERR_ARG;
+        }
+        std::vector<char> host((size_t)sz);
+        const size_t r = fread(host.data(), 1, host.size(), f);
+        fclose(f);
+        BlobHeader h;
+        memcpy(&h, host.data(), sizeof h);
+        if (r != host.size() || h.magic != kBlobMagic || h.bytes > (uint64_t)sz) {
+                set_error("%s is not a vrt octree checkpoint (magic/size mismatch)", path);
+                return VRT_ERR_ARG;
+        }
+        int rc = need_device();
+        if (rc)
+                return rc;
+        DevBuf d;
+        if (d.alloc(h.bytes))
+                return VRT_ERR_NOMEM;
+        VRT_CUDA(cudaMemcpy(d.p, host.data(), h.bytes, cudaMemcpyHostToDevice));
+        return vrt_tree_from_blob_dev(d.p, h.bytes, out);
+}
+
 // ---- camera -----------------------------------------------------------------
 // Host arithmetic identical to Camera::Camera (camera.cc:65-75): jql::normalize
 // = v / sqrtf(((0+x*x)+y*y)+z*z), jql::cross (graphics_math.h:588-592),
