@@ -228,9 +228,11 @@ int vrt_trace_bands16_dev(const vrt_tree* tree, const vrt_camera* cam,
                           const vrt_bands* bands, vrt_hit16* d_out);
 /* Work counters of the reference algorithm for a camera frame:
  * counts[0..4] = rays traced, interior nodes expanded (travorder calls), non-empty
- * leaves visited, triangle tests, hits.  Host pointer out. */
+ * leaves visited, triangle tests, hits; counts[5..7] = kernel statistics: expansions done
+ * by the parametric fast path, slab fallbacks caused by a tie, slab expansions at levels
+ * that are not key-safe for the ray.  Host pointer out. */
 int vrt_count_camera(const vrt_tree* tree, const vrt_camera* cam, int x0, int y0, int x1,
-                     int y1, uint64_t counts[5]);
+                     int y1, uint64_t counts[8]);
 /* One frame step of the multi-GPU render loop: this rank's bands, writing BOTH the
  * compact per-ray hit records (kept sharded in this GPU's HBM) and the shaded film
  * bands (the piece the framebuffer gather collects).  d_hits[local_row][nx][spp],
@@ -254,6 +256,9 @@ int vrt_ipc_close(void* d_ptr);
 /* Test hook: how many node expansions of this process took the general (>4 candidate
  * children) ordering path of the ray kernel. */
 uint64_t vrt_debug_general_order_calls(void);
+/* out = {node expansions cross-checked against the slab expansion, mismatches}; counts only in
+ * a library built with -DVRT_PARAM_CHECK (tests), {0,0} otherwise. */
+int vrt_debug_param_check(uint64_t out[2]);
 /* _dev launches are asynchronous with respect to the host: they return once the work is
  * enqueued on the tree's stream.  vrt_tree_sync waits for it. */
 int vrt_tree_sync(const vrt_tree* tree);

@@ -63,7 +63,7 @@ SYMBOLS = [
     "vrt_render_camera", "vrt_render_camera_dev", "vrt_render_camera_async", "vrt_band_rows", "vrt_render_bands_dev",
     "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_frame_bands_peer_dev",
     "vrt_dev_alloc", "vrt_dev_free", "vrt_ipc_export", "vrt_ipc_open", "vrt_ipc_close", "vrt_tree_sync",
-    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_tribox_batch",
+    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_tribox_batch",
     "vrt_tri_overlap_aabb_batch", "vrt_raytri_batch", "vrt_aabb_isect_batch",
 ]
 
@@ -127,6 +127,7 @@ def load(build_if_missing: bool = True):
     L.vrt_ipc_open.argtypes = [vp, C.POINTER(vp)]
     L.vrt_ipc_close.argtypes = [vp]
     L.vrt_debug_general_order_calls.restype = u64
+    L.vrt_debug_param_check.argtypes = [vp]
     L.vrt_tree_sync.argtypes = [vp]
     L.vrt_mean_kernel_ms.restype = C.c_double
     L.vrt_mean_kernel_ms.argtypes = [vp, i32]
@@ -361,9 +362,10 @@ class Octree:
     def count_camera(self, cam: Camera, rect=None):
         """Work counters of the reference algorithm over a frame."""
         x0, y0, x1, y1 = rect if rect else (0, 0, cam.nx, cam.ny)
-        c = np.zeros(5, np.uint64)
+        c = np.zeros(8, np.uint64)
         _check(load().vrt_count_camera(self._h, C.byref(cam.c), x0, y0, x1, y1, _ptr(c)))
-        return dict(rays=int(c[0]), n_int=int(c[1]), n_leaf=int(c[2]), n_tri=int(c[3]), hits=int(c[4]))
+        return dict(rays=int(c[0]), n_int=int(c[1]), n_leaf=int(c[2]), n_tri=int(c[3]), hits=int(c[4]),
+                    n_param=int(c[5]), n_tie=int(c[6]), n_unsafe=int(c[7]))
 
     def render_async(self, cam: Camera, out, light=None, kd=0.8, rect=None, shadow_eps=None):
         """Pipelined frame loop: enqueue one frame whose film lands in the (pinned) host array
@@ -381,6 +383,13 @@ class Octree:
 
 def debug_general_order_calls() -> int:
     return int(load().vrt_debug_general_order_calls())
+
+
+def debug_param_check():
+    """(expansions cross-checked, mismatches) -- non-zero only with a -DVRT_PARAM_CHECK build."""
+    c = np.zeros(2, np.uint64)
+    _check(load().vrt_debug_param_check(_ptr(c)))
+    return int(c[0]), int(c[1])
 
 
 def dev_alloc(nbytes: int) -> int:

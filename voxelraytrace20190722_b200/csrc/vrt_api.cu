@@ -866,7 +866,7 @@ int vrt_render_camera_dev(const vrt_tree* t, const vrt_camera* cam, const vrt_sh
         return trace_camera_common(t, cam, sh, x0, y0, x1, y1, d_film_rgb, OUT_FILM, true);
 }
 
-int vrt_count_camera(const vrt_tree* tc, const vrt_camera* cam, int x0, int y0, int x1, int y1, uint64_t counts[5])
+int vrt_count_camera(const vrt_tree* tc, const vrt_camera* cam, int x0, int y0, int x1, int y1, uint64_t counts[8])
 {
         int rc = check_tree(tc);
         if (rc)
@@ -882,13 +882,13 @@ int vrt_count_camera(const vrt_tree* tc, const vrt_camera* cam, int x0, int y0, 
         if (t->io_out.reserve(64))
                 return VRT_ERR_NOMEM;
         VRT_CUDA(cudaMemsetAsync(t->io_out.p, 0, 64, t->stream));
-        memset(counts, 0, 5 * sizeof(uint64_t));
+        memset(counts, 0, 8 * sizeof(uint64_t));
         if (x1 > x0 && y1 > y0) {
                 rc = launch_trace_camera(t, cam, nullptr, x0, y0, x1, y1, t->io_out.p, OUT_COUNT);
                 if (rc)
                         return rc;
         }
-        VRT_CUDA(cudaMemcpyAsync(counts, t->io_out.p, 40, cudaMemcpyDeviceToHost, t->stream));
+        VRT_CUDA(cudaMemcpyAsync(counts, t->io_out.p, 64, cudaMemcpyDeviceToHost, t->stream));
         VRT_CUDA(cudaStreamSynchronize(t->stream));
         return VRT_OK;
 }
@@ -953,6 +953,19 @@ double vrt_mean_kernel_ms(const vrt_tree* t, int last_n)
         if (t)
                 trace_ms_mean(t, last_n, &ms);
         return ms;
+}
+
+int vrt_debug_param_check(uint64_t out[2])
+{
+        if (!out) {
+                set_error("null out");
+                return VRT_ERR_ARG;
+        }
+        unsigned long long v[2] = { 0, 0 };
+        int rc = param_check_counts(v);
+        out[0] = v[0];
+        out[1] = v[1];
+        return rc;
 }
 
 uint64_t vrt_debug_general_order_calls(void)

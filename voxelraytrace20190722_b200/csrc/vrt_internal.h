@@ -150,4 +150,5 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
 // mean device time (ms) of the last n trace launches (waits for them)
 int trace_ms_mean(const vrt_tree* t, int last_n, double* ms);
 int general_order_calls(unsigned long long* out);
+int param_check_counts(unsigned long long out[2]);
 }  // namespace vrt

@@ -69,6 +69,10 @@ struct HitState {
 // expanded (travorder calls), non-empty leaves visited, triangle tests.
 struct WorkCount {
         uint32_t n_int, n_leaf, n_tri;
+        // how the interior expansions were evaluated (kernel statistics, not reference work):
+        // parametric fast path / slab fallback because of a tie / slab because the level is
+        // not key-safe for this ray
+        uint32_t n_param, n_tie, n_unsafe;
 };
 
 // Triangle::isect + ray_march_isect for one leaf (voxel_octree.cc:99-129,438-460).
@@ -379,6 +383,116 @@ __device__ __noinline__ uint32_t order_children_general(const float* smin6, cons
         return list;
 }
 
+// Slab expansion of one node for a tame ray: the reference's per-child test and key order
+// evaluated for all 8 children (FMNMX form).  Used by the parametric expansion below as its
+// fallback (ties, key-unsafe levels), so it is kept out of line.  Returns the visiting order
+// as 3-bit child ids, lowest bits first.
+__device__ __noinline__ uint32_t expand_slab(float4 b0, float4 b1, float4 b2, float ox, float oy, float oz,
+                                             float dx, float dy, float dz, float ix, float iy, float iz,
+                                             uint32_t mask, float tmin, float tmax, uint32_t* cnt_out)
+{
+        const float inf = __int_as_float(0x7f800000);
+        const float4 bb[3] = { b0, b1, b2 };
+        const float o[3] = { ox, oy, oz }, d[3] = { dx, dy, dz }, dinv[3] = { ix, iy, iz };
+        float smin[3][2], smax[3][2], kt[3][2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+                // b = (p0, p1, p1, p2): lo child [p0,p1], hi child [p1,p2]
+                const float2 t01 = mul2s(sub2s(bb[a].x, bb[a].y, o[a]), dinv[a]);  // (p-o)*dinv
+                const float2 t12 = mul2s(sub2s(bb[a].z, bb[a].w, o[a]), dinv[a]);
+                smin[a][0] = fminf(t01.x, t01.y);
+                smax[a][0] = fmaxf(t01.x, t01.y);
+                smin[a][1] = fminf(t12.x, t12.y);
+                smax[a][1] = fmaxf(t12.x, t12.y);
+                // travorder key terms d*((min+max)*.5f - o); the subtraction stays scalar
+                // so that it cannot be contracted with the *.5f
+                const float2 h = mul2s(add2(bb[a].x, bb[a].y, bb[a].z, bb[a].w), .5f);
+                kt[a][0] = fmul(d[a], fsub(h.x, o[a]));
+                kt[a][1] = fmul(d[a], fsub(h.y, o[a]));
+        }
+        float kxy[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+                kxy[q] = fadd(kt[0][q >> 1], kt[1][q & 1]);
+        // candidates are inserted into a 4-slot list sorted by key; a later child
+        // (higher index) goes behind equal keys -- the stable order of the
+        // reference's insertion sort.  A line meets at most 4 of the 8 octants,
+        // so a 5th candidate is rare and handled by the general method.
+        float sk0 = inf, sk1 = inf, sk2 = inf, sk3 = inf;
+        uint32_t si0 = 0, si1 = 0, si2 = 0, si3 = 0;
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+                const float t0 = fmax3(smin[0][c >> 2], smin[1][(c >> 1) & 1], smin[2][c & 1]);
+                const float t1 = fmin3(smax[0][c >> 2], smax[1][(c >> 1) & 1], smax[2][c & 1]);
+                if (((mask >> c) & 1u) && slab_accept(t0, t1, tmin, tmax)) {
+                        float ck = fadd(kxy[c >> 1], kt[2][c & 1]);
+                        uint32_t ci = c;
+                        cnt += 1u;
+                        bool p;
+                        float tk;
+                        uint32_t tiq;
+                        p = ck < sk0; tk = sk0; tiq = si0; sk0 = p ? ck : sk0; si0 = p ? ci : si0; ck = p ? tk : ck; ci = p ? tiq : ci;
+                        p = ck < sk1; tk = sk1; tiq = si1; sk1 = p ? ck : sk1; si1 = p ? ci : si1; ck = p ? tk : ck; ci = p ? tiq : ci;
+                        p = ck < sk2; tk = sk2; tiq = si2; sk2 = p ? ck : sk2; si2 = p ? ci : si2; ck = p ? tk : ck; ci = p ? tiq : ci;
+                        p = ck < sk3; sk3 = p ? ck : sk3; si3 = p ? ci : si3;
+                }
+        }
+        uint32_t list = si0 | (si1 << 3) | (si2 << 6) | (si3 << 9);
+        if (cnt > 4u) {
+                const float a_min[6] = { smin[0][0], smin[0][1], smin[1][0], smin[1][1], smin[2][0], smin[2][1] };
+                const float a_max[6] = { smax[0][0], smax[0][1], smax[1][0], smax[1][1], smax[2][0], smax[2][1] };
+                const float a_kt[6] = { kt[0][0], kt[0][1], kt[1][0], kt[1][1], kt[2][0], kt[2][1] };
+                uint32_t cnt_general = 0;
+                list = order_children_general(a_min, a_max, a_kt, mask, tmin, tmax, &cnt_general);
+                cnt = cnt_general;
+        }
+        *cnt_out = cnt;
+        return list;
+}
+
+// Number of tree levels at which the PARAMETRIC expansion (below) provably visits the
+// children in the reference's key order for this ray: consecutive cells along the ray differ
+// in one axis a, their travorder keys differ by |d_a| * (centre step) before rounding, and
+// every rounding in  ((0 + dx*(cx-ox)) + dy*(cy-oy)) + dz*(cz-oz)  is monotone, so the float
+// keys are ordered like the cells as soon as that step exceeds the accumulated rounding
+// error (< 8 * 2^-24 * B, B bounding every intermediate magnitude).  We ask for
+// |d_a| * extent_a * 2^-(l+1) >= 2^-18 * B (4x margin) at expansion level l; below that the slab
+// expansion is used.  Axis-parallel rays (d_a == 0) and flat scenes (extent_a == 0) get 0.
+__device__ __forceinline__ int param_safe_levels(const float root[6], const float o[3], const float d[3])
+{
+        float B = 0.f, pm = 0.f, q = __int_as_float(0x7f800000);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+                B += fmaxf(fabsf(root[a] - o[a]), fabsf(root[3 + a] - o[a]));
+                pm = fmaxf(pm, fmaxf(fabsf(root[a]), fabsf(root[3 + a])));
+                q = fminf(q, fabsf(d[a]) * (root[3 + a] - root[a]));
+        }
+        B = (B + pm) * 3.814697265625e-06f;  // 2^-18
+        if (!(B > 0.f) || !(q > 0.f))
+                return 0;
+        const float r = q / B;  // <= 2^19
+        if (!(r >= 2.f))
+                return 0;
+        return (int)(__float_as_uint(r) >> 23) - 127;  // r >= 2^e: levels 0..e-1 are safe
+}
+
+#ifdef VRT_PARAM_CHECK
+__device__ unsigned long long g_param_check[4] = { 0, 0, 0, 0 };  // checked, mismatches, -, -
+#endif
+
+// FAST path.  Node expansion is PARAMETRIC: with t(p) = (p-o)*dinv the nine child-plane
+// parameters of a node (three planes per axis; exactly the floats the reference's eight slab
+// tests are made of), a child's slab interval is the intersection of three per-axis intervals
+// [e0,em] or [em,e1] (e0/e1 = near/far plane, em = mid plane; rounding is monotone so
+// e0 <= em <= e1 holds in floats).  The children with t0 <= t1 are therefore exactly the cells
+// of a 2x2x2 grid met by the diagonal t -> (t,t,t) on [T0,T1] = [max e0, min e1]: a start cell
+// (axis a is in its far half iff em_a < T0) followed by one flip per axis whose em_a lies in
+// [T0,T1], in ascending em_a.  Closed intervals make this exact unless two flipping axes have
+// EQUAL em (the ray meets a shared edge: extra cells touch) -- then, and at levels that are
+// not key-safe (param_safe_levels), the node is expanded by expand_slab instead.  Each cell
+// knows its own t0 (entry breakpoint) and t1 (next breakpoint), so the reference's window test
+// slab_accept(t0,t1,tmin,tmax) is evaluated on the same values.
 template <bool COUNT>
 __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float root[6], const float o[3],
                                                const float d[3], float tmin, float tmax, uint32_t* s_first,
@@ -403,8 +517,14 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                 }
                 return;
         }
-        const int stride = blockDim.x;
-        const float inf = __int_as_float(0x7f800000);
+        constexpr int stride = kTraceThreads;
+        // per-ray constants of the parametric expansion in ONE register: bits 0-2 negmask (near
+        // half of axis a is the HIGH child when d_a < 0; child id: x bit 2, y bit 1, z bit 0),
+        // bit 3 default window [0, FLT_MAX], bits 4.. number of key-safe levels
+        uint32_t rayflags = (d[0] < 0.f ? 4u : 0u) | (d[1] < 0.f ? 2u : 0u) | (d[2] < 0.f ? 1u : 0u) |
+                            (((tmin == 0.f) && (tmax == FLT_MAX)) ? 8u : 0u) |
+                            ((uint32_t)param_safe_levels(root, o, d) << 4);
+        asm volatile("" : "+r"(rayflags));  // keep it in its register (do not rematerialise per node)
         int level = 0, sp = 0;
         uint32_t x = 0, y = 0, z = 0, node = 0;
         uint32_t first, mask, list, cnt;
@@ -417,60 +537,84 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                         first = rec.x;
                         mask = rec.y;
                         const uint32_t ti = 1u << level;
-                        const float4 bb[3] = { __ldg(&tr.tab4[0][ti + x]), __ldg(&tr.tab4[1][ti + y]),
-                                               __ldg(&tr.tab4[2][ti + z]) };
-                        float smin[3][2], smax[3][2], kt[3][2];
-#pragma unroll
-                        for (int a = 0; a < 3; ++a) {
-                                // b = (p0, p1, p1, p2): lo child [p0,p1], hi child [p1,p2]
-                                const float2 t01 = mul2s(sub2s(bb[a].x, bb[a].y, o[a]), dinv[a]);  // (p-o)*dinv
-                                const float2 t12 = mul2s(sub2s(bb[a].z, bb[a].w, o[a]), dinv[a]);
-                                smin[a][0] = fminf(t01.x, t01.y);
-                                smax[a][0] = fmaxf(t01.x, t01.y);
-                                smin[a][1] = fminf(t12.x, t12.y);
-                                smax[a][1] = fmaxf(t12.x, t12.y);
-                                // travorder key terms d*((min+max)*.5f - o); the subtraction stays scalar
-                                // so that it cannot be contracted with the *.5f
-                                const float2 h = mul2s(add2(bb[a].x, bb[a].y, bb[a].z, bb[a].w), .5f);
-                                kt[a][0] = fmul(d[a], fsub(h.x, o[a]));
-                                kt[a][1] = fmul(d[a], fsub(h.y, o[a]));
-                        }
-                        float kxy[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                                kxy[q] = fadd(kt[0][q >> 1], kt[1][q & 1]);
-                        // candidates are inserted into a 4-slot list sorted by key; a later child
-                        // (higher index) goes behind equal keys -- the stable order of the
-                        // reference's insertion sort.  A line meets at most 4 of the 8 octants,
-                        // so a 5th candidate is rare and handled by the general method.
-                        float sk0 = inf, sk1 = inf, sk2 = inf, sk3 = inf;
-                        uint32_t si0 = 0, si1 = 0, si2 = 0, si3 = 0;
-                        cnt = 0;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                                const float t0 = fmax3(smin[0][c >> 2], smin[1][(c >> 1) & 1], smin[2][c & 1]);
-                                const float t1 = fmin3(smax[0][c >> 2], smax[1][(c >> 1) & 1], smax[2][c & 1]);
-                                if (((mask >> c) & 1u) && slab_accept(t0, t1, tmin, tmax)) {
-                                        float ck = fadd(kxy[c >> 1], kt[2][c & 1]);
-                                        uint32_t ci = c;
-                                        cnt += 1u;
-                                        bool p;
-                                        float tk;
-                                        uint32_t tiq;
-                                        p = ck < sk0; tk = sk0; tiq = si0; sk0 = p ? ck : sk0; si0 = p ? ci : si0; ck = p ? tk : ck; ci = p ? tiq : ci;
-                                        p = ck < sk1; tk = sk1; tiq = si1; sk1 = p ? ck : sk1; si1 = p ? ci : si1; ck = p ? tk : ck; ci = p ? tiq : ci;
-                                        p = ck < sk2; tk = sk2; tiq = si2; sk2 = p ? ck : sk2; si2 = p ? ci : si2; ck = p ? tk : ck; ci = p ? tiq : ci;
-                                        p = ck < sk3; sk3 = p ? ck : sk3; si3 = p ? ci : si3;
+                        const float4 bx = __ldg(&tr.tab4[0][ti + x]);
+                        const float4 by = __ldg(&tr.tab4[1][ti + y]);
+                        const float4 bz = __ldg(&tr.tab4[2][ti + z]);
+                        bool use_slab = (uint32_t)(level * 16 + 15) >= rayflags;  // level >= safe levels
+                        if (COUNT && use_slab)
+                                wc.n_unsafe += 1;
+                        if (!use_slab) {
+                                // t(p0), t(p1) packed, t(p2) scalar -- the reference's (plane-o)*dinv
+                                const float2 ax = mul2s(sub2s(bx.x, bx.y, o[0]), dinv[0]);
+                                const float2 ay = mul2s(sub2s(by.x, by.y, o[1]), dinv[1]);
+                                const float2 az = mul2s(sub2s(bz.x, bz.y, o[2]), dinv[2]);
+                                const float ax2 = fmul(fsub(bx.w, o[0]), dinv[0]);
+                                const float ay2 = fmul(fsub(by.w, o[1]), dinv[1]);
+                                const float az2 = fmul(fsub(bz.w, o[2]), dinv[2]);
+                                const float emx = ax.y, emy = ay.y, emz = az.y;
+                                const float T0 = fmax3(fminf(ax.x, ax2), fminf(ay.x, ay2), fminf(az.x, az2));
+                                const float T1 = fmin3(fmaxf(ax.x, ax2), fmaxf(ay.x, ay2), fmaxf(az.x, az2));
+                                // mid-plane parameters in ascending order s0 <= s1 <= s2
+                                const bool yx = emy < emx, zx = emz < emx, zy = emz < emy;
+                                const float s0 = fmin3(emx, emy, emz), s2 = fmax3(emx, emy, emz);
+                                const float s1 = fmaxf(fminf(emx, emy), fminf(fmaxf(emx, emy), emz));
+                                if (s0 == s1 || s1 == s2) {  // the ray may touch a shared edge: extra cells
+                                        use_slab = true;
+                                        if (COUNT)
+                                                wc.n_tie += 1;
+                                } else {
+                                        if (COUNT)
+                                                wc.n_param += 1;
+                                        // axis bit (x 4, y 2, z 1) of the smallest / largest mid-plane parameter
+                                        const uint32_t b0 = (!yx && !zx) ? 4u : ((yx && !zy) ? 2u : 1u);
+                                        const uint32_t b2 = (yx && zx) ? 4u : ((!yx && zy) ? 2u : 1u);
+                                        // the diagonal visits, in this order, the cells {}, {b0}, {b0,b1}, {all}
+                                        // (set = axes already in their far half); as child ids:
+                                        const uint32_t c0 = rayflags & 7u, c1 = c0 ^ b0, c3 = c0 ^ 7u, c2 = c3 ^ b2;
+                                        // cell j spans [max(T0, s_(j-1)), min(T1, s_j)] -- the very t0/t1 the
+                                        // reference's slab test computes for that child
+                                        const float h0 = fminf(T1, s0), h1 = fminf(T1, s1), h2 = fminf(T1, s2);
+                                        const float l1 = fmaxf(T0, s0), l2 = fmaxf(T0, s1), l3 = fmaxf(T0, s2);
+                                        bool a0, a1, a2, a3;
+                                        if (rayflags & 8u) {  // [0, FLT_MAX], finite t0 <= t1: accepted iff t1 >= 0
+                                                a0 = T0 <= h0 && h0 >= 0.f;
+                                                a1 = l1 <= h1 && h1 >= 0.f;
+                                                a2 = l2 <= h2 && h2 >= 0.f;
+                                                a3 = l3 <= T1 && T1 >= 0.f;
+                                        } else {
+                                                a0 = slab_accept(T0, h0, tmin, tmax);
+                                                a1 = slab_accept(l1, h1, tmin, tmax);
+                                                a2 = slab_accept(l2, h2, tmin, tmax);
+                                                a3 = slab_accept(l3, T1, tmin, tmax);
+                                        }
+                                        a0 = a0 && ((mask >> c0) & 1u);
+                                        a1 = a1 && ((mask >> c1) & 1u);
+                                        a2 = a2 && ((mask >> c2) & 1u);
+                                        a3 = a3 && ((mask >> c3) & 1u);
+                                        // visiting order = chain order; packed lowest bits first
+                                        list = a3 ? c3 : 0u;
+                                        list = a2 ? ((list << 3) | c2) : list;
+                                        list = a1 ? ((list << 3) | c1) : list;
+                                        list = a0 ? ((list << 3) | c0) : list;
+                                        cnt = (a0 ? 1u : 0u) + (a1 ? 1u : 0u) + (a2 ? 1u : 0u) + (a3 ? 1u : 0u);
+#ifdef VRT_PARAM_CHECK
+                                        {
+                                                uint32_t cnt_s = 0;
+                                                const uint32_t list_s = expand_slab(bx, by, bz, o[0], o[1], o[2], d[0], d[1], d[2], dinv[0],
+                                                                                    dinv[1], dinv[2], mask, tmin, tmax, &cnt_s);
+                                                const uint32_t keep = (1u << (3u * cnt_s)) - 1u;
+                                                atomicAdd(&g_param_check[0], 1ull);
+                                                if (cnt_s != cnt || ((list_s ^ list) & keep))
+                                                        atomicAdd(&g_param_check[1], 1ull);
+                                        }
+#endif
                                 }
                         }
-                        list = si0 | (si1 << 3) | (si2 << 6) | (si3 << 9);
-                        if (cnt > 4u) {
-                                const float a_min[6] = { smin[0][0], smin[0][1], smin[1][0], smin[1][1], smin[2][0], smin[2][1] };
-                                const float a_max[6] = { smax[0][0], smax[0][1], smax[1][0], smax[1][1], smax[2][0], smax[2][1] };
-                                const float a_kt[6] = { kt[0][0], kt[0][1], kt[1][0], kt[1][1], kt[2][0], kt[2][1] };
-                                uint32_t cnt_general = 0;  // (keeps `cnt` itself in a register)
-                                list = order_children_general(a_min, a_max, a_kt, mask, tmin, tmax, &cnt_general);
-                                cnt = cnt_general;
+                        if (use_slab) {
+                                uint32_t cnt_s = 0;
+                                list = expand_slab(bx, by, bz, o[0], o[1], o[2], d[0], d[1], d[2], dinv[0], dinv[1], dinv[2],
+                                                   mask, tmin, tmax, &cnt_s);
+                                cnt = cnt_s;
                         }
                 }
                 // ---- visit children in order until we descend, hit, or run out -----------------
@@ -598,8 +742,8 @@ k_trace_rays(TraceParams p)
 {
         extern __shared__ uint32_t s_stack[];
         uint32_t* s_first = s_stack + threadIdx.x;
-        uint32_t* s_meta = s_first + kMaxLevels * blockDim.x;
-        uint32_t* s_list = s_meta + kMaxLevels * blockDim.x;
+        uint32_t* s_meta = s_first + kMaxLevels * kTraceThreads;
+        uint32_t* s_list = s_meta + kMaxLevels * kTraceThreads;
         const unsigned long long nwarp_items = (p.num_rays + 31ull) / 32ull;
         const int lane = threadIdx.x & 31;
         for (;;) {
@@ -630,13 +774,16 @@ template <int MODE>
 #ifndef VRT_FILM_MIN_BLOCKS
 #define VRT_FILM_MIN_BLOCKS 7
 #endif
-__global__ void __launch_bounds__(kTraceThreads, (MODE == OUT_HIT16 || MODE == OUT_COUNT) ? 8 : VRT_FILM_MIN_BLOCKS)
+#ifndef VRT_HIT16_MIN_BLOCKS
+#define VRT_HIT16_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(kTraceThreads, (MODE == OUT_HIT16 || MODE == OUT_COUNT) ? VRT_HIT16_MIN_BLOCKS : VRT_FILM_MIN_BLOCKS)
 k_trace_camera(TraceParams p)
 {
         extern __shared__ uint32_t s_stack[];
         uint32_t* s_first = s_stack + threadIdx.x;
-        uint32_t* s_meta = s_first + kMaxLevels * blockDim.x;
-        uint32_t* s_list = s_meta + kMaxLevels * blockDim.x;
+        uint32_t* s_meta = s_first + kMaxLevels * kTraceThreads;
+        uint32_t* s_list = s_meta + kMaxLevels * kTraceThreads;
         const int lane = threadIdx.x & 31;
         const int W = p.x1 - p.x0, H = p.y1 - p.y0;
         const int spp = p.cam.spp;
@@ -668,7 +815,7 @@ k_trace_camera(TraceParams p)
                 float o[3] = { 0, 0, 0 }, d[3] = { 0, 0, 1 };
                 HitState hs;
                 hs.hit = false;
-                WorkCount wc = { 0, 0, 0 };
+                WorkCount wc = { 0, 0, 0, 0, 0, 0 };
                 if (active) {
                         gen_ray(p.cam, px, py, s, o, d);
                         trace_one<MODE == OUT_COUNT>(p.tree, p.root, o, d, p.cam.tmin, p.cam.tmax, s_first, s_meta,
@@ -679,11 +826,11 @@ k_trace_camera(TraceParams p)
                         if (active)
                                 store_hit48(static_cast<vrt_hit*>(p.out) + pix * spp + s, p.tree, hs, o, d);
                 } else if (MODE == OUT_COUNT) {
-                        // out = uint64[5]: rays, n_int, n_leaf, n_tri, hits
-                        unsigned long long v[5] = { active ? 1ull : 0ull, wc.n_int, wc.n_leaf, wc.n_tri,
-                                                    (active && hs.hit) ? 1ull : 0ull };
+                        // out = uint64[8]: rays, n_int, n_leaf, n_tri, hits, n_param, n_tie, n_unsafe
+                        unsigned long long v[8] = { active ? 1ull : 0ull, wc.n_int, wc.n_leaf, wc.n_tri,
+                                                    (active && hs.hit) ? 1ull : 0ull, wc.n_param, wc.n_tie, wc.n_unsafe };
 #pragma unroll
-                        for (int k = 0; k < 5; ++k) {
+                        for (int k = 0; k < 8; ++k) {
 #pragma unroll
                                 for (int o2 = 16; o2 > 0; o2 >>= 1)
                                         v[k] += __shfl_down_sync(0xffffffffu, v[k], o2);
@@ -868,6 +1015,21 @@ int general_order_calls(unsigned long long* out)
 {
         VRT_CUDA(cudaDeviceSynchronize());
         VRT_CUDA(cudaMemcpyFromSymbol(out, g_general_calls, sizeof(unsigned long long)));
+        return VRT_OK;
+}
+
+// {expansions cross-checked against expand_slab, mismatches}; only a library built with
+// -DVRT_PARAM_CHECK counts (tests/test_gpu_param_check.py), otherwise {0, 0}.
+int param_check_counts(unsigned long long out[2])
+{
+        out[0] = out[1] = 0;
+#ifdef VRT_PARAM_CHECK
+        unsigned long long v[4];
+        VRT_CUDA(cudaDeviceSynchronize());
+        VRT_CUDA(cudaMemcpyFromSymbol(v, g_param_check, sizeof v));
+        out[0] = v[0];
+        out[1] = v[1];
+#endif
         return VRT_OK;
 }
 
