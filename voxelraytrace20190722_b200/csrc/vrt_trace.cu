@@ -525,9 +525,18 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                             (((tmin == 0.f) && (tmax == FLT_MAX)) ? 8u : 0u) |
                             ((uint32_t)param_safe_levels(root, o, d) << 4);
         asm volatile("" : "+r"(rayflags));  // keep it in its register (do not rematerialise per node)
-        int level = 0, sp = 0;
-        uint32_t x = 0, y = 0, z = 0, node = 0;
+        // x,y,z are HEAP indices into the per-axis table: (1 << level) + cell coordinate, so a
+        // child is 2*i + bit and an ancestor i >> k.  The return stack is addressed through one
+        // register holding this thread's shared-memory byte address of the next free record.
+        int level = 0;
+        uint32_t x = 1, y = 1, z = 1, node = 0;
         uint32_t first, mask, list, cnt;
+        uint32_t sp = (uint32_t)__cvta_generic_to_shared(s_first);
+        // bottom-of-stack sentinel (meta bit 31): popping it means the ray left the tree
+        asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(sp), "n"(kMaxLevels * stride * 4u), "r"(0x80000000u) : "memory");
+        sp += stride * 4u;
+        constexpr uint32_t kRec = stride * 4u;               // bytes between records of one thread
+        constexpr uint32_t kCol = kMaxLevels * stride * 4u;  // bytes between the three columns
         for (;;) {
                 // ---- expand `node` (level; x,y,z) -------------------------------------------
                 {
@@ -536,14 +545,11 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 wc.n_int += 1;
                         first = rec.x;
                         mask = rec.y;
-                        const uint32_t ti = 1u << level;
-                        const float4 bx = __ldg(&tr.tab4[0][ti + x]);
-                        const float4 by = __ldg(&tr.tab4[1][ti + y]);
-                        const float4 bz = __ldg(&tr.tab4[2][ti + z]);
-                        bool use_slab = (uint32_t)(level * 16 + 15) >= rayflags;  // level >= safe levels
-                        if (COUNT && use_slab)
-                                wc.n_unsafe += 1;
-                        if (!use_slab) {
+                        const float4 bx = __ldg(&tr.tab4[0][x]);
+                        const float4 by = __ldg(&tr.tab4[1][y]);
+                        const float4 bz = __ldg(&tr.tab4[2][z]);
+                        bool use_slab = false;
+                        {
                                 // t(p0), t(p1) packed, t(p2) scalar -- the reference's (plane-o)*dinv
                                 const float2 ax = mul2s(sub2s(bx.x, bx.y, o[0]), dinv[0]);
                                 const float2 ay = mul2s(sub2s(by.x, by.y, o[1]), dinv[1]);
@@ -558,10 +564,15 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 const bool yx = emy < emx, zx = emz < emx, zy = emz < emy;
                                 const float s0 = fmin3(emx, emy, emz), s2 = fmax3(emx, emy, emz);
                                 const float s1 = fmaxf(fminf(emx, emy), fminf(fmaxf(emx, emy), emz));
-                                if (s0 == s1 || s1 == s2) {  // the ray may touch a shared edge: extra cells
+                                // slab expansion instead: the ray may touch a shared edge (extra cells),
+                                // or this level is not key-safe for the ray (level >= safe levels)
+                                const bool unsafe = (uint32_t)(level * 16 + 15) >= rayflags;
+                                if (s0 == s1 || s1 == s2 || unsafe) {
                                         use_slab = true;
-                                        if (COUNT)
-                                                wc.n_tie += 1;
+                                        if (COUNT) {
+                                                wc.n_unsafe += unsafe ? 1u : 0u;
+                                                wc.n_tie += unsafe ? 0u : 1u;
+                                        }
                                 } else {
                                         if (COUNT)
                                                 wc.n_param += 1;
@@ -620,12 +631,13 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                 // ---- visit children in order until we descend, hit, or run out -----------------
                 for (;;) {
                         if (cnt == 0) {
-                                if (sp == 0)
+                                sp -= kRec;
+                                uint32_t m;
+                                asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(m) : "r"(sp), "n"(kCol));
+                                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(first) : "r"(sp));
+                                asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(list) : "r"(sp), "n"(2u * kCol));
+                                if ((int32_t)m < 0)
                                         return;  // miss
-                                --sp;
-                                first = s_first[sp * stride];
-                                const uint32_t m = s_meta[sp * stride];
-                                list = s_list[sp * stride];
                                 mask = m & 0xffu;
                                 cnt = (m >> 8) & 0xfu;
                                 const int nl = (int)(m >> 12);
@@ -646,18 +658,20 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 if (leaf_isect<COUNT>(tr, child, o, d, hs, wc)) {
                                         hs.hit = true;
                                         hs.leaf = child;
-                                        hs.cx = cx;
-                                        hs.cy = cy;
-                                        hs.cz = cz;
+                                        hs.cx = cx - (1u << L);
+                                        hs.cy = cy - (1u << L);
+                                        hs.cz = cz - (1u << L);
                                         return;
                                 }
                                 continue;
                         }
                         if (cnt != 0u) {  // remember this level only if it has children left
-                                s_first[sp * stride] = first;
-                                s_meta[sp * stride] = mask | (cnt << 8) | ((uint32_t)level << 12);
-                                s_list[sp * stride] = list;
-                                ++sp;
+                                asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(first) : "memory");
+                                asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(sp), "n"(kCol),
+                                             "r"(mask | (cnt << 8) | ((uint32_t)level << 12))
+                                             : "memory");
+                                asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(sp), "n"(2u * kCol), "r"(list) : "memory");
+                                sp += kRec;
                         }
                         ++level;
                         x = cx;
@@ -790,13 +804,17 @@ k_trace_camera(TraceParams p)
         // warp tile: 8x4 pixels (spp 1) or 4x2 pixels x 4 samples (spp 4)
         const int tw = (spp == 4) ? 4 : 8, th = (spp == 4) ? 2 : 4;
         const int tiles_x = (W + tw - 1) / tw;
+        // the next tile index is fetched while the current tile is traced (the atomic's round
+        // trip to L2 stays off the critical path)
+        uint32_t next = 0;
+        if (lane == 0)
+                next = atomicAdd(p.queue, 1u);
         for (;;) {
-                uint32_t tile = 0;
-                if (lane == 0)
-                        tile = atomicAdd(p.queue, 1u);
-                tile = __shfl_sync(0xffffffffu, tile, 0);
+                const uint32_t tile = __shfl_sync(0xffffffffu, next, 0);
                 if (tile >= p.num_tiles)
                         break;
+                if (lane == 0)
+                        next = atomicAdd(p.queue, 1u);
                 const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
                 int s, lx, ly;
                 if (spp == 4) {
@@ -983,7 +1001,7 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         }
         const int tw = (cam->spp == 4) ? 4 : 8, th = (cam->spp == 4) ? 2 : 4;
         const uint64_t tiles = (uint64_t)((x1 - x0 + tw - 1) / tw) * (uint64_t)((y1 - y0 + th - 1) / th);
-        if (tiles >= 0xffffffffull) {
+        if (tiles >= 0xfff00000ull) {  // (the prefetching queue overshoots by one fetch per warp)
                 set_error("too many tiles for one launch");
                 return VRT_ERR_ARG;
         }
