@@ -139,7 +139,8 @@ __device__ __forceinline__ void finish_isect(const TreeDev& tr, const HitState& 
 // EXACT path: one ray through the octree with every min/max/first-extremum rule of
 // the reference restated literally (NaN/Inf/denormal-safe).  Only rays that fail the
 // `ray_is_tame` test below take it, so it is kept out of line.
-// s_first/s_meta/s_list: shared stack columns of this thread (stride = blockDim.x).
+// s_first/s_meta/s_list: the three words of this thread's stack record 0; record r, word w lives
+// at s_first[(3 * r + w) * blockDim.x] (see the kernels).
 template <bool COUNT>
 __device__ __noinline__ void trace_one_exact(const TreeDev& tr, const float* root, const float* o,
                                              const float* d, float tmin, float tmax, uint32_t* s_first,
@@ -240,11 +241,11 @@ __device__ __noinline__ void trace_one_exact(const TreeDev& tr, const float* roo
                         x >>= 1;
                         y >>= 1;
                         z >>= 1;
-                        first = s_first[level * stride];
-                        const uint32_t m = s_meta[level * stride];
+                        first = s_first[level * 3 * stride];
+                        const uint32_t m = s_meta[level * 3 * stride];
                         mask = m & 0xffu;
                         cnt = m >> 8;
-                        list = s_list[level * stride];
+                        list = s_list[level * 3 * stride];
                         continue;
                 }
                 const uint32_t c = list & 7u;
@@ -264,9 +265,9 @@ __device__ __noinline__ void trace_one_exact(const TreeDev& tr, const float* roo
                                 return;
                         }
                 } else {
-                        s_first[level * stride] = first;
-                        s_meta[level * stride] = mask | (cnt << 8);
-                        s_list[level * stride] = list;
+                        s_first[level * 3 * stride] = first;
+                        s_meta[level * 3 * stride] = mask | (cnt << 8);
+                        s_list[level * 3 * stride] = list;
                         ++level;
                         x = cx;
                         y = cy;
@@ -533,10 +534,10 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
         uint32_t first, mask, list, cnt;
         uint32_t sp = (uint32_t)__cvta_generic_to_shared(s_first);
         // bottom-of-stack sentinel (meta bit 31): popping it means the ray left the tree
-        asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(sp), "n"(kMaxLevels * stride * 4u), "r"(0x80000000u) : "memory");
-        sp += stride * 4u;
-        constexpr uint32_t kRec = stride * 4u;               // bytes between records of one thread
-        constexpr uint32_t kCol = kMaxLevels * stride * 4u;  // bytes between the three columns
+        asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(sp), "n"(stride * 4u), "r"(0x80000000u) : "memory");
+        sp += 3u * stride * 4u;
+        constexpr uint32_t kCol = stride * 4u;  // bytes between the three words of a record
+        constexpr uint32_t kRec = 3u * kCol;    // bytes between records of one thread
         for (;;) {
                 // ---- expand `node` (level; x,y,z) -------------------------------------------
                 {
@@ -563,7 +564,9 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 // mid-plane parameters in ascending order s0 <= s1 <= s2
                                 const bool yx = emy < emx, zx = emz < emx, zy = emz < emy;
                                 const float s0 = fmin3(emx, emy, emz), s2 = fmax3(emx, emy, emz);
-                                const float s1 = fmaxf(fminf(emx, emy), fminf(fmaxf(emx, emy), emz));
+                                // median = the one that is neither: a ^ b ^ c ^ min ^ max on the bit patterns
+                                const float s1 = __uint_as_float(__float_as_uint(emx) ^ __float_as_uint(emy) ^ __float_as_uint(emz) ^
+                                                                 __float_as_uint(s0) ^ __float_as_uint(s2));
                                 // slab expansion instead: the ray may touch a shared edge (extra cells),
                                 // or this level is not key-safe for the ray (level >= safe levels)
                                 const bool unsafe = (uint32_t)(level * 16 + 15) >= rayflags;
@@ -584,15 +587,19 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                         const uint32_t c0 = rayflags & 7u, c1 = c0 ^ b0, c3 = c0 ^ 7u, c2 = c3 ^ b2;
                                         // cell j spans [max(T0, s_(j-1)), min(T1, s_j)] -- the very t0/t1 the
                                         // reference's slab test computes for that child
-                                        const float h0 = fminf(T1, s0), h1 = fminf(T1, s1), h2 = fminf(T1, s2);
-                                        const float l1 = fmaxf(T0, s0), l2 = fmaxf(T0, s1), l3 = fmaxf(T0, s2);
                                         bool a0, a1, a2, a3;
-                                        if (rayflags & 8u) {  // [0, FLT_MAX], finite t0 <= t1: accepted iff t1 >= 0
-                                                a0 = T0 <= h0 && h0 >= 0.f;
-                                                a1 = l1 <= h1 && h1 >= 0.f;
-                                                a2 = l2 <= h2 && h2 >= 0.f;
-                                                a3 = l3 <= T1 && T1 >= 0.f;
+                                        if (rayflags & 8u) {
+                                                // window [0, FLT_MAX] and finite t0 <= t1: accepted iff t1 >= 0.  With
+                                                // s0 <= s1 <= s2:  max(T0,s_(j-1)) <= min(T1,s_j)  <=>  T0 <= T1 and
+                                                // s_(j-1) <= T1 and T0 <= s_j;  min(T1,s_j) >= 0  <=>  T1 >= 0 and s_j >= 0
+                                                const bool vw = (T0 <= T1) && (T1 >= 0.f);
+                                                a0 = vw && (T0 <= s0) && (s0 >= 0.f);
+                                                a1 = vw && (s0 <= T1) && (T0 <= s1) && (s1 >= 0.f);
+                                                a2 = vw && (s1 <= T1) && (T0 <= s2) && (s2 >= 0.f);
+                                                a3 = vw && (s2 <= T1);
                                         } else {
+                                                const float h0 = fminf(T1, s0), h1 = fminf(T1, s1), h2 = fminf(T1, s2);
+                                                const float l1 = fmaxf(T0, s0), l2 = fmaxf(T0, s1), l3 = fmaxf(T0, s2);
                                                 a0 = slab_accept(T0, h0, tmin, tmax);
                                                 a1 = slab_accept(l1, h1, tmin, tmax);
                                                 a2 = slab_accept(l2, h2, tmin, tmax);
@@ -756,8 +763,8 @@ k_trace_rays(TraceParams p)
 {
         extern __shared__ uint32_t s_stack[];
         uint32_t* s_first = s_stack + threadIdx.x;
-        uint32_t* s_meta = s_first + kMaxLevels * kTraceThreads;
-        uint32_t* s_list = s_meta + kMaxLevels * kTraceThreads;
+        uint32_t* s_meta = s_first + kTraceThreads;  // record r, word w: s_stack[(3 * r + w) * threads + tid]
+        uint32_t* s_list = s_meta + kTraceThreads;
         const unsigned long long nwarp_items = (p.num_rays + 31ull) / 32ull;
         const int lane = threadIdx.x & 31;
         for (;;) {
@@ -796,8 +803,8 @@ k_trace_camera(TraceParams p)
 {
         extern __shared__ uint32_t s_stack[];
         uint32_t* s_first = s_stack + threadIdx.x;
-        uint32_t* s_meta = s_first + kMaxLevels * kTraceThreads;
-        uint32_t* s_list = s_meta + kMaxLevels * kTraceThreads;
+        uint32_t* s_meta = s_first + kTraceThreads;  // record r, word w: s_stack[(3 * r + w) * threads + tid]
+        uint32_t* s_list = s_meta + kTraceThreads;
         const int lane = threadIdx.x & 31;
         const int W = p.x1 - p.x0, H = p.y1 - p.y0;
         const int spp = p.cam.spp;
@@ -928,6 +935,14 @@ static int persistent_grid(const void* kernel, size_t smem)
         return g_sm_count * per_sm;
 }
 
+// Traversal stack: one 3-word record per thread for the bottom sentinel and for every level
+// that can be left with unvisited children (levels 0 .. L-1).
+static size_t stack_bytes(const vrt_tree* t)
+{
+        const int L = std::max(t->dev.L, 1);
+        return (size_t)3 * (size_t)(L + 1) * kTraceThreads * sizeof(uint32_t);
+}
+
 static void fill_common(const vrt_tree* t, TraceParams& p)
 {
         p.tree = t->dev;
@@ -951,7 +966,7 @@ int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_
         p.rays = d_rays;
         p.num_rays = n;
         p.out = d_out;
-        const size_t smem = (size_t)3 * kMaxLevels * kTraceThreads * sizeof(uint32_t);
+        const size_t smem = stack_bytes(t);
         VRT_CUDA(cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const uint64_t warps = (n + 31) / 32;
         int grid = persistent_grid((const void*)k_trace_rays, smem);
@@ -1006,7 +1021,7 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
                 return VRT_ERR_ARG;
         }
         p.num_tiles = (uint32_t)tiles;
-        const size_t smem = (size_t)3 * kMaxLevels * kTraceThreads * sizeof(uint32_t);
+        const size_t smem = stack_bytes(t);
         const void* kern = nullptr;
         switch (mode) {
         case OUT_HIT48: kern = (const void*)k_trace_camera<OUT_HIT48>; break;
