@@ -92,6 +92,14 @@ class Port:
         L.orc_tri_overlap_aabb_batch.argtypes = [_f32p, _f32p, C.c_uint64, _u8p]
         L.orc_raytri_batch.argtypes = [_f64p, C.c_uint64, _u8p, _f64p]
         L.orc_aabb_isect_batch.argtypes = [_f32p, _f32p, C.c_uint64, _u8p]
+        # GI rows
+        L.orc_gi_reset.argtypes = [C.c_void_p]
+        L.orc_gi_splat.argtypes = [C.c_void_p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int, _f32p]
+        L.orc_gi_filter.argtypes = [C.c_void_p]
+        L.orc_gi_dump_level.restype = C.c_uint64
+        L.orc_gi_dump_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_gi_cone_trace.argtypes = [C.c_void_p, _f32p, _f32p, C.c_uint64, C.c_float, _f32p]
+        L.orc_gi_render.argtypes = [C.c_void_p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, _f32p, _f32p]
 
     # -- tree ---------------------------------------------------------------
     def build(self, tri, nrm, max_depth):
@@ -188,6 +196,46 @@ class PortTree:
                               n_leaf=int(cn[3]), n_tri=int(cn[4]), max_stack=int(cn[5]))
         return o
 
+    def _gi(self, name):
+        return getattr(self.port.lib, "orc_gi_" + name)
+
+    # -- GI rows: same method names on PortTree and RefScene -----------------
+    def gi_reset(self):
+        self._gi("reset")(self.h)
+
+    def gi_filter(self):
+        self._gi("filter")(self.h)
+
+    def gi_level(self, level):
+        """(cells[n,3], coverage[n], illum[n,6,3]) of the nodes of `level` with coverage > 0, Morton order."""
+        f = self._gi("dump_level")
+        n = int(f(self.h, int(level), None, None, None, 0))
+        cells = np.zeros((n, 3), np.uint32)
+        cov = np.zeros(n, np.float32)
+        il = np.zeros((n, 6, 3), np.float32)
+        if n:
+            f(self.h, int(level), cells.ctypes.data, cov.ctypes.data, il.ctypes.data, n)
+        return cells, cov, il
+
+    def gi_cone_trace(self, pos, nrm, res):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1, 3)
+        out = np.zeros((len(pos), 3), np.float32)
+        self._gi("cone_trace")(self.h, pos, nrm, len(pos), float(np.float32(res)), out)
+        return out
+
+    def gi_splat(self, cam10, film_h, nx, ny, spp, kd):
+        self.kd = np.ascontiguousarray(kd, np.float32)
+        self.port.lib.orc_gi_splat(self.h, np.ascontiguousarray(cam10, np.float32), float(film_h), nx, ny, spp,
+                                   self.kd)
+
+    def gi_render(self, cam10, film_h, nx, ny, spp, res, kd=None, nthreads=1):
+        kd = self.kd if kd is None else np.ascontiguousarray(kd, np.float32)
+        film = np.zeros((ny, nx, 3), np.float32)
+        self.port.lib.orc_gi_render(self.h, np.ascontiguousarray(cam10, np.float32), float(film_h), nx, ny, spp,
+                                    float(np.float32(res)), kd, film)
+        return film
+
 
 # ----------------------------------------------------------------------------
 class Ref:
@@ -221,6 +269,17 @@ class Ref:
         L.ref_raytri_batch.argtypes = [_f64p, C.c_uint64, _u8p, _f64p]
         L.ref_aabb_isect_batch.argtypes = [_f32p, _f32p, C.c_uint64, _u8p]
         L.ref_camera_matrix.argtypes = [_f32p, _f32p]
+        # GI rows
+        L.ref_scene_set_diffuse.argtypes = [C.c_void_p, _f32p]
+        L.ref_gi_reset.argtypes = [C.c_void_p]
+        L.ref_gi_splat.argtypes = [C.c_void_p, _f32p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.ref_gi_filter.argtypes = [C.c_void_p]
+        L.ref_gi_dump_level.restype = C.c_uint64
+        L.ref_gi_dump_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.ref_gi_cone_trace.argtypes = [C.c_void_p, _f32p, _f32p, C.c_uint64, C.c_float, _f32p]
+        L.ref_gi_render.restype = C.c_double
+        L.ref_gi_render.argtypes = [C.c_void_p, _f32p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_float,
+                                    _f32p, C.c_int]
 
     def hardware_concurrency(self):
         return int(self.lib.ref_hardware_concurrency())
@@ -333,3 +392,45 @@ class RefScene:
             _opt(o.hit) if o else None, _opt(o.cell) if o else None, _opt(o.tri) if o else None,
             _opt(o.pos) if o else None, _opt(o.nrm) if o else None, C.byref(n))
         return float(sec), int(n.value), o
+
+    def _gi(self, name):
+        return getattr(self.ref.lib, "ref_gi_" + name)
+
+    # -- GI rows: same method names on PortTree and RefScene -----------------
+    def gi_reset(self):
+        self._gi("reset")(self.h)
+
+    def gi_filter(self):
+        self._gi("filter")(self.h)
+
+    def gi_level(self, level):
+        """(cells[n,3], coverage[n], illum[n,6,3]) of the nodes of `level` with coverage > 0, Morton order."""
+        f = self._gi("dump_level")
+        n = int(f(self.h, int(level), None, None, None, 0))
+        cells = np.zeros((n, 3), np.uint32)
+        cov = np.zeros(n, np.float32)
+        il = np.zeros((n, 6, 3), np.float32)
+        if n:
+            f(self.h, int(level), cells.ctypes.data, cov.ctypes.data, il.ctypes.data, n)
+        return cells, cov, il
+
+    def gi_cone_trace(self, pos, nrm, res):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1, 3)
+        out = np.zeros((len(pos), 3), np.float32)
+        self._gi("cone_trace")(self.h, pos, nrm, len(pos), float(np.float32(res)), out)
+        return out
+
+    def gi_splat(self, cam10, film_h, nx, ny, spp, kd, film_w=1.0):
+        self.ref.lib.ref_scene_set_diffuse(self.h, np.ascontiguousarray(kd, np.float32))
+        self.ref.lib.ref_gi_splat(self.h, np.ascontiguousarray(cam10, np.float32), float(film_w), float(film_h),
+                                  nx, ny, spp)
+
+    def gi_render(self, cam10, film_h, nx, ny, spp, res, kd=None, nthreads=1, film_w=1.0):
+        if kd is not None:
+            self.ref.lib.ref_scene_set_diffuse(self.h, np.ascontiguousarray(kd, np.float32))
+        film = np.zeros((ny, nx, 3), np.float32)
+        self.seconds = float(self.ref.lib.ref_gi_render(self.h, np.ascontiguousarray(cam10, np.float32), float(film_w),
+                                                        float(film_h), nx, ny, spp, float(np.float32(res)), film,
+                                                        int(nthreads)))
+        return film

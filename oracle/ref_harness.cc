@@ -11,6 +11,11 @@
 //   render_mt            camera.h:41-68
 //   triBoxOverlap        tribox2.cc:112-186
 //   intersect_triangle3  raytri.cc:197-249
+//   gi::cone_trace_init_filter / gi::cone_trace   voxel_octree.cc:190-303
+//   VoxelOctree::compute_illum, Triangle::get_diffuse/get_albedo
+//   (the two main.cc lambdas -- light-map splat main.cc:81-96 and trace()
+//   main.cc:10-30 -- are not linkable, main.cc holds main(); the GI section at the
+//   end of this file drives the same reference calls in the same order)
 // and is only re-shaped into flat arrays so that Python tests (ctypes) and
 // bench.py's `--impl reference` / `cpu_baseline` legs can read it.
 //
@@ -442,6 +447,196 @@ void ref_camera_matrix(const float* cam10, float* out16)
         const Vec3 up_ = normalize(cross(s, forward_));
         Mat4 C = jql::affine_transform(Mat3{ s, up_, -forward_ }, eye);
         std::memcpy(out16, jql::begin(C), 16 * sizeof(float));
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// GI rows of SURVEY.md 8(f): light-map splat, bottom-up filter, cone trace and
+// the final trace() pixel.  All arithmetic is the reference's (ray_march,
+// get_diffuse, compute_illum, cone_trace_init_filter, cone_trace); the harness
+// only sequences the calls like main.cc does.
+// ---------------------------------------------------------------------------
+namespace {
+
+void gi_reset_walk(gi::VoxelOctree* n)
+{
+        n->coverage = 0.f;
+        for (int f = 0; f < 6; ++f)
+                n->illum[f] = Vec3{ 0, 0, 0 };
+        if (!node_is_leaf(n))
+                for (int i = 0; i < 8; ++i)
+                        gi_reset_walk(n->children[i].get());
+}
+
+struct GiDump {
+        int level;
+        uint32_t* cells;
+        float* cov;
+        float* illum;
+        uint64_t cap, n;
+};
+
+void gi_dump_walk(const gi::VoxelOctree* n, uint32_t x, uint32_t y, uint32_t z, int level, GiDump* d)
+{
+        if (level == d->level) {
+                if (n->coverage > 0.f) {
+                        if (d->n < d->cap) {
+                                if (d->cells) {
+                                        d->cells[3 * d->n] = x;
+                                        d->cells[3 * d->n + 1] = y;
+                                        d->cells[3 * d->n + 2] = z;
+                                }
+                                if (d->cov)
+                                        d->cov[d->n] = n->coverage;
+                                if (d->illum)
+                                        for (int f = 0; f < 6; ++f) {
+                                                d->illum[18 * d->n + 3 * f] = n->illum[f].x;
+                                                d->illum[18 * d->n + 3 * f + 1] = n->illum[f].y;
+                                                d->illum[18 * d->n + 3 * f + 2] = n->illum[f].z;
+                                        }
+                        }
+                        d->n++;
+                }
+                return;
+        }
+        if (node_is_leaf(n))
+                return;
+        for (int i = 0; i < 8; ++i)
+                gi_dump_walk(n->children[i].get(), 2 * x + ((i >> 2) & 1), 2 * y + ((i >> 1) & 1),
+                             2 * z + (i & 1), level + 1, d);
+}
+
+// main.cc:10-30 trace(), with the reference's calls in the reference's order.
+Vec3 gi_trace_pixel(gi::VoxelOctree& root, const jql::Ray& ray, float res)
+{
+        gi::VoxelOctree* leaf_ptr{};
+        gi::VoxelBase* voxel_ptr{};
+        ISect isect{};
+        if (!gi::ray_march(&root, ray, &leaf_ptr, &voxel_ptr, &isect, true)) {
+                float t = 0.5 * (ray.d.y + 1.0);
+                return jql::lerp(Vec3{ 1.0f, 1.0f, 1.0f }, Vec3{ 0.6f, 0.8f, 1.0f }, t);
+        }
+        auto indirect_light = gi::cone_trace(root, isect, res);
+        Vec3 direct_light = leaf_ptr->compute_illum(-ray.d);
+        if (voxel_ptr->is_visible())
+                return voxel_ptr->get_albedo(isect) * (indirect_light + direct_light);
+        return voxel_ptr->get_albedo(isect);
+}
+
+}  // namespace
+
+extern "C" {
+
+// tinyobj::material_t::diffuse of the scene's (single, untextured) material
+void ref_scene_set_diffuse(void* h, const float* rgb)
+{
+        auto* s = static_cast<RefScene*>(h);
+        for (int k = 0; k < 3; ++k)
+                s->mtl.diffuse[k] = rgb[k];
+}
+
+void ref_gi_reset(void* h)
+{
+        gi_reset_walk(static_cast<RefScene*>(h)->root.get());
+}
+
+// The light-map pass of main.cc:81-96, executed SEQUENTIALLY in pixel order (py outer,
+// px inner, samples in gen_rays order).  The reference runs the same lambda on pool
+// threads without synchronising the += on the shared leaf, so its own result depends on
+// the interleaving; the sequential order is the deterministic member of that family.
+void ref_gi_splat(void* h, const float* cam10, float film_w, float film_h, int nx, int ny, int spp)
+{
+        auto* s = static_cast<RefScene*>(h);
+        Camera scam = make_camera(cam10);
+        Film film(film_w, film_h, nx, ny);
+        gi::VoxelOctree& root = *s->root;
+        for (int py = 0; py < ny; ++py)
+                for (int px = 0; px < nx; ++px) {
+                        auto rays = (spp == 4) ? scam.gen_rays4(film, px, py) : scam.gen_rays1(film, px, py);
+                        for (const auto& ray : rays) {
+                                gi::VoxelOctree* leaf_ptr{};
+                                jql::ISect isect{};
+                                gi::VoxelBase* voxel_ptr{};
+                                if (!gi::ray_march(&root, ray, &leaf_ptr, &voxel_ptr, &isect))
+                                        continue;
+                                auto illum = voxel_ptr->get_diffuse(isect, ray, Vec3{ 1, 1, 1 });
+                                for (int i = 0; i < 6; ++i) {
+                                        float coeff = jql::dot(leaf_ptr->illum_d[i], isect.normal);
+                                        coeff = jql::clamp(coeff, 0.f, 1.f);
+                                        leaf_ptr->illum[i] += coeff * illum;
+                                }
+                        }
+                }
+}
+
+void ref_gi_filter(void* h)
+{
+        gi::cone_trace_init_filter(static_cast<RefScene*>(h)->root.get());
+}
+
+// Nodes of tree level `level` (root = 0) with coverage > 0, in Morton order (x bit 2, y bit 1,
+// z bit 0 per level).  Returns their number; fills up to `cap` entries of the non-NULL arrays.
+uint64_t ref_gi_dump_level(void* h, int level, uint32_t* cells, float* cov, float* illum18, uint64_t cap)
+{
+        GiDump d{ level, cells, cov, illum18, cap, 0 };
+        gi_dump_walk(static_cast<RefScene*>(h)->root.get(), 0, 0, 0, 0, &d);
+        return d.n;
+}
+
+// gi::cone_trace(root, ISect{hit, normal}, res) for n surface points.
+void ref_gi_cone_trace(void* h, const float* pos, const float* nrm, uint64_t n, float res, float* out3)
+{
+        auto* s = static_cast<RefScene*>(h);
+        for (uint64_t i = 0; i < n; ++i) {
+                ISect is{};
+                is.hit = Vec3{ pos[3 * i], pos[3 * i + 1], pos[3 * i + 2] };
+                is.normal = Vec3{ nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2] };
+                Vec3 c = gi::cone_trace(*s->root, is, res);
+                out3[3 * i] = c.x;
+                out3[3 * i + 1] = c.y;
+                out3[3 * i + 2] = c.z;
+        }
+}
+
+// The final image loop of main.cc:117-123 on a harness-owned [ny][nx][3] film: every sample's
+// trace() colour times 1/spp, added in sample order.  Rows are split over `nthreads` threads
+// (the tree is read-only here).  Returns wall seconds.
+double ref_gi_render(void* h, const float* cam10, float film_w, float film_h, int nx, int ny, int spp,
+                     float res, float* film3, int nthreads)
+{
+        auto* s = static_cast<RefScene*>(h);
+        Camera cam = make_camera(cam10);
+        Film film(film_w, film_h, nx, ny);
+        gi::VoxelOctree& root = *s->root;
+        const float w = (spp == 4) ? .25f : 1.f;
+        auto work = [&](int y0, int y1) {
+                for (int py = y0; py < y1; ++py)
+                        for (int px = 0; px < nx; ++px) {
+                                Vec3 acc{ 0, 0, 0 };
+                                auto rays = (spp == 4) ? cam.gen_rays4(film, px, py) : cam.gen_rays1(film, px, py);
+                                for (const auto& ray : rays) {
+                                        auto c = gi_trace_pixel(root, ray, res);
+                                        acc += c * w;
+                                }
+                                float* o = film3 + 3 * ((size_t)py * nx + px);
+                                o[0] = acc.x;
+                                o[1] = acc.y;
+                                o[2] = acc.z;
+                        }
+        };
+        auto t0 = std::chrono::steady_clock::now();
+        if (nthreads <= 1) {
+                work(0, ny);
+        } else {
+                std::vector<std::thread> th;
+                for (int t = 0; t < nthreads; ++t)
+                        th.emplace_back(work, (int)((long long)ny * t / nthreads), (int)((long long)ny * (t + 1) / nthreads));
+                for (auto& t : th)
+                        t.join();
+        }
+        auto t1 = std::chrono::steady_clock::now();
+        return std::chrono::duration<double>(t1 - t0).count();
 }
 
 }  // extern "C"

@@ -332,6 +332,9 @@ typedef struct {
         int32_t child[8]; /* -1 = this node is a leaf (never split) */
         uint32_t* refs;   /* triangle indices, insertion (= ascending) order */
         uint32_t nrefs, cap;
+        /* cone-trace state (voxel_octree.h:66-70): coverage, illum[6] (Vec3 each) */
+        float coverage;
+        float illum[18];
 } orc_node;
 
 typedef struct {
@@ -357,6 +360,8 @@ static int32_t orc_new_node(orc_tree* t, const float mn[3], const float mx[3])
                 n->child[i] = -1;
         n->refs = NULL;
         n->nrefs = n->cap = 0;
+        n->coverage = 0.f;
+        memset(n->illum, 0, sizeof n->illum);
         return (int32_t)t->n_nodes++;
 }
 
@@ -625,9 +630,22 @@ static int orc_leaf_isect(const orc_tree* t, const orc_node* leaf, const float* 
 
 /* voxel_octree.cc:131-188 ray_march.  Returns 1 on hit and fills the hit
  * record (cell xyz at level max_depth-1, triangle index, t, hit, normal). */
+static int orc_ray_march_ex(const orc_tree* t, const float ray[8], uint32_t cell[3],
+                            uint32_t* tri, float* tt, float hit[3], float nrm[3],
+                            orc_counters* cn, int32_t* leaf_node);
+
 int orc_ray_march(const orc_tree* t, const float ray[8], uint32_t cell[3],
                   uint32_t* tri, float* tt, float hit[3], float nrm[3],
                   orc_counters* cn)
+{
+        int32_t leaf = -1;
+        return orc_ray_march_ex(t, ray, cell, tri, tt, hit, nrm, cn, &leaf);
+}
+
+/* as above; *leaf_node = pool index of the leaf that produced the hit */
+static int orc_ray_march_ex(const orc_tree* t, const float ray[8], uint32_t cell[3],
+                            uint32_t* tri, float* tt, float hit[3], float nrm[3],
+                            orc_counters* cn, int32_t* leaf_node)
 {
         const orc_node* root = &t->nodes[0];
         if (cn)
@@ -642,6 +660,7 @@ int orc_ray_march(const orc_tree* t, const float ray[8], uint32_t cell[3],
                 }
                 if (orc_leaf_isect(t, root, ray, tri, hit, nrm, tt, cn)) {
                         cell[0] = cell[1] = cell[2] = 0;
+                        *leaf_node = 0;
                         return 1;
                 }
                 return 0;
@@ -697,6 +716,7 @@ int orc_ray_march(const orc_tree* t, const float ray[8], uint32_t cell[3],
                         cell[0] = cx;
                         cell[1] = cy;
                         cell[2] = cz;
+                        *leaf_node = cidx;
                         return 1;
                 }
         }
@@ -743,6 +763,281 @@ void orc_trace_rays(const orc_tree* t, const float* rays, uint64_t R, uint8_t* h
                 counters6[4] = cn.n_tri;
                 counters6[5] = cn.max_stack;
         }
+}
+
+/* ------------------------------------------------------------------ */
+/* GI rows of SURVEY.md 8(f): light-map splat (main.cc:75-97), bottom-up */
+/* filter and cone trace (voxel_octree.cc:190-303), final pixel          */
+/* (main.cc:10-30,117-123).  One untextured material: kd = material_t    */
+/* diffuse (voxel_octree.cc:474-476).                                    */
+/* ------------------------------------------------------------------ */
+static float orc_clampf(float s, float lo, float hi) /* graphics_math.h:905-909 */
+{
+        return s > hi ? hi : (s < lo ? lo : s);
+}
+
+static float orc_dot3(const float a[3], const float b[3]) /* value_sum starts at 0 */
+{
+        float s = 0.f;
+        s += a[0] * b[0];
+        s += a[1] * b[1];
+        s += a[2] * b[2];
+        return s;
+}
+
+static const float orc_illum_d[6][3] = { { 1, 0, 0 },  { 0, 1, 0 },  { 0, 0, 1 },
+                                         { -1, 0, 0 }, { 0, -1, 0 }, { 0, 0, -1 } }; /* voxel_octree.cc:19-20 */
+
+void orc_gi_reset(orc_tree* t)
+{
+        for (size_t i = 0; i < t->n_nodes; ++i) {
+                t->nodes[i].coverage = 0.f;
+                memset(t->nodes[i].illum, 0, sizeof t->nodes[i].illum);
+        }
+}
+
+/* main.cc:81-96, sequential in pixel order (py outer, px inner, samples in order). */
+void orc_gi_splat(orc_tree* t, const float cam10[10], float film_h, int nx, int ny, int spp,
+                  const float kd[3])
+{
+        float C[16];
+        orc_camera_matrix(cam10, C);
+        const float z = orc_camera_z(cam10[0], film_h);
+        for (int py = 0; py < ny; ++py)
+                for (int px = 0; px < nx; ++px) {
+                        float rays[4 * 8];
+                        orc_gen_rays_pixel(C, z, nx, ny, spp, px, py, rays);
+                        for (int s = 0; s < spp; ++s) {
+                                const float* ray = rays + 8 * s;
+                                uint32_t cell[3], tri;
+                                float tt, hit[3], n[3];
+                                int32_t leaf = -1;
+                                if (!orc_ray_march_ex(t, ray, cell, &tri, &tt, hit, n, NULL, &leaf))
+                                        continue;
+                                /* Triangle::get_diffuse voxel_octree.cc:462-469: albedo * tmp * color(1,1,1) */
+                                const float nd[3] = { -ray[3], -ray[4], -ray[5] };
+                                float tmp = orc_clampf(orc_dot3(n, nd), 0.f, 1.f);
+                                float illum[3];
+                                for (int k = 0; k < 3; ++k)
+                                        illum[k] = (kd[k] * tmp) * 1.f;
+                                orc_node* ln = &t->nodes[leaf];
+                                for (int i = 0; i < 6; ++i) {
+                                        float coeff = orc_clampf(orc_dot3(orc_illum_d[i], n), 0.f, 1.f);
+                                        for (int k = 0; k < 3; ++k)
+                                                ln->illum[3 * i + k] += coeff * illum[k];
+                                }
+                        }
+                }
+}
+
+/* voxel_octree.cc:190-214 cone_trace_init_filter */
+static void orc_gi_filter_node(orc_tree* t, int32_t ni)
+{
+        orc_node* n = &t->nodes[ni];
+        if (n->child[0] < 0) {
+                if (n->nrefs == 0) {
+                        n->coverage = 0.f;
+                        memset(n->illum, 0, sizeof n->illum);
+                        return;
+                }
+                n->coverage = 1.f;
+                return;
+        }
+        float cov = 0.f, il[18];
+        memset(il, 0, sizeof il);
+        for (int i = 0; i < 8; ++i) {
+                orc_gi_filter_node(t, t->nodes[ni].child[i]);
+                const orc_node* c = &t->nodes[t->nodes[ni].child[i]];
+                cov += c->coverage;
+                for (int f = 0; f < 18; ++f)
+                        il[f] += c->illum[f];
+        }
+        n = &t->nodes[ni];
+        for (int f = 0; f < 18; ++f)
+                n->illum[f] = il[f] / 8;
+        n->coverage = cov / 8.f;
+}
+
+void orc_gi_filter(orc_tree* t)
+{
+        if (t->n_nodes)
+                orc_gi_filter_node(t, 0);
+}
+
+typedef struct {
+        int level;
+        uint32_t* cells;
+        float* cov;
+        float* illum;
+        uint64_t cap, n;
+} orc_gi_dump;
+
+static void orc_gi_dump_walk(const orc_tree* t, int32_t ni, uint32_t x, uint32_t y, uint32_t z, int level,
+                             orc_gi_dump* d)
+{
+        const orc_node* n = &t->nodes[ni];
+        if (level == d->level) {
+                if (n->coverage > 0.f) {
+                        if (d->n < d->cap) {
+                                if (d->cells) {
+                                        d->cells[3 * d->n] = x;
+                                        d->cells[3 * d->n + 1] = y;
+                                        d->cells[3 * d->n + 2] = z;
+                                }
+                                if (d->cov)
+                                        d->cov[d->n] = n->coverage;
+                                if (d->illum)
+                                        memcpy(d->illum + 18 * d->n, n->illum, sizeof n->illum);
+                        }
+                        d->n++;
+                }
+                return;
+        }
+        if (n->child[0] < 0)
+                return;
+        for (int i = 0; i < 8; ++i)
+                orc_gi_dump_walk(t, n->child[i], 2 * x + ((i >> 2) & 1), 2 * y + ((i >> 1) & 1), 2 * z + (i & 1),
+                                 level + 1, d);
+}
+
+/* nodes of level `level` with coverage > 0 in Morton order; returns their number */
+uint64_t orc_gi_dump_level(const orc_tree* t, int level, uint32_t* cells, float* cov, float* illum18,
+                           uint64_t cap)
+{
+        orc_gi_dump d = { level, cells, cov, illum18, cap, 0 };
+        if (t->n_nodes)
+                orc_gi_dump_walk(t, 0, 0, 0, 0, 0, &d);
+        return d.n;
+}
+
+/* VoxelOctree::compute_illum voxel_octree.h:71-81 */
+static void orc_compute_illum(const orc_node* n, const float d[3], float out[3])
+{
+        out[0] = out[1] = out[2] = 0.f;
+        for (int i = 0; i < 6; ++i) {
+                float coeff = orc_clampf(orc_dot3(orc_illum_d[i], d), 0.f, 1.f);
+                for (int k = 0; k < 3; ++k)
+                        out[k] += coeff * n->illum[3 * i + k];
+        }
+}
+
+/* voxel_octree.cc:247-283 cone_trace(root, cone, min_voxel_size); aperture .577350269f, step .1f,
+ * litness_decay 1.f (voxel_octree.cc:216-225) */
+static void orc_cone_trace_one(const orc_tree* t, const float o[3], const float d[3], float min_voxel_size,
+                               float out[3])
+{
+        const float aperture = 0.577350269f, step = .1f, decay = 1.f;
+        const orc_node* root = &t->nodes[0];
+        float mindist = 1.414f * min_voxel_size;
+        float sz[3] = { root->mx[0] - root->mn[0], root->mx[1] - root->mn[1], root->mx[2] - root->mn[2] };
+        float maxdist = sqrtf(orc_dot3(sz, sz));
+        float dist = mindist, opacity = 0.f;
+        float diffuse[3] = { 0, 0, 0 };
+        const float nd[3] = { -d[0], -d[1], -d[2] };
+        while (dist < maxdist && opacity < 1.f) {
+                float p[3] = { o[0] + d[0] * dist, o[1] + d[1] * dist, o[2] + d[2] * dist };
+                float diam = std_maxf(mindist, aperture * 2.f * dist);
+                if (maxdist < diam)
+                        break;
+                int split_level = (int)log2f(maxdist / diam);
+                const orc_node* tree = root;
+                while (tree->child[0] >= 0 && split_level) {
+                        int i = 0;
+                        i += (p[0] > (tree->mn[0] + tree->mx[0]) * .5f ? 4 : 0);
+                        i += (p[1] > (tree->mn[1] + tree->mx[1]) * .5f ? 2 : 0);
+                        i += (p[2] > (tree->mn[2] + tree->mx[2]) * .5f ? 1 : 0);
+                        tree = &t->nodes[tree->child[i]];
+                        split_level--;
+                }
+                if (split_level == 0) {
+                        float illum[3];
+                        orc_compute_illum(tree, nd, illum);
+                        float transparency = orc_clampf(1.f - opacity, 0.f, 1.f);
+                        float a = tree->coverage * step;
+                        float w = ((1.f / (1 + decay * dist)) * transparency) * tree->coverage;
+                        for (int k = 0; k < 3; ++k)
+                                diffuse[k] += w * illum[k];
+                        opacity += transparency * a;
+                }
+                dist += step * diam;
+        }
+        memcpy(out, diffuse, sizeof diffuse);
+}
+
+/* voxel_octree.cc:227-245 HemiCones + orthonormal_basis, :285-303 cone_trace(root, isect, res) */
+void orc_gi_cone_trace_point(const orc_tree* t, const float pos[3], const float n[3], float res, float out[3])
+{
+        static const float hemi[6][4] = {
+                { 0.000000f, 0.000000f, 1.0f, 0.25f },   { 0.000000f, 0.866025f, 0.5f, 0.15f },
+                { 0.823639f, 0.267617f, 0.5f, 0.15f },   { 0.509037f, -0.700629f, 0.5f, 0.15f },
+                { -0.509037f, -0.700629f, 0.5f, 0.15f }, { -0.823639f, 0.267617f, 0.5f, 0.15f },
+        };
+        float s = (0.0f > n[2]) ? -1.0f : 1.0f;
+        float a0 = -1.0f / (s + n[2]);
+        float a1 = n[0] * n[1] * a0;
+        float tv[3] = { 1.0f + s * n[0] * n[0] * a0, s * a1, -s * n[0] };
+        float bv[3] = { a1, s + n[1] * n[1] * a0, -n[1] };
+        float diffuse[3] = { 0, 0, 0 };
+        for (int i = 0; i < 6; ++i) {
+                float d[3];
+                for (int k = 0; k < 3; ++k) { /* dot(Mat3{t,b,n}, d): result += column * v[i] */
+                        float r = 0.f;
+                        r += tv[k] * hemi[i][0];
+                        r += bv[k] * hemi[i][1];
+                        r += n[k] * hemi[i][2];
+                        d[k] = r;
+                }
+                v3_normalize(d);
+                float c[3];
+                orc_cone_trace_one(t, pos, d, res, c);
+                for (int k = 0; k < 3; ++k)
+                        diffuse[k] += hemi[i][3] * c[k];
+        }
+        memcpy(out, diffuse, sizeof diffuse);
+}
+
+void orc_gi_cone_trace(const orc_tree* t, const float* pos, const float* nrm, uint64_t n, float res, float* out3)
+{
+        for (uint64_t i = 0; i < n; ++i)
+                orc_gi_cone_trace_point(t, pos + 3 * i, nrm + 3 * i, res, out3 + 3 * i);
+}
+
+/* main.cc:10-30 trace() + :117-123: film[py][px] = sum over samples of colour * (1/spp) */
+void orc_gi_render(const orc_tree* t, const float cam10[10], float film_h, int nx, int ny, int spp, float res,
+                   const float kd[3], float* film3)
+{
+        float C[16];
+        orc_camera_matrix(cam10, C);
+        const float z = orc_camera_z(cam10[0], film_h);
+        const float w = (spp == 4) ? .25f : 1.f;
+        for (int py = 0; py < ny; ++py)
+                for (int px = 0; px < nx; ++px) {
+                        float rays[4 * 8];
+                        float acc[3] = { 0, 0, 0 };
+                        orc_gen_rays_pixel(C, z, nx, ny, spp, px, py, rays);
+                        for (int s = 0; s < spp; ++s) {
+                                const float* ray = rays + 8 * s;
+                                uint32_t cell[3], tri;
+                                float tt, hit[3], n[3], c[3];
+                                int32_t leaf = -1;
+                                if (!orc_ray_march_ex(t, ray, cell, &tri, &tt, hit, n, NULL, &leaf)) {
+                                        float tl = (float)(0.5 * ((double)ray[4] + 1.0));
+                                        const float v1[3] = { 0.6f, 0.8f, 1.0f };
+                                        for (int k = 0; k < 3; ++k)
+                                                c[k] = 1.0f + (v1[k] - 1.0f) * tl;
+                                } else {
+                                        float ind[3], dir[3];
+                                        const float nd[3] = { -ray[3], -ray[4], -ray[5] };
+                                        orc_gi_cone_trace_point(t, hit, n, res, ind);
+                                        orc_compute_illum(&t->nodes[leaf], nd, dir);
+                                        for (int k = 0; k < 3; ++k)
+                                                c[k] = kd[k] * (ind[k] + dir[k]);
+                                }
+                                for (int k = 0; k < 3; ++k)
+                                        acc[k] += c[k] * w;
+                        }
+                        memcpy(film3 + 3 * ((size_t)py * nx + px), acc, sizeof acc);
+                }
 }
 
 /* Batch predicate entry points for the KATs. */

@@ -101,3 +101,12 @@ def small_scenes():
     tri, nrm = scenes.atrium(detail=0.35)
     out.append(("atrium_d7", tri, nrm, 7, CAM_MAIN))
     return out
+
+
+def gi_res(root_aabb, max_depth):
+    """main.cc:69-70: Res = min over axes of root.aabb.size() / powf(2, max_depth)."""
+    root = np.asarray(root_aabb, np.float32)
+    return np.float32(((root[3:] - root[:3]) / np.float32(2.0 ** max_depth)).min())
+
+
+GI_KD = np.array([0.7, 0.6, 0.5], np.float32)  # the scene's single untextured material (material_t::diffuse)

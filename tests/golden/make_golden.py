@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle.bindings import Ref  # noqa: E402
-from tests.common import CAM_LIGHT, CAM_MAIN, CAM_SPHERE  # noqa: E402
+from tests.common import CAM_LIGHT, CAM_MAIN, CAM_SPHERE, GI_KD, gi_res  # noqa: E402
 from tests.test_gpu_parity import _predicate_inputs  # noqa: E402
 from voxelraytrace20190722_b200 import scenes  # noqa: E402
 
@@ -77,6 +77,27 @@ def main():
                             leaf_count=counts, leaf_refs=refs, leaf_boxes=boxes_, rays=r, hit=hit.hit,
                             hit_cell=hit.cell, hit_tri=hit.tri, hit_pos=hit.pos, hit_nrm=hit.nrm)
         print(name, "tris", len(tri), "leaves", len(counts), "refs", len(refs), "hits", int(hit.hit.sum()), "/", len(r))
+    # ---- GI rows: splat -> filter -> cone trace -> trace() film, from the reference ----
+    tri, nrm = scenes.atrium(detail=0.12)
+    depth, lnx, lny, nx, ny, spp = 6, 96, 96, 40, 32, 4
+    s = ref.build(tri, nrm, depth)
+    s.gi_reset()
+    s.gi_splat(CAM_LIGHT, 1.0, lnx, lny, 4, GI_KD)
+    s.gi_filter()
+    res = gi_res(s.root_aabb(), depth)
+    out = dict(tri=tri, nrm=nrm, depth=depth, kd=GI_KD, light_cam10=CAM_LIGHT, light_dims=np.array([lnx, lny, 4]),
+               cam10=CAM_MAIN, dims=np.array([nx, ny, spp]), res=res)
+    for level in range(depth):
+        cells, cov, il = s.gi_level(level)
+        out[f"l{level}_cells"], out[f"l{level}_cov"], out[f"l{level}_illum"] = cells, cov, il
+    r = ref.gen_rays(CAM_MAIN, 1.0, nx, ny, spp)
+    hit = s.trace(r)
+    m = hit.hit.astype(bool)
+    out["cone_pos"], out["cone_nrm"] = hit.pos[m], hit.nrm[m]
+    out["cone"] = s.gi_cone_trace(hit.pos[m], hit.nrm[m], res)
+    out["film"] = s.gi_render(CAM_MAIN, 1.0, nx, ny, spp, res, GI_KD)
+    np.savez_compressed(os.path.join(HERE, "gi_atrium.npz"), **out)
+    print("gi_atrium: lit leaves", int((out[f"l{depth - 1}_illum"] > 0).any(axis=(1, 2)).sum()), "cone points", int(m.sum()))
 
 
 if __name__ == "__main__":

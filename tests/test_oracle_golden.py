@@ -49,3 +49,24 @@ def test_scene_golden(port, path):
     assert_bits_equal(h.tri, z["hit_tri"], "triangle")
     assert_bits_equal(h.pos, z["hit_pos"], "ISect.hit")
     assert_bits_equal(h.nrm, z["hit_nrm"], "ISect.normal")
+
+
+def test_gi_golden(port):
+    """splat -> filter -> cone trace -> trace() film against vectors produced by
+    the reference's own functions (tests/golden/make_golden.py)."""
+    z = np.load(os.path.join(G, "gi_atrium.npz"))
+    depth = int(z["depth"])
+    tree = port.build(z["tri"], z["nrm"], depth)
+    lnx, lny, lspp = (int(v) for v in z["light_dims"])
+    tree.gi_reset()
+    tree.gi_splat(z["light_cam10"], 1.0, lnx, lny, lspp, z["kd"])
+    tree.gi_filter()
+    for level in range(depth):
+        cells, cov, il = tree.gi_level(level)
+        assert_bits_equal(cells, z[f"l{level}_cells"], f"level {level} cells")
+        assert_bits_equal(cov, z[f"l{level}_cov"], f"level {level} coverage")
+        assert_bits_equal(il, z[f"l{level}_illum"], f"level {level} illum")
+    res = np.float32(z["res"])
+    assert_bits_equal(tree.gi_cone_trace(z["cone_pos"], z["cone_nrm"], res), z["cone"], "cone_trace")
+    nx, ny, spp = (int(v) for v in z["dims"])
+    assert_bits_equal(tree.gi_render(z["cam10"], 1.0, nx, ny, spp, res, z["kd"]), z["film"], "trace() film")

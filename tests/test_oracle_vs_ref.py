@@ -4,7 +4,7 @@ oracle/_ref exists."""
 import numpy as np
 import pytest
 
-from tests.common import CAM_MAIN, CAM_SPHERE, assert_bits_equal
+from tests.common import CAM_LIGHT, CAM_MAIN, CAM_SPHERE, GI_KD, assert_bits_equal, gi_res
 from tests.test_gpu_parity import _predicate_inputs
 from voxelraytrace20190722_b200 import scenes
 
@@ -46,3 +46,32 @@ def test_build_and_march_live(port, ref, name, maker, depth, cam10, dims):
         assert n == nx * ny * spp
         for nm in ("hit", "cell", "tri", "pos", "nrm"):
             assert_bits_equal(getattr(hm, nm), getattr(hb, nm), "render_mt " + nm)
+
+
+@pytest.mark.parametrize("name,maker,depth,cam10", [
+    ("atrium", lambda: scenes.atrium(detail=0.3), 6, CAM_MAIN),
+    ("sphere", lambda: scenes.uv_sphere(64, 32), 6, CAM_SPHERE),
+])
+def test_gi_rows_live(port, ref, name, maker, depth, cam10):
+    """light-map splat (main.cc:81-96, sequential order), cone_trace_init_filter,
+    cone_trace and the final trace() pixel -- restatement vs the reference's own functions."""
+    tri, nrm = maker()
+    a = port.build(tri, nrm, depth)
+    b = ref.build(tri, nrm, depth)
+    for o in (a, b):
+        o.gi_reset()
+        o.gi_splat(CAM_LIGHT, 1.0, 192, 192, 4, GI_KD)
+        o.gi_filter()
+    lit = 0
+    for level in range(depth):
+        for x, y, nm in zip(a.gi_level(level), b.gi_level(level), ("cells", "coverage", "illum")):
+            assert_bits_equal(x, y, f"level {level} {nm}")
+        lit += int((a.gi_level(level)[2] > 0).sum())
+    assert lit > 0, "the light camera lit nothing"
+    res = gi_res(b.root_aabb(), depth)
+    rays = port.gen_rays(cam10, 1.0, 48, 40, 4)
+    h = a.trace(rays)
+    m = h.hit.astype(bool)
+    assert_bits_equal(a.gi_cone_trace(h.pos[m], h.nrm[m], res), b.gi_cone_trace(h.pos[m], h.nrm[m], res), "cone_trace")
+    assert_bits_equal(a.gi_render(cam10, 1.0, 48, 40, 4, res, GI_KD), b.gi_render(cam10, 1.0, 48, 40, 4, res, GI_KD, nthreads=4),
+                      "trace() film")
