@@ -256,6 +256,33 @@ int vrt_ipc_close(void* d_ptr);
 /* Test hook: how many node expansions of this process took the general (>4 candidate
  * children) ordering path of the ray kernel. */
 uint64_t vrt_debug_general_order_calls(void);
+/* ---- GI rows (SURVEY.md 8f "next"): light-map splat (main.cc:75-97), cone_trace_init_filter
+ *      and cone_trace (voxel_octree.cc:190-303), the final trace() pixel (main.cc:10-30).
+ *      One untextured material: kd = tinyobj material_t::diffuse (voxel_octree.cc:474-476).
+ *      Per-node state (coverage, illum[6]) lives beside the node array; it belongs to one
+ *      build: call vrt_gi_init again after vrt_rebuild. ------------------------------------ */
+/* allocate + zero the per-node GI state (VoxelOctree::coverage / illum, voxel_octree.h:66-70) */
+int vrt_gi_init(vrt_tree* tree);
+/* The light-map lambda of main.cc:81-96 for every sample of the light camera's film:
+ * leaf.illum[i] += clamp(dot(illum_d[i], normal),0,1) * get_diffuse(isect, ray, (1,1,1)).
+ * Contributions are added per leaf in the order of the sequential loop (py, px, sample), which
+ * makes the result deterministic (the reference races on the += from its pool threads). */
+int vrt_gi_splat_camera(vrt_tree* tree, const vrt_camera* light_cam, const float kd[3]);
+/* gi::cone_trace_init_filter(root): coverage 1 on non-empty leaves, parents = child sum / 8 */
+int vrt_gi_filter(vrt_tree* tree);
+/* host copies of one level's state, node order (= Morton order): coverage[n], illum18[n][6][3];
+ * n = level_offset[level+1] - level_offset[level] (vrt_tree_get_info) */
+int vrt_gi_get_level(const vrt_tree* tree, int level, float* coverage, float* illum18);
+/* gi::cone_trace(root, ISect{hit=pos, normal=nrm}, res) for n surface points; host pointers */
+int vrt_gi_cone_trace(const vrt_tree* tree, const float* pos, const float* nrm, uint64_t n, float res,
+                      float* out_rgb);
+/* The final image loop of main.cc:117-123: per sample trace() = sky | albedo * (cone_trace +
+ * leaf.compute_illum(-ray.d)), film += colour / spp.  film_rgb[(y1-y0)][(x1-x0)][3]. */
+int vrt_gi_render_camera(const vrt_tree* tree, const vrt_camera* cam, const float kd[3], float res, int x0,
+                         int y0, int x1, int y1, float* film_rgb);
+int vrt_gi_render_camera_dev(const vrt_tree* tree, const vrt_camera* cam, const float kd[3], float res,
+                             int x0, int y0, int x1, int y1, float* d_film_rgb);
+
 /* out = {node expansions cross-checked against the slab expansion, mismatches}; counts only in
  * a library built with -DVRT_PARAM_CHECK (tests), {0,0} otherwise. */
 int vrt_debug_param_check(uint64_t out[2]);

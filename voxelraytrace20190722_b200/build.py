@@ -14,8 +14,8 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libvrt%s.so" % os.environ.get("VRT_LIB_SUFFIX", ""))
-SOURCES = ["vrt_api.cu", "vrt_build.cu", "vrt_trace.cu"]
-HEADERS = ["vrt_exact.cuh", "vrt_internal.h", "vrt_prims.cuh", os.path.join("..", "..", "include", "vrt.h")]
+SOURCES = ["vrt_api.cu", "vrt_build.cu", "vrt_trace.cu", "vrt_gi.cu"]
+HEADERS = ["vrt_exact.cuh", "vrt_internal.h", "vrt_prims.cuh", "vrt_gi.cuh", os.path.join("..", "..", "include", "vrt.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -63,7 +63,8 @@ SYMBOLS = [
     "vrt_render_camera", "vrt_render_camera_dev", "vrt_render_camera_async", "vrt_band_rows", "vrt_render_bands_dev",
     "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_frame_bands_peer_dev",
     "vrt_dev_alloc", "vrt_dev_free", "vrt_ipc_export", "vrt_ipc_open", "vrt_ipc_close", "vrt_tree_sync",
-    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_tribox_batch",
+    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_gi_init", "vrt_gi_splat_camera", "vrt_gi_filter",
+    "vrt_gi_get_level", "vrt_gi_cone_trace", "vrt_gi_render_camera", "vrt_gi_render_camera_dev", "vrt_tribox_batch",
     "vrt_tri_overlap_aabb_batch", "vrt_raytri_batch", "vrt_aabb_isect_batch",
 ]
 
@@ -128,6 +129,13 @@ def load(build_if_missing: bool = True):
     L.vrt_ipc_close.argtypes = [vp]
     L.vrt_debug_general_order_calls.restype = u64
     L.vrt_debug_param_check.argtypes = [vp]
+    L.vrt_gi_init.argtypes = [vp]
+    L.vrt_gi_splat_camera.argtypes = [vp, C.POINTER(vrt_camera), vp]
+    L.vrt_gi_filter.argtypes = [vp]
+    L.vrt_gi_get_level.argtypes = [vp, i32, vp, vp]
+    L.vrt_gi_cone_trace.argtypes = [vp, vp, vp, u64, f32, vp]
+    L.vrt_gi_render_camera.argtypes = [vp, C.POINTER(vrt_camera), vp, f32, i32, i32, i32, i32, vp]
+    L.vrt_gi_render_camera_dev.argtypes = L.vrt_gi_render_camera.argtypes
     L.vrt_tree_sync.argtypes = [vp]
     L.vrt_mean_kernel_ms.restype = C.c_double
     L.vrt_mean_kernel_ms.argtypes = [vp, i32]
@@ -366,6 +374,47 @@ class Octree:
         _check(load().vrt_count_camera(self._h, C.byref(cam.c), x0, y0, x1, y1, _ptr(c)))
         return dict(rays=int(c[0]), n_int=int(c[1]), n_leaf=int(c[2]), n_tri=int(c[3]), hits=int(c[4]),
                     n_param=int(c[5]), n_tie=int(c[6]), n_unsafe=int(c[7]))
+
+    # ---- GI rows ------------------------------------------------
+    def gi_init(self):
+        _check(load().vrt_gi_init(self._h))
+
+    def gi_splat(self, light_cam: Camera, kd):
+        kd = np.ascontiguousarray(kd, np.float32)
+        _check(load().vrt_gi_splat_camera(self._h, C.byref(light_cam.c), _ptr(kd)))
+
+    def gi_filter(self):
+        _check(load().vrt_gi_filter(self._h))
+
+    def gi_level(self, level):
+        """(coverage[n], illum[n,6,3]) of tree level `level`, node (= Morton) order."""
+        off = self.info()["level_offset"]
+        n = int(off[level + 1] - off[level])
+        cov = np.zeros(n, np.float32)
+        il = np.zeros((n, 6, 3), np.float32)
+        _check(load().vrt_gi_get_level(self._h, int(level), _ptr(cov), _ptr(il)))
+        return cov, il
+
+    def gi_cone_trace(self, pos, nrm, res):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1, 3)
+        out = np.zeros((len(pos), 3), np.float32)
+        _check(load().vrt_gi_cone_trace(self._h, _ptr(pos), _ptr(nrm), len(pos), float(np.float32(res)), _ptr(out)))
+        return out
+
+    def gi_render(self, cam: Camera, kd, res, rect=None):
+        x0, y0, x1, y1 = rect if rect else (0, 0, cam.nx, cam.ny)
+        kd = np.ascontiguousarray(kd, np.float32)
+        out = np.zeros((y1 - y0, x1 - x0, 3), np.float32)
+        _check(load().vrt_gi_render_camera(self._h, C.byref(cam.c), _ptr(kd), float(np.float32(res)), x0, y0, x1, y1,
+                                           _ptr(out)))
+        return out
+
+    def gi_render_dev(self, cam: Camera, kd, res, d_film_ptr, rect=None):
+        x0, y0, x1, y1 = rect if rect else (0, 0, cam.nx, cam.ny)
+        kd = np.ascontiguousarray(kd, np.float32)
+        _check(load().vrt_gi_render_camera_dev(self._h, C.byref(cam.c), _ptr(kd), float(np.float32(res)), x0, y0, x1,
+                                               y1, C.c_void_p(d_film_ptr)))
 
     def render_async(self, cam: Camera, out, light=None, kd=0.8, rect=None, shadow_eps=None):
         """Pipelined frame loop: enqueue one frame whose film lands in the (pinned) host array

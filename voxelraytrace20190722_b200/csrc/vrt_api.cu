@@ -111,6 +111,7 @@ void tree_bind_views(vrt_tree* t)
                 d.tab2[a] = reinterpret_cast<const float2*>(base + h.off_axis_tab) + a * h.axis_tab_stride;
                 d.tab4[a] = reinterpret_cast<const float4*>(d.tab2[a]);
         }
+        d.gi = nullptr;  // GI state belongs to one node array: vrt_gi_init after every (re)build
         d.num_nodes = (uint32_t)h.num_nodes;
         d.num_leaves = (uint32_t)h.num_leaves;
         d.L = h.max_depth - 1;
@@ -396,6 +397,8 @@ void vrt_tree_free(vrt_tree* t)
         t->refs_s.release();
         t->tab_s.release();
         t->io_in.release();
+        t->gi_buf.release();
+        t->gi_recs.release();
         t->io_out.release();
         t->film_dev[0].release();
         t->film_dev[1].release();
@@ -787,7 +790,7 @@ static int trace_camera_common(const vrt_tree* tc, const vrt_camera* cam, const 
         if (dev)
                 return launch_trace_camera(tc, cam, sh, x0, y0, x1, y1, out, mode);
         vrt_tree* t = const_cast<vrt_tree*>(tc);
-        const uint64_t bytes = mode == OUT_FILM ? npix * 12 : npix * cam->spp * (mode == OUT_HIT48 ? 48 : 16);
+        const uint64_t bytes = (mode == OUT_FILM || mode == OUT_GI_FILM) ? npix * 12 : npix * cam->spp * (mode == OUT_HIT48 ? 48 : 16);
         if (t->io_out.reserve(bytes))
                 return VRT_ERR_NOMEM;
         rc = launch_trace_camera(t, cam, sh, x0, y0, x1, y1, t->io_out.p, mode);
@@ -953,6 +956,119 @@ double vrt_mean_kernel_ms(const vrt_tree* t, int last_n)
         if (t)
                 trace_ms_mean(t, last_n, &ms);
         return ms;
+}
+
+// ---- GI rows -------------------------------------------------------
+int vrt_gi_init(vrt_tree* t)
+{
+        int rc = check_tree(t);
+        return rc ? rc : gi_init(t);
+}
+
+int vrt_gi_splat_camera(vrt_tree* t, const vrt_camera* light_cam, const float kd[3])
+{
+        int rc = check_tree(t);
+        if (rc)
+                return rc;
+        if (!light_cam || !kd) {
+                set_error("null argument");
+                return VRT_ERR_ARG;
+        }
+        rc = check_camera(light_cam, 0, 0, light_cam->nx, light_cam->ny);
+        return rc ? rc : gi_splat_camera(t, light_cam, kd);
+}
+
+int vrt_gi_filter(vrt_tree* t)
+{
+        int rc = check_tree(t);
+        return rc ? rc : gi_filter(t);
+}
+
+int vrt_gi_get_level(const vrt_tree* t, int level, float* coverage, float* illum18)
+{
+        int rc = check_tree(t);
+        if (rc)
+                return rc;
+        if (!t->dev.gi || level < 0 || level > t->hdr.max_depth - 1) {
+                set_error("vrt_gi_get_level: no GI state or level out of range");
+                return VRT_ERR_ARG;
+        }
+        const uint64_t first = t->hdr.level_offset[level], n = t->hdr.level_offset[level + 1] - first;
+        if (level == t->hdr.max_depth - 1 && n != t->hdr.num_leaves) {
+                set_error("inconsistent level table");
+                return VRT_ERR_ARG;
+        }
+        std::vector<float> host(n * 20);
+        VRT_CUDA(cudaStreamSynchronize(t->stream));
+        if (n)
+                VRT_CUDA(cudaMemcpy(host.data(), t->dev.gi + first * 20, n * 20 * sizeof(float), cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < n; ++i) {
+                if (coverage)
+                        coverage[i] = host[20 * i + 18];
+                if (illum18)
+                        memcpy(illum18 + 18 * i, &host[20 * i], 18 * sizeof(float));
+        }
+        return VRT_OK;
+}
+
+int vrt_gi_cone_trace(const vrt_tree* tc, const float* pos, const float* nrm, uint64_t n, float res, float* out_rgb)
+{
+        int rc = check_tree(tc);
+        if (rc)
+                return rc;
+        if (n && (!pos || !nrm || !out_rgb)) {
+                set_error("null argument");
+                return VRT_ERR_ARG;
+        }
+        if (n == 0)
+                return VRT_OK;
+        vrt_tree* t = const_cast<vrt_tree*>(tc);
+        if (t->io_in.reserve(n * 24) || t->io_out.reserve(n * 12))
+                return VRT_ERR_NOMEM;
+        float* d_pos = t->io_in.as<float>();
+        float* d_nrm = d_pos + 3 * n;
+        VRT_CUDA(cudaMemcpyAsync(d_pos, pos, n * 12, cudaMemcpyHostToDevice, t->stream));
+        VRT_CUDA(cudaMemcpyAsync(d_nrm, nrm, n * 12, cudaMemcpyHostToDevice, t->stream));
+        rc = gi_cone_points(t, d_pos, d_nrm, n, res, t->io_out.as<float>());
+        if (rc)
+                return rc;
+        VRT_CUDA(cudaMemcpyAsync(out_rgb, t->io_out.p, n * 12, cudaMemcpyDeviceToHost, t->stream));
+        VRT_CUDA(cudaStreamSynchronize(t->stream));
+        return VRT_OK;
+}
+
+static int gi_render_common(const vrt_tree* tc, const vrt_camera* cam, const float kd[3], float res, int x0, int y0,
+                            int x1, int y1, float* film, bool dev)
+{
+        int rc = check_tree(tc);
+        if (rc)
+                return rc;
+        if (!cam || !kd || !film) {
+                set_error("null argument");
+                return VRT_ERR_ARG;
+        }
+        if (!tc->dev.gi) {
+                set_error("vrt_gi_init has not been called on this tree");
+                return VRT_ERR_ARG;
+        }
+        vrt_shade sh{};
+        sh.light_dir[0] = kd[0];
+        sh.light_dir[1] = kd[1];
+        sh.light_dir[2] = kd[2];
+        sh.shadow_eps = res;
+        return trace_camera_common(tc, cam, &sh, x0, y0, x1, y1, film, OUT_GI_FILM, dev);
+}
+
+int vrt_gi_render_camera(const vrt_tree* t, const vrt_camera* cam, const float kd[3], float res, int x0, int y0, int x1,
+                         int y1, float* film_rgb)
+{
+        return gi_render_common(t, cam, kd, res, x0, y0, x1, y1, film_rgb, false);
+}
+
+int vrt_gi_render_camera_dev(const vrt_tree* t, const vrt_camera* cam, const float kd[3], float res, int x0, int y0,
+                             int x1, int y1, float* d_film_rgb)
+{
+        return gi_render_common(t, cam, kd, res, x0, y0, x1, y1, d_film_rgb, true);
 }
 
 int vrt_debug_param_check(uint64_t out[2])

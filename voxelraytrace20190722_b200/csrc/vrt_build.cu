@@ -646,6 +646,19 @@ static int finish_from_keys(vrt_tree* t, unsigned long long* keys, uint64_t n, i
         return VRT_OK;
 }
 
+int sort_keys_u64(vrt_tree* t, uint64_t n, int lo, int hi, unsigned long long** sorted)
+{
+        *sorted = t->keys_a.as<unsigned long long>();
+        if (n < 2 || hi <= lo)
+                return VRT_OK;
+        const uint64_t he = sort_hist_elems(n);
+        if (t->keys_b.reserve(n * 8) || t->hist.reserve(he * 4) || t->tmp_c.reserve(scan_scratch_elems(he) * 4))
+                return VRT_ERR_NOMEM;
+        radix_sort_u64(t->keys_a.as<unsigned long long>(), t->keys_b.as<unsigned long long>(), n, lo, hi,
+                       t->hist.as<uint32_t>(), t->tmp_c.as<uint32_t>(), t->stream, sorted);
+        return VRT_OK;
+}
+
 int build_tree(vrt_tree* t, int max_depth)
 {
         cudaStream_t s = t->stream;

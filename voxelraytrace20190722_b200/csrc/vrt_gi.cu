@@ -1,0 +1,224 @@
+// vrt_gi.cu -- the GI rows of SURVEY.md 8(f) on the flat octree:
+//   light-map splat      main.cc:75-97     -> gi_splat_camera (ray kernel in OUT_SPLAT mode, radix sort
+//                                             by (leaf, ray), ordered per-leaf accumulation)
+//   cone_trace_init_filter voxel_octree.cc:190-214 -> gi_filter (one kernel per level, bottom-up)
+//   cone_trace           voxel_octree.cc:247-303 -> gi_cone_points (and, fused after the traversal, the
+//                                             OUT_GI_FILM mode of the ray kernel in vrt_trace.cu)
+// The reference accumulates the light map from pool threads without synchronisation; the result of
+// this file is the SEQUENTIAL member of that family (pixel order, samples in order), reproduced
+// exactly by summing every leaf's contributions in ray order.
+#include <algorithm>
+
+#include "vrt_gi.cuh"
+
+namespace vrt {
+
+static inline unsigned gi_grid(uint64_t n, unsigned block)
+{
+        return (unsigned)std::max<uint64_t>(1, (n + block - 1) / block);
+}
+
+int gi_init(vrt_tree* t)
+{
+        const uint64_t n = std::max<uint64_t>(t->hdr.num_nodes, 1);
+        if (t->gi_buf.reserve(n * kGiStride * sizeof(float)))
+                return VRT_ERR_NOMEM;
+        VRT_CUDA(cudaMemsetAsync(t->gi_buf.p, 0, n * kGiStride * sizeof(float), t->stream));
+        t->dev.gi = t->gi_buf.as<float>();
+        return VRT_OK;
+}
+
+// One thread per sorted key; the thread that holds the first key of a leaf walks the leaf's
+// segment in order (ascending ray index) and adds coeff_i * illum to the six lobes exactly like
+// main.cc:88-95: illum = albedo * clamp(dot(normal, -ray.d),0,1) * color(1,1,1)
+// (Triangle::get_diffuse voxel_octree.cc:462-469, untextured albedo = material diffuse).
+__global__ void k_gi_accumulate(const unsigned long long* __restrict__ keys, uint64_t n,
+                                const float4* __restrict__ recs, float kd0, float kd1, float kd2,
+                                uint32_t leaf_node0, float* __restrict__ gi)
+{
+        const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n)
+                return;
+        const unsigned long long k = keys[i];
+        if (k == ~0ull)
+                return;
+        const uint32_t leaf = (uint32_t)(k >> 32);
+        if (i > 0 && (uint32_t)(keys[i - 1] >> 32) == leaf)
+                return;
+        float* g = gi + (size_t)kGiStride * (leaf_node0 + leaf);
+        float acc[18];
+#pragma unroll
+        for (int f = 0; f < 18; ++f)
+                acc[f] = g[f];
+        const float kd[3] = { kd0, kd1, kd2 };
+        for (uint64_t j = i; j < n; ++j) {
+                const unsigned long long kj = keys[j];
+                if (kj == ~0ull || (uint32_t)(kj >> 32) != leaf)
+                        break;
+                const float4 r = __ldg(&recs[(uint32_t)kj]);  // normal.xyz, tmp
+                float illum[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                        illum[c] = fmul(fmul(kd[c], r.w), 1.f);
+#pragma unroll
+                for (int f = 0; f < 6; ++f) {
+                        const float s = (f < 3) ? 1.f : -1.f;
+                        const float ax = (f % 3 == 0) ? s : 0.f, ay = (f % 3 == 1) ? s : 0.f, az = (f % 3 == 2) ? s : 0.f;
+                        const float coeff = clampf(dot3(ax, ay, az, r.x, r.y, r.z), 0.f, 1.f);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                                acc[3 * f + c] = fadd(acc[3 * f + c], fmul(coeff, illum[c]));
+                }
+        }
+#pragma unroll
+        for (int f = 0; f < 18; ++f)
+                g[f] = acc[f];
+}
+
+int gi_splat_camera(vrt_tree* t, const vrt_camera* cam, const float kd[3])
+{
+        if (!t->dev.gi) {
+                set_error("vrt_gi_init has not been called on this tree");
+                return VRT_ERR_ARG;
+        }
+        const uint64_t R = (uint64_t)cam->nx * cam->ny * cam->spp;
+        if (R == 0 || t->hdr.num_nodes == 0)
+                return VRT_OK;
+        if (R >= 0xffffffffull) {
+                set_error("light camera has too many rays for 32-bit ray indices");
+                return VRT_ERR_ARG;
+        }
+        if (t->keys_a.reserve(R * 8) || t->gi_recs.reserve(R * 16))
+                return VRT_ERR_NOMEM;
+        int rc = launch_trace_camera(t, cam, nullptr, 0, 0, cam->nx, cam->ny, t->keys_a.p, OUT_SPLAT, 0, 0, t->gi_recs.p);
+        if (rc)
+                return rc;
+        int lb = 1;
+        while ((1ull << lb) < t->hdr.num_leaves)
+                ++lb;
+        unsigned long long* sorted = nullptr;
+        rc = sort_keys_u64(t, R, 0, 32 + lb, &sorted);
+        if (rc)
+                return rc;
+        k_gi_accumulate<<<gi_grid(R, 128), 128, 0, t->stream>>>(sorted, R, t->gi_recs.as<float4>(), kd[0], kd[1], kd[2],
+                                                                (uint32_t)(t->hdr.num_nodes - t->hdr.num_leaves),
+                                                                t->gi_buf.as<float>());
+        count_launch();
+        VRT_CUDA(cudaGetLastError());
+        return VRT_OK;
+}
+
+// cone_trace_init_filter: a leaf that holds voxels has coverage 1 (its illum is the light map) ...
+__global__ void k_gi_leaf_coverage(uint32_t first, uint32_t n, float* __restrict__ gi)
+{
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < n)
+                gi[(size_t)kGiStride * (first + i) + kGiCoverage] = 1.f;
+}
+
+// ... an interior node is the sum over its eight children in child order (absent children are the
+// reference's empty leaves: exact zeros), divided by 8.
+__global__ void k_gi_filter_level(const uint2* __restrict__ nodes, uint32_t first, uint32_t n, float* __restrict__ gi)
+{
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n)
+                return;
+        const uint2 rec = nodes[first + i];
+        float acc[19];
+#pragma unroll
+        for (int f = 0; f < 19; ++f)
+                acc[f] = 0.f;
+        uint32_t child = rec.x;
+        for (uint32_t c = 0; c < 8; ++c) {
+                if (!((rec.y >> c) & 1u))
+                        continue;
+                const float4* g4 = reinterpret_cast<const float4*>(gi + (size_t)kGiStride * child);
+                const float4 q0 = g4[0], q1 = g4[1], q2 = g4[2], q3 = g4[3], q4 = g4[4];
+                const float v[19] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y,
+                                      q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z };
+#pragma unroll
+                for (int f = 0; f < 19; ++f)
+                        acc[f] = fadd(acc[f], v[f]);
+                ++child;
+        }
+        float* g = gi + (size_t)kGiStride * (first + i);
+#pragma unroll
+        for (int f = 0; f < 18; ++f)
+                g[f] = fdiv(acc[f], 8.f);
+        g[kGiCoverage] = fdiv(acc[18], 8.f);
+}
+
+int gi_filter(vrt_tree* t)
+{
+        if (!t->dev.gi) {
+                set_error("vrt_gi_init has not been called on this tree");
+                return VRT_ERR_ARG;
+        }
+        const BlobHeader& h = t->hdr;
+        if (h.num_nodes == 0)
+                return VRT_OK;
+        const int L = h.max_depth - 1;
+        float* gi = t->gi_buf.as<float>();
+        k_gi_leaf_coverage<<<gi_grid(h.num_leaves, 256), 256, 0, t->stream>>>((uint32_t)h.level_offset[L],
+                                                                             (uint32_t)h.num_leaves, gi);
+        count_launch();
+        for (int l = L - 1; l >= 0; --l) {
+                const uint64_t n = h.level_offset[l + 1] - h.level_offset[l];
+                if (!n)
+                        continue;
+                k_gi_filter_level<<<gi_grid(n, 128), 128, 0, t->stream>>>(t->dev.nodes, (uint32_t)h.level_offset[l],
+                                                                          (uint32_t)n, gi);
+                count_launch();
+        }
+        VRT_CUDA(cudaGetLastError());
+        return VRT_OK;
+}
+
+struct GiPointParams {
+        TreeDev tree;
+        float root[6];
+        const float* pos;
+        const float* nrm;
+        uint64_t n;
+        float res;
+        float* out;
+};
+
+__global__ void __launch_bounds__(128) k_gi_cone_points(GiPointParams p)
+{
+        const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= p.n)
+                return;
+        const float pos[3] = { p.pos[3 * i], p.pos[3 * i + 1], p.pos[3 * i + 2] };
+        const float nrm[3] = { p.nrm[3 * i], p.nrm[3 * i + 1], p.nrm[3 * i + 2] };
+        float out[3];
+        gi_cone_trace_point(p.tree, p.root, pos, nrm, p.res, out);
+        p.out[3 * i] = out[0];
+        p.out[3 * i + 1] = out[1];
+        p.out[3 * i + 2] = out[2];
+}
+
+int gi_cone_points(const vrt_tree* t, const float* d_pos, const float* d_nrm, uint64_t n, float res, float* d_out)
+{
+        if (!t->dev.gi) {
+                set_error("vrt_gi_init has not been called on this tree");
+                return VRT_ERR_ARG;
+        }
+        if (n == 0)
+                return VRT_OK;
+        GiPointParams p{};
+        p.tree = t->dev;
+        for (int k = 0; k < 6; ++k)
+                p.root[k] = t->hdr.root_aabb[k];
+        p.pos = d_pos;
+        p.nrm = d_nrm;
+        p.n = n;
+        p.res = res;
+        p.out = d_out;
+        k_gi_cone_points<<<gi_grid(n, 128), 128, 0, t->stream>>>(p);
+        count_launch();
+        VRT_CUDA(cudaGetLastError());
+        return VRT_OK;
+}
+
+}  // namespace vrt

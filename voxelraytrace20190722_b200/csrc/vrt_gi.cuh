@@ -1,0 +1,144 @@
+// vrt_gi.cuh -- device side of the GI rows: VoxelOctree::compute_illum
+// (voxel_octree.h:71-81), cone_trace / orthonormal_basis / HemiCones (voxel_octree.cc:216-303)
+// on the flat node array.  Per-node GI state lives in a side array of kGiStride floats per
+// node: illum[6][3] (the six axis lobes), coverage, one pad float (80 B = five LDG.128).
+// Arithmetic follows the reference expression by expression (vrt_exact.cuh rules: no FMA,
+// IEEE division and sqrt).  One deviation, documented in DESIGN.md: std::log2f is evaluated as
+// float(log2(double(x))) -- the host libm's log2f is not specified to the last bit, so the
+// integer `split_level` can differ from a given libm when maxdist/diam sits within an ulp of
+// a power of two.
+#pragma once
+
+#include "vrt_exact.cuh"
+#include "vrt_internal.h"
+
+namespace vrt {
+
+constexpr int kGiStride = 20;  // floats per node
+constexpr int kGiCoverage = 18;
+
+// VoxelOctree::compute_illum(d): sum_i clamp(dot(illum_d[i], d), 0, 1) * illum[i]
+__device__ __forceinline__ void gi_compute_illum(const float* __restrict__ g, const float d[3], float out[3])
+{
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        const float4 q0 = __ldg(g4), q1 = __ldg(g4 + 1), q2 = __ldg(g4 + 2), q3 = __ldg(g4 + 3), q4 = __ldg(g4 + 4);
+        const float il[18] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x,
+                               q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y };
+        out[0] = out[1] = out[2] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+                // illum_d[] = +x +y +z -x -y -z (voxel_octree.cc:19-20); jql::dot keeps the zero terms
+                const float s = (i < 3) ? 1.f : -1.f;
+                const float ax = (i % 3 == 0) ? s : 0.f, ay = (i % 3 == 1) ? s : 0.f, az = (i % 3 == 2) ? s : 0.f;
+                const float coeff = clampf(dot3(ax, ay, az, d[0], d[1], d[2]), 0.f, 1.f);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                        out[k] = fadd(out[k], fmul(coeff, il[3 * i + k]));
+        }
+}
+
+__device__ __forceinline__ float gi_log2f(float x)
+{
+        return __double2float_rn(log2((double)x));
+}
+
+// cone_trace(root, cone, min_voxel_size) voxel_octree.cc:247-283.
+__device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[6], const float o[3],
+                                            const float d[3], float min_voxel_size, float out[3])
+{
+        const float aperture = 0.577350269f, step = .1f, decay = 1.f;
+        const float mindist = fmul(1.414f, min_voxel_size);
+        const float sx = fsub(root[3], root[0]), sy = fsub(root[4], root[1]), sz = fsub(root[5], root[2]);
+        const float maxdist = __fsqrt_rn(dot3(sx, sy, sz, sx, sy, sz));
+        const float nd[3] = { -d[0], -d[1], -d[2] };
+        float dist = mindist, opacity = 0.f;
+        float diffuse[3] = { 0.f, 0.f, 0.f };
+        while (dist < maxdist && opacity < 1.f) {
+                const float p[3] = { fadd(o[0], fmul(d[0], dist)), fadd(o[1], fmul(d[1], dist)),
+                                     fadd(o[2], fmul(d[2], dist)) };
+                const float diam = std_max(mindist, fmul(fmul(aperture, 2.f), dist));
+                if (maxdist < diam)
+                        break;
+                int split_level = (int)gi_log2f(fdiv(maxdist, diam));
+                // point location: descend `split_level` levels (or to a leaf); an absent child is one of
+                // the reference's empty leaves -- sampling it adds exact zeros, so it is skipped
+                uint32_t node = 0, x = 1, y = 1, z = 1;
+                int level = 0;
+                bool present = tr.num_nodes != 0;
+                while (present && level < tr.L && split_level) {
+                        const uint2 rec = __ldg(&tr.nodes[node]);
+                        const float2 bx = __ldg(&tr.tab2[0][x]), by = __ldg(&tr.tab2[1][y]), bz = __ldg(&tr.tab2[2][z]);
+                        uint32_t i = 0;
+                        i += (p[0] > fmul(fadd(bx.x, bx.y), .5f)) ? 4u : 0u;
+                        i += (p[1] > fmul(fadd(by.x, by.y), .5f)) ? 2u : 0u;
+                        i += (p[2] > fmul(fadd(bz.x, bz.y), .5f)) ? 1u : 0u;
+                        split_level--;
+                        if (!((rec.y >> i) & 1u)) {
+                                present = false;
+                                break;
+                        }
+                        node = rec.x + __popc(rec.y & ((1u << i) - 1u));
+                        x = 2u * x + (i >> 2);
+                        y = 2u * y + ((i >> 1) & 1u);
+                        z = 2u * z + (i & 1u);
+                        ++level;
+                }
+                if (present && split_level == 0) {
+                        const float* g = tr.gi + (size_t)kGiStride * node;
+                        float illum[3];
+                        gi_compute_illum(g, nd, illum);
+                        const float coverage = __ldg(g + kGiCoverage);
+                        const float transparency = clampf(fsub(1.f, opacity), 0.f, 1.f);
+                        const float a = fmul(coverage, step);
+                        const float w = fmul(fmul(fdiv(1.f, fadd(1.f, fmul(decay, dist))), transparency), coverage);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                                diffuse[k] = fadd(diffuse[k], fmul(w, illum[k]));
+                        opacity = fadd(opacity, fmul(transparency, a));
+                }
+                dist = fadd(dist, fmul(step, diam));
+        }
+        out[0] = diffuse[0];
+        out[1] = diffuse[1];
+        out[2] = diffuse[2];
+}
+
+// cone_trace(root, isect, min_voxel_size) voxel_octree.cc:285-303 with orthonormal_basis :236-245
+// and the six HemiCones :227-234.
+__device__ __forceinline__ void gi_cone_trace_point(const TreeDev& tr, const float root[6], const float pos[3],
+                                                    const float n[3], float res, float out[3])
+{
+        const float hemi[6][4] = {
+                { 0.000000f, 0.000000f, 1.0f, 0.25f },   { 0.000000f, 0.866025f, 0.5f, 0.15f },
+                { 0.823639f, 0.267617f, 0.5f, 0.15f },   { 0.509037f, -0.700629f, 0.5f, 0.15f },
+                { -0.509037f, -0.700629f, 0.5f, 0.15f }, { -0.823639f, 0.267617f, 0.5f, 0.15f },
+        };
+        const float s = (0.0f > n[2]) ? -1.0f : 1.0f;
+        const float a0 = fdiv(-1.0f, fadd(s, n[2]));
+        const float a1 = fmul(fmul(n[0], n[1]), a0);
+        const float tv[3] = { fadd(1.0f, fmul(fmul(fmul(s, n[0]), n[0]), a0)), fmul(s, a1), fmul(-s, n[0]) };
+        const float bv[3] = { a1, fadd(s, fmul(fmul(n[1], n[1]), a0)), -n[1] };
+        float diffuse[3] = { 0.f, 0.f, 0.f };
+#pragma unroll 1
+        for (int i = 0; i < 6; ++i) {
+                float d[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {  // dot(Mat3{t,b,n}, v): result += column_j * v[j], from 0
+                        float r = fadd(0.f, fmul(tv[k], hemi[i][0]));
+                        r = fadd(r, fmul(bv[k], hemi[i][1]));
+                        r = fadd(r, fmul(n[k], hemi[i][2]));
+                        d[k] = r;
+                }
+                normalize3(d[0], d[1], d[2]);
+                float c[3];
+                gi_cone_one(tr, root, pos, d, res, c);
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                        diffuse[k] = fadd(diffuse[k], fmul(hemi[i][3], c[k]));
+        }
+        out[0] = diffuse[0];
+        out[1] = diffuse[1];
+        out[2] = diffuse[2];
+}
+
+}  // namespace vrt

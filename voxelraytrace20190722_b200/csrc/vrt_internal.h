@@ -69,6 +69,7 @@ struct TreeDev {
                                 // (lo.min, lo.max, hi.min, hi.max) of the two
                                 // children of cell x at level l
         const float2* tab2[3];
+        const float* gi;  // per-node GI state (vrt_gi.cuh), or null before vrt_gi_init
         uint32_t num_nodes;
         uint32_t num_leaves;
         int L;  // leaf level = max_depth-1
@@ -116,6 +117,8 @@ struct vrt_tree {
         uint32_t* h_counter = nullptr;  // pinned mirror
         // trace scratch (host-pointer entry points)
         vrt::Scratch io_in, io_out;
+        // GI rows: per-node coverage + illum[6], see vrt_gi.cuh
+        vrt::Scratch gi_buf, gi_recs;
         // pipelined host-film path (vrt_render_camera_async): two device films, a copy stream
         vrt::Scratch film_dev[2];
         cudaStream_t copy_stream = nullptr;
@@ -140,7 +143,7 @@ int import_leaves(vrt_tree* t, int max_depth, const float root_aabb[6], uint64_t
                   const uint32_t* leaf_cell, const uint32_t* leaf_count,
                   const uint32_t* leaf_refs);
 // trace (vrt_trace.cu)
-enum OutMode { OUT_HIT48 = 0, OUT_HIT16 = 1, OUT_FILM = 2, OUT_COUNT = 3, OUT_HIT16_FILM = 4 };
+enum OutMode { OUT_HIT48 = 0, OUT_HIT16 = 1, OUT_FILM = 2, OUT_COUNT = 3, OUT_HIT16_FILM = 4, OUT_SPLAT = 5, OUT_GI_FILM = 6 };
 int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_hit* d_out);
 // band_h > 0: rows [y0,y1) are LOCAL rows of a banded shard; local row r maps to film row
 // y0_film + (r / band_h) * band_pitch + r % band_h (y0 then carries y0_film, y1 = y0 + local rows).
@@ -150,5 +153,12 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
 // mean device time (ms) of the last n trace launches (waits for them)
 int trace_ms_mean(const vrt_tree* t, int last_n, double* ms);
 int general_order_calls(unsigned long long* out);
+// GI (vrt_gi.cu)
+int gi_init(vrt_tree* t);
+int gi_splat_camera(vrt_tree* t, const vrt_camera* cam, const float kd[3]);
+int gi_filter(vrt_tree* t);
+int gi_cone_points(const vrt_tree* t, const float* d_pos, const float* d_nrm, uint64_t n, float res, float* d_out);
+// sort `n` 64-bit keys held in t->keys_a on bits [lo,hi) with the build's radix sort (vrt_build.cu)
+int sort_keys_u64(vrt_tree* t, uint64_t n, int lo, int hi, unsigned long long** sorted);
 int param_check_counts(unsigned long long out[2]);
 }  // namespace vrt

@@ -25,6 +25,7 @@
 #include <cfloat>
 
 #include "vrt_exact.cuh"
+#include "vrt_gi.cuh"
 #include "vrt_internal.h"
 
 namespace vrt {
@@ -55,6 +56,8 @@ struct TraceParams {
         float shadow_eps;
         int shadow;  // harness shadow ray per hit (BASELINE config 5)
         float root[6];
+        float kd3[3];  // GI modes: the material's diffuse colour (untextured albedo)
+        float gi_res;  // GI film: min_voxel_size of cone_trace (main.cc:69-70)
 };
 
 struct HitState {
@@ -755,6 +758,29 @@ __device__ __forceinline__ void shade(const TraceParams& p, const HitState& hs, 
         rgb[0] = rgb[1] = rgb[2] = c;
 }
 
+// trace() of main.cc:10-30: sky on a miss, else albedo * (cone-traced indirect light + the leaf's
+// direct light toward the eye); Triangle::is_visible() is true, albedo = material diffuse.
+__device__ __forceinline__ void shade_gi(const TraceParams& p, const HitState& hs, const float o[3], const float d[3],
+                                         float rgb[3])
+{
+        if (!hs.hit) {
+                const float t = __double2float_rn(dmul(0.5, dadd((double)d[1], 1.0)));
+                const float v1[3] = { 0.6f, 0.8f, 1.0f };
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                        rgb[k] = fadd(1.0f, fmul(fsub(v1[k], 1.0f), t));
+                return;
+        }
+        float pos[3], nrm[3], ind[3], dir[3];
+        finish_isect(p.tree, hs, o, d, pos, nrm);
+        gi_cone_trace_point(p.tree, p.root, pos, nrm, p.gi_res, ind);
+        const float nd[3] = { -d[0], -d[1], -d[2] };
+        gi_compute_illum(p.tree.gi + (size_t)kGiStride * hs.leaf, nd, dir);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+                rgb[k] = fmul(p.kd3[k], fadd(ind[k], dir[k]));
+}
+
 // ---------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------
@@ -798,7 +824,9 @@ template <int MODE>
 #ifndef VRT_HIT16_MIN_BLOCKS
 #define VRT_HIT16_MIN_BLOCKS 8
 #endif
-__global__ void __launch_bounds__(kTraceThreads, (MODE == OUT_HIT16 || MODE == OUT_COUNT) ? VRT_HIT16_MIN_BLOCKS : VRT_FILM_MIN_BLOCKS)
+__global__ void __launch_bounds__(kTraceThreads, (MODE == OUT_HIT16 || MODE == OUT_COUNT) ? VRT_HIT16_MIN_BLOCKS
+                                                 : (MODE == OUT_GI_FILM)                  ? 4
+                                                                                          : VRT_FILM_MIN_BLOCKS)
 k_trace_camera(TraceParams p)
 {
         extern __shared__ uint32_t s_stack[];
@@ -862,6 +890,23 @@ k_trace_camera(TraceParams p)
                                 if (lane == 0)
                                         atomicAdd(static_cast<unsigned long long*>(p.out) + k, v[k]);
                         }
+                } else if (MODE == OUT_SPLAT) {
+                        // light-map pass (main.cc:81-96): key = (leaf, ray index in the reference's sequential
+                        // loop order), record = (ISect.normal, clamp(dot(normal, -ray.d), 0, 1))
+                        if (active) {
+                                unsigned long long key = ~0ull;
+                                float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (hs.hit) {
+                                        float pos[3], nrm[3];
+                                        finish_isect(p.tree, hs, o, d, pos, nrm);
+                                        const float tmp = clampf(dot3(nrm[0], nrm[1], nrm[2], -d[0], -d[1], -d[2]), 0.f, 1.f);
+                                        rec = make_float4(nrm[0], nrm[1], nrm[2], tmp);
+                                        key = ((unsigned long long)(hs.leaf - (p.tree.num_nodes - p.tree.num_leaves)) << 32) |
+                                              (unsigned long long)(pix * spp + s);
+                                }
+                                static_cast<unsigned long long*>(p.out)[pix * spp + s] = key;
+                                static_cast<float4*>(p.out2)[pix * spp + s] = rec;
+                        }
                 } else if (MODE == OUT_HIT16) {  // (OUT_HIT16_FILM handled below)
                         if (active) {
                                 uint4 q;
@@ -881,8 +926,12 @@ k_trace_camera(TraceParams p)
                                 reinterpret_cast<uint4*>(p.out)[pix * spp + s] = q;
                         }
                         float rgb[3] = { 0, 0, 0 };
-                        if (active)
-                                shade<MODE == OUT_COUNT>(p, hs, o, d, s_first, s_meta, s_list, wc, rgb);
+                        if (active) {
+                                if (MODE == OUT_GI_FILM)
+                                        shade_gi(p, hs, o, d, rgb);
+                                else
+                                        shade<MODE == OUT_COUNT>(p, hs, o, d, s_first, s_meta, s_list, wc, rgb);
+                        }
                         // film->add(px,py, c * (1/spp)) in sample order (main.cc:119-122)
                         const float wgt = (spp == 4) ? .25f : 1.f;
                         float acc[3];
@@ -1006,7 +1055,12 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         p.out = d_out;
         p.out2 = d_out2;
         p.film_full = film_full;
-        if (sh) {
+        if (mode == OUT_GI_FILM && sh) {  // (light_dir carries the material colour, shadow_eps the cone-trace res)
+                p.kd3[0] = sh->light_dir[0];
+                p.kd3[1] = sh->light_dir[1];
+                p.kd3[2] = sh->light_dir[2];
+                p.gi_res = sh->shadow_eps;
+        } else if (sh) {
                 p.light[0] = sh->light_dir[0];
                 p.light[1] = sh->light_dir[1];
                 p.light[2] = sh->light_dir[2];
@@ -1028,6 +1082,8 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         case OUT_HIT16: kern = (const void*)k_trace_camera<OUT_HIT16>; break;
         case OUT_COUNT: kern = (const void*)k_trace_camera<OUT_COUNT>; break;
         case OUT_HIT16_FILM: kern = (const void*)k_trace_camera<OUT_HIT16_FILM>; break;
+        case OUT_SPLAT: kern = (const void*)k_trace_camera<OUT_SPLAT>; break;
+        case OUT_GI_FILM: kern = (const void*)k_trace_camera<OUT_GI_FILM>; break;
         default: kern = (const void*)k_trace_camera<OUT_FILM>; break;
         }
         VRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
