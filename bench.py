@@ -134,7 +134,20 @@ def make_scene(wl):
 # ----------------------------------------------------------------------------
 # reference arm / cpu baseline (oracle/_ref = the unmodified reference)
 # ----------------------------------------------------------------------------
-def cpu_reference(tri, nrm, depth, cam10, spp, steps, warmup, sample=CPU_SAMPLE):
+GI_KD = [0.7, 0.6, 0.5]        # the single untextured material of the GI rows
+GI_LIGHT_CAM = [60 * RAD, 1, 10, 1, 0, 0, 0, 0, 1, 0]  # main.cc:76-78
+GI_LIGHT_FILM = (2048, 2048, 4)                          # main.cc:75 + gen_rays4
+GI_CPU_SAMPLE = (160, 90)
+GI_CPU_LIGHT = (256, 256)
+
+
+def gi_res_of(root_aabb, depth):
+    """main.cc:69-70: Res = min over axes of root.aabb.size() / powf(2, max_depth)."""
+    r = np.asarray(root_aabb, np.float32)
+    return float(np.float32(((r[3:] - r[:3]) / np.float32(2.0 ** depth)).min()))
+
+
+def cpu_reference(tri, nrm, depth, cam10, spp, steps, warmup, sample=CPU_SAMPLE, gi=False):
     from oracle.bindings import Ref
     ref = Ref()
     scene = ref.scene(tri, nrm)
@@ -146,7 +159,24 @@ def cpu_reference(tri, nrm, depth, cam10, spp, steps, warmup, sample=CPU_SAMPLE)
         if i >= warmup:
             times.append(sec)
     cores = ref.hardware_concurrency()
-    return dict(build_s=build_s, mtris=len(tri) / build_s / 1e6, ms_per_step=1e3 * float(np.mean(times)),
+    gi_out = None
+    if gi:
+        # GI rows on the reference: splat (sequential, bounded light film), filter, then the final trace() loop on
+        # a bounded film with all host threads (the tree is read-only there)
+        lx, ly = GI_CPU_LIGHT
+        t0 = time.perf_counter()
+        scene.gi_reset()
+        scene.gi_splat(GI_LIGHT_CAM, 1.0, lx, ly, 4, GI_KD)
+        t1 = time.perf_counter()
+        scene.gi_filter()
+        t2 = time.perf_counter()
+        gx, gy = GI_CPU_SAMPLE
+        scene.gi_render(cam10, 1.0, gx, gy, spp, gi_res_of(scene.root_aabb(), depth), GI_KD, nthreads=cores)
+        gi_out = {"splat_mrays_per_s": lx * ly * 4 / (t1 - t0) / 1e6, "splat_threads": 1,
+                  "filter_s": t2 - t1, "render_mrays_per_s": gx * gy * spp / scene.seconds / 1e6,
+                  "render_threads": cores,
+                  "sample": f"light film {lx}x{ly}x4 (sequential, as the deterministic order requires), trace() film {gx}x{gy}x{spp}"}
+    return dict(build_s=build_s, mtris=len(tri) / build_s / 1e6, ms_per_step=1e3 * float(np.mean(times)), gi=gi_out,
                 mrays=rays / float(np.mean(times)) / 1e6, rays=rays, cores=cores,
                 sample=f"same scene/camera/spp at {nx}x{ny} ({rays} rays per step) through render_mt + gen_rays{spp} + "
                        f"gi::ray_march on {min(cores, 64)} pool threads; octree built once by gi::ray_march_init "
@@ -436,13 +466,48 @@ def run_ours(args):
                  "roofline_frac": b_tri * T / (build["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
                  "leaves": info["num_leaves"], "nodes": info["num_nodes"], "refs": info["num_refs"]}
 
+    # ---- GI rows (SURVEY.md 8f "next"): splat / filter / trace() film, device-timed (rank 0, N=1) ----
+    gi_out = None
+    if world == 1 and not args.no_gi:
+        tree.set_stream(0)
+        lx, ly, lspp = GI_LIGHT_FILM
+        lcam = capi.Camera(GI_LIGHT_CAM[0], GI_LIGHT_CAM[1:4], GI_LIGHT_CAM[4:7], GI_LIGHT_CAM[7:10], lx, ly, lspp)
+        res = gi_res_of(info["root_aabb"], depth)
+        gfilm = torch.empty((ny, nx, 3), dtype=torch.float32, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        tree.gi_init()
+        tree.gi_splat(lcam, GI_KD)      # warm-up (allocations)
+        tree.gi_render_dev(cam, GI_KD, res, gfilm.data_ptr())
+        tree.gi_init()
+        tree.sync()
+        ev[0].record()
+        tree.gi_splat(lcam, GI_KD)
+        ev[1].record()
+        tree.gi_filter()
+        ev[2].record()
+        tree.gi_render_dev(cam, GI_KD, res, gfilm.data_ptr())
+        ev[3].record()
+        tree.gi_render_dev(cam, GI_KD, res, gfilm.data_ptr())
+        ev[4].record()
+        tree.sync()
+        torch.cuda.synchronize(dev)
+        splat_ms, filter_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+        render_ms = min(ev[2].elapsed_time(ev[3]), ev[3].elapsed_time(ev[4]))
+        gi_out = {"splat_ms": splat_ms, "splat_mrays_per_s": lx * ly * lspp / (splat_ms * 1e-3) / 1e6,
+                  "light_film": f"{lx}x{ly}x{lspp} (main.cc:75-78)", "filter_ms": filter_ms,
+                  "render_ms": render_ms, "render_mrays_per_s": rays_per_step / (render_ms * 1e-3) / 1e6,
+                  "render": "trace() of main.cc:10-30 per sample: ray march + 6 cones + direct + albedo, same film as the headline",
+                  "res": res, "film_mean": [float(v) for v in gfilm.mean(dim=(0, 1)).cpu()]}
+        del gfilm
+
     # ---- cpu baseline (rank 0, N=1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = cpu_reference(tri, nrm, depth, cam10, spp, steps=1, warmup=0)
+            r = cpu_reference(tri, nrm, depth, cam10, spp, steps=1, warmup=0, gi=not args.no_gi)
             cpu = {"value": r["mrays"], "unit": "Mrays/s", "cores": r["cores"], "kind": "reference",
-                   "sample": r["sample"], "build_mtris_per_s": r["mtris"], "build_seconds": r["build_s"]}
+                   "sample": r["sample"], "build_mtris_per_s": r["mtris"], "build_seconds": r["build_s"],
+                   "gi": r["gi"]}
         except Exception as e:  # oracle/_ref missing on this box
             cpu = {"value": None, "unit": "Mrays/s", "cores": None, "kind": "reference",
                    "sample": f"unavailable: {e}"}
@@ -463,6 +528,7 @@ def run_ours(args):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "build": build_out,
+        "gi": gi_out,
         "octree": {"device_bytes": info["device_bytes"], "nodes": info["num_nodes"], "leaves": info["num_leaves"]},
         "frame_check": {"n_gpu_frame_equals_1_gpu_frame_bytewise": frame_check},
         "assemble": ("nccl gather + re-order copy" if use_gather else
@@ -484,6 +550,7 @@ def main():
     ap.add_argument("--build-reps", type=int, default=3)
     ap.add_argument("--assemble", default="peer", choices=["peer", "gather"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gi", action="store_true", help="skip the GI rows (splat/filter/cone-trace film)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
