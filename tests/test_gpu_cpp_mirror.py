@@ -6,7 +6,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from tests.common import compare_hits
+from tests.common import CAM_LIGHT, GI_KD, compare_hits, gi_res
 from voxelraytrace20190722_b200 import capi, scenes
 
 pytestmark = pytest.mark.gpu
@@ -32,8 +32,9 @@ def test_demo_main_matches_oracle(tmp_path, port, gpu):
     _write_obj(obj, tri, nrm)
     nx, ny, depth, spp = 96, 64, 6, 4
     dump = tmp_path / "hits.bin"
+    gi_dump = tmp_path / "gi_film.bin"
     out = subprocess.run([os.path.join(CPP, "demo_main"), str(tmp_path / "o.bmp"), str(depth), str(nx), str(ny),
-                          str(obj), "--dump", str(dump)], capture_output=True, text=True, timeout=300)
+                          str(obj), "--dump", str(dump), "--gi", str(gi_dump)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "success." in out.stdout and f"#tris={len(tri)}" in out.stdout
     hits = np.fromfile(dump, capi.HIT_DTYPE)
@@ -45,3 +46,12 @@ def test_demo_main_matches_oracle(tmp_path, port, gpu):
     assert exp.hit.sum() > 100
     assert compare_hits(hits, exp, "demo_main") == 0
     assert os.path.getsize(tmp_path / "o.bmp") == 54 + nx * ny * 3
+    # the GI half of main.cc through the mirror (light_map_gpu, gi::cone_trace_init_filter, render_gi_gpu)
+    film = np.fromfile(gi_dump, np.float32).reshape(ny, nx, 3)
+    orc.gi_reset()
+    orc.gi_splat(np.concatenate([[fov], CAM_LIGHT[1:]]).astype(np.float32), 1.0, nx, ny, 4, GI_KD)
+    orc.gi_filter()
+    exp_film = orc.gi_render(cam10, 1.0, nx, ny, spp, gi_res(orc.root_aabb(), depth), GI_KD)
+    same = (film.view(np.uint32) == exp_film.view(np.uint32)).all(axis=2)
+    assert same.mean() >= 0.999, f"{int((~same).sum())} GI pixels differ"
+    assert "centre ray indirect light" in out.stdout

@@ -5,6 +5,7 @@
 // checkout), or "v/vn/f" triangles from an OBJ given on the command line.
 //   demo_main [out.bmp] [max_depth] [nx] [ny] [scene.obj]
 // With --dump <file> it also writes (hit,tri,cell,pos,nrm) per ray for the parity test.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -94,10 +95,12 @@ int main(int argc, char** argv)
 {
         const char* out = "demo.bmp";
         const char* dump = nullptr;
+        const char* gi_dump = nullptr;  // --gi <file>: also run main.cc's light map + filter + cone-traced film
         const char* obj = nullptr;
         int depth = 6, nx = 1024, ny = 1024, pos = 0;  // main.cc:34-35,67
         for (int i = 1; i < argc; ++i) {
                 if (!std::strcmp(argv[i], "--dump") && i + 1 < argc) { dump = argv[++i]; continue; }
+                if (!std::strcmp(argv[i], "--gi") && i + 1 < argc) { gi_dump = argv[++i]; continue; }
                 switch (pos++) {
                 case 0: out = argv[i]; break;
                 case 1: depth = std::atoi(argv[i]); break;
@@ -134,6 +137,31 @@ int main(int argc, char** argv)
                 if (dump) {
                         FILE* f = std::fopen(dump, "wb");
                         std::fwrite(hits.data(), sizeof(vrt_hit), hits.size(), f);
+                        std::fclose(f);
+                }
+                if (gi_dump) {
+                        // main.cc:69-123 on the GPU: light map (Film(1,1,2048,2048) there; nx x ny here), filter,
+                        // then the cone-traced film of the same camera
+                        std::printf("light map...\n");
+                        Film sfilm(1.f, 1.f, nx, ny);
+                        Camera scam{ 60.f * 3.1415926535897932384626f / 180.f, { 1, 10, 1 }, { 0, 0, 0 }, { 0, 1, 0 } };
+                        const Vec3 kd{ 0.7f, 0.6f, 0.5f };
+                        light_map_gpu(sfilm, scam, &root, 4, kd);
+                        std::printf("filtering...\n");
+                        gi::cone_trace_init_filter(&root);
+                        std::printf("cone tracing...\n");
+                        float res = 3.4e38f;
+                        for (int k = 0; k < 3; ++k)
+                                res = std::min(res, (root.aabb.max[k] - root.aabb.min[k]) / std::pow(2.f, (float)depth));
+                        Film gfilm(1.f, 1.f, nx, ny);
+                        render_gi_gpu(&gfilm, cam, &root, 4, kd, res);
+                        if (hit) {
+                                const Vec3 c = gi::cone_trace(root, is, res);
+                                std::printf("centre ray indirect light (%g,%g,%g)\n", c.x, c.y, c.z);
+                        }
+                        const auto d = gfilm.to_float_array();
+                        FILE* f = std::fopen(gi_dump, "wb");
+                        std::fwrite(d.data(), sizeof(float), d.size(), f);
                         std::fclose(f);
                 }
                 std::printf("success.\n");

@@ -275,6 +275,59 @@ void render_gpu(Film* film, Camera& cam, gi::VoxelOctree* root, int spp, const j
         }
 }
 
+// ---- GI rows (voxel_octree.h:90-92, main.cc:75-97,117-123) ------------------------------------
+namespace gi {
+static vrt_tree* gi_tree(const VoxelOctree* root, const char* what)
+{
+        if (!root || !root->gpu)
+                throw std::runtime_error(std::string(what) + ": octree not initialised (call ray_march_init)");
+        return root->gpu->tree;
+}
+
+void cone_trace_init_filter(VoxelOctree* root)
+{
+        check(vrt_gi_filter(gi_tree(root, "cone_trace_init_filter")), "cone_trace_init_filter");
+}
+
+void cone_trace_batch(const VoxelOctree& root, const std::vector<ISect>& isects, float min_voxel_size, std::vector<Vec3>* out)
+{
+        std::vector<float> pos(3 * isects.size()), nrm(3 * isects.size());
+        for (size_t i = 0; i < isects.size(); ++i)
+                for (int k = 0; k < 3; ++k) {
+                        pos[3 * i + k] = isects[i].hit[k];
+                        nrm[3 * i + k] = isects[i].normal[k];
+                }
+        out->resize(isects.size());
+        check(vrt_gi_cone_trace(gi_tree(&root, "cone_trace"), pos.data(), nrm.data(), isects.size(), min_voxel_size,
+                                out->empty() ? nullptr : &(*out)[0].x),
+              "cone_trace");
+}
+
+Vec3 cone_trace(const VoxelOctree& root, const ISect& isect, float min_voxel_size)
+{
+        std::vector<Vec3> out;
+        cone_trace_batch(root, { isect }, min_voxel_size, &out);
+        return out[0];
+}
+}  // namespace gi
+
+void light_map_gpu(const Film& sfilm, Camera& scam, gi::VoxelOctree* root, int spp, const jql::Vec3& kd)
+{
+        vrt_tree* t = gi::gi_tree(root, "light_map_gpu");
+        const vrt_camera c = scam.native(sfilm, spp);
+        const float k[3] = { kd.x, kd.y, kd.z };
+        check(vrt_gi_init(t), "light_map_gpu");
+        check(vrt_gi_splat_camera(t, &c, k), "light_map_gpu");
+}
+
+void render_gi_gpu(Film* film, Camera& cam, gi::VoxelOctree* root, int spp, const jql::Vec3& kd, float res)
+{
+        vrt_tree* t = gi::gi_tree(root, "render_gi_gpu");
+        const vrt_camera c = cam.native(*film, spp);
+        const float k[3] = { kd.x, kd.y, kd.z };
+        check(vrt_gi_render_camera(t, &c, k, res, 0, 0, film->nx, film->ny, &film->data()->x), "render_gi_gpu");
+}
+
 // ---- predicates ----------------------------------------------------------------------------
 int triBoxOverlap(float boxcenter[3], float boxhalfsize[3], float triverts[3][3])
 {

@@ -104,6 +104,12 @@ struct MarchResult {
 };
 void ray_march_batch(VoxelOctree* root, const std::vector<Ray>& rays, std::vector<MarchResult>* out);
 const vrt_tree* native_handle(const VoxelOctree* root);
+// voxel_octree.h:90-92 (GI rows): the filter runs over the GPU-resident per-node state that
+// light_map_gpu() filled; cone_trace evaluates one surface point (one launch), cone_trace_batch many.
+void cone_trace_init_filter(VoxelOctree* root);
+Vec3 cone_trace(const VoxelOctree& root, const ISect& isect, float min_voxel_size);
+void cone_trace_batch(const VoxelOctree& root, const std::vector<ISect>& isects, float min_voxel_size,
+                      std::vector<Vec3>* out);
 }  // namespace gi
 
 class Film {  // camera.h:24-39 -- storage is y*nx+x (the reference's y*ny+x is only right for nx==ny)
@@ -143,6 +149,13 @@ private:
 // then sample.  The film receives the harness pixel (sky / kd*n.l).
 void render_gpu(Film* film, Camera& cam, gi::VoxelOctree* root, int spp, const jql::Vec3& light_dir, float kd,
                 std::vector<vrt_hit>* hits = nullptr);
+
+// Replacement of the light-map render_mt loop of main.cc:81-96: every sample of the light camera's
+// film splats clamp(dot(illum_d[i], n)) * get_diffuse(...) into its leaf, in the sequential loop
+// order (deterministic; the reference races here).  kd = the material's diffuse colour.
+void light_map_gpu(const Film& sfilm, Camera& scam, gi::VoxelOctree* root, int spp, const jql::Vec3& kd);
+// Replacement of the final render_mt loop of main.cc:117-123 (trace() per sample, film += c / spp).
+void render_gi_gpu(Film* film, Camera& cam, gi::VoxelOctree* root, int spp, const jql::Vec3& kd, float res);
 
 // tribox2.h:15 and raytri.h:5-7 -- same signatures, evaluated on the GPU.
 int triBoxOverlap(float boxcenter[3], float boxhalfsize[3], float triverts[3][3]);
