@@ -105,3 +105,32 @@ def test_band_partition_covers_film(ny, world):
     cam = capi.Camera(CAM_MAIN[0], CAM_MAIN[1:4], CAM_MAIN[4:7], CAM_MAIN[7:10], 64, ny, 1)
     for r in range(world):
         assert capi.band_rows(cam, vdist.BAND_H, r, world) == rows[r]
+
+
+def test_split_level_closed_form_equals_rounded_log2f():
+    """csrc/vrt_gi.cuh gi_split_level(): int(log2f(x)) with log2f rounded to nearest = exponent + 1 for the
+    top floor(2^j ln 2) floats of a binade (j = floor(log2(exponent|1))).  Python mirror of the device
+    integer code against float32(log2(float64(x))) around every binade boundary and on random inputs."""
+    T = np.array([0, 1, 2, 5, 11, 22, 44])
+
+    def split_level(x):
+        b = np.asarray(x, np.float32).view(np.uint32).astype(np.int64)
+        k = (b >> 23) - 127
+        j = np.floor(np.log2(k | 1)).astype(np.int64)
+        return k + (((b & 0x7FFFFF) + T[j]) >= 0x800000)
+
+    xs = []
+    for k in range(0, 64):
+        y = np.float32(2.0 ** (k + 1))
+        for _ in range(64):
+            xs.append(y)
+            y = np.nextafter(y, np.float32(0))
+        y = np.float32(2.0 ** k)
+        for _ in range(64):
+            xs.append(y)
+            y = np.nextafter(y, np.float32(np.inf))
+    rng = np.random.default_rng(1)
+    xs = np.concatenate([np.array(xs, np.float32), np.exp2(rng.uniform(0, 60, 500_000)).astype(np.float32)])
+    ref = np.log2(xs.astype(np.float64)).astype(np.float32).astype(np.int64)
+    assert np.array_equal(split_level(xs), ref)
+    assert (ref != np.floor(np.log2(xs.astype(np.float64)))).sum() > 100  # the rounded-up floats are in the sample

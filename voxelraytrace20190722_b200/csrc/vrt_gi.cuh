@@ -3,10 +3,10 @@
 // on the flat node array.  Per-node GI state lives in a side array of kGiStride floats per
 // node: illum[6][3] (the six axis lobes), coverage, one pad float (80 B = five LDG.128).
 // Arithmetic follows the reference expression by expression (vrt_exact.cuh rules: no FMA,
-// IEEE division and sqrt).  One deviation, documented in DESIGN.md: std::log2f is evaluated as
-// float(log2(double(x))) -- the host libm's log2f is not specified to the last bit, so the
-// integer `split_level` can differ from a given libm when maxdist/diam sits within an ulp of
-// a power of two.
+// IEEE division and sqrt).  One deviation, documented in DESIGN.md: int(std::log2f(x)) is
+// evaluated for the correctly rounded log2f (gi_split_level) -- the host libm's log2f is not
+// specified to the last bit, so the integer `split_level` can differ from a given libm when
+// maxdist/diam is one of the few floats just below a power of two.
 #pragma once
 
 #include "vrt_exact.cuh"
@@ -37,9 +37,19 @@ __device__ __forceinline__ void gi_compute_illum(const float* __restrict__ g, co
         }
 }
 
-__device__ __forceinline__ float gi_log2f(float x)
+// int(std::log2f(x)) for a finite x >= 1 with log2f ROUNDED TO NEAREST: the exponent k of x,
+// plus one when x is one of the last n floats below 2^(k+1) whose logarithm rounds up to k+1.
+// log2(x) >= (k+1) - h with h = half the float spacing just below k+1 = 2^(j-24), j = floor(log2(k))
+// (k >= 1), holds for the top floor(2^24 * h * ln 2) = floor(2^j * ln 2) = 0,1,2,5,11,22,.. floats of the binade
+// (tests/test_abi_host.py checks this closed form against float(log2(double(x))) around every
+// binade boundary).  Integer-only: the cone trace evaluates it once per step.
+__device__ __forceinline__ int gi_split_level(float x)
 {
-        return __double2float_rn(log2((double)x));
+        const uint32_t b = __float_as_uint(x);
+        const int k = (int)(b >> 23) - 127;
+        const int j = 31 - __clz(k | 1);
+        const uint32_t n = (uint32_t)((0x2c160b05020100ull >> (8 * j)) & 0xffull);  // floor(2^j ln 2), j < 7
+        return k + (((b & 0x7fffffu) + n >= 0x800000u) ? 1 : 0);
 }
 
 // cone_trace(root, cone, min_voxel_size) voxel_octree.cc:247-283.
@@ -59,7 +69,7 @@ __device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[
                 const float diam = std_max(mindist, fmul(fmul(aperture, 2.f), dist));
                 if (maxdist < diam)
                         break;
-                int split_level = (int)gi_log2f(fdiv(maxdist, diam));
+                int split_level = gi_split_level(fdiv(maxdist, diam));
                 // point location: descend `split_level` levels (or to a leaf); an absent child is one of
                 // the reference's empty leaves -- sampling it adds exact zeros, so it is skipped
                 uint32_t node = 0, x = 1, y = 1, z = 1;
