@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(128) k_gi_cone_points(GiPointParams p)
         const float pos[3] = { p.pos[3 * i], p.pos[3 * i + 1], p.pos[3 * i + 2] };
         const float nrm[3] = { p.nrm[3 * i], p.nrm[3 * i + 1], p.nrm[3 * i + 2] };
         float out[3];
-        gi_cone_trace_point(p.tree, p.root, pos, nrm, p.res, out);
+        extern __shared__ float s_gi_path[];
+        gi_cone_trace_point(p.tree, p.root, s_gi_path + threadIdx.x, blockDim.x, pos, nrm, p.res, out);
         p.out[3 * i] = out[0];
         p.out[3 * i + 1] = out[1];
         p.out[3 * i + 2] = out[2];
@@ -215,7 +216,9 @@ int gi_cone_points(const vrt_tree* t, const float* d_pos, const float* d_nrm, ui
         p.n = n;
         p.res = res;
         p.out = d_out;
-        k_gi_cone_points<<<gi_grid(n, 128), 128, 0, t->stream>>>(p);
+        const size_t smem = (size_t)kGiPathWords * std::max(t->dev.L, 1) * 128 * sizeof(float);
+        VRT_CUDA(cudaFuncSetAttribute(k_gi_cone_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_gi_cone_points<<<gi_grid(n, 128), 128, smem, t->stream>>>(p);
         count_launch();
         VRT_CUDA(cudaGetLastError());
         return VRT_OK;

@@ -52,15 +52,119 @@ __device__ __forceinline__ int gi_split_level(float x)
         return k + (((b & 0x7fffffu) + n >= 0x800000u) ? 1 : 0);
 }
 
+// ---------------------------------------------------------------------------
+// Point location with a cached path.  The reference descends from the root at every step of a
+// cone (voxel_octree.cc:261-271): child i = (p.x > c.x ? 4:0) + (p.y > c.y ? 2:0) + (p.z > c.z ? 1:0)
+// with c the node's centre.  Consecutive steps move p by a tenth of the sampled cell, so the path
+// rarely changes.  We keep ONE cached path per thread: for every level l of it the cumulative
+// per-axis interval (LO_l, HI_l] of coordinates that reproduce the first l choices exactly --
+// LO = max of the centres passed with "p > c" true, HI = min of the centres passed with it false
+// -- and the node reached.  A query at depth s is then six compares against level min(s, len);
+// only when they fail (or the path is too short) are nodes and table entries loaded again, from
+// the deepest level that still holds.  The decisions are the reference's own comparisons, so the
+// located node is identical.  Cache record (7 words) per level 1..L in shared memory,
+// [level][word][thread].
+// ---------------------------------------------------------------------------
+constexpr int kGiPathWords = 7;
+constexpr uint32_t kGiAbsent = 0xffffffffu;
+
+struct GiPath {
+        uint32_t x, y, z;  // heap coordinates of the deepest cached level
+        int len;           // number of cached choices (levels 1..len are valid)
+};
+
+__device__ __forceinline__ void gi_path_reset(GiPath& gp)
+{
+        gp.x = gp.y = gp.z = 1u;
+        gp.len = 0;
+}
+
+// Node of level s (1 <= s <= L) that the reference's descent reaches for p, or kGiAbsent when the
+// descent ends earlier in one of the reference's empty leaves (an absent child).
+__device__ __forceinline__ uint32_t gi_locate(const TreeDev& tr, float* __restrict__ sc, int stride, GiPath& gp,
+                                              const float p[3], int s)
+{
+        const float inf = __int_as_float(0x7f800000);
+        int l = min(s, gp.len);
+        float lo[3] = { -inf, -inf, -inf }, hi[3] = { inf, inf, inf };
+        uint32_t node = 0;
+        while (l > 0) {
+                const float* e = sc + (size_t)(kGiPathWords * (l - 1)) * stride;
+                lo[0] = e[0];
+                lo[1] = e[stride];
+                lo[2] = e[2 * stride];
+                hi[0] = e[3 * stride];
+                hi[1] = e[4 * stride];
+                hi[2] = e[5 * stride];
+                if (p[0] > lo[0] && p[0] <= hi[0] && p[1] > lo[1] && p[1] <= hi[1] && p[2] > lo[2] && p[2] <= hi[2]) {
+                        node = __float_as_uint(e[6 * stride]);
+                        break;
+                }
+                --l;
+        }
+        if (l == s)
+                return node;
+        if (l == 0) {
+                lo[0] = lo[1] = lo[2] = -inf;
+                hi[0] = hi[1] = hi[2] = inf;
+                node = 0;
+        }
+        if (node == kGiAbsent)
+                return kGiAbsent;  // the valid part of the path already ends in an empty leaf
+        // re-descend from level l with the reference's loads and comparisons, refreshing the cache
+        uint32_t x = gp.x >> (gp.len - l), y = gp.y >> (gp.len - l), z = gp.z >> (gp.len - l);
+        while (l < s) {
+                const uint2 rec = __ldg(&tr.nodes[node]);
+                const float2 bx = __ldg(&tr.tab2[0][x]), by = __ldg(&tr.tab2[1][y]), bz = __ldg(&tr.tab2[2][z]);
+                const float c[3] = { fmul(fadd(bx.x, bx.y), .5f), fmul(fadd(by.x, by.y), .5f), fmul(fadd(bz.x, bz.y), .5f) };
+                uint32_t i = 0;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                        const bool up = p[a] > c[a];
+                        i = 2u * i + (up ? 1u : 0u);
+                        lo[a] = up ? fmaxf(lo[a], c[a]) : lo[a];
+                        hi[a] = up ? hi[a] : fminf(hi[a], c[a]);
+                }
+                x = 2u * x + (i >> 2);
+                y = 2u * y + ((i >> 1) & 1u);
+                z = 2u * z + (i & 1u);
+                node = ((rec.y >> i) & 1u) ? rec.x + __popc(rec.y & ((1u << i) - 1u)) : kGiAbsent;
+                float* e = sc + (size_t)(kGiPathWords * l) * stride;
+                ++l;
+                e[0] = lo[0];
+                e[stride] = lo[1];
+                e[2 * stride] = lo[2];
+                e[3 * stride] = hi[0];
+                e[4 * stride] = hi[1];
+                e[5 * stride] = hi[2];
+                e[6 * stride] = __uint_as_float(node);
+                if (node == kGiAbsent)
+                        break;
+        }
+        gp.x = x;
+        gp.y = y;
+        gp.z = z;
+        gp.len = l;
+        return (l == s) ? node : kGiAbsent;
+}
+
 // cone_trace(root, cone, min_voxel_size) voxel_octree.cc:247-283.
-__device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[6], const float o[3],
-                                            const float d[3], float min_voxel_size, float out[3])
+__device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[6], float* sc, int stride, GiPath& gp,
+                                            const float o[3], const float d[3], float min_voxel_size, float out[3])
 {
         const float aperture = 0.577350269f, step = .1f, decay = 1.f;
         const float mindist = fmul(1.414f, min_voxel_size);
         const float sx = fsub(root[3], root[0]), sy = fsub(root[4], root[1]), sz = fsub(root[5], root[2]);
         const float maxdist = __fsqrt_rn(dot3(sx, sy, sz, sx, sy, sz));
-        const float nd[3] = { -d[0], -d[1], -d[2] };
+        // compute_illum(-cone.d): the six lobe coefficients clamp(dot(illum_d[i], -d), 0, 1) do not depend
+        // on the sample (illum_d[] = +x +y +z -x -y -z, voxel_octree.cc:19-20; jql::dot keeps the zero terms)
+        float coeff[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+                const float sg = (i < 3) ? 1.f : -1.f;
+                const float ax = (i % 3 == 0) ? sg : 0.f, ay = (i % 3 == 1) ? sg : 0.f, az = (i % 3 == 2) ? sg : 0.f;
+                coeff[i] = clampf(dot3(ax, ay, az, -d[0], -d[1], -d[2]), 0.f, 1.f);
+        }
         float dist = mindist, opacity = 0.f;
         float diffuse[3] = { 0.f, 0.f, 0.f };
         while (dist < maxdist && opacity < 1.f) {
@@ -69,35 +173,24 @@ __device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[
                 const float diam = std_max(mindist, fmul(fmul(aperture, 2.f), dist));
                 if (maxdist < diam)
                         break;
-                int split_level = gi_split_level(fdiv(maxdist, diam));
-                // point location: descend `split_level` levels (or to a leaf); an absent child is one of
-                // the reference's empty leaves -- sampling it adds exact zeros, so it is skipped
-                uint32_t node = 0, x = 1, y = 1, z = 1;
-                int level = 0;
-                bool present = tr.num_nodes != 0;
-                while (present && level < tr.L && split_level) {
-                        const uint2 rec = __ldg(&tr.nodes[node]);
-                        const float2 bx = __ldg(&tr.tab2[0][x]), by = __ldg(&tr.tab2[1][y]), bz = __ldg(&tr.tab2[2][z]);
-                        uint32_t i = 0;
-                        i += (p[0] > fmul(fadd(bx.x, bx.y), .5f)) ? 4u : 0u;
-                        i += (p[1] > fmul(fadd(by.x, by.y), .5f)) ? 2u : 0u;
-                        i += (p[2] > fmul(fadd(bz.x, bz.y), .5f)) ? 1u : 0u;
-                        split_level--;
-                        if (!((rec.y >> i) & 1u)) {
-                                present = false;
-                                break;
-                        }
-                        node = rec.x + __popc(rec.y & ((1u << i) - 1u));
-                        x = 2u * x + (i >> 2);
-                        y = 2u * y + ((i >> 1) & 1u);
-                        z = 2u * z + (i & 1u);
-                        ++level;
-                }
-                if (present && split_level == 0) {
-                        const float* g = tr.gi + (size_t)kGiStride * node;
-                        float illum[3];
-                        gi_compute_illum(g, nd, illum);
-                        const float coverage = __ldg(g + kGiCoverage);
+                const int split_level = gi_split_level(fdiv(maxdist, diam));
+                // descend `split_level` levels (or to a leaf): deeper than the tree, or into an absent child
+                // (one of the reference's empty leaves, whose sample adds exact zeros) -> nothing to add
+                uint32_t node = kGiAbsent;
+                if (tr.num_nodes != 0 && split_level <= tr.L)
+                        node = (split_level == 0) ? 0u : gi_locate(tr, sc, stride, gp, p, split_level);
+                if (node != kGiAbsent) {
+                        const float4* g4 = reinterpret_cast<const float4*>(tr.gi + (size_t)kGiStride * node);
+                        const float4 q0 = __ldg(g4), q1 = __ldg(g4 + 1), q2 = __ldg(g4 + 2), q3 = __ldg(g4 + 3), q4 = __ldg(g4 + 4);
+                        const float il[18] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x,
+                                               q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y };
+                        const float coverage = q4.z;
+                        float illum[3] = { 0.f, 0.f, 0.f };
+#pragma unroll
+                        for (int i = 0; i < 6; ++i)
+#pragma unroll
+                                for (int k = 0; k < 3; ++k)
+                                        illum[k] = fadd(illum[k], fmul(coeff[i], il[3 * i + k]));
                         const float transparency = clampf(fsub(1.f, opacity), 0.f, 1.f);
                         const float a = fmul(coverage, step);
                         const float w = fmul(fmul(fdiv(1.f, fadd(1.f, fmul(decay, dist))), transparency), coverage);
@@ -115,9 +208,12 @@ __device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[
 
 // cone_trace(root, isect, min_voxel_size) voxel_octree.cc:285-303 with orthonormal_basis :236-245
 // and the six HemiCones :227-234.
-__device__ __forceinline__ void gi_cone_trace_point(const TreeDev& tr, const float root[6], const float pos[3],
-                                                    const float n[3], float res, float out[3])
+// sc: this thread's column of the path cache (kGiPathWords * L words, element stride `stride`).
+__device__ __forceinline__ void gi_cone_trace_point(const TreeDev& tr, const float root[6], float* sc, int stride,
+                                                    const float pos[3], const float n[3], float res, float out[3])
 {
+        GiPath gp;
+        gi_path_reset(gp);
         const float hemi[6][4] = {
                 { 0.000000f, 0.000000f, 1.0f, 0.25f },   { 0.000000f, 0.866025f, 0.5f, 0.15f },
                 { 0.823639f, 0.267617f, 0.5f, 0.15f },   { 0.509037f, -0.700629f, 0.5f, 0.15f },
@@ -141,7 +237,7 @@ __device__ __forceinline__ void gi_cone_trace_point(const TreeDev& tr, const flo
                 }
                 normalize3(d[0], d[1], d[2]);
                 float c[3];
-                gi_cone_one(tr, root, pos, d, res, c);
+                gi_cone_one(tr, root, sc, stride, gp, pos, d, res, c);
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                         diffuse[k] = fadd(diffuse[k], fmul(hemi[i][3], c[k]));

@@ -761,7 +761,7 @@ __device__ __forceinline__ void shade(const TraceParams& p, const HitState& hs, 
 // trace() of main.cc:10-30: sky on a miss, else albedo * (cone-traced indirect light + the leaf's
 // direct light toward the eye); Triangle::is_visible() is true, albedo = material diffuse.
 __device__ __forceinline__ void shade_gi(const TraceParams& p, const HitState& hs, const float o[3], const float d[3],
-                                         float rgb[3])
+                                         uint32_t* s_col, float rgb[3])
 {
         if (!hs.hit) {
                 const float t = __double2float_rn(dmul(0.5, dadd((double)d[1], 1.0)));
@@ -773,7 +773,8 @@ __device__ __forceinline__ void shade_gi(const TraceParams& p, const HitState& h
         }
         float pos[3], nrm[3], ind[3], dir[3];
         finish_isect(p.tree, hs, o, d, pos, nrm);
-        gi_cone_trace_point(p.tree, p.root, pos, nrm, p.gi_res, ind);
+        // the traversal is over: this thread's stack column doubles as the cone trace's path cache
+        gi_cone_trace_point(p.tree, p.root, reinterpret_cast<float*>(s_col), kTraceThreads, pos, nrm, p.gi_res, ind);
         const float nd[3] = { -d[0], -d[1], -d[2] };
         gi_compute_illum(p.tree.gi + (size_t)kGiStride * hs.leaf, nd, dir);
 #pragma unroll
@@ -928,7 +929,7 @@ k_trace_camera(TraceParams p)
                         float rgb[3] = { 0, 0, 0 };
                         if (active) {
                                 if (MODE == OUT_GI_FILM)
-                                        shade_gi(p, hs, o, d, rgb);
+                                        shade_gi(p, hs, o, d, s_first, rgb);
                                 else
                                         shade<MODE == OUT_COUNT>(p, hs, o, d, s_first, s_meta, s_list, wc, rgb);
                         }
@@ -986,10 +987,13 @@ static int persistent_grid(const void* kernel, size_t smem)
 
 // Traversal stack: one 3-word record per thread for the bottom sentinel and for every level
 // that can be left with unvisited children (levels 0 .. L-1).
-static size_t stack_bytes(const vrt_tree* t)
+static size_t stack_bytes(const vrt_tree* t, OutMode mode = OUT_HIT48)
 {
         const int L = std::max(t->dev.L, 1);
-        return (size_t)3 * (size_t)(L + 1) * kTraceThreads * sizeof(uint32_t);
+        size_t words = (size_t)3 * (size_t)(L + 1);
+        if (mode == OUT_GI_FILM)  // the same column then holds the cone trace's path cache (vrt_gi.cuh)
+                words = std::max(words, (size_t)kGiPathWords * (size_t)L);
+        return words * kTraceThreads * sizeof(uint32_t);
 }
 
 static void fill_common(const vrt_tree* t, TraceParams& p)
@@ -1075,7 +1079,7 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
                 return VRT_ERR_ARG;
         }
         p.num_tiles = (uint32_t)tiles;
-        const size_t smem = stack_bytes(t);
+        const size_t smem = stack_bytes(t, mode);
         const void* kern = nullptr;
         switch (mode) {
         case OUT_HIT48: kern = (const void*)k_trace_camera<OUT_HIT48>; break;
