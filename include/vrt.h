@@ -261,6 +261,21 @@ uint64_t vrt_debug_general_order_calls(void);
  *      One untextured material: kd = tinyobj material_t::diffuse (voxel_octree.cc:474-476).
  *      Per-node state (coverage, illum[6]) lives beside the node array; it belongs to one
  *      build: call vrt_gi_init again after vrt_rebuild. ------------------------------------ */
+/* Materials (Triangle::get_albedo, voxel_octree.cc:471-484): tri_uv[T][3][2] per-vertex texture
+ * coordinates, tri_mtl[T] material ids, per material kd[m][3] (tinyobj material_t::diffuse) and
+ * mtl_tex[m] = index into tex[] or -1 (empty diffuse_texname).  Textures are the bytes stbi_load
+ * returns (row 0 = top, `channels` interleaved).  Without this call every triangle has the colour
+ * passed to the GI entry points.  Host pointers; the data is copied. */
+typedef struct vrt_texture {
+        int32_t width, height, channels;
+        const uint8_t* data;
+} vrt_texture;
+int vrt_set_materials(vrt_tree* tree, const float* tri_uv, const uint32_t* tri_mtl, uint32_t num_mtl,
+                      const float* kd, const int32_t* mtl_tex, uint32_t num_tex, const vrt_texture* tex);
+/* Triangle::get_albedo(ISect{hit = pos[i]}) of triangle tri[i] (barycentric + unit_cycle + nearest
+ * texel with the vertical flip, texel_fetch voxel_octree.cc:401-422); host pointers */
+int vrt_albedo(const vrt_tree* tree, const uint32_t* tri, const float* pos, uint64_t n,
+               const float kd_default[3], float* out_rgb);
 /* allocate + zero the per-node GI state (VoxelOctree::coverage / illum, voxel_octree.h:66-70) */
 int vrt_gi_init(vrt_tree* tree);
 /* The light-map lambda of main.cc:81-96 for every sample of the light camera's film:

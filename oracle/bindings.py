@@ -100,6 +100,10 @@ class Port:
         L.orc_gi_dump_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_gi_cone_trace.argtypes = [C.c_void_p, _f32p, _f32p, C.c_uint64, C.c_float, _f32p]
         L.orc_gi_render.argtypes = [C.c_void_p, _f32p, C.c_float, C.c_int, C.c_int, C.c_int, C.c_float, _f32p, _f32p]
+        # materials / textures
+        L.orc_set_materials.argtypes = [C.c_void_p, _f32p, _u32p, C.c_uint32, _f32p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                        C.c_void_p]
+        L.orc_albedo.argtypes = [C.c_void_p, _u32p, _f32p, C.c_uint64, _f32p, _f32p]
 
     # -- tree ---------------------------------------------------------------
     def build(self, tri, nrm, max_depth):
@@ -224,6 +228,25 @@ class PortTree:
         self._gi("cone_trace")(self.h, pos, nrm, len(pos), float(np.float32(res)), out)
         return out
 
+    def set_materials(self, tri_uv, tri_mtl, kd, mtl_tex, textures):
+        """textures: list of uint8 arrays [h, w, channels] as the reference's stbi_load returns them."""
+        tri_uv = np.ascontiguousarray(tri_uv, np.float32).reshape(-1, 6)
+        tri_mtl = np.ascontiguousarray(tri_mtl, np.uint32)
+        kd = np.ascontiguousarray(kd, np.float32).reshape(-1, 3)
+        mtl_tex = np.ascontiguousarray(mtl_tex, np.int32)
+        texs = [np.ascontiguousarray(t, np.uint8) for t in textures]
+        whc = np.array([[t.shape[1], t.shape[0], t.shape[2]] for t in texs], np.int32).reshape(-1, 3)
+        ptrs = (C.c_void_p * max(len(texs), 1))(*[t.ctypes.data for t in texs])
+        self.port.lib.orc_set_materials(self.h, tri_uv, tri_mtl, len(kd), kd, mtl_tex.ctypes.data, len(texs),
+                                        whc.ctypes.data, C.cast(ptrs, C.c_void_p))
+
+    def albedo(self, tri, pos, kd_default=(0.8, 0.8, 0.8)):
+        tri = np.ascontiguousarray(tri, np.uint32)
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        out = np.zeros((len(tri), 3), np.float32)
+        self.port.lib.orc_albedo(self.h, tri, pos, len(tri), np.ascontiguousarray(kd_default, np.float32), out)
+        return out
+
     def gi_splat(self, cam10, film_h, nx, ny, spp, kd):
         self.kd = np.ascontiguousarray(kd, np.float32)
         self.port.lib.orc_gi_splat(self.h, np.ascontiguousarray(cam10, np.float32), float(film_h), nx, ny, spp,
@@ -277,6 +300,12 @@ class Ref:
         L.ref_gi_dump_level.restype = C.c_uint64
         L.ref_gi_dump_level.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.ref_gi_cone_trace.argtypes = [C.c_void_p, _f32p, _f32p, C.c_uint64, C.c_float, _f32p]
+        L.ref_scene_create_mat.restype = C.c_void_p
+        L.ref_scene_create_mat.argtypes = [_f32p, _f32p, _f32p, _u32p, C.c_uint32, C.c_uint32, _f32p, C.c_void_p]
+        L.ref_albedo.argtypes = [C.c_void_p, _u32p, _f32p, C.c_uint64, _f32p]
+        L.ref_load_image.restype = C.c_uint64
+        L.ref_load_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,
+                                     C.c_uint64]
         L.ref_gi_render.restype = C.c_double
         L.ref_gi_render.argtypes = [C.c_void_p, _f32p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_float,
                                     _f32p, C.c_int]
@@ -294,6 +323,29 @@ class Ref:
         s = self.scene(tri, nrm)
         s.build(max_depth)
         return s
+
+    def scene_mat(self, tri, nrm, tri_uv, tri_mtl, kd, texpaths):
+        """Triangles with texture coordinates and per-triangle materials; texpaths[m] = image file or ''."""
+        tri = _as_tri(tri)
+        nrm_c = np.ascontiguousarray(nrm, np.float32).reshape(-1, 9)
+        uv = np.ascontiguousarray(tri_uv, np.float32).reshape(-1, 6)
+        mt = np.ascontiguousarray(tri_mtl, np.uint32)
+        kd = np.ascontiguousarray(kd, np.float32).reshape(-1, 3)
+        arr = (C.c_char_p * len(kd))(*[os.fsencode(p) for p in texpaths])
+        h = self.lib.ref_scene_create_mat(tri, nrm_c, uv, mt, tri.shape[0], len(kd), kd, C.cast(arr, C.c_void_p))
+        sc = RefScene(self, h)
+        sc._keep = arr
+        return sc
+
+    def load_image(self, path):
+        """The bytes the reference's load_image() sees (stbi_load): uint8 [h, w, channels]."""
+        w, h, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        n = self.lib.ref_load_image(os.fsencode(path), C.byref(w), C.byref(h), C.byref(c), None, 0)
+        if n == 0:
+            raise FileNotFoundError(path)
+        out = np.zeros(int(n), np.uint8)
+        self.lib.ref_load_image(os.fsencode(path), C.byref(w), C.byref(h), C.byref(c), out.ctypes.data, int(n))
+        return out.reshape(h.value, w.value, c.value)
 
     def camera_matrix(self, cam10):
         out = np.zeros(16, np.float32)
@@ -419,6 +471,13 @@ class RefScene:
         nrm = np.ascontiguousarray(nrm, np.float32).reshape(-1, 3)
         out = np.zeros((len(pos), 3), np.float32)
         self._gi("cone_trace")(self.h, pos, nrm, len(pos), float(np.float32(res)), out)
+        return out
+
+    def albedo(self, tri, pos):
+        tri = np.ascontiguousarray(tri, np.uint32)
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        out = np.zeros((len(tri), 3), np.float32)
+        self.ref.lib.ref_albedo(self.h, tri, pos, len(tri), out)
         return out
 
     def gi_splat(self, cam10, film_h, nx, ny, spp, kd, film_w=1.0):

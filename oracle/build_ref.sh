@@ -57,11 +57,16 @@ EOF
 CXX="${CXX:-g++}"
 CXXFLAGS="-std=c++17 -O2 -ffp-contract=off -fPIC -w -include $TMP/libm_shim.h -I$TMP/src"
 
+pids=()
 for f in camera voxel_octree tribox2 raytri tiny_obj_loader; do
         $CXX $CXXFLAGS -c "$TMP/src/$f.cc" -o "$TMP/$f.o" &
+        pids+=($!)
 done
 $CXX $CXXFLAGS -c "$HERE/ref_harness.cc" -o "$TMP/ref_harness.o" &
-wait
+pids+=($!)
+for p in "${pids[@]}"; do
+        wait "$p"  # (set -e: a failed compile stops the build instead of linking a partial library)
+done
 
 $CXX -shared -o "$OUT/libvrt_ref.so" "$TMP"/*.o -lpthread
 

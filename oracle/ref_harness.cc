@@ -24,6 +24,7 @@
 
 #include "voxel_octree.h"
 #include "camera.h"
+#include "stb_image.h"  // declarations only; the implementation is compiled into voxel_octree.cc:13-14
 
 #include <chrono>
 #include <cstdint>
@@ -40,6 +41,7 @@ struct LeafInfo {
 
 struct RefScene {
         tinyobj::material_t mtl{};
+        std::vector<tinyobj::material_t> mtls;  // ref_scene_create_mat: per-triangle materials
         std::vector<gi::Triangle> tris;
         std::vector<gi::VoxelBase*> ptrs;
         std::unique_ptr<gi::VoxelOctree> root;
@@ -637,6 +639,72 @@ double ref_gi_render(void* h, const float* cam10, float film_w, float film_h, in
         }
         auto t1 = std::chrono::steady_clock::now();
         return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Materials and textures: Triangle::get_albedo voxel_octree.cc:471-484,
+// VoxelBase::texel_fetch + unit_cycle + load_image (stb_image) voxel_octree.cc:373-422.
+// ---------------------------------------------------------------------------
+extern "C" {
+
+// Like ref_scene_create, with per-vertex texture coordinates tri_uv[T][3][2] and a material id per
+// triangle; material m has diffuse kd[m] and, when texpath[m] is a non-empty string, that image file
+// as its diffuse texture (loaded by the reference's own load_image on first use).
+void* ref_scene_create_mat(const float* tri_xyz, const float* tri_nrm, const float* tri_uv, const uint32_t* tri_mtl,
+                           uint32_t T, uint32_t M, const float* kd, const char* const* texpath)
+{
+        auto* s = new RefScene;
+        s->mtls.resize(M);
+        for (uint32_t m = 0; m < M; ++m) {
+                for (int k = 0; k < 3; ++k)
+                        s->mtls[m].diffuse[k] = kd[3 * m + k];
+                s->mtls[m].diffuse_texname = texpath && texpath[m] ? texpath[m] : "";
+        }
+        s->tris.reserve(T);
+        for (uint32_t t = 0; t < T; ++t) {
+                const float* p = tri_xyz + 9 * (size_t)t;
+                const float* n = tri_nrm + 9 * (size_t)t;
+                const float* u = tri_uv + 6 * (size_t)t;
+                s->tris.emplace_back(Vec3{ p[0], p[1], p[2] }, Vec3{ p[3], p[4], p[5] }, Vec3{ p[6], p[7], p[8] },
+                                     Vec3{ n[0], n[1], n[2] }, Vec3{ n[3], n[4], n[5] }, Vec3{ n[6], n[7], n[8] },
+                                     Vec2{ u[0], u[1] }, Vec2{ u[2], u[3] }, Vec2{ u[4], u[5] }, &s->mtls[tri_mtl[t]]);
+        }
+        s->ptrs.reserve(T);
+        for (auto& tri : s->tris)
+                s->ptrs.push_back(&tri);
+        for (uint32_t t = 0; t < T; ++t)
+                s->tri_of[s->ptrs[t]] = t;
+        return s;
+}
+
+// Triangle::get_albedo(ISect{hit = pos}) of triangle tri[i]
+void ref_albedo(void* h, const uint32_t* tri, const float* pos, uint64_t n, float* out3)
+{
+        auto* s = static_cast<RefScene*>(h);
+        for (uint64_t i = 0; i < n; ++i) {
+                ISect is{};
+                is.hit = Vec3{ pos[3 * i], pos[3 * i + 1], pos[3 * i + 2] };
+                Vec3 a = s->tris[tri[i]].get_albedo(is);
+                out3[3 * i] = a.x;
+                out3[3 * i + 1] = a.y;
+                out3[3 * i + 2] = a.z;
+        }
+}
+
+// The bytes the reference sees for an image file: stbi_load(path, &w, &h, &channels, 0) as in load_image
+// (voxel_octree.cc:373-388).  Returns w*h*channels (0 on failure); copies at most cap bytes.
+uint64_t ref_load_image(const char* path, int* w, int* hgt, int* channels, uint8_t* out, uint64_t cap)
+{
+        unsigned char* data = stbi_load(path, w, hgt, channels, 0);
+        if (!data)
+                return 0;
+        const uint64_t size = (uint64_t)(*w) * (*hgt) * (*channels);
+        if (out)
+                std::memcpy(out, data, size < cap ? size : cap);
+        stbi_image_free(data);
+        return size;
 }
 
 }  // extern "C"

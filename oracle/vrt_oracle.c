@@ -345,6 +345,14 @@ typedef struct {
         float* tri_own;   /* owned copy of the vertices */
         uint32_t T;
         int max_depth;
+        /* materials (orc_set_materials): per-vertex uv, material id per triangle, per material kd + texture id */
+        float* uv;          /* [T][3][2] */
+        uint32_t* tri_mtl;  /* [T] */
+        uint32_t n_mtl, n_tex;
+        float* mtl_kd;      /* [M][3] */
+        int32_t* mtl_tex;   /* [M], -1 = untextured */
+        int32_t* tex_whc;   /* [n_tex][3] */
+        uint8_t** tex_data;
 } orc_tree;
 
 static int32_t orc_new_node(orc_tree* t, const float mn[3], const float mx[3])
@@ -469,6 +477,14 @@ void orc_free(orc_tree* t)
         free(t->nodes);
         free(t->nrm);
         free(t->tri_own);
+        free(t->uv);
+        free(t->tri_mtl);
+        free(t->mtl_kd);
+        free(t->mtl_tex);
+        free(t->tex_whc);
+        for (uint32_t i = 0; i < t->n_tex; ++i)
+                free(t->tex_data[i]);
+        free(t->tex_data);
         free(t);
 }
 
@@ -796,6 +812,100 @@ void orc_gi_reset(orc_tree* t)
         }
 }
 
+/* ------------------------------------------------------------------ */
+/* Materials and textures                          */
+/* ------------------------------------------------------------------ */
+void orc_set_materials(orc_tree* t, const float* tri_uv, const uint32_t* tri_mtl, uint32_t M, const float* kd,
+                       const int32_t* mtl_tex, uint32_t n_tex, const int32_t* tex_whc, const uint8_t* const* tex_data)
+{
+        t->uv = (float*)malloc(sizeof(float) * 6 * (size_t)(t->T ? t->T : 1));
+        memcpy(t->uv, tri_uv, sizeof(float) * 6 * (size_t)t->T);
+        t->tri_mtl = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(t->T ? t->T : 1));
+        memcpy(t->tri_mtl, tri_mtl, sizeof(uint32_t) * (size_t)t->T);
+        t->n_mtl = M;
+        t->mtl_kd = (float*)malloc(sizeof(float) * 3 * (size_t)(M ? M : 1));
+        memcpy(t->mtl_kd, kd, sizeof(float) * 3 * (size_t)M);
+        t->mtl_tex = (int32_t*)malloc(sizeof(int32_t) * (size_t)(M ? M : 1));
+        memcpy(t->mtl_tex, mtl_tex, sizeof(int32_t) * (size_t)M);
+        t->n_tex = n_tex;
+        t->tex_whc = (int32_t*)malloc(sizeof(int32_t) * 3 * (size_t)(n_tex ? n_tex : 1));
+        memcpy(t->tex_whc, tex_whc, sizeof(int32_t) * 3 * (size_t)n_tex);
+        t->tex_data = (uint8_t**)malloc(sizeof(uint8_t*) * (size_t)(n_tex ? n_tex : 1));
+        for (uint32_t i = 0; i < n_tex; ++i) {
+                size_t sz = (size_t)tex_whc[3 * i] * tex_whc[3 * i + 1] * tex_whc[3 * i + 2];
+                t->tex_data[i] = (uint8_t*)malloc(sz ? sz : 1);
+                memcpy(t->tex_data[i], tex_data[i], sz);
+        }
+}
+
+static float orc_unit_cycle(float s) /* voxel_octree.cc:392-399 */
+{
+        while (s > 1.f)
+                s -= 1.f;
+        while (s < 0.f)
+                s += 1.f;
+        return s;
+}
+
+static int orc_clampi(int s, int lo, int hi)
+{
+        return s > hi ? hi : (s < lo ? lo : s);
+}
+
+/* Triangle::get_albedo voxel_octree.cc:471-484 with barycentric graphics_math.h:1082-1100 and
+ * texel_fetch voxel_octree.cc:401-422.  kd_default: the colour used when no materials are set. */
+static void orc_albedo_one(const orc_tree* t, uint32_t tri, const float hit[3], const float kd_default[3], float out[3])
+{
+        if (!t->tri_mtl) {
+                memcpy(out, kd_default, 3 * sizeof(float));
+                return;
+        }
+        const uint32_t m = t->tri_mtl[tri];
+        const int32_t tx = t->mtl_tex[m];
+        if (tx < 0) {
+                memcpy(out, t->mtl_kd + 3 * (size_t)m, 3 * sizeof(float));
+                return;
+        }
+        const float* p = t->tri + 9 * (size_t)tri;
+        float v0[3], v1[3], v2[3];
+        for (int k = 0; k < 3; ++k) {
+                v0[k] = p[3 + k] - p[k];
+                v1[k] = p[6 + k] - p[k];
+                v2[k] = hit[k] - p[k];
+        }
+        float d00 = orc_dot3(v0, v0), d01 = orc_dot3(v0, v1), d11 = orc_dot3(v1, v1);
+        float d20 = orc_dot3(v2, v0), d21 = orc_dot3(v2, v1);
+        float denom = d00 * d11 - d01 * d01;
+        float bc[3] = { 0.f, 0.f, 0.f };
+        if (denom != 0) {
+                bc[1] = (d11 * d20 - d01 * d21) / denom;
+                bc[2] = (d00 * d21 - d01 * d20) / denom;
+                bc[0] = 1.0f - bc[1] - bc[2];
+        }
+        for (int k = 0; k < 3; ++k)
+                bc[k] = orc_clampf(bc[k], 0.f, 1.f);
+        const float* uv = t->uv + 6 * (size_t)tri;
+        float tc[2];
+        for (int k = 0; k < 2; ++k)
+                tc[k] = (bc[0] * uv[k] + bc[1] * uv[2 + k]) + bc[2] * uv[4 + k];
+        const int w = t->tex_whc[3 * tx], h = t->tex_whc[3 * tx + 1], ch = t->tex_whc[3 * tx + 2];
+        int x = orc_clampi((int)(orc_unit_cycle(tc[0]) * w), 0, w - 1);
+        int y = orc_clampi((int)(orc_unit_cycle(tc[1]) * h), 0, h - 1);
+        y = h - 1 - y;
+        const uint8_t* px = t->tex_data[tx] + ((size_t)y * w + x) * ch;
+        float pixel[4] = { 0, 0, 0, 0 };
+        for (int k = 0; k < ch && k < 4; ++k)
+                pixel[k] = (float)px[k];
+        for (int k = 0; k < 3; ++k)
+                out[k] = pixel[k] / 255.f;
+}
+
+void orc_albedo(const orc_tree* t, const uint32_t* tri, const float* pos, uint64_t n, const float kd_default[3], float* out3)
+{
+        for (uint64_t i = 0; i < n; ++i)
+                orc_albedo_one(t, tri[i], pos + 3 * i, kd_default, out3 + 3 * i);
+}
+
 /* main.cc:81-96, sequential in pixel order (py outer, px inner, samples in order). */
 void orc_gi_splat(orc_tree* t, const float cam10[10], float film_h, int nx, int ny, int spp,
                   const float kd[3])
@@ -817,9 +927,10 @@ void orc_gi_splat(orc_tree* t, const float cam10[10], float film_h, int nx, int 
                                 /* Triangle::get_diffuse voxel_octree.cc:462-469: albedo * tmp * color(1,1,1) */
                                 const float nd[3] = { -ray[3], -ray[4], -ray[5] };
                                 float tmp = orc_clampf(orc_dot3(n, nd), 0.f, 1.f);
-                                float illum[3];
+                                float illum[3], albedo[3];
+                                orc_albedo_one(t, tri, hit, kd, albedo);
                                 for (int k = 0; k < 3; ++k)
-                                        illum[k] = (kd[k] * tmp) * 1.f;
+                                        illum[k] = (albedo[k] * tmp) * 1.f;
                                 orc_node* ln = &t->nodes[leaf];
                                 for (int i = 0; i < 6; ++i) {
                                         float coeff = orc_clampf(orc_dot3(orc_illum_d[i], n), 0.f, 1.f);
@@ -1026,12 +1137,13 @@ void orc_gi_render(const orc_tree* t, const float cam10[10], float film_h, int n
                                         for (int k = 0; k < 3; ++k)
                                                 c[k] = 1.0f + (v1[k] - 1.0f) * tl;
                                 } else {
-                                        float ind[3], dir[3];
+                                        float ind[3], dir[3], albedo[3];
                                         const float nd[3] = { -ray[3], -ray[4], -ray[5] };
                                         orc_gi_cone_trace_point(t, hit, n, res, ind);
                                         orc_compute_illum(&t->nodes[leaf], nd, dir);
+                                        orc_albedo_one(t, tri, hit, kd, albedo);
                                         for (int k = 0; k < 3; ++k)
-                                                c[k] = kd[k] * (ind[k] + dir[k]);
+                                                c[k] = albedo[k] * (ind[k] + dir[k]);
                                 }
                                 for (int k = 0; k < 3; ++k)
                                         acc[k] += c[k] * w;

@@ -110,3 +110,31 @@ def gi_res(root_aabb, max_depth):
 
 
 GI_KD = np.array([0.7, 0.6, 0.5], np.float32)  # the scene's single untextured material (material_t::diffuse)
+
+
+def write_tga(path, img):
+    """Uncompressed top-left-origin TGA (24/32-bit true colour or 8-bit grey) from a uint8 [h, w, c] array --
+    a format the reference's stb_image decodes back to exactly these bytes."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, c = img.shape
+    hdr = bytearray(18)
+    hdr[2] = 2 if c >= 3 else 3
+    hdr[12], hdr[13], hdr[14], hdr[15] = w & 255, w >> 8, h & 255, h >> 8
+    hdr[16] = 8 * c
+    hdr[17] = 0x20 | (8 if c == 4 else 0)
+    data = img[..., [2, 1, 0, 3][:c]] if c >= 3 else img
+    with open(path, "wb") as f:
+        f.write(bytes(hdr) + np.ascontiguousarray(data).tobytes())
+
+
+def textured_case(seed=3, nu=48, nv=24):
+    """A sphere with random texture coordinates (outside [0,1] too: unit_cycle), four materials, two of them
+    textured (3- and 4-channel images).  Returns a dict of plain arrays."""
+    rng = np.random.default_rng(seed)
+    tri, nrm = scenes.uv_sphere(nu, nv)
+    T = len(tri)
+    uv = rng.uniform(-0.5, 2.5, (T, 3, 2)).astype(np.float32)
+    uv[: T // 8] = np.round(uv[: T // 8] * 4) / 4   # coordinates exactly on texel / cycle boundaries
+    return dict(tri=tri, nrm=nrm, uv=uv, mtl=rng.integers(0, 4, T).astype(np.uint32),
+                kd=rng.uniform(0.2, 0.9, (4, 3)).astype(np.float32), mtl_tex=np.array([-1, 0, -1, 1], np.int32),
+                tex0=rng.integers(0, 256, (17, 23, 3), dtype=np.uint8), tex1=rng.integers(0, 256, (8, 8, 4), dtype=np.uint8))

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
 from oracle.bindings import Ref  # noqa: E402
-from tests.common import CAM_LIGHT, CAM_MAIN, CAM_SPHERE, GI_KD, gi_res  # noqa: E402
+from tests.common import CAM_LIGHT, CAM_MAIN, CAM_SPHERE, GI_KD, gi_res, textured_case, write_tga  # noqa: E402
 from tests.test_gpu_parity import _predicate_inputs  # noqa: E402
 from voxelraytrace20190722_b200 import scenes  # noqa: E402
 
@@ -97,6 +97,32 @@ def main():
     out["cone"] = s.gi_cone_trace(hit.pos[m], hit.nrm[m], res)
     out["film"] = s.gi_render(CAM_MAIN, 1.0, nx, ny, spp, res, GI_KD)
     np.savez_compressed(os.path.join(HERE, "gi_atrium.npz"), **out)
+    # ---- textured materials: get_albedo + the GI rows on a textured sphere, from the reference -----------
+    import tempfile
+    c = textured_case()
+    tmp = tempfile.mkdtemp()
+    paths = ["", os.path.join(tmp, "a.tga"), "", os.path.join(tmp, "b.tga")]
+    write_tga(paths[1], c["tex0"])
+    write_tga(paths[3], c["tex1"])
+    depth, nx, ny, spp = 6, 48, 32, 4
+    s2 = ref.scene_mat(c["tri"], c["nrm"], c["uv"], c["mtl"], c["kd"], paths)
+    s2.build(depth)
+    r2 = ref.gen_rays(CAM_SPHERE, 1.0, 128, 96, 4)
+    h2 = s2.trace(r2)
+    m2 = h2.hit.astype(bool)
+    s2.gi_reset()
+    s2.gi_splat(CAM_LIGHT, 1.0, 128, 128, 4, GI_KD)
+    s2.gi_filter()
+    res2 = gi_res(s2.root_aabb(), depth)
+    tout = dict(c, depth=depth, tex0_seen=ref.load_image(paths[1]), tex1_seen=ref.load_image(paths[3]),
+                alb_tri=h2.tri[m2], alb_pos=h2.pos[m2], albedo=s2.albedo(h2.tri[m2], h2.pos[m2]), res=res2,
+                light_cam10=CAM_LIGHT, light_dims=np.array([128, 128, 4]), cam10=CAM_SPHERE, dims=np.array([nx, ny, spp]),
+                film=s2.gi_render(CAM_SPHERE, 1.0, nx, ny, spp, res2, None))
+    for level in range(depth):
+        cells, cov, il = s2.gi_level(level)
+        tout[f"l{level}_cov"], tout[f"l{level}_illum"] = cov, il
+    np.savez_compressed(os.path.join(HERE, "gi_textured.npz"), **tout)
+    print("gi_textured: albedo points", int(m2.sum()))
     print("gi_atrium: lit leaves", int((out[f"l{depth - 1}_illum"] > 0).any(axis=(1, 2)).sum()), "cone points", int(m.sum()))
 
 

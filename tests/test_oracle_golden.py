@@ -70,3 +70,24 @@ def test_gi_golden(port):
     assert_bits_equal(tree.gi_cone_trace(z["cone_pos"], z["cone_nrm"], res), z["cone"], "cone_trace")
     nx, ny, spp = (int(v) for v in z["dims"])
     assert_bits_equal(tree.gi_render(z["cam10"], 1.0, nx, ny, spp, res, z["kd"]), z["film"], "trace() film")
+
+
+def test_textured_golden(port):
+    """Triangle::get_albedo with textures and the GI rows on a textured sphere against vectors produced by the
+    reference (textures as the reference's stbi_load returned them)."""
+    z = np.load(os.path.join(G, "gi_textured.npz"))
+    depth = int(z["depth"])
+    tree = port.build(z["tri"], z["nrm"], depth)
+    tree.set_materials(z["uv"], z["mtl"], z["kd"], z["mtl_tex"], [z["tex0_seen"], z["tex1_seen"]])
+    assert_bits_equal(tree.albedo(z["alb_tri"], z["alb_pos"]), z["albedo"], "get_albedo")
+    lnx, lny, lspp = (int(v) for v in z["light_dims"])
+    tree.gi_reset()
+    tree.gi_splat(z["light_cam10"], 1.0, lnx, lny, lspp, np.array([0.7, 0.6, 0.5], np.float32))
+    tree.gi_filter()
+    for level in range(depth):
+        _, cov, il = tree.gi_level(level)
+        assert_bits_equal(cov, z[f"l{level}_cov"], f"level {level} coverage")
+        assert_bits_equal(il, z[f"l{level}_illum"], f"level {level} illum")
+    nx, ny, spp = (int(v) for v in z["dims"])
+    assert_bits_equal(tree.gi_render(z["cam10"], 1.0, nx, ny, spp, np.float32(z["res"]), np.array([0.7, 0.6, 0.5], np.float32)),
+                      z["film"], "textured trace() film")

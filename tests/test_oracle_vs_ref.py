@@ -4,7 +4,8 @@ oracle/_ref exists."""
 import numpy as np
 import pytest
 
-from tests.common import CAM_LIGHT, CAM_MAIN, CAM_SPHERE, GI_KD, assert_bits_equal, gi_res
+from tests.common import (CAM_LIGHT, CAM_MAIN, CAM_SPHERE, GI_KD, assert_bits_equal, gi_res, textured_case,
+                          write_tga)
 from tests.test_gpu_parity import _predicate_inputs
 from voxelraytrace20190722_b200 import scenes
 
@@ -75,3 +76,34 @@ def test_gi_rows_live(port, ref, name, maker, depth, cam10):
     assert_bits_equal(a.gi_cone_trace(h.pos[m], h.nrm[m], res), b.gi_cone_trace(h.pos[m], h.nrm[m], res), "cone_trace")
     assert_bits_equal(a.gi_render(cam10, 1.0, 48, 40, 4, res, GI_KD), b.gi_render(cam10, 1.0, 48, 40, 4, res, GI_KD, nthreads=4),
                       "trace() film")
+
+
+def test_textured_materials_live(port, ref, tmp_path):
+    """Triangle::get_albedo with textures (barycentric, unit_cycle, texel_fetch + stb_image decode) and the GI rows
+    on a textured scene: restatement vs the reference's own functions, images read by the reference's stbi_load."""
+    c = textured_case()
+    paths = ["", str(tmp_path / "a.tga"), "", str(tmp_path / "b.tga")]
+    write_tga(paths[1], c["tex0"])
+    write_tga(paths[3], c["tex1"])
+    seen = [ref.load_image(paths[1]), ref.load_image(paths[3])]
+    assert np.array_equal(seen[0], c["tex0"]) and np.array_equal(seen[1], c["tex1"])
+    depth = 6
+    b = ref.scene_mat(c["tri"], c["nrm"], c["uv"], c["mtl"], c["kd"], paths)
+    b.build(depth)
+    a = port.build(c["tri"], c["nrm"], depth)
+    a.set_materials(c["uv"], c["mtl"], c["kd"], c["mtl_tex"], seen)
+    h = a.trace(port.gen_rays(CAM_SPHERE, 1.0, 128, 96, 4))
+    m = h.hit.astype(bool)
+    alb = a.albedo(h.tri[m], h.pos[m])
+    assert_bits_equal(alb, b.albedo(h.tri[m], h.pos[m]), "get_albedo")
+    assert len(np.unique(alb.round(3), axis=0)) > 100, "textures were not sampled"
+    for o in (a, b):
+        o.gi_reset()
+        o.gi_splat(CAM_LIGHT, 1.0, 128, 128, 4, GI_KD)
+        o.gi_filter()
+    for level in range(depth):
+        for x, y, nm in zip(a.gi_level(level), b.gi_level(level), ("cells", "coverage", "illum")):
+            assert_bits_equal(x, y, f"textured level {level} {nm}")
+    res = gi_res(b.root_aabb(), depth)
+    assert_bits_equal(a.gi_render(CAM_SPHERE, 1.0, 48, 32, 4, res, GI_KD), b.gi_render(CAM_SPHERE, 1.0, 48, 32, 4, res, None, nthreads=4),
+                      "textured trace() film")

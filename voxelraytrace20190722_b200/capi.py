@@ -35,6 +35,10 @@ class vrt_bands(C.Structure):
     _fields_ = [("band_h", C.c_int32), ("band_first", C.c_int32), ("band_stride", C.c_int32)]
 
 
+class vrt_texture(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32), ("data", C.c_void_p)]
+
+
 class vrt_tree_info(C.Structure):
     _fields_ = [("num_tris", C.c_uint32), ("max_depth", C.c_int32), ("root_aabb", C.c_float * 6),
                 ("num_nodes", C.c_uint64), ("num_leaves", C.c_uint64), ("num_refs", C.c_uint64),
@@ -63,7 +67,7 @@ SYMBOLS = [
     "vrt_render_camera", "vrt_render_camera_dev", "vrt_render_camera_async", "vrt_band_rows", "vrt_render_bands_dev",
     "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_frame_bands_peer_dev",
     "vrt_dev_alloc", "vrt_dev_free", "vrt_ipc_export", "vrt_ipc_open", "vrt_ipc_close", "vrt_tree_sync",
-    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_gi_init", "vrt_gi_splat_camera", "vrt_gi_filter",
+    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_set_materials", "vrt_albedo", "vrt_gi_init", "vrt_gi_splat_camera", "vrt_gi_filter",
     "vrt_gi_get_level", "vrt_gi_cone_trace", "vrt_gi_render_camera", "vrt_gi_render_camera_dev", "vrt_tribox_batch",
     "vrt_tri_overlap_aabb_batch", "vrt_raytri_batch", "vrt_aabb_isect_batch",
 ]
@@ -130,6 +134,8 @@ def load(build_if_missing: bool = True):
     L.vrt_debug_general_order_calls.restype = u64
     L.vrt_debug_param_check.argtypes = [vp]
     L.vrt_gi_init.argtypes = [vp]
+    L.vrt_set_materials.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp]
+    L.vrt_albedo.argtypes = [vp, vp, vp, u64, vp, vp]
     L.vrt_gi_splat_camera.argtypes = [vp, C.POINTER(vrt_camera), vp]
     L.vrt_gi_filter.argtypes = [vp]
     L.vrt_gi_get_level.argtypes = [vp, i32, vp, vp]
@@ -374,6 +380,28 @@ class Octree:
         _check(load().vrt_count_camera(self._h, C.byref(cam.c), x0, y0, x1, y1, _ptr(c)))
         return dict(rays=int(c[0]), n_int=int(c[1]), n_leaf=int(c[2]), n_tri=int(c[3]), hits=int(c[4]),
                     n_param=int(c[5]), n_tie=int(c[6]), n_unsafe=int(c[7]))
+
+    # ---- materials / textures -------------------------------
+    def set_materials(self, tri_uv, tri_mtl, kd, mtl_tex, textures):
+        """textures: list of uint8 arrays [h, w, channels] (as stbi_load returns them)."""
+        tri_uv = np.ascontiguousarray(tri_uv, np.float32).reshape(-1, 6)
+        tri_mtl = np.ascontiguousarray(tri_mtl, np.uint32)
+        kd = np.ascontiguousarray(kd, np.float32).reshape(-1, 3)
+        mtl_tex = np.ascontiguousarray(mtl_tex, np.int32)
+        texs = [np.ascontiguousarray(t, np.uint8) for t in textures]
+        arr = (vrt_texture * max(len(texs), 1))()
+        for i, t in enumerate(texs):
+            arr[i] = vrt_texture(t.shape[1], t.shape[0], t.shape[2], t.ctypes.data)
+        _check(load().vrt_set_materials(self._h, _ptr(tri_uv), _ptr(tri_mtl), len(kd), _ptr(kd), _ptr(mtl_tex), len(texs),
+                                        C.cast(arr, C.c_void_p)))
+
+    def albedo(self, tri, pos, kd_default=(0.8, 0.8, 0.8)):
+        tri = np.ascontiguousarray(tri, np.uint32)
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        kd = np.ascontiguousarray(kd_default, np.float32)
+        out = np.zeros((len(tri), 3), np.float32)
+        _check(load().vrt_albedo(self._h, _ptr(tri), _ptr(pos), len(tri), _ptr(kd), _ptr(out)))
+        return out
 
     # ---- GI rows (SURVEY.md 8f) ------------------------------------------------
     def gi_init(self):

@@ -399,6 +399,7 @@ void vrt_tree_free(vrt_tree* t)
         t->io_in.release();
         t->gi_buf.release();
         t->gi_recs.release();
+        t->mat_buf.release();
         t->io_out.release();
         t->film_dev[0].release();
         t->film_dev[1].release();
@@ -1030,6 +1031,109 @@ int vrt_gi_cone_trace(const vrt_tree* tc, const float* pos, const float* nrm, ui
         VRT_CUDA(cudaMemcpyAsync(d_pos, pos, n * 12, cudaMemcpyHostToDevice, t->stream));
         VRT_CUDA(cudaMemcpyAsync(d_nrm, nrm, n * 12, cudaMemcpyHostToDevice, t->stream));
         rc = gi_cone_points(t, d_pos, d_nrm, n, res, t->io_out.as<float>());
+        if (rc)
+                return rc;
+        VRT_CUDA(cudaMemcpyAsync(out_rgb, t->io_out.p, n * 12, cudaMemcpyDeviceToHost, t->stream));
+        VRT_CUDA(cudaStreamSynchronize(t->stream));
+        return VRT_OK;
+}
+
+// Materials: per-vertex texture coordinates, a material id per triangle, per material a diffuse colour and
+// an optional texture (the untextured / textured branches of Triangle::get_albedo).  Host pointers.
+int vrt_set_materials(vrt_tree* t, const float* tri_uv, const uint32_t* tri_mtl, uint32_t num_mtl, const float* kd,
+                      const int32_t* mtl_tex, uint32_t num_tex, const vrt_texture* tex)
+{
+        int rc = check_tree(t);
+        if (rc)
+                return rc;
+        const uint64_t T = t->hdr.num_tris;
+        if (!tri_uv || !tri_mtl || !num_mtl || !kd || !mtl_tex || (num_tex && !tex)) {
+                set_error("vrt_set_materials: null argument");
+                return VRT_ERR_ARG;
+        }
+        for (uint64_t i = 0; i < T; ++i)
+                if (tri_mtl[i] >= num_mtl) {
+                        set_error("tri_mtl[%llu]=%u out of range", (unsigned long long)i, tri_mtl[i]);
+                        return VRT_ERR_ARG;
+                }
+        std::vector<float> hkd(4 * (size_t)num_mtl);
+        for (uint32_t m = 0; m < num_mtl; ++m) {
+                if (mtl_tex[m] >= (int32_t)num_tex) {
+                        set_error("mtl_tex[%u]=%d out of range", m, mtl_tex[m]);
+                        return VRT_ERR_ARG;
+                }
+                const int32_t tx = mtl_tex[m] < 0 ? -1 : mtl_tex[m];
+                memcpy(&hkd[4 * m], kd + 3 * m, 12);
+                memcpy(&hkd[4 * m + 3], &tx, 4);
+        }
+        std::vector<int32_t> htex(4 * (size_t)std::max<uint32_t>(num_tex, 1));
+        uint64_t texel_bytes = 0;
+        for (uint32_t i = 0; i < num_tex; ++i) {
+                if (tex[i].width < 1 || tex[i].height < 1 || tex[i].channels < 1 || tex[i].channels > 4 || !tex[i].data) {
+                        set_error("texture %u: bad dimensions or null data", i);
+                        return VRT_ERR_ARG;
+                }
+                if (texel_bytes > 0xfff00000ull) {
+                        set_error("textures exceed 4 GB");
+                        return VRT_ERR_CAPACITY;
+                }
+                htex[4 * i] = (int32_t)(uint32_t)texel_bytes;
+                htex[4 * i + 1] = tex[i].width;
+                htex[4 * i + 2] = tex[i].height;
+                htex[4 * i + 3] = tex[i].channels;
+                texel_bytes += align256((uint64_t)tex[i].width * tex[i].height * tex[i].channels);
+        }
+        const uint64_t o_uv = 0, o_tri = align256(o_uv + std::max<uint64_t>(T, 1) * 24);
+        const uint64_t o_kd = align256(o_tri + std::max<uint64_t>(T, 1) * 4), o_tex = align256(o_kd + (uint64_t)num_mtl * 16);
+        const uint64_t o_px = align256(o_tex + (uint64_t)std::max<uint32_t>(num_tex, 1) * 16);
+        if (t->mat_buf.reserve(o_px + std::max<uint64_t>(texel_bytes, 256)))
+                return VRT_ERR_NOMEM;
+        char* base = static_cast<char*>(t->mat_buf.p);
+        VRT_CUDA(cudaStreamSynchronize(t->stream));
+        if (T) {
+                VRT_CUDA(cudaMemcpy(base + o_uv, tri_uv, T * 24, cudaMemcpyHostToDevice));
+                VRT_CUDA(cudaMemcpy(base + o_tri, tri_mtl, T * 4, cudaMemcpyHostToDevice));
+        }
+        VRT_CUDA(cudaMemcpy(base + o_kd, hkd.data(), (size_t)num_mtl * 16, cudaMemcpyHostToDevice));
+        VRT_CUDA(cudaMemcpy(base + o_tex, htex.data(), htex.size() * 4, cudaMemcpyHostToDevice));
+        for (uint32_t i = 0; i < num_tex; ++i)
+                VRT_CUDA(cudaMemcpy(base + o_px + (uint32_t)htex[4 * i], tex[i].data,
+                                    (size_t)tex[i].width * tex[i].height * tex[i].channels, cudaMemcpyHostToDevice));
+        t->dev.mat_uv = reinterpret_cast<const float2*>(base + o_uv);
+        t->dev.mat_tri = reinterpret_cast<const uint32_t*>(base + o_tri);
+        t->dev.mat_kd = reinterpret_cast<const float4*>(base + o_kd);
+        t->dev.mat_tex = reinterpret_cast<const int4*>(base + o_tex);
+        t->dev.mat_texels = reinterpret_cast<const uint8_t*>(base + o_px);
+        return VRT_OK;
+}
+
+// Triangle::get_albedo(ISect{hit = pos[i]}) of triangle tri[i]; host pointers.  kd_default is the colour of
+// a tree without materials.
+int vrt_albedo(const vrt_tree* tc, const uint32_t* tri, const float* pos, uint64_t n, const float kd_default[3],
+               float* out_rgb)
+{
+        int rc = check_tree(tc);
+        if (rc)
+                return rc;
+        if (n && (!tri || !pos || !out_rgb || !kd_default)) {
+                set_error("null argument");
+                return VRT_ERR_ARG;
+        }
+        if (n == 0)
+                return VRT_OK;
+        for (uint64_t i = 0; i < n; ++i)
+                if (tri[i] >= tc->hdr.num_tris) {
+                        set_error("tri[%llu]=%u out of range", (unsigned long long)i, tri[i]);
+                        return VRT_ERR_ARG;
+                }
+        vrt_tree* t = const_cast<vrt_tree*>(tc);
+        if (t->io_in.reserve(n * 16) || t->io_out.reserve(n * 12))
+                return VRT_ERR_NOMEM;
+        float* d_pos = t->io_in.as<float>();
+        uint32_t* d_tri = reinterpret_cast<uint32_t*>(d_pos + 3 * n);
+        VRT_CUDA(cudaMemcpyAsync(d_pos, pos, n * 12, cudaMemcpyHostToDevice, t->stream));
+        VRT_CUDA(cudaMemcpyAsync(d_tri, tri, n * 4, cudaMemcpyHostToDevice, t->stream));
+        rc = gi_albedo_points(t, d_tri, d_pos, n, kd_default, t->io_out.as<float>());
         if (rc)
                 return rc;
         VRT_CUDA(cudaMemcpyAsync(out_rgb, t->io_out.p, n * 12, cudaMemcpyDeviceToHost, t->stream));

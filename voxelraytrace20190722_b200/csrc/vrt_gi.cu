@@ -33,8 +33,7 @@ int gi_init(vrt_tree* t)
 // main.cc:88-95: illum = albedo * clamp(dot(normal, -ray.d),0,1) * color(1,1,1)
 // (Triangle::get_diffuse voxel_octree.cc:462-469, untextured albedo = material diffuse).
 __global__ void k_gi_accumulate(const unsigned long long* __restrict__ keys, uint64_t n,
-                                const float4* __restrict__ recs, float kd0, float kd1, float kd2,
-                                uint32_t leaf_node0, float* __restrict__ gi)
+                                const float4* __restrict__ recs, uint32_t leaf_node0, float* __restrict__ gi)
 {
         const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= n)
@@ -50,16 +49,13 @@ __global__ void k_gi_accumulate(const unsigned long long* __restrict__ keys, uin
 #pragma unroll
         for (int f = 0; f < 18; ++f)
                 acc[f] = g[f];
-        const float kd[3] = { kd0, kd1, kd2 };
         for (uint64_t j = i; j < n; ++j) {
                 const unsigned long long kj = keys[j];
                 if (kj == ~0ull || (uint32_t)(kj >> 32) != leaf)
                         break;
-                const float4 r = __ldg(&recs[(uint32_t)kj]);  // normal.xyz, tmp
-                float illum[3];
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-                        illum[c] = fmul(fmul(kd[c], r.w), 1.f);
+                const float4 r = __ldg(&recs[2ull * (uint32_t)kj]);  // normal.xyz, illum.x
+                const float4 r1 = __ldg(&recs[2ull * (uint32_t)kj + 1]);  // illum.yz
+                const float illum[3] = { r.w, r1.x, r1.y };
 #pragma unroll
                 for (int f = 0; f < 6; ++f) {
                         const float s = (f < 3) ? 1.f : -1.f;
@@ -88,9 +84,13 @@ int gi_splat_camera(vrt_tree* t, const vrt_camera* cam, const float kd[3])
                 set_error("light camera has too many rays for 32-bit ray indices");
                 return VRT_ERR_ARG;
         }
-        if (t->keys_a.reserve(R * 8) || t->gi_recs.reserve(R * 16))
+        if (t->keys_a.reserve(R * 8) || t->gi_recs.reserve(R * 32))
                 return VRT_ERR_NOMEM;
-        int rc = launch_trace_camera(t, cam, nullptr, 0, 0, cam->nx, cam->ny, t->keys_a.p, OUT_SPLAT, 0, 0, t->gi_recs.p);
+        vrt_shade sh{};  // (carries the default material colour to the kernel)
+        sh.light_dir[0] = kd[0];
+        sh.light_dir[1] = kd[1];
+        sh.light_dir[2] = kd[2];
+        int rc = launch_trace_camera(t, cam, &sh, 0, 0, cam->nx, cam->ny, t->keys_a.p, OUT_SPLAT, 0, 0, t->gi_recs.p);
         if (rc)
                 return rc;
         int lb = 1;
@@ -100,7 +100,7 @@ int gi_splat_camera(vrt_tree* t, const vrt_camera* cam, const float kd[3])
         rc = sort_keys_u64(t, R, 0, 32 + lb, &sorted);
         if (rc)
                 return rc;
-        k_gi_accumulate<<<gi_grid(R, 128), 128, 0, t->stream>>>(sorted, R, t->gi_recs.as<float4>(), kd[0], kd[1], kd[2],
+        k_gi_accumulate<<<gi_grid(R, 128), 128, 0, t->stream>>>(sorted, R, t->gi_recs.as<float4>(),
                                                                 (uint32_t)(t->hdr.num_nodes - t->hdr.num_leaves),
                                                                 t->gi_buf.as<float>());
         count_launch();
@@ -219,6 +219,47 @@ int gi_cone_points(const vrt_tree* t, const float* d_pos, const float* d_nrm, ui
         const size_t smem = (size_t)kGiPathWords * std::max(t->dev.L, 1) * 128 * sizeof(float);
         VRT_CUDA(cudaFuncSetAttribute(k_gi_cone_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_gi_cone_points<<<gi_grid(n, 128), 128, smem, t->stream>>>(p);
+        count_launch();
+        VRT_CUDA(cudaGetLastError());
+        return VRT_OK;
+}
+
+struct GiAlbedoParams {
+        TreeDev tree;
+        const uint32_t* tri;
+        const float* pos;
+        uint64_t n;
+        float kd[3];
+        float* out;
+};
+
+__global__ void k_gi_albedo_points(GiAlbedoParams p)
+{
+        const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= p.n)
+                return;
+        const float pos[3] = { p.pos[3 * i], p.pos[3 * i + 1], p.pos[3 * i + 2] };
+        float out[3];
+        gi_albedo(p.tree, p.tri[i], pos, p.kd, out);
+        p.out[3 * i] = out[0];
+        p.out[3 * i + 1] = out[1];
+        p.out[3 * i + 2] = out[2];
+}
+
+int gi_albedo_points(const vrt_tree* t, const uint32_t* d_tri, const float* d_pos, uint64_t n, const float kd[3], float* d_out)
+{
+        if (n == 0)
+                return VRT_OK;
+        GiAlbedoParams p{};
+        p.tree = t->dev;
+        p.tri = d_tri;
+        p.pos = d_pos;
+        p.n = n;
+        p.kd[0] = kd[0];
+        p.kd[1] = kd[1];
+        p.kd[2] = kd[2];
+        p.out = d_out;
+        k_gi_albedo_points<<<gi_grid(n, 128), 128, 0, t->stream>>>(p);
         count_launch();
         VRT_CUDA(cudaGetLastError());
         return VRT_OK;

@@ -17,6 +17,77 @@ namespace vrt {
 constexpr int kGiStride = 20;  // floats per node
 constexpr int kGiCoverage = 18;
 
+// Triangle::get_albedo (voxel_octree.cc:471-484): the material's diffuse colour, or -- for a
+// textured material -- the nearest texel at the clamped barycentric interpolation of the vertex
+// texture coordinates: jql::barycentric (graphics_math.h:1082-1100), unit_cycle + texel_fetch with
+// the vertical flip (voxel_octree.cc:392-422).  kd_default is used when no materials are set.
+__device__ __forceinline__ float gi_unit_cycle(float s)
+{
+        // while (s > 1) s -= 1; while (s < 0) s += 1;  -- the reference does not terminate for |s| >= 2^24
+        // (s -+ 1 == s); such coordinates are cut off after 2^24 steps here
+        for (int i = 0; i < (1 << 24) && s > 1.f; ++i)
+                s = fsub(s, 1.f);
+        for (int i = 0; i < (1 << 24) && s < 0.f; ++i)
+                s = fadd(s, 1.f);
+        return s;
+}
+
+__device__ __forceinline__ void gi_albedo(const TreeDev& tr, uint32_t tri, const float hit[3], const float kd_default[3],
+                                          float out[3])
+{
+        if (!tr.mat_tri) {
+                out[0] = kd_default[0];
+                out[1] = kd_default[1];
+                out[2] = kd_default[2];
+                return;
+        }
+        const float4 m = __ldg(&tr.mat_kd[__ldg(&tr.mat_tri[tri])]);
+        const int tx = __float_as_int(m.w);
+        if (tx < 0) {
+                out[0] = m.x;
+                out[1] = m.y;
+                out[2] = m.z;
+                return;
+        }
+        const float4 a = __ldg(&tr.tri4[3ull * tri]), b = __ldg(&tr.tri4[3ull * tri + 1]), c = __ldg(&tr.tri4[3ull * tri + 2]);
+        const float v0[3] = { fsub(b.x, a.x), fsub(b.y, a.y), fsub(b.z, a.z) };
+        const float v1[3] = { fsub(c.x, a.x), fsub(c.y, a.y), fsub(c.z, a.z) };
+        const float v2[3] = { fsub(hit[0], a.x), fsub(hit[1], a.y), fsub(hit[2], a.z) };
+        const float d00 = dot3(v0[0], v0[1], v0[2], v0[0], v0[1], v0[2]);
+        const float d01 = dot3(v0[0], v0[1], v0[2], v1[0], v1[1], v1[2]);
+        const float d11 = dot3(v1[0], v1[1], v1[2], v1[0], v1[1], v1[2]);
+        const float d20 = dot3(v2[0], v2[1], v2[2], v0[0], v0[1], v0[2]);
+        const float d21 = dot3(v2[0], v2[1], v2[2], v1[0], v1[1], v1[2]);
+        const float denom = fsub(fmul(d00, d11), fmul(d01, d01));
+        float bc[3] = { 0.f, 0.f, 0.f };
+        if (denom != 0.f) {
+                bc[1] = fdiv(fsub(fmul(d11, d20), fmul(d01, d21)), denom);
+                bc[2] = fdiv(fsub(fmul(d00, d21), fmul(d01, d20)), denom);
+                bc[0] = fsub(fsub(1.0f, bc[1]), bc[2]);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+                bc[k] = clampf(bc[k], 0.f, 1.f);
+        const float2 t0 = __ldg(&tr.mat_uv[3ull * tri]), t1 = __ldg(&tr.mat_uv[3ull * tri + 1]), t2 = __ldg(&tr.mat_uv[3ull * tri + 2]);
+        const float tcx = fadd(fadd(fmul(bc[0], t0.x), fmul(bc[1], t1.x)), fmul(bc[2], t2.x));
+        const float tcy = fadd(fadd(fmul(bc[0], t0.y), fmul(bc[1], t1.y)), fmul(bc[2], t2.y));
+        const int4 td = __ldg(&tr.mat_tex[tx]);  // byte offset, width, height, channels
+        int x = (int)fmul(gi_unit_cycle(tcx), (float)td.y);
+        int y = (int)fmul(gi_unit_cycle(tcy), (float)td.z);
+        x = x > td.y - 1 ? td.y - 1 : (x < 0 ? 0 : x);
+        y = y > td.z - 1 ? td.z - 1 : (y < 0 ? 0 : y);
+        y = td.z - 1 - y;
+        const uint8_t* px = tr.mat_texels + (size_t)(uint32_t)td.x + ((size_t)y * td.y + x) * td.w;
+        float pixel[3] = { 0.f, 0.f, 0.f };
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+                if (k < td.w)
+                        pixel[k] = (float)__ldg(px + k);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+                out[k] = fdiv(pixel[k], 255.f);
+}
+
 // VoxelOctree::compute_illum(d): sum_i clamp(dot(illum_d[i], d), 0, 1) * illum[i]
 __device__ __forceinline__ void gi_compute_illum(const float* __restrict__ g, const float d[3], float out[3])
 {

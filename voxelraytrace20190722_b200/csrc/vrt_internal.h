@@ -70,6 +70,13 @@ struct TreeDev {
                                 // children of cell x at level l
         const float2* tab2[3];
         const float* gi;  // per-node GI state (vrt_gi.cuh), or null before vrt_gi_init
+        // materials (vrt_set_materials), all null when unset: per-vertex texture coordinates, material id per
+        // triangle, per material (kd.xyz, texture id or -1 as int bits), per texture (byte offset, w, h, channels)
+        const float2* mat_uv;
+        const uint32_t* mat_tri;
+        const float4* mat_kd;
+        const int4* mat_tex;
+        const uint8_t* mat_texels;
         uint32_t num_nodes;
         uint32_t num_leaves;
         int L;  // leaf level = max_depth-1
@@ -118,7 +125,7 @@ struct vrt_tree {
         // trace scratch (host-pointer entry points)
         vrt::Scratch io_in, io_out;
         // GI rows: per-node coverage + illum[6], see vrt_gi.cuh
-        vrt::Scratch gi_buf, gi_recs;
+        vrt::Scratch gi_buf, gi_recs, mat_buf;
         // pipelined host-film path (vrt_render_camera_async): two device films, a copy stream
         vrt::Scratch film_dev[2];
         cudaStream_t copy_stream = nullptr;
@@ -158,6 +165,7 @@ int gi_init(vrt_tree* t);
 int gi_splat_camera(vrt_tree* t, const vrt_camera* cam, const float kd[3]);
 int gi_filter(vrt_tree* t);
 int gi_cone_points(const vrt_tree* t, const float* d_pos, const float* d_nrm, uint64_t n, float res, float* d_out);
+int gi_albedo_points(const vrt_tree* t, const uint32_t* d_tri, const float* d_pos, uint64_t n, const float kd[3], float* d_out);
 // sort `n` 64-bit keys held in t->keys_a on bits [lo,hi) with the build's radix sort (vrt_build.cu)
 int sort_keys_u64(vrt_tree* t, uint64_t n, int lo, int hi, unsigned long long** sorted);
 int param_check_counts(unsigned long long out[2]);

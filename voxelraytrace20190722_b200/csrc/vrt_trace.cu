@@ -771,15 +771,16 @@ __device__ __forceinline__ void shade_gi(const TraceParams& p, const HitState& h
                         rgb[k] = fadd(1.0f, fmul(fsub(v1[k], 1.0f), t));
                 return;
         }
-        float pos[3], nrm[3], ind[3], dir[3];
+        float pos[3], nrm[3], ind[3], dir[3], albedo[3];
         finish_isect(p.tree, hs, o, d, pos, nrm);
+        gi_albedo(p.tree, hs.tri, pos, p.kd3, albedo);
         // the traversal is over: this thread's stack column doubles as the cone trace's path cache
         gi_cone_trace_point(p.tree, p.root, reinterpret_cast<float*>(s_col), kTraceThreads, pos, nrm, p.gi_res, ind);
         const float nd[3] = { -d[0], -d[1], -d[2] };
         gi_compute_illum(p.tree.gi + (size_t)kGiStride * hs.leaf, nd, dir);
 #pragma unroll
         for (int k = 0; k < 3; ++k)
-                rgb[k] = fmul(p.kd3[k], fadd(ind[k], dir[k]));
+                rgb[k] = fmul(albedo[k], fadd(ind[k], dir[k]));
 }
 
 // ---------------------------------------------------------------------------
@@ -893,20 +894,24 @@ k_trace_camera(TraceParams p)
                         }
                 } else if (MODE == OUT_SPLAT) {
                         // light-map pass (main.cc:81-96): key = (leaf, ray index in the reference's sequential
-                        // loop order), record = (ISect.normal, clamp(dot(normal, -ray.d), 0, 1))
+                        // loop order), record = ISect.normal and illum = get_diffuse(isect, ray, (1,1,1)) =
+                        // albedo * clamp(dot(normal, -ray.d), 0, 1) * color (voxel_octree.cc:462-469)
                         if (active) {
                                 unsigned long long key = ~0ull;
-                                float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+                                float4 rec0 = make_float4(0.f, 0.f, 0.f, 0.f), rec1 = rec0;
                                 if (hs.hit) {
-                                        float pos[3], nrm[3];
+                                        float pos[3], nrm[3], albedo[3];
                                         finish_isect(p.tree, hs, o, d, pos, nrm);
+                                        gi_albedo(p.tree, hs.tri, pos, p.kd3, albedo);
                                         const float tmp = clampf(dot3(nrm[0], nrm[1], nrm[2], -d[0], -d[1], -d[2]), 0.f, 1.f);
-                                        rec = make_float4(nrm[0], nrm[1], nrm[2], tmp);
+                                        rec0 = make_float4(nrm[0], nrm[1], nrm[2], fmul(fmul(albedo[0], tmp), 1.f));
+                                        rec1 = make_float4(fmul(fmul(albedo[1], tmp), 1.f), fmul(fmul(albedo[2], tmp), 1.f), 0.f, 0.f);
                                         key = ((unsigned long long)(hs.leaf - (p.tree.num_nodes - p.tree.num_leaves)) << 32) |
                                               (unsigned long long)(pix * spp + s);
                                 }
                                 static_cast<unsigned long long*>(p.out)[pix * spp + s] = key;
-                                static_cast<float4*>(p.out2)[pix * spp + s] = rec;
+                                static_cast<float4*>(p.out2)[2 * (pix * spp + s)] = rec0;
+                                static_cast<float4*>(p.out2)[2 * (pix * spp + s) + 1] = rec1;
                         }
                 } else if (MODE == OUT_HIT16) {  // (OUT_HIT16_FILM handled below)
                         if (active) {
@@ -1059,7 +1064,7 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         p.out = d_out;
         p.out2 = d_out2;
         p.film_full = film_full;
-        if (mode == OUT_GI_FILM && sh) {  // (light_dir carries the material colour, shadow_eps the cone-trace res)
+        if ((mode == OUT_GI_FILM || mode == OUT_SPLAT) && sh) {  // (light_dir carries the material colour, shadow_eps the cone-trace res)
                 p.kd3[0] = sh->light_dir[0];
                 p.kd3[1] = sh->light_dir[1];
                 p.kd3[2] = sh->light_dir[2];
