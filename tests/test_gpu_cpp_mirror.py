@@ -55,3 +55,6 @@ def test_demo_main_matches_oracle(tmp_path, port, gpu):
     same = (film.view(np.uint32) == exp_film.view(np.uint32)).all(axis=2)
     assert same.mean() >= 0.999, f"{int((~same).sum())} GI pixels differ"
     assert "centre ray indirect light" in out.stdout
+    with open(str(gi_dump) + ".hdr", "rb") as f:  # the stbi_write_hdr step of main.cc:125-126
+        hdr = f.read()
+    assert hdr.startswith(b"#?RADIANCE") and hdr.endswith(hdr[-4 * nx * ny:]) and len(hdr) > 4 * nx * ny

@@ -91,6 +91,31 @@ static void write_bmp(const char* path, const Film& film)
         std::fclose(f);
 }
 
+// Radiance .hdr (RGBE, no run-length encoding) of the float film -- the host-side job stbi_write_hdr does in
+// main.cc:125-126.
+static void write_hdr(const char* path, const Film& film)
+{
+        const auto d = film.to_float_array();
+        FILE* f = std::fopen(path, "wb");
+        if (!f) return;
+        std::fprintf(f, "#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n", film.ny, film.nx);
+        for (size_t i = 0; i < (size_t)film.nx * film.ny; ++i) {
+                const float r = d[3 * i], g = d[3 * i + 1], b = d[3 * i + 2];
+                const float m = std::max(r, std::max(g, b));
+                unsigned char px[4] = { 0, 0, 0, 0 };
+                if (m >= 1e-32f) {
+                        int e;
+                        const float sc = std::frexp(m, &e) * 256.0f / m;
+                        px[0] = (unsigned char)(r * sc);
+                        px[1] = (unsigned char)(g * sc);
+                        px[2] = (unsigned char)(b * sc);
+                        px[3] = (unsigned char)(e + 128);
+                }
+                std::fwrite(px, 1, 4, f);
+        }
+        std::fclose(f);
+}
+
 int main(int argc, char** argv)
 {
         const char* out = "demo.bmp";
@@ -159,6 +184,7 @@ int main(int argc, char** argv)
                                 const Vec3 c = gi::cone_trace(root, is, res);
                                 std::printf("centre ray indirect light (%g,%g,%g)\n", c.x, c.y, c.z);
                         }
+                        write_hdr((std::string(gi_dump) + ".hdr").c_str(), gfilm);  // main.cc:125-126
                         const auto d = gfilm.to_float_array();
                         FILE* f = std::fopen(gi_dump, "wb");
                         std::fwrite(d.data(), sizeof(float), d.size(), f);

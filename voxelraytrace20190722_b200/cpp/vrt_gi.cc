@@ -328,6 +328,26 @@ void render_gi_gpu(Film* film, Camera& cam, gi::VoxelOctree* root, int spp, cons
         check(vrt_gi_render_camera(t, &c, k, res, 0, 0, film->nx, film->ny, &film->data()->x), "render_gi_gpu");
 }
 
+void set_materials_gpu(gi::VoxelOctree* root, const std::vector<jql::Vec2>& uv, const std::vector<std::uint32_t>& tri_material,
+                       const std::vector<GpuMaterial>& materials, const std::vector<GpuTexture>& textures)
+{
+        vrt_tree* t = gi::gi_tree(root, "set_materials_gpu");
+        std::vector<float> kd(3 * materials.size());
+        std::vector<int32_t> mt(materials.size());
+        for (size_t m = 0; m < materials.size(); ++m) {
+                kd[3 * m] = materials[m].diffuse.x;
+                kd[3 * m + 1] = materials[m].diffuse.y;
+                kd[3 * m + 2] = materials[m].diffuse.z;
+                mt[m] = materials[m].texture;
+        }
+        std::vector<vrt_texture> tx(textures.size());
+        for (size_t i = 0; i < textures.size(); ++i)
+                tx[i] = vrt_texture{ textures[i].width, textures[i].height, textures[i].channels, textures[i].data };
+        check(vrt_set_materials(t, uv.empty() ? nullptr : &uv[0].x, tri_material.data(), (uint32_t)materials.size(), kd.data(),
+                                mt.data(), (uint32_t)tx.size(), tx.data()),
+              "set_materials_gpu");
+}
+
 // ---- predicates ----------------------------------------------------------------------------
 int triBoxOverlap(float boxcenter[3], float boxhalfsize[3], float triverts[3][3])
 {

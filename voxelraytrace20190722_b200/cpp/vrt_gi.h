@@ -157,6 +157,21 @@ void light_map_gpu(const Film& sfilm, Camera& scam, gi::VoxelOctree* root, int s
 // Replacement of the final render_mt loop of main.cc:117-123 (trace() per sample, film += c / spp).
 void render_gi_gpu(Film* film, Camera& cam, gi::VoxelOctree* root, int spp, const jql::Vec3& kd, float res);
 
+// Materials for the GI passes (the half of gi::Triangle the geometry mirror leaves out: t_[3] and
+// tinyobj::material_t::diffuse / diffuse_texname, voxel_octree.h:110-111).  uv holds three texture
+// coordinates per triangle in the order of the voxels given to ray_march_init; a material with
+// texture < 0 is untextured.  Texture bytes are what stbi_load returns (row 0 = top).
+struct GpuMaterial {
+        jql::Vec3 diffuse;
+        int texture;  // index into the textures, or -1
+};
+struct GpuTexture {
+        int width, height, channels;
+        const std::uint8_t* data;
+};
+void set_materials_gpu(gi::VoxelOctree* root, const std::vector<jql::Vec2>& uv, const std::vector<std::uint32_t>& tri_material,
+                       const std::vector<GpuMaterial>& materials, const std::vector<GpuTexture>& textures);
+
 // tribox2.h:15 and raytri.h:5-7 -- same signatures, evaluated on the GPU.
 int triBoxOverlap(float boxcenter[3], float boxhalfsize[3], float triverts[3][3]);
 int intersect_triangle3(double orig[3], double dir[3], double vert0[3], double vert1[3], double vert2[3], double* t,
