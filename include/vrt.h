@@ -139,6 +139,13 @@ int vrt_build(const float* tri_xyz, const float* tri_nrm, uint32_t num_tris,
               int max_depth, vrt_tree** out);
 int vrt_build_dev(const float* d_tri_xyz, const float* d_tri_nrm, uint32_t num_tris,
                   int max_depth, vrt_tree** out);
+/* Indexed ingest (obj2voxel, voxel_octree.cc:305-371): the arrays tinyobj::LoadObj returns --
+ * attrib.vertices[num_vertices][3], attrib.normals[num_normals][3] (NULL: geometric normals) and the
+ * per-face-vertex tinyobj::index_t records index3[T][3] = {vertex_index, normal_index,
+ * texcoord_index} -- are uploaded as they are and gathered into triangles on the device. */
+int vrt_build_indexed(const float* vertices, uint64_t num_vertices, const float* normals,
+                      uint64_t num_normals, const int32_t* index3, uint32_t num_tris, int max_depth,
+                      vrt_tree** out);
 /* Re-run the build on the triangles already held by the handle (timing loops). */
 int vrt_rebuild(vrt_tree* tree, int max_depth);
 void vrt_tree_free(vrt_tree* tree);

@@ -35,6 +35,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(capi.vrt_camera) == 16 * 4 + 3 * 4 + 3 * 4
     assert ctypes.sizeof(capi.vrt_shade) == 24
     assert ctypes.sizeof(capi.vrt_bands) == 12
+    assert ctypes.sizeof(capi.vrt_texture) == 24 and capi.vrt_texture.data.offset == 16
     assert capi.HIT_DTYPE.itemsize == 48 and capi.RAY_DTYPE.itemsize == 32
 
 

@@ -457,3 +457,28 @@ def test_render_async_pipeline_matches_sync(case, gpu):
     tree.sync()
     for e, b in zip(expect, bufs):
         assert np.array_equal(e.view(np.uint32), b.numpy().view(np.uint32))
+
+
+def test_build_indexed_equals_flat_build(gpu, port):
+    """vrt_build_indexed (tinyobj-style attrib arrays + index_t records, gathered on the device) produces the
+    same octree as vrt_build on the expanded triangles, i.e. as obj2voxel + ray_march_init."""
+    rng = np.random.default_rng(4)
+    tri, nrm = scenes.uv_sphere(64, 32)
+    T = len(tri)
+    # de-duplicate into attribute arrays like an OBJ file holds them
+    verts, vinv = np.unique(tri.reshape(-1, 3), axis=0, return_inverse=True)
+    norms, ninv = np.unique(nrm.reshape(-1, 3), axis=0, return_inverse=True)
+    idx = np.stack([vinv.reshape(-1), ninv.reshape(-1), rng.integers(-1, 5, 3 * T)], axis=1).astype(np.int32).reshape(T, 3, 3)
+    a = gpu.Octree.build_indexed(verts, norms, idx, 7)
+    b = gpu.Octree.build(tri, nrm, 7)
+    leaves_equal(a.leaves(), b.leaves())
+    cam = gpu.Camera(CAM_SPHERE[0], CAM_SPHERE[1:4], CAM_SPHERE[4:7], CAM_SPHERE[7:10], 96, 64, 4)
+    assert a.trace_camera(cam).tobytes() == b.trace_camera(cam).tobytes()
+    c = gpu.Octree.build_indexed(verts, None, idx, 5)  # geometric normals
+    leaves_equal(c.leaves(), port.build(tri, None, 5).leaves())
+    bad = idx.copy()
+    bad[3, 1, 0] = len(verts)
+    with pytest.raises(gpu.VrtError):
+        gpu.Octree.build_indexed(verts, norms, bad, 5)
+    for t in (a, b, c):
+        t.close()

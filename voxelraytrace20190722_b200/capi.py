@@ -60,7 +60,7 @@ assert HIT_DTYPE.itemsize == 48 and HIT16_DTYPE.itemsize == 16 and RAY_DTYPE.ite
 # every symbol include/vrt.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "vrt_abi_version", "vrt_last_error", "vrt_device_count", "vrt_launch_count",
-    "vrt_build", "vrt_build_dev", "vrt_rebuild", "vrt_tree_free", "vrt_tree_get_info",
+    "vrt_build", "vrt_build_dev", "vrt_build_indexed", "vrt_rebuild", "vrt_tree_free", "vrt_tree_get_info",
     "vrt_tree_export", "vrt_tree_import", "vrt_tree_set_stream", "vrt_tree_blob_dev",
     "vrt_tree_from_blob_dev", "vrt_tree_save", "vrt_tree_load", "vrt_camera_init", "vrt_gen_rays", "vrt_trace_rays",
     "vrt_trace_rays_dev", "vrt_trace_camera", "vrt_trace_camera_dev", "vrt_trace_camera16_dev",
@@ -134,6 +134,7 @@ def load(build_if_missing: bool = True):
     L.vrt_debug_general_order_calls.restype = u64
     L.vrt_debug_param_check.argtypes = [vp]
     L.vrt_gi_init.argtypes = [vp]
+    L.vrt_build_indexed.argtypes = [vp, u64, vp, u64, vp, C.c_uint32, i32, C.POINTER(vp)]
     L.vrt_set_materials.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp]
     L.vrt_albedo.argtypes = [vp, vp, vp, u64, vp, vp]
     L.vrt_gi_splat_camera.argtypes = [vp, C.POINTER(vrt_camera), vp]
@@ -232,6 +233,18 @@ class Octree:
         nrm = None if tri_nrm is None else _f32(tri_nrm, (-1, 9))
         h = C.c_void_p()
         _check(load().vrt_build(_ptr(tri), _ptr(nrm), tri.shape[0], int(max_depth), C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def build_indexed(cls, vertices, normals, index3, max_depth):
+        """tinyobj-style arrays: vertices [nv,3], normals [nn,3] or None, index3 [T,3,3] int32
+        (vertex_index, normal_index, texcoord_index per face vertex)."""
+        v = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+        n = None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(index3, np.int32).reshape(-1, 3, 3)
+        h = C.c_void_p()
+        _check(load().vrt_build_indexed(_ptr(v), len(v), None if n is None else _ptr(n), 0 if n is None else len(n),
+                                        _ptr(idx), len(idx), int(max_depth), C.byref(h)))
         return cls(h.value)
 
     @classmethod

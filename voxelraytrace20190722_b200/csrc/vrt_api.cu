@@ -186,6 +186,83 @@ static int build_common(const float* tri, const float* nrm, uint32_t T, int max_
         return VRT_OK;
 }
 
+// ---- indexed ingest: the arrays tinyobj::LoadObj produces, gathered on the device ------------------
+// (obj2voxel voxel_octree.cc:334-366 copies attrib->vertices / normals through mesh.indices into one
+// Triangle per face; here that gather is one kernel and no per-triangle host object exists.)
+__global__ void k_gather_indexed(const float* __restrict__ vertices, const float* __restrict__ normals,
+                                 const int32_t* __restrict__ index3, uint32_t T, float* __restrict__ tri,
+                                 float* __restrict__ nrm)
+{
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // one face vertex
+        if (i >= 3u * T)
+                return;
+        const int32_t vi = index3[3 * i], ni = index3[3 * i + 1];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+                tri[3ull * i + k] = vertices[3ull * vi + k];
+                if (nrm)
+                        nrm[3ull * i + k] = normals[3ull * ni + k];
+        }
+}
+
+static int build_indexed_impl(const float* vertices, uint64_t num_vertices, const float* normals, uint64_t num_normals,
+                              const int32_t* index3, uint32_t num_tris, int max_depth, vrt_tree** out)
+{
+        if (!out || (num_tris && (!vertices || !index3))) {
+                set_error("vrt_build_indexed: null argument");
+                return VRT_ERR_ARG;
+        }
+        *out = nullptr;
+        if (max_depth < 1 || max_depth > (int)VRT_MAX_DEPTH) {
+                set_error("vrt_build_indexed: max_depth %d out of range [1,%u]", max_depth, VRT_MAX_DEPTH);
+                return VRT_ERR_ARG;
+        }
+        for (uint64_t i = 0; i < 3ull * num_tris; ++i) {
+                const int32_t vi = index3[3 * i], ni = index3[3 * i + 1];
+                if (vi < 0 || (uint64_t)vi >= num_vertices || (normals && (ni < 0 || (uint64_t)ni >= num_normals))) {
+                        set_error("vrt_build_indexed: face vertex %llu has vertex_index %d / normal_index %d out of range",
+                                  (unsigned long long)i, vi, ni);  // (the reference asserts normal_index != -1)
+                        return VRT_ERR_ARG;
+                }
+        }
+        vrt_tree* t = nullptr;
+        int rc = tree_alloc(&t);
+        if (rc)
+                return rc;
+        auto fail = [&](int code) {
+                vrt_tree_free(t);
+                return code;
+        };
+        const size_t tb = (size_t)std::max<uint32_t>(num_tris, 1) * 36;
+        if (!cuda_ok(cudaMalloc(&t->d_tri_in, tb), "cudaMalloc(tri)") ||
+            (normals && !cuda_ok(cudaMalloc(&t->d_nrm_in, tb), "cudaMalloc(nrm)")))
+                return fail(VRT_ERR_NOMEM);
+        t->hdr.num_tris = num_tris;
+        if (num_tris) {
+                const size_t vb = (size_t)num_vertices * 12, nb = normals ? (size_t)num_normals * 12 : 0, ib = (size_t)num_tris * 36;
+                if (t->io_in.reserve(align256(vb) + align256(nb) + ib))
+                        return fail(VRT_ERR_NOMEM);
+                char* d = static_cast<char*>(t->io_in.p);
+                float* d_v = reinterpret_cast<float*>(d);
+                float* d_n = normals ? reinterpret_cast<float*>(d + align256(vb)) : nullptr;
+                int32_t* d_i = reinterpret_cast<int32_t*>(d + align256(vb) + align256(nb));
+                if (!cuda_ok(cudaMemcpyAsync(d_v, vertices, vb, cudaMemcpyHostToDevice, t->stream), "copy vertices") ||
+                    (normals && !cuda_ok(cudaMemcpyAsync(d_n, normals, nb, cudaMemcpyHostToDevice, t->stream), "copy normals")) ||
+                    !cuda_ok(cudaMemcpyAsync(d_i, index3, ib, cudaMemcpyHostToDevice, t->stream), "copy indices"))
+                        return fail(VRT_ERR_CUDA);
+                k_gather_indexed<<<(3u * num_tris + 255u) / 256u, 256, 0, t->stream>>>(d_v, d_n, d_i, num_tris, t->d_tri_in,
+                                                                                      t->d_nrm_in);
+                count_launch();
+                if (!cuda_ok(cudaGetLastError(), "k_gather_indexed"))
+                        return fail(VRT_ERR_CUDA);
+        }
+        rc = build_tree(t, max_depth);
+        if (rc)
+                return fail(rc);
+        *out = t;
+        return VRT_OK;
+}
+
 // ---------------------------------------------------------------------------
 // predicate KAT kernels
 // ---------------------------------------------------------------------------
@@ -358,6 +435,12 @@ uint64_t vrt_launch_count(void) { return g_launches.load(); }
 int vrt_build(const float* tri_xyz, const float* tri_nrm, uint32_t num_tris, int max_depth, vrt_tree** out)
 {
         return build_common(tri_xyz, tri_nrm, num_tris, max_depth, false, out);
+}
+
+int vrt_build_indexed(const float* vertices, uint64_t num_vertices, const float* normals, uint64_t num_normals,
+                      const int32_t* index3, uint32_t num_tris, int max_depth, vrt_tree** out)
+{
+        return build_indexed_impl(vertices, num_vertices, normals, num_normals, index3, num_tris, max_depth, out);
 }
 
 int vrt_build_dev(const float* d_tri_xyz, const float* d_tri_nrm, uint32_t num_tris, int max_depth, vrt_tree** out)
