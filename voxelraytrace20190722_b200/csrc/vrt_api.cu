@@ -39,20 +39,40 @@ bool cuda_ok(cudaError_t e, const char* what)
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+// Scratch buffers come from the device's default stream-ordered pool (kept resident: release threshold
+// = max), so the many grow / free steps of a first build and of every new handle do not go back to the
+// driver; a buffer that has to grow grows by at least 1.5x.  (Buffers that are shared over CUDA IPC --
+// vrt_dev_alloc -- and the octree blob itself stay plain cudaMalloc allocations.)
+static void pool_setup_once()
+{
+        static bool done = false;
+        if (done)
+                return;
+        done = true;
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+}
+
 int Scratch::reserve(size_t bytes)
 {
         if (bytes <= cap && p)
                 return 0;
-        if (p) {
-                cudaFree(p);
-                p = nullptr;
-                cap = 0;
-        }
+        pool_setup_once();
         size_t want = std::max<size_t>(bytes, 256);
-        if (cudaMalloc(&p, want) != cudaSuccess) {
+        if (p) {
+                want = std::max(want, cap + cap / 2);
+                release();
+        }
+        if (cudaMallocAsync(&p, want, cudaStreamPerThread) != cudaSuccess ||
+            cudaStreamSynchronize(cudaStreamPerThread) != cudaSuccess) {
                 cudaGetLastError();
                 p = nullptr;
-                set_error("cudaMalloc(%zu) failed", want);
+                set_error("cudaMallocAsync(%zu) failed", want);
                 return VRT_ERR_NOMEM;
         }
         cap = want;
@@ -61,8 +81,10 @@ int Scratch::reserve(size_t bytes)
 
 void Scratch::release()
 {
-        if (p)
-                cudaFree(p);
+        if (p) {
+                cudaDeviceSynchronize();  // (what cudaFree did implicitly: nothing may still be using the buffer)
+                cudaFreeAsync(p, cudaStreamPerThread);
+        }
         p = nullptr;
         cap = 0;
 }
