@@ -291,7 +291,11 @@ class Octree:
             load().vrt_tree_free(self._h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown: module globals are already gone
+            pass
 
     def set_stream(self, cuda_stream_ptr):
         _check(load().vrt_tree_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))

@@ -787,7 +787,7 @@ __device__ __forceinline__ void shade_gi(const TraceParams& p, const HitState& h
 // kernels
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTraceThreads, VRT_TRACE_MIN_BLOCKS)
-k_trace_rays(TraceParams p)
+k_trace_rays(const __grid_constant__ TraceParams p)
 {
         extern __shared__ uint32_t s_stack[];
         uint32_t* s_first = s_stack + threadIdx.x;
@@ -829,7 +829,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kTraceThreads, (MODE == OUT_HIT16 || MODE == OUT_COUNT) ? VRT_HIT16_MIN_BLOCKS
                                                  : (MODE == OUT_GI_FILM)                  ? 4
                                                                                           : VRT_FILM_MIN_BLOCKS)
-k_trace_camera(TraceParams p)
+k_trace_camera(const __grid_constant__ TraceParams p)
 {
         extern __shared__ uint32_t s_stack[];
         uint32_t* s_first = s_stack + threadIdx.x;
