@@ -136,6 +136,10 @@ struct vrt_tree {
         static constexpr int kEvRing = 64;
         cudaEvent_t ring0[kEvRing] = {}, ring1[kEvRing] = {};
         mutable uint64_t n_trace_launches = 0;
+        // L2 access-policy window over the top levels of the node array (vrt_trace.cu)
+        mutable void* l2_window_stream = nullptr;
+        mutable const void* l2_window_nodes = nullptr;
+        mutable uint64_t l2_window_bytes = 0;
         double build_ms = 0;
         mutable double last_kernel_ms = 0;
         uint64_t scratch_bytes() const;
