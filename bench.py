@@ -48,6 +48,8 @@ WORKLOADS = {
     "atrium1024_4k_spp1": ("atrium", {}, 11, [90 * RAD, 1, 1.3, -.2, 0, .4, 0, 0, 1, 0], 3840, 2160, 1),
     "sphere256_1080p_spp1": ("sphere", {}, 9, [60 * RAD, 0, 1, 3, 0, 0, 0, 0, 1, 0], 1920, 1080, 1),
     "atrium32_1k_spp4": ("atrium", {}, 6, [90 * RAD, 1, 1.3, -.2, 0, .4, 0, 0, 1, 0], 1024, 1024, 4),
+    # BASELINE config 4 geometry traced: 2M-triangle random soup voxelized at 2048^3, 4K, camera outside the cloud
+    "soup2m_2048_4k_spp4": ("soup", {}, 12, [60 * RAD, 0, 1, 3, 0, 0, 0, 0, 1, 0], 3840, 2160, 4),
     # BASELINE config 5: 2048^3, 8K, 64-frame camera orbit, primary + one shadow ray per hit
     "atrium2048_8k_orbit_shadow": ("atrium", {}, 12, [90 * RAD, 1, 1.3, -.2, 0, .4, 0, 0, 1, 0], 7680, 4320, 4),
 }
