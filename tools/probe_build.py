@@ -1,9 +1,12 @@
-import sys
+"""Build timing probe: atrium at 1024^3 and the 2M-triangle soup at 2048^3 (device ms, mean of rebuilds)."""
+import sys, numpy as np
 sys.path.insert(0, '.')
 from voxelraytrace20190722_b200 import capi, scenes
 capi.load()
-tri, nrm = scenes.atrium()
-tree = capi.Octree.build(tri, nrm, 11)
-for i in range(3):
-    tree.rebuild(11)
-    print("build ms", tree.info()["build_ms"])
+for name, (tri, nrm), D in (("atrium", scenes.atrium(), 11), ("soup2m", scenes.soup(2_000_000), 12)):
+    tree = capi.Octree.build(tri, nrm, D)
+    ms = []
+    for i in range(5):
+        tree.rebuild(D); ms.append(tree.info()['build_ms'])
+    print(f"{name} D{D}: build ms {np.round(ms, 3).tolist()} -> {len(tri) / np.mean(ms[1:]) / 1e3:.1f} Mtris/s", flush=True)
+    tree.close()
