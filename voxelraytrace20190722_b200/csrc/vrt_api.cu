@@ -878,7 +878,7 @@ int vrt_trace_rays(const vrt_tree* tc, const vrt_ray* rays, uint64_t n, vrt_hit*
 }
 
 static int trace_camera_common(const vrt_tree* tc, const vrt_camera* cam, const vrt_shade* sh, int x0, int y0, int x1,
-                               int y1, void* out, OutMode mode, bool dev)
+                               int y1, void* out, OutMode mode, bool dev, const GiArgs* gi = nullptr)
 {
         int rc = check_tree(tc);
         if (rc)
@@ -894,12 +894,12 @@ static int trace_camera_common(const vrt_tree* tc, const vrt_camera* cam, const 
                 return VRT_ERR_ARG;
         }
         if (dev)
-                return launch_trace_camera(tc, cam, sh, x0, y0, x1, y1, out, mode);
+                return launch_trace_camera(tc, cam, sh, x0, y0, x1, y1, out, mode, 0, 0, nullptr, 0, gi);
         vrt_tree* t = const_cast<vrt_tree*>(tc);
         const uint64_t bytes = (mode == OUT_FILM || mode == OUT_GI_FILM) ? npix * 12 : npix * cam->spp * (mode == OUT_HIT48 ? 48 : 16);
         if (t->io_out.reserve(bytes))
                 return VRT_ERR_NOMEM;
-        rc = launch_trace_camera(t, cam, sh, x0, y0, x1, y1, t->io_out.p, mode);
+        rc = launch_trace_camera(t, cam, sh, x0, y0, x1, y1, t->io_out.p, mode, 0, 0, nullptr, 0, gi);
         if (rc)
                 return rc;
         VRT_CUDA(cudaMemcpyAsync(out, t->io_out.p, bytes, cudaMemcpyDeviceToHost, t->stream));
@@ -1104,15 +1104,15 @@ int vrt_gi_get_level(const vrt_tree* t, int level, float* coverage, float* illum
                 set_error("inconsistent level table");
                 return VRT_ERR_ARG;
         }
-        std::vector<float> host(n * 20);
+        std::vector<float> host(n * kGiStride);
         VRT_CUDA(cudaStreamSynchronize(t->stream));
         if (n)
-                VRT_CUDA(cudaMemcpy(host.data(), t->dev.gi + first * 20, n * 20 * sizeof(float), cudaMemcpyDeviceToHost));
+                VRT_CUDA(cudaMemcpy(host.data(), t->dev.gi + first * kGiStride, n * kGiStride * sizeof(float), cudaMemcpyDeviceToHost));
         for (uint64_t i = 0; i < n; ++i) {
                 if (coverage)
-                        coverage[i] = host[20 * i + 18];
+                        coverage[i] = host[kGiStride * i + kGiCoverage];
                 if (illum18)
-                        memcpy(illum18 + 18 * i, &host[20 * i], 18 * sizeof(float));
+                        memcpy(illum18 + 18 * i, &host[kGiStride * i], 18 * sizeof(float));
         }
         return VRT_OK;
 }
@@ -1260,12 +1260,8 @@ static int gi_render_common(const vrt_tree* tc, const vrt_camera* cam, const flo
                 set_error("vrt_gi_init has not been called on this tree");
                 return VRT_ERR_ARG;
         }
-        vrt_shade sh{};
-        sh.light_dir[0] = kd[0];
-        sh.light_dir[1] = kd[1];
-        sh.light_dir[2] = kd[2];
-        sh.shadow_eps = res;
-        return trace_camera_common(tc, cam, &sh, x0, y0, x1, y1, film, OUT_GI_FILM, dev);
+        const GiArgs ga = { { kd[0], kd[1], kd[2] }, res };
+        return trace_camera_common(tc, cam, nullptr, x0, y0, x1, y1, film, OUT_GI_FILM, dev, &ga);
 }
 
 int vrt_gi_render_camera(const vrt_tree* t, const vrt_camera* cam, const float kd[3], float res, int x0, int y0, int x1,

@@ -86,11 +86,9 @@ int gi_splat_camera(vrt_tree* t, const vrt_camera* cam, const float kd[3])
         }
         if (t->keys_a.reserve(R * 8) || t->gi_recs.reserve(R * 32))
                 return VRT_ERR_NOMEM;
-        vrt_shade sh{};  // (carries the default material colour to the kernel)
-        sh.light_dir[0] = kd[0];
-        sh.light_dir[1] = kd[1];
-        sh.light_dir[2] = kd[2];
-        int rc = launch_trace_camera(t, cam, &sh, 0, 0, cam->nx, cam->ny, t->keys_a.p, OUT_SPLAT, 0, 0, t->gi_recs.p);
+        const GiArgs ga = { { kd[0], kd[1], kd[2] }, 0.f };
+        int rc = launch_trace_camera(t, cam, nullptr, 0, 0, cam->nx, cam->ny, t->keys_a.p, OUT_SPLAT, 0, 0, t->gi_recs.p, 0,
+                                     &ga);
         if (rc)
                 return rc;
         int lb = 1;

@@ -14,8 +14,6 @@
 
 namespace vrt {
 
-constexpr int kGiStride = 20;  // floats per node
-constexpr int kGiCoverage = 18;
 
 // Triangle::get_albedo (voxel_octree.cc:471-484): the material's diffuse colour, or -- for a
 // textured material -- the nearest texel at the clamped barycentric interpolation of the vertex

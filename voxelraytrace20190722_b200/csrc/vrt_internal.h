@@ -55,6 +55,8 @@ struct BlobHeader {
 static_assert(sizeof(BlobHeader) <= 512, "header grew");
 constexpr uint64_t kBlobMagic = 0x3142305452565856ull;  // "VXVRT0B1"
 constexpr uint64_t kHeaderBytes = 512;
+constexpr int kGiStride = 20;    // floats of GI state per node: illum[6][3], coverage, pad (vrt_gi.cuh)
+constexpr int kGiCoverage = 18;
 
 inline uint64_t align256(uint64_t x) { return (x + 255ull) & ~255ull; }
 
@@ -158,9 +160,14 @@ enum OutMode { OUT_HIT48 = 0, OUT_HIT16 = 1, OUT_FILM = 2, OUT_COUNT = 3, OUT_HI
 int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_hit* d_out);
 // band_h > 0: rows [y0,y1) are LOCAL rows of a banded shard; local row r maps to film row
 // y0_film + (r / band_h) * band_pitch + r % band_h (y0 then carries y0_film, y1 = y0 + local rows).
+struct GiArgs {  // OUT_SPLAT / OUT_GI_FILM: default material colour, cone-trace min_voxel_size
+        float kd[3];
+        float res;
+};
 int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, int x0,
                         int y0, int x1, int y1, void* d_out, OutMode mode, int band_h = 0,
-                        int band_pitch = 0, void* d_out2 = nullptr, int film_full = 0);
+                        int band_pitch = 0, void* d_out2 = nullptr, int film_full = 0,
+                        const GiArgs* gi = nullptr);
 // mean device time (ms) of the last n trace launches (waits for them)
 int trace_ms_mean(const vrt_tree* t, int last_n, double* ms);
 int general_order_calls(unsigned long long* out);

@@ -1092,7 +1092,8 @@ int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_
 }
 
 int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, int x0, int y0,
-                        int x1, int y1, void* d_out, OutMode mode, int band_h, int band_pitch, void* d_out2, int film_full)
+                        int x1, int y1, void* d_out, OutMode mode, int band_h, int band_pitch, void* d_out2, int film_full,
+                        const GiArgs* gi)
 {
         if (x1 <= x0 || y1 <= y0)
                 return VRT_OK;
@@ -1115,12 +1116,13 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         p.out = d_out;
         p.out2 = d_out2;
         p.film_full = film_full;
-        if ((mode == OUT_GI_FILM || mode == OUT_SPLAT) && sh) {  // (light_dir carries the material colour, shadow_eps the cone-trace res)
-                p.kd3[0] = sh->light_dir[0];
-                p.kd3[1] = sh->light_dir[1];
-                p.kd3[2] = sh->light_dir[2];
-                p.gi_res = sh->shadow_eps;
-        } else if (sh) {
+        if (gi) {
+                p.kd3[0] = gi->kd[0];
+                p.kd3[1] = gi->kd[1];
+                p.kd3[2] = gi->kd[2];
+                p.gi_res = gi->res;
+        }
+        if (sh) {
                 p.light[0] = sh->light_dir[0];
                 p.light[1] = sh->light_dir[1];
                 p.light[2] = sh->light_dir[2];
