@@ -283,20 +283,20 @@ __device__ __noinline__ void trace_one_exact(const TreeDev& tr, const float* roo
 }
 
 // ---------------------------------------------------------------------------
-// FAST path (taken by every ray with finite, moderately sized origin/direction whose
-// direction components are zero or normal floats).  For such rays no NaN can appear in
-// the slab or key arithmetic -- (plane-o) is finite and 1/d' is finite and non-zero --
-// so std::min/std::max/min_element/max_element coincide with FMNMX up to the sign of a
-// zero, which none of the comparisons below can observe.  Same operations, same order,
-// same roundings as the exact path; only the instruction selection differs:
-//   * hi.min of a child pair is bitwise lo.max (both are min+size in the recurrence), so
-//     3 planes per axis instead of 4; FMNMX3 per child; branch-free slab verdicts;
-//   * children that pass the slab test (22 % on average) are inserted into a 4-slot
-//     list kept sorted by key (stable), packed into 3-bit ids; the rare 5th candidate
-//     falls back to a general packed-rank ordering of all 8 (order_children_general);
-//   * packed FADD2/FMUL2 for the per-axis plane and centre arithmetic;
-//   * only levels that still have unvisited children are pushed on the (shared-memory)
-//     return stack.
+// TAME rays (finite, moderately sized origin/direction whose direction components are zero or
+// normal floats) take trace_one_fast.  For such rays no NaN can appear in the slab or key
+// arithmetic -- (plane-o) is finite and 1/d' is finite and non-zero -- so
+// std::min/std::max/min_element/max_element coincide with FMNMX up to the sign of a zero, which
+// none of the comparisons below can observe.  Two node expansions exist for them:
+//   * expand_slab (out of line, the fallback): the reference's eight per-child slab tests in
+//     FMNMX form -- hi.min of a child pair is bitwise lo.max (both are min+size in the
+//     recurrence), so 3 planes per axis instead of 4; children that pass are inserted into a
+//     4-slot list kept sorted by key (stable), the rare 5th candidate falls back to a general
+//     packed-rank ordering of all 8 (order_children_general);
+//   * the parametric expansion inside trace_one_fast (see there), used whenever it is provably
+//     equivalent.
+// Packed FADD2/FMUL2 carry the per-axis plane arithmetic; only levels that still have unvisited
+// children are pushed on the (shared-memory) return stack.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ bool ray_is_tame(const TreeDev& tr, const float o[3], const float d[3])
 {
