@@ -482,3 +482,34 @@ def test_build_indexed_equals_flat_build(gpu, port):
         gpu.Octree.build_indexed(verts, norms, bad, 5)
     for t in (a, b, c):
         t.close()
+
+
+def test_maximum_depth(gpu, port):
+    """max_depth = VRT_MAX_DEPTH (17: a 65536^3 leaf grid, 48 Morton bits + triangle bits in the 64-bit key):
+    a few tiny, far-apart triangles keep the leaf count small; leaf sets and rays against the oracle."""
+    rng = np.random.default_rng(17)
+    centres = np.array([[-0.5, -0.5, -0.5], [0.5, 0.4, 0.3], [0.1, -0.2, 0.45], [-0.3, 0.5, -0.1]], np.float32)
+    tri = (centres[:, None, :] + rng.uniform(-1, 1, (4, 3, 3)).astype(np.float32) * np.float32(3e-3)).astype(np.float32)  # (|det| must exceed raytri.cc EPSILON 1e-6)
+    depth = gpu.VRT_MAX_DEPTH
+    orc = port.build(tri, None, depth)
+    tree = gpu.Octree.build(tri, None, depth)
+    assert tree.info()["max_depth"] == depth
+    leaves_equal(tree.leaves(), orc.leaves())
+    # rays from a point outside toward points on / near the triangles, plus random ones
+    n = 4000
+    eye = np.array([0.2, 0.1, 2.0], np.float32)
+    w = rng.dirichlet([1, 1, 1], n).astype(np.float32)
+    tgt = (tri[rng.integers(0, 4, n)] * w[:, :, None]).sum(axis=1) + rng.normal(0, 1e-3, (n, 3)).astype(np.float32)
+    d = (tgt - eye).astype(np.float64)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = eye
+    rays[:, 3:6] = d
+    rays[:, 7] = np.finfo(np.float32).max
+    got = tree.trace_rays(rays)
+    exp = orc.trace(rays)
+    assert exp.hit.sum() > 100
+    assert compare_hits(got, exp, "max depth") == 0
+    with pytest.raises(gpu.VrtError):
+        gpu.Octree.build(tri, None, depth + 1)
+    tree.close()
