@@ -827,8 +827,11 @@ template <int MODE>
 #ifndef VRT_HIT16_MIN_BLOCKS
 #define VRT_HIT16_MIN_BLOCKS 8
 #endif
+#ifndef VRT_GI_MIN_BLOCKS
+#define VRT_GI_MIN_BLOCKS 5
+#endif
 __global__ void __launch_bounds__(kTraceThreads, (MODE == OUT_HIT16 || MODE == OUT_COUNT) ? VRT_HIT16_MIN_BLOCKS
-                                                 : (MODE == OUT_GI_FILM)                  ? 4
+                                                 : (MODE == OUT_GI_FILM)                  ? VRT_GI_MIN_BLOCKS
                                                                                           : VRT_FILM_MIN_BLOCKS)
 k_trace_camera(const __grid_constant__ TraceParams p)
 {
