@@ -20,6 +20,11 @@ for spp in (1, 4):
             else: tree.frame_bands_dev(cam, out.data_ptr(), frame.data_ptr(), 8, 0, 1, full_frame=True)
             ts.append(tree.last_kernel_ms)
         res.append(f"x{spp} {mode} {min(ts):.3f} ms")
+    # checksums of the last hit16+film frame: library variants must agree bit for bit
+    torch.cuda.synchronize()
+    n16 = nx * ny * spp * 16
+    res.append(f"sum{spp} {int(out[:n16].view(torch.int64).sum().item()) & 0xffffffffffff:x}/"
+               f"{int(frame.view(torch.int32).to(torch.int64).sum().item()) & 0xffffffffffff:x}")
 cam = capi.Camera(CAM_MAIN[0], CAM_MAIN[1:4], CAM_MAIN[4:7], CAM_MAIN[7:10], nx, ny, 4)
 c = tree.count_camera(cam)
 print(" | ".join(res), "| counts/ray:", {k: round(v / c['rays'], 3) for k, v in c.items() if k != 'rays'}, flush=True)

@@ -456,6 +456,20 @@ __device__ __noinline__ uint32_t expand_slab(float4 b0, float4 b1, float4 b2, fl
         return list;
 }
 
+// expand_slab with the result in the fast path's list format: 4 bits per entry, lowest first,
+// entry = 8 | child id, empty list = 0 (at most 8 entries).
+__device__ __noinline__ uint32_t expand_slab4(float4 b0, float4 b1, float4 b2, float ox, float oy, float oz,
+                                              float dx, float dy, float dz, float ix, float iy, float iz,
+                                              uint32_t mask, float tmin, float tmax)
+{
+        uint32_t cnt = 0;
+        const uint32_t l3 = expand_slab(b0, b1, b2, ox, oy, oz, dx, dy, dz, ix, iy, iz, mask, tmin, tmax, &cnt);
+        uint32_t l4 = 0;
+        for (uint32_t i = cnt; i-- > 0u;)
+                l4 = (l4 << 4) | 8u | ((l3 >> (3u * i)) & 7u);
+        return l4;
+}
+
 // Number of tree levels at which the PARAMETRIC expansion (below) provably visits the
 // children in the reference's key order for this ray: consecutive cells along the ray differ
 // in one axis a, their travorder keys differ by |d_a| * (centre step) before rounding, and
@@ -525,17 +539,20 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
         constexpr int stride = kTraceThreads;
         // per-ray constants of the parametric expansion in ONE register: bits 0-2 negmask (near
         // half of axis a is the HIGH child when d_a < 0; child id: x bit 2, y bit 1, z bit 0),
-        // bit 3 default window [0, FLT_MAX], bits 4.. number of key-safe levels
-        uint32_t rayflags = (d[0] < 0.f ? 4u : 0u) | (d[1] < 0.f ? 2u : 0u) | (d[2] < 0.f ? 1u : 0u) |
-                            (((tmin == 0.f) && (tmax == FLT_MAX)) ? 8u : 0u) |
-                            ((uint32_t)param_safe_levels(root, o, d) << 4);
+        // bit 3 always set (the "entry present" bit of a visiting-list entry, see below), bit 4
+        // default window [0, FLT_MAX], bits 5.. number of key-safe levels
+        uint32_t rayflags = (d[0] < 0.f ? 4u : 0u) | (d[1] < 0.f ? 2u : 0u) | (d[2] < 0.f ? 1u : 0u) | 8u |
+                            (((tmin == 0.f) && (tmax == FLT_MAX)) ? 16u : 0u) |
+                            ((uint32_t)param_safe_levels(root, o, d) << 5);
         asm volatile("" : "+r"(rayflags));  // keep it in its register (do not rematerialise per node)
         // x,y,z are HEAP indices into the per-axis table: (1 << level) + cell coordinate, so a
         // child is 2*i + bit and an ancestor i >> k.  The return stack is addressed through one
         // register holding this thread's shared-memory byte address of the next free record.
         int level = 0;
         uint32_t x = 1, y = 1, z = 1, node = 0;
-        uint32_t first, mask, list, cnt;
+        // visiting list of the node being iterated: 4 bits per entry, lowest first, entry =
+        // 8 | child id -- an empty list is the value 0, so no separate count is carried
+        uint32_t first, mask, list;
         uint32_t sp = (uint32_t)__cvta_generic_to_shared(s_first);
         // bottom-of-stack sentinel (meta bit 31): popping it means the ray left the tree
         asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(sp), "n"(stride * 4u), "r"(0x80000000u) : "memory");
@@ -573,7 +590,7 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                                                  __float_as_uint(s0) ^ __float_as_uint(s2));
                                 // slab expansion instead: the ray may touch a shared edge (extra cells),
                                 // or this level is not key-safe for the ray (level >= safe levels)
-                                const bool unsafe = (uint32_t)(level * 16 + 15) >= rayflags;
+                                const bool unsafe = (uint32_t)(level * 32 + 31) >= rayflags;
                                 if (s0 == s1 || s1 == s2 || unsafe) {
                                         use_slab = true;
                                         if (COUNT) {
@@ -588,18 +605,22 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                         const uint32_t b2 = (yx && zx) ? 4u : ((!yx && zy) ? 2u : 1u);
                                         // the diagonal visits, in this order, the cells {}, {b0}, {b0,b1}, {all}
                                         // (set = axes already in their far half); as child ids:
-                                        const uint32_t c0 = rayflags & 7u, c1 = c0 ^ b0, c3 = c0 ^ 7u, c2 = c3 ^ b2;
+                                        // (each with the entry bit 8 of the visiting list already set)
+                                        const uint32_t c0 = rayflags & 15u, c1 = c0 ^ b0, c3 = c0 ^ 7u, c2 = c3 ^ b2;
                                         // cell j spans [max(T0, s_(j-1)), min(T1, s_j)] -- the very t0/t1 the
                                         // reference's slab test computes for that child
                                         bool a0, a1, a2, a3;
-                                        if (rayflags & 8u) {
+                                        if (rayflags & 16u) {
                                                 // window [0, FLT_MAX] and finite t0 <= t1: accepted iff t1 >= 0.  With
                                                 // s0 <= s1 <= s2:  max(T0,s_(j-1)) <= min(T1,s_j)  <=>  T0 <= T1 and
-                                                // s_(j-1) <= T1 and T0 <= s_j;  min(T1,s_j) >= 0  <=>  T1 >= 0 and s_j >= 0
-                                                const bool vw = (T0 <= T1) && (T1 >= 0.f);
-                                                a0 = vw && (T0 <= s0) && (s0 >= 0.f);
-                                                a1 = vw && (s0 <= T1) && (T0 <= s1) && (s1 >= 0.f);
-                                                a2 = vw && (s1 <= T1) && (T0 <= s2) && (s2 >= 0.f);
+                                                // s_(j-1) <= T1 and T0 <= s_j;  min(T1,s_j) >= 0  <=>  T1 >= 0 and s_j >= 0.
+                                                // The two lower bounds fold into TL = max(T0, 0):  T0 <= x and 0 <= x  <=>
+                                                // TL <= x  (no NaN on this path; the sign of a zero is invisible to <=)
+                                                const float TL = fmaxf(T0, 0.f);
+                                                const bool vw = TL <= T1;
+                                                a0 = vw && (TL <= s0);
+                                                a1 = vw && (s0 <= T1) && (TL <= s1);
+                                                a2 = vw && (s1 <= T1) && (TL <= s2);
                                                 a3 = vw && (s2 <= T1);
                                         } else {
                                                 const float h0 = fminf(T1, s0), h1 = fminf(T1, s1), h2 = fminf(T1, s2);
@@ -609,39 +630,35 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                                 a2 = slab_accept(l2, h2, tmin, tmax);
                                                 a3 = slab_accept(l3, T1, tmin, tmax);
                                         }
-                                        a0 = a0 && ((mask >> c0) & 1u);
-                                        a1 = a1 && ((mask >> c1) & 1u);
-                                        a2 = a2 && ((mask >> c2) & 1u);
-                                        a3 = a3 && ((mask >> c3) & 1u);
+                                        // child present?  (c_j carries the entry bit 8, so test bit 8+id of mask << 8)
+                                        const uint32_t m8 = mask << 8;
+                                        a0 = a0 && ((m8 & (1u << c0)) != 0u);
+                                        a1 = a1 && ((m8 & (1u << c1)) != 0u);
+                                        a2 = a2 && ((m8 & (1u << c2)) != 0u);
+                                        a3 = a3 && ((m8 & (1u << c3)) != 0u);
                                         // visiting order = chain order; packed lowest bits first
                                         list = a3 ? c3 : 0u;
-                                        list = a2 ? ((list << 3) | c2) : list;
-                                        list = a1 ? ((list << 3) | c1) : list;
-                                        list = a0 ? ((list << 3) | c0) : list;
-                                        cnt = (a0 ? 1u : 0u) + (a1 ? 1u : 0u) + (a2 ? 1u : 0u) + (a3 ? 1u : 0u);
+                                        list = a2 ? ((list << 4) | c2) : list;
+                                        list = a1 ? ((list << 4) | c1) : list;
+                                        list = a0 ? ((list << 4) | c0) : list;
 #ifdef VRT_PARAM_CHECK
                                         {
-                                                uint32_t cnt_s = 0;
-                                                const uint32_t list_s = expand_slab(bx, by, bz, o[0], o[1], o[2], d[0], d[1], d[2], dinv[0],
-                                                                                    dinv[1], dinv[2], mask, tmin, tmax, &cnt_s);
-                                                const uint32_t keep = (1u << (3u * cnt_s)) - 1u;
+                                                const uint32_t list_s = expand_slab4(bx, by, bz, o[0], o[1], o[2], d[0], d[1], d[2], dinv[0],
+                                                                                     dinv[1], dinv[2], mask, tmin, tmax);
                                                 atomicAdd(&g_param_check[0], 1ull);
-                                                if (cnt_s != cnt || ((list_s ^ list) & keep))
+                                                if (list_s != list)
                                                         atomicAdd(&g_param_check[1], 1ull);
                                         }
 #endif
                                 }
                         }
-                        if (use_slab) {
-                                uint32_t cnt_s = 0;
-                                list = expand_slab(bx, by, bz, o[0], o[1], o[2], d[0], d[1], d[2], dinv[0], dinv[1], dinv[2],
-                                                   mask, tmin, tmax, &cnt_s);
-                                cnt = cnt_s;
-                        }
+                        if (use_slab)
+                                list = expand_slab4(bx, by, bz, o[0], o[1], o[2], d[0], d[1], d[2], dinv[0], dinv[1], dinv[2],
+                                                    mask, tmin, tmax);
                 }
                 // ---- visit children in order until we descend, hit, or run out -----------------
                 for (;;) {
-                        if (cnt == 0) {
+                        if (list == 0u) {
                                 sp -= kRec;
                                 uint32_t m;
                                 asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(m) : "r"(sp), "n"(kCol));
@@ -650,8 +667,7 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 if ((int32_t)m < 0)
                                         return;  // miss
                                 mask = m & 0xffu;
-                                cnt = (m >> 8) & 0xfu;
-                                const int nl = (int)(m >> 12);
+                                const int nl = (int)(m >> 8);
                                 x >>= (level - nl);
                                 y >>= (level - nl);
                                 z >>= (level - nl);
@@ -659,8 +675,7 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 continue;
                         }
                         const uint32_t c = list & 7u;
-                        list >>= 3;
-                        --cnt;
+                        list >>= 4;
                         const uint32_t child = first + __popc(mask & ((1u << c) - 1u));
                         const uint32_t cx = 2u * x + ((c >> 2) & 1u);
                         const uint32_t cy = 2u * y + ((c >> 1) & 1u);
@@ -676,10 +691,10 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 }
                                 continue;
                         }
-                        if (cnt != 0u) {  // remember this level only if it has children left
+                        if (list != 0u) {  // remember this level only if it has children left
                                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(first) : "memory");
                                 asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(sp), "n"(kCol),
-                                             "r"(mask | (cnt << 8) | ((uint32_t)level << 12))
+                                             "r"(mask + ((uint32_t)level << 8))
                                              : "memory");
                                 asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(sp), "n"(2u * kCol), "r"(list) : "memory");
                                 sp += kRec;
