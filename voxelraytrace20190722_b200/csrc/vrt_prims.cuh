@@ -143,17 +143,24 @@ k_sort_hist(const unsigned long long* __restrict__ keys, uint64_t n, int shift,
         hist[(uint64_t)threadIdx.x * tiles + blockIdx.x] = h[threadIdx.x];
 }
 
+// Scatter pass.  The tile is first reordered by digit in shared memory (stable: digit, then
+// memory order), then written out position by position, so that the keys of one digit leave
+// as one contiguous run (16 keys = 128 B on average) instead of one 8-byte store per sector.
 __global__ void __launch_bounds__(kSortThreads)
 k_sort_scatter(const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out,
                uint64_t n, int shift, const uint32_t* __restrict__ offs /* scanned [256][tiles] */,
                uint32_t tiles)
 {
         __shared__ uint32_t cnt[kSortWarps][256];
+        __shared__ uint32_t gbase[256];  // global position of the digit's run minus its tile-local start
+        __shared__ uint32_t wtot[kSortWarps];
+        __shared__ unsigned long long stage[kSortTile];
         for (int i = threadIdx.x; i < kSortWarps * 256; i += kSortThreads)
                 (&cnt[0][0])[i] = 0;
         __syncthreads();
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-        const uint64_t wbase = (uint64_t)blockIdx.x * kSortTile + (uint64_t)w * kSortWarpSlice;
+        const uint64_t tbase = (uint64_t)blockIdx.x * kSortTile;
+        const uint64_t wbase = tbase + (uint64_t)w * kSortWarpSlice;
         unsigned long long key[kSortRounds];
         uint32_t rank[kSortRounds];
 #pragma unroll
@@ -174,16 +181,36 @@ k_sort_scatter(const unsigned long long* __restrict__ in, unsigned long long* __
                 rank[r] = old + before;
         }
         __syncthreads();
-        // per digit: exclusive prefix over warps + global offset of (digit, tile)
+        // per digit d (= threadIdx.x): exclusive prefix over the warps, then the tile-local start of
+        // the digit (exclusive scan of the digit totals over the 256 threads)
         {
                 const uint32_t d = threadIdx.x;
-                uint32_t run = offs[(uint64_t)d * tiles + blockIdx.x];
+                uint32_t run = 0;
 #pragma unroll
                 for (int i = 0; i < kSortWarps; ++i) {
                         uint32_t c = cnt[i][d];
                         cnt[i][d] = run;
                         run += c;
                 }
+                uint32_t inc = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o)
+                                inc += t;
+                }
+                if (lane == 31)
+                        wtot[w] = inc;
+                __syncthreads();
+                uint32_t woff = 0;
+#pragma unroll
+                for (int i = 0; i < kSortWarps; ++i)
+                        woff += (i < w) ? wtot[i] : 0u;
+                const uint32_t dstart = woff + inc - run;
+#pragma unroll
+                for (int i = 0; i < kSortWarps; ++i)
+                        cnt[i][d] += dstart;
+                gbase[d] = offs[(uint64_t)d * tiles + blockIdx.x] - dstart;
         }
         __syncthreads();
 #pragma unroll
@@ -191,8 +218,16 @@ k_sort_scatter(const unsigned long long* __restrict__ in, unsigned long long* __
                 uint64_t k = wbase + (uint64_t)r * 32 + lane;
                 if (k < n) {
                         uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
-                        out[cnt[w][d] + rank[r]] = key[r];
+                        stage[cnt[w][d] + rank[r]] = key[r];
                 }
+        }
+        __syncthreads();
+        const uint32_t tile_n = (uint32_t)((n - tbase < (uint64_t)kSortTile) ? (n - tbase) : (uint64_t)kSortTile);
+#pragma unroll 4
+        for (uint32_t j = threadIdx.x; j < tile_n; j += kSortThreads) {
+                const unsigned long long kv = stage[j];
+                const uint32_t d = (uint32_t)(kv >> shift) & 255u;
+                out[gbase[d] + j] = kv;
         }
 }
 
