@@ -13,8 +13,10 @@ per step.  A step = one frame = one launch of the persistent ray kernel per GPU.
             bands and writes 16-byte hit records + the shaded film bands to HBM; N>1: the film
             bands are gathered to rank 0 (NCCL, double-buffered under the next frame's kernel)
             and re-ordered into the frame inside the timed region
-  e2e       Mrays/s through the host-buffer C-ABI call vrt_render_camera: camera in,
-            shaded float film copied back to pinned host memory inside the timed region
+  e2e       Mrays/s through the host-buffer C-ABI call (vrt_render_camera_async; N>1:
+            vrt_render_bands_async on every rank): camera in, shaded float film copied back to
+            pinned host memory inside the timed region (N>1: one host frame shared by the ranks,
+            every rank DMA-copies its own bands)
   roofline  algorithmic bytes per ray (8*N_int + 8*N_leaf + 40*N_tri + 16,
             N_* counted on the same frame) * rays / kernel time, against the measured HBM
             copy bandwidth of MEASURED_PEAKS.json
@@ -359,6 +361,8 @@ def run_ours(args):
     value = rays_per_step / (ms_per_step * 1e-3) / 1e6
 
     # ---- e2e: host-buffer C-ABI call, film copied back to pinned host memory every step ----
+    e2e_host_frame_ok = None
+    e2e_note = None
     if world == 1:
         # frame loop through the host-buffer C ABI: vrt_render_camera_async enqueues the frame and
         # its device->host copy (pinned film, alternating between two host buffers); the copy of
@@ -385,38 +389,69 @@ def run_ours(args):
         e2e_sync_ms = (time.perf_counter() - t0) * 1e3 / min(args.steps, 5)
         d2h = film_np.nbytes
     else:
-        film_host = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
+        # N ranks: the same frame loop through vrt_render_bands_async -- every rank renders its
+        # bands and DMA-copies them to their final rows of a host frame that all ranks of the node
+        # map (POSIX shared memory, pinned in every process): N PCIe links in parallel, the copy of
+        # frame k overlapping the kernel of frame k+1; every frame is complete in host memory when
+        # the timed region ends (vrt_tree_sync on every rank + barrier)
+        try:
+            shf = vdist.SharedHostFrame(ny, nx, nbuf=2)
+        except RuntimeError as ex:  # raised on every rank or on none
+            shf = None
+            e2e_note = f"no shared pinned host frame ({ex}): per-frame barrier + copy from rank 0's GPU"
+        if shf is not None:
+            tree.set_stream(0)
 
-        tree.set_stream(stream.cuda_stream)
+            def e2e_step(i):
+                tree.render_bands_async(cams[i % len(cams)], shf.ptr(i), vdist.BAND_H, rank, world,
+                                        shadow_eps=shadow_eps)
 
-        def e2e_step():
-            if use_gather:
-                tree.render_bands_dev(cam, fg.buffer(0).data_ptr(), vdist.BAND_H, rank, world, shadow_eps=shadow_eps)
-                fg.gather_async(0)
-                full = fg.assemble(0)
-            else:
-                tree.frame_bands_dev(cam, hits[0].data_ptr(), pf.ptr(0), vdist.BAND_H, rank, world, full_frame=True,
-                                     shadow_eps=shadow_eps)
+            def e2e_drain():
+                tree.sync()
+        else:
+            film_host = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
+            tree.set_stream(stream.cuda_stream)
+
+            def e2e_step(i):
+                if use_gather:
+                    tree.render_bands_dev(cams[i % len(cams)], fg.buffer(0).data_ptr(), vdist.BAND_H, rank, world,
+                                          shadow_eps=shadow_eps)
+                    fg.gather_async(0)
+                    full = fg.assemble(0)
+                else:
+                    tree.frame_bands_dev(cams[i % len(cams)], hits[0].data_ptr(), pf.ptr(0), vdist.BAND_H, rank, world,
+                                         full_frame=True, shadow_eps=shadow_eps)
+                    torch.cuda.synchronize(dev)
+                    td.barrier()  # every rank's pixels have landed in rank 0's frame
+                    full = pf.frame(0)
+                if rank == 0:
+                    film_host.copy_(full, non_blocking=True)
                 torch.cuda.synchronize(dev)
-                td.barrier()  # every rank's pixels have landed in rank 0's frame
-                full = pf.frame(0)
-            if rank == 0:
-                film_host.copy_(full, non_blocking=True)
-            torch.cuda.synchronize(dev)
 
-        for _ in range(max(1, args.warmup // 2)):
-            e2e_step()
+            def e2e_drain():
+                pass
+        for i in range(max(2, args.warmup // 2)):
+            e2e_step(i)
+        e2e_drain()
         sync_all()
         sampler.mark("e0")
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
+        for i in range(args.steps):
+            e2e_step(i)
+        e2e_drain()
         sync_all()
         sampler.mark("e1")
         tt = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=dev)
         td.all_reduce(tt, op=td.ReduceOp.MAX)
         e2e_ms = float(tt[0])
         d2h = ny * nx * 12
+        # the last host frame of the loop against the same camera rendered by rank 0 alone
+        if rank == 0:
+            k_last = args.steps - 1
+            alone = tree.render(cams[k_last % len(cams)], shadow_eps=shadow_eps)
+            got_host = shf.frame(k_last) if shf is not None else film_host.numpy()
+            e2e_host_frame_ok = bool(np.array_equal(got_host.view(np.uint32), alone.view(np.uint32)))
+        tree.set_stream(stream.cuda_stream)
     e2e_value = rays_per_step / (e2e_ms * 1e-3) / 1e6
     clocks = sampler.stop() if rank == 0 else None
 
@@ -524,15 +559,18 @@ def run_ours(args):
                 "ms_per_step": e2e_ms,
                 "call": ("vrt_render_camera_async per frame + vrt_tree_sync (camera struct in, shaded float film out to pinned "
                          "host; frame k's copy overlaps frame k+1's kernel)" if world == 1 else
-                         "vrt_frame_bands_peer_dev per rank + barrier + film copied to pinned host on rank 0, per frame"),
-                "sync_single_frame_ms": e2e_sync_ms if world == 1 else None},
+                         "vrt_render_bands_async per rank and frame + vrt_tree_sync + barrier (camera struct in; every rank "
+                         "DMA-copies its bands to their final rows of one host frame shared and pinned by all ranks; "
+                         "frame k's copy overlaps frame k+1's kernel)"),
+                "sync_single_frame_ms": e2e_sync_ms if world == 1 else None, "note": e2e_note},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
         "build": build_out,
         "gi": gi_out,
         "octree": {"device_bytes": info["device_bytes"], "nodes": info["num_nodes"], "leaves": info["num_leaves"]},
-        "frame_check": {"n_gpu_frame_equals_1_gpu_frame_bytewise": frame_check},
+        "frame_check": {"n_gpu_frame_equals_1_gpu_frame_bytewise": frame_check,
+                        "e2e_host_frame_equals_1_gpu_render_bytewise": e2e_host_frame_ok},
         "assemble": ("nccl gather + re-order copy" if use_gather else
                      "fused: peer stores into rank 0's IPC-mapped frame over NVLink" if world > 1 else "local frame"),
     }

@@ -233,6 +233,14 @@ int vrt_render_bands_dev(const vrt_tree* tree, const vrt_camera* cam, const vrt_
                          const vrt_bands* bands, float* d_film_rgb);
 int vrt_trace_bands16_dev(const vrt_tree* tree, const vrt_camera* cam,
                           const vrt_bands* bands, vrt_hit16* d_out);
+/* The multi-GPU form of vrt_render_camera_async (render_mt camera.h:41-68 with the film in
+ * host memory): film_rgb_full is the FULL [ny][nx][3] host frame -- on a multi-process node a
+ * shared mapping that every rank has pinned (cudaHostRegister) -- and this rank's bands are
+ * DMA-copied straight to their final rows, asynchronously (two device band buffers per handle:
+ * the copy of frame k overlaps the kernel of frame k+1).  vrt_tree_sync() on every rank, then a
+ * process barrier, and the frame is complete.  Alternate between two host frames. */
+int vrt_render_bands_async(const vrt_tree* tree, const vrt_camera* cam, const vrt_shade* sh,
+                           const vrt_bands* bands, float* film_rgb_full);
 /* Work counters of the reference algorithm for a camera frame:
  * counts[0..4] = rays traced, interior nodes expanded (travorder calls), non-empty
  * leaves visited, triangle tests, hits; counts[5..7] = kernel statistics: expansions done
@@ -257,6 +265,10 @@ int vrt_frame_bands_peer_dev(const vrt_tree* tree, const vrt_camera* cam, const 
  * (cudaMalloc + CUDA IPC): export a 64-byte handle on the owner, open it on the peers. */
 int vrt_dev_alloc(uint64_t bytes, void** d_ptr);
 int vrt_dev_free(void* d_ptr);
+/* Page-lock a host range for DMA (e.g. a frame in POSIX shared memory that all ranks of a node
+ * map: the target of vrt_render_bands_async). */
+int vrt_host_register(void* ptr, uint64_t bytes);
+int vrt_host_unregister(void* ptr);
 int vrt_ipc_export(const void* d_ptr, uint8_t handle[64]);
 int vrt_ipc_open(const uint8_t handle[64], void** d_ptr);
 int vrt_ipc_close(void* d_ptr);

@@ -78,3 +78,47 @@ def test_banded_gather_world2(ny):
         p.join(120)
         assert p.exitcode == 0
     assert ok.value == 1
+
+
+def _worker_shared(rank, world, port, ny, nx, ok):
+    import torch.distributed as td
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from voxelraytrace20190722_b200 import dist as vdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    # the host frame every rank maps (unpinned here: no GPU); each rank fills ITS bands of both frames the way
+    # vrt_render_bands_async's strided copy does: band k of rank r lands at film rows [k*BAND_H, (k+1)*BAND_H)
+    shf = vdist.SharedHostFrame(ny, nx, nbuf=2, pin=False)
+    for f in range(2):
+        fr = shf.frame(f)
+        k = rank
+        while k * vdist.BAND_H < ny:
+            for y in range(k * vdist.BAND_H, min((k + 1) * vdist.BAND_H, ny)):
+                fr[y, :, :] = (y * 1000 + np.arange(nx, dtype=np.float32))[:, None] * (f + 1)
+            k += world
+    td.barrier()
+    if rank == 0:
+        exp = (np.arange(ny, dtype=np.float32)[:, None] * 1000 + np.arange(nx, dtype=np.float32)[None, :])[..., None]
+        good = all(np.array_equal(shf.frame(f), np.broadcast_to(exp * (f + 1), (ny, nx, 3))) for f in range(2))
+        good = good and shf.ptr(0) != shf.ptr(1) and shf.ptr(2) == shf.ptr(0) and shf.ptr(0) % 4096 == 0
+        ok.value = int(good)
+    td.barrier()
+    shf.close()
+    td.destroy_process_group()
+
+
+@pytest.mark.parametrize("ny", [37, 2160])
+def test_shared_host_frame_world2(ny):
+    """The host frame of the N-GPU end-to-end loop: one POSIX shared-memory segment mapped by every rank;
+    what rank 1 writes into its bands is what rank 0 reads."""
+    ctx = mp.get_context("spawn")
+    ok = ctx.Value("i", 0)
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_shared, args=(r, 2, port, ny, 16, ok)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ok.value == 1

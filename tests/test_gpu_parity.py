@@ -459,6 +459,33 @@ def test_render_async_pipeline_matches_sync(case, gpu):
         assert np.array_equal(e.view(np.uint32), b.numpy().view(np.uint32))
 
 
+@pytest.mark.parametrize("world", [1, 3])
+def test_render_bands_async_assembles_host_frame(case, gpu, world):
+    """vrt_render_bands_async: every "rank" (here: the ranks of a 3-GPU run one after the other on one GPU)
+    DMA-copies its bands to their final rows of ONE pinned host frame; several frames in flight on two
+    alternating host frames; the result equals the synchronous whole-film render bytewise.  ny is not a
+    multiple of the band height, so the last band is short."""
+    from voxelraytrace20190722_b200 import dist as vdist
+    cam10 = case["cam10"]
+    nx, ny, spp = 120, 70, 4
+    cams = [gpu.Camera(cam10[0], cam10[1:4] + np.float32(0.01 * k), cam10[4:7], cam10[7:10], nx, ny, spp)
+            for k in range(4)]
+    tree = case["tree"]
+    expect = [tree.render(c) for c in cams]
+    shf = vdist.SharedHostFrame(ny, nx, nbuf=2)
+    try:
+        for k0 in (0, 2):  # two frames in flight, then read them back, twice
+            for k in (k0, k0 + 1):
+                shf.frame(k)[:] = -1.0
+                for r in range(world):
+                    tree.render_bands_async(cams[k], shf.ptr(k), vdist.BAND_H, r, world)
+            tree.sync()
+            for k in (k0, k0 + 1):
+                assert np.array_equal(expect[k].view(np.uint32), shf.frame(k).view(np.uint32)), (world, k)
+    finally:
+        shf.close()
+
+
 def test_build_indexed_equals_flat_build(gpu, port):
     """vrt_build_indexed (tinyobj-style attrib arrays + index_t records, gathered on the device) produces the
     same octree as vrt_build on the expanded triangles, i.e. as obj2voxel + ray_march_init."""

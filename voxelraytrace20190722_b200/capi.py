@@ -64,9 +64,9 @@ SYMBOLS = [
     "vrt_tree_export", "vrt_tree_import", "vrt_tree_set_stream", "vrt_tree_blob_dev",
     "vrt_tree_from_blob_dev", "vrt_tree_save", "vrt_tree_load", "vrt_camera_init", "vrt_gen_rays", "vrt_trace_rays",
     "vrt_trace_rays_dev", "vrt_trace_camera", "vrt_trace_camera_dev", "vrt_trace_camera16_dev",
-    "vrt_render_camera", "vrt_render_camera_dev", "vrt_render_camera_async", "vrt_band_rows", "vrt_render_bands_dev",
+    "vrt_render_camera", "vrt_render_camera_dev", "vrt_render_camera_async", "vrt_band_rows", "vrt_render_bands_dev", "vrt_render_bands_async",
     "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_frame_bands_peer_dev",
-    "vrt_dev_alloc", "vrt_dev_free", "vrt_ipc_export", "vrt_ipc_open", "vrt_ipc_close", "vrt_tree_sync",
+    "vrt_dev_alloc", "vrt_dev_free", "vrt_host_register", "vrt_host_unregister", "vrt_ipc_export", "vrt_ipc_open", "vrt_ipc_close", "vrt_tree_sync",
     "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_set_materials", "vrt_albedo", "vrt_gi_init", "vrt_gi_splat_camera", "vrt_gi_filter",
     "vrt_gi_get_level", "vrt_gi_cone_trace", "vrt_gi_render_camera", "vrt_gi_render_camera_dev", "vrt_tribox_batch",
     "vrt_tri_overlap_aabb_batch", "vrt_raytri_batch", "vrt_aabb_isect_batch",
@@ -122,12 +122,15 @@ def load(build_if_missing: bool = True):
         getattr(L, name).argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), i32, i32, i32, i32, vp]
     L.vrt_band_rows.argtypes = [C.POINTER(vrt_camera), C.POINTER(vrt_bands)]
     L.vrt_render_bands_dev.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), C.POINTER(vrt_bands), vp]
+    L.vrt_render_bands_async.argtypes = L.vrt_render_bands_dev.argtypes
     L.vrt_trace_bands16_dev.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_bands), vp]
     L.vrt_count_camera.argtypes = [vp, C.POINTER(vrt_camera), i32, i32, i32, i32, vp]
     L.vrt_frame_bands_dev.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), C.POINTER(vrt_bands), vp, vp]
     L.vrt_frame_bands_peer_dev.argtypes = L.vrt_frame_bands_dev.argtypes
     L.vrt_dev_alloc.argtypes = [u64, C.POINTER(vp)]
     L.vrt_dev_free.argtypes = [vp]
+    L.vrt_host_register.argtypes = [vp, u64]
+    L.vrt_host_unregister.argtypes = [vp]
     L.vrt_ipc_export.argtypes = [vp, vp]
     L.vrt_ipc_open.argtypes = [vp, C.POINTER(vp)]
     L.vrt_ipc_close.argtypes = [vp]
@@ -370,6 +373,15 @@ class Octree:
         b = vrt_bands(int(band_h), int(band_first), int(band_stride))
         _check(load().vrt_render_bands_dev(self._h, C.byref(cam.c), C.byref(sh), C.byref(b), C.c_void_p(d_film_ptr)))
 
+    def render_bands_async(self, cam: Camera, host_frame_ptr, band_h, band_first, band_stride, light=None, kd=0.8,
+                           shadow_eps=None):
+        """Rank `band_first` of `band_stride`: render this rank's bands and DMA them to their final rows
+        of the full (pinned, possibly shared between the ranks) host frame; asynchronous, see sync()."""
+        sh = _shade(light, kd, shadow_eps)
+        b = vrt_bands(int(band_h), int(band_first), int(band_stride))
+        _check(load().vrt_render_bands_async(self._h, C.byref(cam.c), C.byref(sh), C.byref(b),
+                                             C.c_void_p(int(host_frame_ptr))))
+
     def frame_bands_dev(self, cam: Camera, d_hits_ptr, d_film_ptr, band_h, band_first, band_stride, light=None,
                         kd=0.8, full_frame=False, shadow_eps=None):
         """One frame step of rank `band_first` of `band_stride`: hit16 records + film (async).
@@ -494,6 +506,14 @@ def dev_alloc(nbytes: int) -> int:
 
 def dev_free(ptr: int):
     _check(load().vrt_dev_free(C.c_void_p(ptr)))
+
+
+def host_register(ptr: int, nbytes: int):
+    _check(load().vrt_host_register(C.c_void_p(ptr), int(nbytes)))
+
+
+def host_unregister(ptr: int):
+    _check(load().vrt_host_unregister(C.c_void_p(ptr)))
 
 
 def ipc_export(ptr: int) -> bytes:

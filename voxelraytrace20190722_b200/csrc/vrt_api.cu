@@ -1043,6 +1043,71 @@ int vrt_render_bands_dev(const vrt_tree* t, const vrt_camera* cam, const vrt_sha
         return bands_common(t, cam, sh, b, d_film_rgb, OUT_FILM);
 }
 
+// Multi-GPU frame loop to HOST memory: this rank's bands are rendered into one of two device
+// band buffers and copied by one strided DMA (cudaMemcpy2DAsync: one row per band) straight to
+// their final rows of the full host frame, which every rank of the node maps (shared + pinned),
+// so the N ranks use their N PCIe links in parallel and the copy of frame k overlaps the kernel
+// of frame k+1 -- the N-GPU counterpart of vrt_render_camera_async.
+int vrt_render_bands_async(const vrt_tree* tc, const vrt_camera* cam, const vrt_shade* sh, const vrt_bands* b,
+                           float* film_rgb_full)
+{
+        int rc = check_tree(tc);
+        if (rc)
+                return rc;
+        rc = check_camera(cam, 0, 0, cam ? cam->nx : 0, cam ? cam->ny : 0);
+        if (rc)
+                return rc;
+        const int rows = vrt_band_rows(cam, b);
+        if (rows < 0)
+                return rows;
+        if (rows == 0)
+                return VRT_OK;
+        if (!film_rgb_full || !sh) {
+                set_error("null out/shade pointer");
+                return VRT_ERR_ARG;
+        }
+        vrt_tree* t = const_cast<vrt_tree*>(tc);
+        if (!t->copy_stream) {
+                VRT_CUDA(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+                for (int i = 0; i < 2; ++i) {
+                        VRT_CUDA(cudaEventCreateWithFlags(&t->film_ready[i], cudaEventDisableTiming));
+                        VRT_CUDA(cudaEventCreateWithFlags(&t->film_copied[i], cudaEventDisableTiming));
+                }
+        }
+        const int k = (int)(t->n_async_frames & 1);
+        const size_t row_bytes = (size_t)cam->nx * 12;
+        const uint64_t bytes = (uint64_t)rows * row_bytes;
+        if (t->film_dev[k].cap < bytes) {
+                VRT_CUDA(cudaStreamSynchronize(t->copy_stream));  // nothing may still read the old buffer
+                if (t->film_dev[k].reserve(bytes))
+                        return VRT_ERR_NOMEM;
+        }
+        if (t->n_async_frames >= 2)  // the copy that last read this device buffer must be done
+                VRT_CUDA(cudaStreamWaitEvent(t->stream, t->film_copied[k], 0));
+        const int y0 = b->band_first * b->band_h;
+        rc = launch_trace_camera(t, cam, sh, 0, y0, cam->nx, y0 + rows, t->film_dev[k].p, OUT_FILM, b->band_h,
+                                 b->band_stride * b->band_h);
+        if (rc)
+                return rc;
+        VRT_CUDA(cudaEventRecord(t->film_ready[k], t->stream));
+        VRT_CUDA(cudaStreamWaitEvent(t->copy_stream, t->film_ready[k], 0));
+        // full bands: one 2-D copy, "row" = one band of band_h film rows; then the last, shorter band
+        const size_t band_bytes = (size_t)b->band_h * row_bytes;
+        const int full_bands = rows / b->band_h, tail_rows = rows % b->band_h;
+        char* dst = reinterpret_cast<char*>(film_rgb_full) + (size_t)y0 * row_bytes;
+        const char* src = static_cast<const char*>(t->film_dev[k].p);
+        if (full_bands)
+                VRT_CUDA(cudaMemcpy2DAsync(dst, (size_t)b->band_stride * band_bytes, src, band_bytes, band_bytes,
+                                           (size_t)full_bands, cudaMemcpyDeviceToHost, t->copy_stream));
+        if (tail_rows)
+                VRT_CUDA(cudaMemcpyAsync(dst + (size_t)full_bands * b->band_stride * band_bytes,
+                                         src + (size_t)full_bands * band_bytes, (size_t)tail_rows * row_bytes,
+                                         cudaMemcpyDeviceToHost, t->copy_stream));
+        VRT_CUDA(cudaEventRecord(t->film_copied[k], t->copy_stream));
+        t->n_async_frames++;
+        return VRT_OK;
+}
+
 int vrt_trace_bands16_dev(const vrt_tree* t, const vrt_camera* cam, const vrt_bands* b, vrt_hit16* d_out)
 {
         return bands_common(t, cam, nullptr, b, d_out, OUT_HIT16);
@@ -1358,6 +1423,26 @@ int vrt_dev_alloc(uint64_t bytes, void** d_ptr)
 int vrt_dev_free(void* d_ptr)
 {
         VRT_CUDA(cudaFree(d_ptr));
+        return VRT_OK;
+}
+
+int vrt_host_register(void* ptr, uint64_t bytes)
+{
+        if (!ptr || !bytes) {
+                set_error("vrt_host_register: bad argument");
+                return VRT_ERR_ARG;
+        }
+        if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+                cudaGetLastError();
+                set_error("cudaHostRegister(%llu bytes) failed", (unsigned long long)bytes);
+                return VRT_ERR_CUDA;
+        }
+        return VRT_OK;
+}
+
+int vrt_host_unregister(void* ptr)
+{
+        VRT_CUDA(cudaHostUnregister(ptr));
         return VRT_OK;
 }
 

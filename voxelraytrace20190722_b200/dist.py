@@ -131,6 +131,88 @@ class PeerFrame:
         self.ptrs, self.owned = [], []
 
 
+class SharedHostFrame:
+    """Frames in HOST memory that every rank of the node writes into: `nbuf` full
+    [ny, nx, 3] float32 frames in one POSIX shared-memory segment, mapped and page-locked
+    (vrt_host_register) by every process.  Rank r's vrt_render_bands_async DMA-copies its
+    bands straight to their final rows, so the N GPUs use their N PCIe links in parallel and
+    nothing funnels through rank `dst`'s GPU; the frame is complete once every rank has
+    synchronised its handle and the ranks have met at a barrier.  Without an initialised
+    process group it is simply `nbuf` pinned frames of one process."""
+
+    def __init__(self, ny, nx, nbuf: int = 2, dst: int = 0, pin: bool = True):
+        import mmap
+        import os
+        try:
+            import torch.distributed as dist
+            on = dist.is_initialized()
+        except Exception:  # pragma: no cover
+            dist, on = None, False
+        self.world = dist.get_world_size() if on else 1
+        self.rank = dist.get_rank() if on else 0
+        self.ny, self.nx, self.nbuf, self.dst = ny, nx, nbuf, dst
+        self.frame_bytes = ny * nx * 12
+        self.stride = (self.frame_bytes + 4095) // 4096 * 4096  # page-aligned frames
+        total = self.stride * nbuf
+        # Failures (no /dev/shm, page-locking refused) are made COLLECTIVE: either every rank
+        # holds a pinned mapping afterwards or every rank raises, so callers can fall back together.
+        name, fd, err = [None], -1, None
+        if self.rank == dst:
+            try:
+                name[0] = "/dev/shm/vrt_frame_%d_%x" % (os.getpid(), id(self) & 0xffffff)
+                fd = os.open(name[0], os.O_CREAT | os.O_EXCL | os.O_RDWR, 0o600)
+                os.ftruncate(fd, total)
+            except OSError as e:
+                name[0], err = None, e
+        if self.world > 1:
+            dist.broadcast_object_list(name, src=dst)
+        if name[0] is None:
+            raise RuntimeError(f"SharedHostFrame: cannot create the shared segment ({err})")
+        self._mm, self._np, self._registered = None, None, False
+        try:
+            if self.rank != dst:
+                fd = os.open(name[0], os.O_RDWR)
+            self._mm = mmap.mmap(fd, total)
+            os.close(fd)
+            self._np = np.frombuffer(self._mm, dtype=np.uint8)
+            self.base = int(self._np.ctypes.data)
+            if pin:  # (pin=False: the CPU-only tests of the sharing logic)
+                capi.host_register(self.base, total)
+                self._registered = True
+        except Exception as e:  # noqa: BLE001 -- reported collectively below
+            err = e
+        if self.world > 1:
+            flags = [None] * self.world
+            dist.all_gather_object(flags, err is None)  # also: every rank holds its mapping, the name can go
+            all_ok = all(flags)
+        else:
+            all_ok = err is None
+        if self.rank == dst:
+            os.unlink(name[0])
+        if not all_ok:
+            self.close()
+            raise RuntimeError(f"SharedHostFrame: mapping / page-locking failed on some rank ({err})")
+
+    def ptr(self, k: int) -> int:
+        return self.base + (k % self.nbuf) * self.stride
+
+    def frame(self, k: int) -> np.ndarray:
+        """[ny, nx, 3] float32 numpy view of host frame k (any rank; the memory is shared)."""
+        o = (k % self.nbuf) * self.stride
+        return self._np[o:o + self.frame_bytes].view(np.float32).reshape(self.ny, self.nx, 3)
+
+    def close(self):
+        if getattr(self, "_registered", False):
+            capi.host_unregister(self.base)
+            self._registered = False
+        self._np = None
+        try:
+            if self._mm is not None:
+                self._mm.close()
+        except BufferError:  # a numpy view is still alive somewhere; the mapping goes with the process
+            pass
+
+
 class FrameGather:
     """Framebuffer assembly on rank `dst` (the ncclGather of SURVEY.md 8e), double-buffered
     and asynchronous so that the gather of frame k overlaps the ray kernel of frame k+1.
