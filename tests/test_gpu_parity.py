@@ -4,6 +4,7 @@ Bar (BASELINE.json north_star): leaf sets bit-exact, per-ray (hit, leaf cell,
 triangle) identical, ISect bit-exact, pixels within 1/255.  In practice every
 comparison below is exact.
 """
+import os
 import numpy as np
 import pytest
 
@@ -484,6 +485,52 @@ def test_render_bands_async_assembles_host_frame(case, gpu, world):
                 assert np.array_equal(expect[k].view(np.uint32), shf.frame(k).view(np.uint32)), (world, k)
     finally:
         shf.close()
+
+
+def _clustered_soup(T, seed=3):
+    """T small triangles inside one tiny region plus a few far ones that span the root box: at depth >= 5 one
+    leaf holds (almost) all of them -- more than the ranked build sorts inside a leaf."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(0.40, 0.41, (T, 1, 3)).astype(np.float32)
+    tri = (c + rng.uniform(-0.004, 0.004, (T, 3, 3))).astype(np.float32)
+    tri[:4] = rng.uniform(-1, 1, (4, 3, 3)).astype(np.float32)
+    nrm = np.zeros_like(tri)
+    nrm[..., 1] = 1
+    return tri, nrm
+
+
+@pytest.mark.parametrize("name,depth", [("sphere_big_leaves", 5), ("atrium", 8), ("soup", 9), ("clustered", 6)])
+def test_ranked_build_equals_sorted_build(gpu, name, depth):
+    """The ranked top-down build (node arrays produced on the way down, counting sort of the leaf references,
+    dead ends pruned afterwards) and the sorted build (Morton keys, radix sort, bottom-up parents) deliver the
+    same octree bit for bit: leaf cells, counts, reference lists, node records.  `sphere_big_leaves` puts
+    hundreds of references into every leaf (block-level sort), `clustered` more than the ranked path sorts
+    inside one leaf (it must hand the build over to the sorted path)."""
+    tri, nrm = {"sphere_big_leaves": lambda: scenes.uv_sphere(256, 128), "atrium": lambda: scenes.atrium(0.5),
+                "soup": lambda: scenes.soup(150_000), "clustered": lambda: _clustered_soup(20_000)}[name]()
+    out = {}
+    old = os.environ.get("VRT_BUILD_SORTED")
+    try:
+        for mode in ("1", "0"):
+            os.environ["VRT_BUILD_SORTED"] = mode
+            t = gpu.Octree.build(tri, nrm, depth)
+            out[mode] = (t.info(), t.leaves(nodes=True))
+            t.close()
+    finally:
+        if old is None:
+            os.environ.pop("VRT_BUILD_SORTED", None)
+        else:
+            os.environ["VRT_BUILD_SORTED"] = old
+    (ia, a), (ib, b) = out["1"], out["0"]
+    for k in ("num_nodes", "num_leaves", "num_refs", "level_offset"):
+        assert np.array_equal(np.asarray(ia[k]), np.asarray(ib[k])), k
+    assert ia["num_leaves"] > 0
+    for nm, x, y in zip(("cell", "count", "refs", "nodes"), a, b):
+        assert np.array_equal(x, y), nm
+    if name == "sphere_big_leaves":
+        assert a[1].max() > 24
+    if name == "clustered":
+        assert a[1].max() > 8192
 
 
 def test_build_indexed_equals_flat_build(gpu, port):

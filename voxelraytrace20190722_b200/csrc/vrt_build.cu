@@ -17,6 +17,7 @@
 // bottom-up parent derivation -> flat pointerless node array.
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -467,6 +468,305 @@ static inline unsigned grid_for(uint64_t n, unsigned block)
         return (unsigned)std::max<uint64_t>(1, (n + block - 1) / block);
 }
 
+// ---------------------------------------------------------------------------
+// RANKED top-down build (the default for trees of depth >= 5).  The level-synchronous expansion
+// above already visits every (triangle, non-empty cell) pair of every level, so the node arrays
+// can be produced on the way down instead of being re-derived bottom-up from sorted leaf keys:
+//   * a frontier pair carries the RANK of its cell among the non-empty cells of its level (the
+//     cell's index in the BFS node array) instead of the cell's Morton code;
+//   * the mask pass records "child c of node i exists" as one flag byte per (node, child) -- plain
+//     stores of the constant 1, no atomics, the result cannot depend on any order;
+//   * an exclusive scan of popc(mask) over the nodes of the level gives first_child, hence the
+//     rank of every child = first_child + popc(mask & below(c)) -- children of one node are
+//     contiguous and nodes stay in Morton order level by level (induction from the root);
+//   * the leaf reference lists are a counting sort of the last frontier by leaf rank (atomic
+//     cursors) followed by an ascending sort of every leaf's short list, which restores the
+//     reference's insertion order (ascending triangle index) whatever order the atomics took.
+// No radix sort, no head flags, no bottom-up pass; the output arrays are the same ones
+// assemble_blob() consumes, bit for bit (tests: leaf sets, node records, checkpoint bytes).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_expand_mask_r(const float* __restrict__ tri, const float2* __restrict__ tab, uint64_t stride,
+                const unsigned long long* __restrict__ in, uint32_t n_in, int level /* of the input cells */,
+                const unsigned long long* __restrict__ node_morton,
+                uint8_t* __restrict__ child_seen /* [nodes][8], zeroed */, int crowded, uint8_t* __restrict__ masks,
+                uint32_t* __restrict__ block_counts)
+{
+        const uint32_t c = threadIdx.x & 7;
+        const uint32_t lane = threadIdx.x & 31;
+        const uint32_t child_base = 2u << level;  // table offset of level+1
+        uint32_t cnt = 0;
+#pragma unroll 1
+        for (int it = 0; it < kPairsPerBlock / 32; ++it) {
+                const uint32_t idx = blockIdx.x * kPairsPerBlock + it * 32 + (threadIdx.x >> 3);
+                bool ov = false;
+                uint32_t node = 0;
+                if (idx < n_in) {
+                        const unsigned long long key = in[idx];
+                        const uint32_t t = (uint32_t)key;
+                        node = (uint32_t)(key >> 32);
+                        const unsigned long long m = node_morton[node];
+                        const uint32_t cx = 2u * compact1by2(m >> 2) + ((c >> 2) & 1u);
+                        const uint32_t cy = 2u * compact1by2(m >> 1) + ((c >> 1) & 1u);
+                        const uint32_t cz = 2u * compact1by2(m) + (c & 1u);
+                        const float2 bx = tab[0 * stride + child_base + cx];
+                        const float2 by = tab[1 * stride + child_base + cy];
+                        const float2 bz = tab[2 * stride + child_base + cz];
+                        const float* p = tri + 9ull * t;
+                        float v0[3] = { p[0], p[1], p[2] }, v1[3] = { p[3], p[4], p[5] }, v2[3] = { p[6], p[7], p[8] };
+                        float mn[3] = { bx.x, by.x, bz.x };
+                        float mx[3] = { bx.y, by.y, bz.y };
+                        ov = tri_overlaps_aabb(mn, mx, v0, v1, v2);
+                }
+                const uint32_t bal = __ballot_sync(0xffffffffu, ov);
+                if (c == 0 && idx < n_in)
+                        masks[idx] = (uint8_t)((bal >> (lane & 24u)) & 0xffu);
+                // "child c of this node exists": a plain byte store -- every writer stores the same 1, so no
+                // atomic is needed; the 8 lanes of a pair hit one 8-byte word
+                // (`crowded` levels -- near the root thousands of pairs share a node -- read first: re-storing
+                // a flag that is already set would only queue up behind the other writers of the same sector)
+                if (ov) {
+                        uint8_t* f = child_seen + 8ull * node + c;
+                        if (!crowded || !__ldcg(f))
+                                *f = 1;
+                }
+                cnt += ov ? 1u : 0u;
+        }
+        const uint32_t tot = block_sum_256(cnt);
+        if (threadIdx.x == 0)
+                block_counts[blockIdx.x] = tot;
+}
+
+// child mask (the 8 flag bytes packed into 8 bits) and children per node; *dead_ends counts the nodes
+// none of whose children any triangle reached
+__global__ void k_node_counts(const unsigned long long* __restrict__ child_seen, uint32_t n,
+                              uint32_t* __restrict__ mask, uint32_t* __restrict__ cnt, uint32_t* __restrict__ dead_ends)
+{
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < n) {
+                // byte c (0 or 1) -> bit c: the eight products land on distinct bit positions, no carries
+                const unsigned long long x = child_seen[i] & 0x0101010101010101ull;
+                const uint32_t m = (uint32_t)((x * 0x0102040810204080ull) >> 56);
+                mask[i] = m;
+                cnt[i] = __popc(m);
+                if (!m)
+                        atomicAdd(dead_ends, 1u);
+        }
+}
+
+// totals of one level in one place: out[0] = pairs produced, out[1] = nodes of the next level
+// (out[2] = dead ends so far, accumulated by k_node_counts)
+__global__ void k_publish_totals(const uint32_t* __restrict__ pairs_total, const uint32_t* __restrict__ first_last,
+                                 const uint32_t* __restrict__ cnt_last, uint32_t* __restrict__ out)
+{
+        out[0] = *pairs_total;
+        out[1] = *first_last + *cnt_last;
+}
+
+// ---- dead ends.  A triangle can pass a cell's SAT test and fail all eight children's; the reference
+// then holds an interior node with eight empty leaves, which can never produce a hit, and the flat
+// array does not store such nodes (nor ancestors left without any stored child) -- exactly what the
+// bottom-up derivation of the sorted path yields.  The ranked path removes them afterwards: alive
+// masks bottom-up (in place), an exclusive scan of the alive flags per level = the new ranks, one
+// compaction per level.
+__global__ void k_alive_mask(uint32_t* __restrict__ mask, const uint32_t* __restrict__ first, uint32_t n,
+                             const uint32_t* __restrict__ mask_next)
+{
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n)
+                return;
+        uint32_t m = mask[i], out = 0, pos = first[i];
+        while (m) {
+                const uint32_t c = __ffs((int)m) - 1;
+                m &= m - 1u;
+                if (mask_next[pos++])
+                        out |= 1u << c;
+        }
+        mask[i] = out;
+}
+
+__global__ void k_alive_flags(const uint32_t* __restrict__ mask, uint32_t n, uint32_t* __restrict__ flag)
+{
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i <= n)
+                flag[i] = (i < n && mask[i]) ? 1u : 0u;  // flag[n] = 0: the scan leaves the total there
+}
+
+struct LevelOffsets {
+        uint32_t total_at[VRT_MAX_DEPTH + 1];  // index (into the new-rank buffer) of every level's total
+};
+__global__ void k_collect_totals(const uint32_t* __restrict__ idx_buf, LevelOffsets lo, int levels,
+                                 uint32_t* __restrict__ out)
+{
+        const int l = threadIdx.x;
+        if (l < levels)
+                out[l] = idx_buf[lo.total_at[l]];
+}
+
+__global__ void k_compact_level(const unsigned long long* __restrict__ morton, const uint32_t* __restrict__ mask,
+                                const uint32_t* __restrict__ first, const uint32_t* __restrict__ newidx,
+                                const uint32_t* __restrict__ newidx_next /* null: children are leaves */, uint32_t n,
+                                unsigned long long* __restrict__ out_morton, uint32_t* __restrict__ out_mask,
+                                uint32_t* __restrict__ out_first)
+{
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n)
+                return;
+        const uint32_t m = mask[i];
+        if (!m)
+                return;
+        const uint32_t j = newidx[i];
+        out_morton[j] = morton[i];
+        out_mask[j] = m;
+        // new rank of the first stored child: the exclusive scan counts the stored nodes before first[i]
+        out_first[j] = newidx_next ? newidx_next[first[i]] : first[i];
+}
+
+// Morton codes of the next level's nodes: child c of node i sits at first[i] + popc(mask & below(c))
+__global__ void k_children_morton(const unsigned long long* __restrict__ morton, const uint32_t* __restrict__ mask,
+                                  const uint32_t* __restrict__ first, uint32_t n,
+                                  unsigned long long* __restrict__ child_morton)
+{
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n)
+                return;
+        uint32_t m = mask[i];
+        uint32_t pos = first[i];
+        const unsigned long long base = morton[i] << 3;
+        while (m) {
+                const uint32_t c = __ffs((int)m) - 1;
+                m &= m - 1u;
+                child_morton[pos++] = base | c;
+        }
+}
+
+// Emit pass of the ranked expansion: out key = child rank << 32 | triangle.  At the last level
+// (leaf_cnt != null) it also counts the references of every leaf.
+__global__ void __launch_bounds__(256)
+k_expand_emit_r(const unsigned long long* __restrict__ in, uint32_t n_in, const uint8_t* __restrict__ masks,
+                const uint32_t* __restrict__ block_offs, const uint32_t* __restrict__ node_mask,
+                const uint32_t* __restrict__ node_first, unsigned long long* __restrict__ out,
+                uint32_t* __restrict__ leaf_cnt)
+{
+        const uint32_t idx = blockIdx.x * kPairsPerBlock + threadIdx.x;
+        uint32_t m = 0;
+        unsigned long long key = 0;
+        if (idx < n_in) {
+                m = masks[idx];
+                key = in[idx];
+        }
+        uint32_t pos = block_offs[blockIdx.x] + block_excl_scan_256(__popc(m));
+        if (!m)
+                return;
+        const uint32_t node = (uint32_t)(key >> 32);
+        const unsigned long long t = key & 0xffffffffull;
+        const uint32_t nm = node_mask[node];
+        const uint32_t first = node_first[node];
+        while (m) {
+                const uint32_t c = __ffs((int)m) - 1;
+                m &= m - 1u;
+                const uint32_t rank = first + __popc(nm & ((1u << c) - 1u));
+                out[pos++] = ((unsigned long long)rank << 32) | t;
+                if (leaf_cnt)
+                        atomicAdd(&leaf_cnt[rank], 1u);
+        }
+}
+
+// Counting sort of the last frontier by leaf rank: cursor[leaf] counts DOWN from the leaf's size.
+__global__ void k_leaf_scatter(const unsigned long long* __restrict__ keys, uint64_t n,
+                               const uint32_t* __restrict__ leaf_start, uint32_t* __restrict__ cursor,
+                               uint32_t* __restrict__ refs)
+{
+        const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n)
+                return;
+        const unsigned long long k = keys[i];
+        const uint32_t leaf = (uint32_t)(k >> 32);
+        const uint32_t slot = atomicSub(&cursor[leaf], 1u) - 1u;
+        refs[leaf_start[leaf] + slot] = (uint32_t)k;
+}
+
+constexpr uint32_t kLeafSortSmall = 24;    // up to here: insertion sort by the leaf's thread
+constexpr uint32_t kLeafSortBig = 8192;    // up to here: bitonic sort by one block in shared memory
+
+// Ascending triangle index inside every leaf (= the reference's insertion order).  Leaves with more
+// than kLeafSortSmall references are queued for k_leaf_sort_big.  big[0] = queue length,
+// big[1] = overflow flag (a leaf beyond kLeafSortBig: the caller rebuilds through the sorted path),
+// big[2..] = queued leaf ranks.
+__global__ void k_leaf_sort_small(const uint32_t* __restrict__ leaf_start, uint32_t num_leaves, uint32_t num_refs,
+                                  uint32_t* __restrict__ refs, uint32_t* __restrict__ big, uint32_t big_cap)
+{
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= num_leaves)
+                return;
+        const uint32_t s = leaf_start[i];
+        const uint32_t e = (i + 1 < num_leaves) ? leaf_start[i + 1] : num_refs;
+        const uint32_t cnt = e - s;
+        if (cnt < 2)
+                return;
+        if (cnt > kLeafSortSmall) {
+                if (cnt > kLeafSortBig) {
+                        big[1] = 1u;
+                        return;
+                }
+                const uint32_t q = atomicAdd(&big[0], 1u);
+                if (q < big_cap)
+                        big[2 + q] = i;
+                else
+                        big[1] = 1u;
+                return;
+        }
+        uint32_t* r = refs + s;
+        for (uint32_t a = 1; a < cnt; ++a) {
+                const uint32_t v = r[a];
+                uint32_t b = a;
+                while (b > 0 && r[b - 1] > v) {
+                        r[b] = r[b - 1];
+                        --b;
+                }
+                r[b] = v;
+        }
+}
+
+__global__ void __launch_bounds__(256)
+k_leaf_sort_big(const uint32_t* __restrict__ leaf_start, uint32_t num_leaves, uint32_t num_refs,
+                uint32_t* __restrict__ refs, const uint32_t* __restrict__ big, uint32_t big_cap)
+{
+        __shared__ uint32_t sh[kLeafSortBig];
+        const uint32_t nq = min(big[0], big_cap);
+        for (uint32_t q = blockIdx.x; q < nq; q += gridDim.x) {
+                const uint32_t i = big[2 + q];
+                const uint32_t s = leaf_start[i];
+                const uint32_t e = (i + 1 < num_leaves) ? leaf_start[i + 1] : num_refs;
+                const uint32_t cnt = e - s;
+                uint32_t p2 = 1;
+                while (p2 < cnt)
+                        p2 <<= 1;
+                for (uint32_t k = threadIdx.x; k < p2; k += blockDim.x)
+                        sh[k] = (k < cnt) ? refs[s + k] : 0xffffffffu;
+                __syncthreads();
+                for (uint32_t size = 2; size <= p2; size <<= 1) {
+                        for (uint32_t str = size >> 1; str > 0; str >>= 1) {
+                                for (uint32_t k = threadIdx.x; k < p2; k += blockDim.x) {
+                                        const uint32_t j = k ^ str;
+                                        if (j > k) {
+                                                const uint32_t a = sh[k], b = sh[j];
+                                                const bool up = (k & size) == 0;
+                                                if ((a > b) == up) {
+                                                        sh[k] = b;
+                                                        sh[j] = a;
+                                                }
+                                        }
+                                }
+                                __syncthreads();
+                        }
+                }
+                for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x)
+                        refs[s + k] = sh[k];
+                __syncthreads();
+        }
+}
+
 static int tri_bits_for(uint32_t T)
 {
         int tb = 1;
@@ -474,6 +774,8 @@ static int tri_bits_for(uint32_t T)
                 ++tb;
         return tb;
 }
+
+static int assemble_blob(vrt_tree* t, int L, uint64_t n, const uint64_t* level_n, const float* d_root6);
 
 // Everything after the keys are known: sort (by Morton bits, or by the full key
 // when `sort_full`), leaves, bottom-up levels, blob assembly.
@@ -564,7 +866,17 @@ static int finish_from_keys(vrt_tree* t, unsigned long long* keys, uint64_t n, i
                                                                  t->level_mask[l].as<uint32_t>());
                 count_launch();
         }
-        // --- blob -----------------------------------------------------------------
+        return assemble_blob(t, L, n, level_n, d_root6);
+}
+
+// Blob assembly from the per-level arrays (level_morton / level_first / level_mask, leaf level L:
+// level_first = first ref) and the reference list in refs_s.
+static int assemble_blob(vrt_tree* t, int L, uint64_t n, const uint64_t* level_n, const float* d_root6)
+{
+        cudaStream_t s = t->stream;
+        const uint32_t T = t->hdr.num_tris;
+        const uint64_t num_leaves = level_n[L];
+        Scratch& refs_s = t->refs_s;
         BlobHeader& h = t->hdr;
         h.magic = kBlobMagic;
         h.max_depth = L + 1;
@@ -659,6 +971,197 @@ int sort_keys_u64(vrt_tree* t, uint64_t n, int lo, int hi, unsigned long long** 
         return VRT_OK;
 }
 
+constexpr int VRT_RANKED_FALLBACK = 1000;  // internal: "use the sorted path" (never leaves this file)
+
+// Removes the dead ends of the ranked build (see k_alive_mask); level_n[0..L-1] are updated.
+static int prune_dead_ends(vrt_tree* t, int L, uint64_t* level_n)
+{
+        cudaStream_t s = t->stream;
+        // alive masks, bottom-up, in place (the children of level L-1 are leaves: all stored)
+        for (int l = L - 2; l >= 0; --l) {
+                k_alive_mask<<<grid_for(level_n[l], 256), 256, 0, s>>>(t->level_mask[l].as<uint32_t>(),
+                                                                      t->level_first[l].as<uint32_t>(), (uint32_t)level_n[l],
+                                                                      t->level_mask[l + 1].as<uint32_t>());
+                count_launch();
+        }
+        // new ranks per level: idx_buf[off[l] + i], the level's stored-node total at idx_buf[off[l] + n_l]
+        uint64_t off[VRT_MAX_DEPTH + 1] = { 0 }, tot = 0, nmax = 0;
+        for (int l = 0; l < L; ++l) {
+                off[l] = tot;
+                tot += level_n[l] + 1;
+                nmax = std::max(nmax, level_n[l]);
+        }
+        if (tot >= 0xfffffff0ull) {
+                set_error("octree too large for 32-bit node indices");
+                return VRT_ERR_CAPACITY;
+        }
+        if (t->keys_a.reserve(tot * 4) || t->tmp_b.reserve((nmax + 1) * 4) ||
+            t->tmp_c.reserve(std::max<uint64_t>(scan_scratch_elems(nmax + 1), 16) * 4))
+                return VRT_ERR_NOMEM;
+        uint32_t* idx_buf = t->keys_a.as<uint32_t>();  // (the frontier buffers are free by now)
+        uint32_t* flag = t->tmp_b.as<uint32_t>();
+        LevelOffsets lo{};
+        for (int l = 0; l < L; ++l) {
+                const uint64_t nn = level_n[l];
+                k_alive_flags<<<grid_for(nn + 1, 256), 256, 0, s>>>(t->level_mask[l].as<uint32_t>(), (uint32_t)nn, flag);
+                count_launch();
+                exclusive_scan_u32(flag, idx_buf + off[l], nn + 1, t->tmp_c.as<uint32_t>(), s);
+                lo.total_at[l] = (uint32_t)(off[l] + nn);
+        }
+        uint32_t* d_new = t->d_counter + 40;  // L <= 17 values
+        k_collect_totals<<<1, 32, 0, s>>>(idx_buf, lo, L, d_new);
+        count_launch();
+        VRT_CUDA(cudaMemcpyAsync(t->h_counter + 8, d_new, (size_t)L * 4, cudaMemcpyDeviceToHost, s));
+        VRT_CUDA(cudaStreamSynchronize(s));
+        uint64_t new_n[VRT_MAX_DEPTH + 1];
+        for (int l = 0; l < L; ++l)
+                new_n[l] = t->h_counter[8 + l];
+        // compaction, level by level, through temporaries (an element moves to a lower or equal index,
+        // but in parallel that is only safe out of place)
+        if (t->keys_b.reserve(nmax * 8) || t->tmp_a.reserve(nmax * 4) || t->tmp_b.reserve((nmax + 1) * 4))
+                return VRT_ERR_NOMEM;
+        for (int l = 0; l < L; ++l) {
+                const uint64_t nn = level_n[l];
+                const bool next_changed = (l + 1 < L) && new_n[l + 1] != level_n[l + 1];
+                if (new_n[l] == nn && !next_changed)
+                        continue;
+                k_compact_level<<<grid_for(nn, 256), 256, 0, s>>>(
+                        t->level_morton[l].as<unsigned long long>(), t->level_mask[l].as<uint32_t>(),
+                        t->level_first[l].as<uint32_t>(), idx_buf + off[l], (l + 1 < L) ? idx_buf + off[l + 1] : nullptr,
+                        (uint32_t)nn, t->keys_b.as<unsigned long long>(), t->tmp_a.as<uint32_t>(), t->tmp_b.as<uint32_t>());
+                count_launch();
+                const uint64_t m = new_n[l];
+                if (m) {
+                        VRT_CUDA(cudaMemcpyAsync(t->level_morton[l].p, t->keys_b.p, m * 8, cudaMemcpyDeviceToDevice, s));
+                        VRT_CUDA(cudaMemcpyAsync(t->level_mask[l].p, t->tmp_a.p, m * 4, cudaMemcpyDeviceToDevice, s));
+                        VRT_CUDA(cudaMemcpyAsync(t->level_first[l].p, t->tmp_b.p, m * 4, cudaMemcpyDeviceToDevice, s));
+                }
+        }
+        for (int l = 0; l < L; ++l)
+                level_n[l] = new_n[l];
+        return VRT_OK;
+}
+
+// The ranked top-down build (see the kernels above).  keys_a holds the level-0 frontier
+// (key = triangle index, node rank 0), n0 pairs.
+static int build_ranked(vrt_tree* t, int L, uint64_t n0, const float* d_root6, const float2* tab, uint64_t stride)
+{
+        cudaStream_t s = t->stream;
+        uint32_t* d_tot = t->d_counter + 32;  // [0] pairs produced, [1] nodes of the next level, [2] dead ends
+        VRT_CUDA(cudaMemsetAsync(d_tot, 0, 12, s));
+        uint32_t dead_ends = 0;
+        uint64_t level_n[VRT_MAX_DEPTH + 1] = { 0 };
+        level_n[0] = 1;
+        if (t->level_morton[0].reserve(8) || t->level_mask[0].reserve(4) || t->level_first[0].reserve(4))
+                return VRT_ERR_NOMEM;
+        VRT_CUDA(cudaMemsetAsync(t->level_morton[0].p, 0, 8, s));
+        Scratch* cur = &t->keys_a;
+        Scratch* nxt = &t->keys_b;
+        uint64_t n = n0;
+        for (int l = 0; l < L; ++l) {
+                const uint64_t nn = level_n[l];
+                const uint32_t nblk = (uint32_t)((n + kPairsPerBlock - 1) / kPairsPerBlock);
+                if (t->tmp_b.reserve(n) || t->hist.reserve((nblk + 1ull) * 4) || t->tmp_a.reserve((nn + 1) * 4) ||
+                    t->refs_s.reserve(nn * 8) ||
+                    t->tmp_c.reserve(std::max(scan_scratch_elems(nblk + 1ull), scan_scratch_elems(nn)) * 4))
+                        return VRT_ERR_NOMEM;
+                uint32_t* bc = t->hist.as<uint32_t>();
+                uint32_t* node_mask = t->level_mask[l].as<uint32_t>();
+                uint32_t* node_first = t->level_first[l].as<uint32_t>();
+                uint32_t* node_cnt = t->tmp_a.as<uint32_t>();
+                VRT_CUDA(cudaMemsetAsync(bc + nblk, 0, 4, s));
+                uint8_t* child_seen = t->refs_s.as<uint8_t>();  // (the reference list is written after the last level)
+                VRT_CUDA(cudaMemsetAsync(child_seen, 0, nn * 8, s));
+                k_expand_mask_r<<<nblk, 256, 0, s>>>(t->d_tri_in, tab, stride, cur->as<unsigned long long>(), (uint32_t)n, l,
+                                                     t->level_morton[l].as<unsigned long long>(), child_seen,
+                                                     (n > 16 * nn && n >= (1ull << 20)) ? 1 : 0, t->tmp_b.as<uint8_t>(), bc);
+                count_launch();
+                exclusive_scan_u32(bc, bc, nblk + 1ull, t->tmp_c.as<uint32_t>(), s);
+                k_node_counts<<<grid_for(nn, 256), 256, 0, s>>>(t->refs_s.as<unsigned long long>(), (uint32_t)nn, node_mask,
+                                                                node_cnt, d_tot + 2);
+                count_launch();
+                exclusive_scan_u32(node_cnt, node_first, nn, t->tmp_c.as<uint32_t>(), s);
+                k_publish_totals<<<1, 1, 0, s>>>(bc + nblk, node_first + (nn - 1), node_cnt + (nn - 1), d_tot);
+                count_launch();
+                VRT_CUDA(cudaMemcpyAsync(t->h_counter, d_tot, 12, cudaMemcpyDeviceToHost, s));
+                VRT_CUDA(cudaStreamSynchronize(s));
+                const uint64_t produced = t->h_counter[0], nodes_next = t->h_counter[1];
+                dead_ends = t->h_counter[2];
+                if (produced >= 0xfffffff0ull) {
+                        set_error("more than 2^32 (triangle, cell) pairs at level %d", l + 1);
+                        return VRT_ERR_CAPACITY;
+                }
+                level_n[l + 1] = nodes_next;
+                const bool last = (l + 1 == L);
+                if (nxt->reserve(std::max<uint64_t>(produced, 1) * 8) ||
+                    t->level_morton[l + 1].reserve(std::max<uint64_t>(nodes_next, 1) * 8) ||
+                    t->level_first[l + 1].reserve((nodes_next + 1) * 4) ||
+                    (!last && t->level_mask[l + 1].reserve(std::max<uint64_t>(nodes_next, 1) * 4)))
+                        return VRT_ERR_NOMEM;
+                uint32_t* leaf_cnt = nullptr;
+                if (last) {  // per-leaf reference counters (later: the scatter cursors)
+                        if (t->tmp_a.reserve((nodes_next + 1) * 4))
+                                return VRT_ERR_NOMEM;
+                        leaf_cnt = t->tmp_a.as<uint32_t>();
+                        VRT_CUDA(cudaMemsetAsync(leaf_cnt, 0, (nodes_next + 1) * 4, s));
+                }
+                if (nodes_next) {
+                        k_children_morton<<<grid_for(nn, 256), 256, 0, s>>>(
+                                t->level_morton[l].as<unsigned long long>(), node_mask, node_first, (uint32_t)nn,
+                                t->level_morton[l + 1].as<unsigned long long>());
+                        count_launch();
+                }
+                if (produced) {
+                        k_expand_emit_r<<<nblk, 256, 0, s>>>(cur->as<unsigned long long>(), (uint32_t)n,
+                                                             t->tmp_b.as<uint8_t>(), bc, node_mask, node_first,
+                                                             nxt->as<unsigned long long>(), leaf_cnt);
+                        count_launch();
+                }
+                n = produced;
+                std::swap(cur, nxt);
+                if (!n) {  // nothing below this level (cannot happen for l < L with n > 0 pairs overlapping, kept for safety)
+                        for (int k = l + 2; k <= L; ++k)
+                                level_n[k] = 0;
+                        break;
+                }
+        }
+        const uint64_t num_leaves = level_n[L];
+        if (num_leaves >= 0xfffffff0ull || n >= 0xfffffff0ull) {
+                set_error("octree too large for 32-bit node indices (%llu leaves, %llu refs)",
+                          (unsigned long long)num_leaves, (unsigned long long)n);
+                return VRT_ERR_CAPACITY;
+        }
+        if (!n || !num_leaves)
+                return VRT_RANKED_FALLBACK;
+        // ---- leaf reference lists: counting sort by leaf rank, then ascending inside every leaf ----
+        const uint32_t big_cap = 1u << 16;
+        if (t->refs_s.reserve(n * 4) || t->tmp_c.reserve(std::max<uint64_t>(scan_scratch_elems(num_leaves), 16) * 4) ||
+            t->hist.reserve((2ull + big_cap) * 4))
+                return VRT_ERR_NOMEM;
+        uint32_t* leaf_cnt = t->tmp_a.as<uint32_t>();
+        uint32_t* leaf_start = t->level_first[L].as<uint32_t>();
+        uint32_t* big = t->hist.as<uint32_t>();
+        exclusive_scan_u32(leaf_cnt, leaf_start, num_leaves, t->tmp_c.as<uint32_t>(), s);
+        VRT_CUDA(cudaMemsetAsync(big, 0, 8, s));
+        k_leaf_scatter<<<grid_for(n, 256), 256, 0, s>>>(cur->as<unsigned long long>(), n, leaf_start, leaf_cnt,
+                                                         t->refs_s.as<uint32_t>());
+        k_leaf_sort_small<<<grid_for(num_leaves, 256), 256, 0, s>>>(leaf_start, (uint32_t)num_leaves, (uint32_t)n,
+                                                                    t->refs_s.as<uint32_t>(), big, big_cap);
+        k_leaf_sort_big<<<592, 256, 0, s>>>(leaf_start, (uint32_t)num_leaves, (uint32_t)n, t->refs_s.as<uint32_t>(), big,
+                                            big_cap);
+        count_launch(3);
+        VRT_CUDA(cudaMemcpyAsync(t->h_counter, big, 8, cudaMemcpyDeviceToHost, s));
+        VRT_CUDA(cudaStreamSynchronize(s));
+        if (t->h_counter[1])
+                return VRT_RANKED_FALLBACK;
+        if (dead_ends) {
+                int rc = prune_dead_ends(t, L, level_n);
+                if (rc)
+                        return rc;
+        }
+        return assemble_blob(t, L, n, level_n, d_root6);
+}
+
 int build_tree(vrt_tree* t, int max_depth)
 {
         cudaStream_t s = t->stream;
@@ -703,6 +1206,37 @@ int build_tree(vrt_tree* t, int max_depth)
                 VRT_CUDA(cudaMemcpyAsync(t->h_counter, bc + nblk, 4, cudaMemcpyDeviceToHost, s));
                 VRT_CUDA(cudaStreamSynchronize(s));
                 n = t->h_counter[0];
+        }
+        // the ranked top-down build for everything but shallow trees (whose few leaves hold long
+        // reference lists: those keep the sorted path); VRT_BUILD_SORTED=1 forces the sorted path
+        const char* env_sorted = getenv("VRT_BUILD_SORTED");
+        const bool force_sorted = env_sorted && env_sorted[0] == '1';
+        if (L >= 4 && n && !force_sorted) {
+                int rc = build_ranked(t, L, n, d_root6, tab_s.as<float2>(), stride);
+                if (rc != VRT_RANKED_FALLBACK) {
+                        if (rc)
+                                return rc;
+                        VRT_CUDA(cudaEventRecord(t->ev1, s));
+                        VRT_CUDA(cudaEventSynchronize(t->ev1));
+                        float ms = 0;
+                        VRT_CUDA(cudaEventElapsedTime(&ms, t->ev0, t->ev1));
+                        t->build_ms = ms;
+                        return VRT_OK;
+                }
+                // a leaf with more than kLeafSortBig references: redo the expansion with Morton keys.
+                // keys_a still holds the level-0 frontier only if the ranked build did not swap it away:
+                // simply rebuild it
+                const uint32_t nblk = (T + kPairsPerBlock - 1) / kPairsPerBlock;
+                uint32_t* bc = t->hist.as<uint32_t>();
+                if (t->keys_a.reserve(std::max<uint64_t>(T, 1) * 8) || t->tmp_b.reserve(T) ||
+                    t->hist.reserve((nblk + 1ull) * 4) || t->tmp_c.reserve(scan_scratch_elems(nblk + 1ull) * 4))
+                        return VRT_ERR_NOMEM;
+                bc = t->hist.as<uint32_t>();
+                VRT_CUDA(cudaMemsetAsync(bc + nblk, 0, 4, s));
+                k_root_mask<<<nblk, 256, 0, s>>>(t->d_tri_in, T, d_root6, t->tmp_b.as<uint8_t>(), bc);
+                exclusive_scan_u32(bc, bc, nblk + 1ull, t->tmp_c.as<uint32_t>(), s);
+                k_root_emit<<<nblk, 256, 0, s>>>(T, t->tmp_b.as<uint8_t>(), bc, t->keys_a.as<unsigned long long>());
+                count_launch(2);
         }
         Scratch* cur = &t->keys_a;
         Scratch* nxt = &t->keys_b;
