@@ -489,16 +489,18 @@ __global__ void __launch_bounds__(256)
 k_expand_mask_r(const float* __restrict__ tri, const float2* __restrict__ tab, uint64_t stride,
                 const unsigned long long* __restrict__ in, uint32_t n_in, int level /* of the input cells */,
                 const unsigned long long* __restrict__ node_morton,
-                uint8_t* __restrict__ child_seen /* [nodes][8], zeroed */, int crowded, uint8_t* __restrict__ masks,
-                uint32_t* __restrict__ block_counts)
+                uint8_t* __restrict__ child_seen /* [nodes][8], zeroed */, int crowded, int iters,
+                uint8_t* __restrict__ masks, uint32_t* __restrict__ block_counts)
 {
+        // a block handles 32 * iters pairs (iters = 8: kPairsPerBlock; small frontiers use iters = 1, i.e. 8x
+        // the blocks and no serial loop -- those levels are bound by the latency of one pair's load chain)
         const uint32_t c = threadIdx.x & 7;
         const uint32_t lane = threadIdx.x & 31;
         const uint32_t child_base = 2u << level;  // table offset of level+1
         uint32_t cnt = 0;
 #pragma unroll 1
-        for (int it = 0; it < kPairsPerBlock / 32; ++it) {
-                const uint32_t idx = blockIdx.x * kPairsPerBlock + it * 32 + (threadIdx.x >> 3);
+        for (int it = 0; it < iters; ++it) {
+                const uint32_t idx = (blockIdx.x * iters + it) * 32 + (threadIdx.x >> 3);
                 bool ov = false;
                 uint32_t node = 0;
                 if (idx < n_in) {
@@ -646,7 +648,7 @@ __global__ void __launch_bounds__(256)
 k_expand_emit_r(const unsigned long long* __restrict__ in, uint32_t n_in, const uint8_t* __restrict__ masks,
                 const uint32_t* __restrict__ block_offs, const uint32_t* __restrict__ node_mask,
                 const uint32_t* __restrict__ node_first, unsigned long long* __restrict__ out,
-                uint32_t* __restrict__ leaf_cnt)
+                uint32_t* __restrict__ leaf_cnt, uint32_t offs_per_block /* mask-pass blocks per 256 pairs */)
 {
         const uint32_t idx = blockIdx.x * kPairsPerBlock + threadIdx.x;
         uint32_t m = 0;
@@ -655,7 +657,7 @@ k_expand_emit_r(const unsigned long long* __restrict__ in, uint32_t n_in, const 
                 m = masks[idx];
                 key = in[idx];
         }
-        uint32_t pos = block_offs[blockIdx.x] + block_excl_scan_256(__popc(m));
+        uint32_t pos = block_offs[blockIdx.x * offs_per_block] + block_excl_scan_256(__popc(m));
         if (!m)
                 return;
         const uint32_t node = (uint32_t)(key >> 32);
@@ -1060,7 +1062,10 @@ static int build_ranked(vrt_tree* t, int L, uint64_t n0, const float* d_root6, c
         uint64_t n = n0;
         for (int l = 0; l < L; ++l) {
                 const uint64_t nn = level_n[l];
-                const uint32_t nblk = (uint32_t)((n + kPairsPerBlock - 1) / kPairsPerBlock);
+                const int iters = (n < (1ull << 20)) ? 1 : kPairsPerBlock / 32;
+                const uint32_t ppb = 32u * (uint32_t)iters;  // pairs per block of the mask pass
+                const uint32_t nblk = (uint32_t)((n + ppb - 1) / ppb);
+                const uint32_t nblk_emit = (uint32_t)((n + kPairsPerBlock - 1) / kPairsPerBlock);
                 if (t->tmp_b.reserve(n) || t->hist.reserve((nblk + 1ull) * 4) || t->tmp_a.reserve((nn + 1) * 4) ||
                     t->refs_s.reserve(nn * 8) ||
                     t->tmp_c.reserve(std::max(scan_scratch_elems(nblk + 1ull), scan_scratch_elems(nn)) * 4))
@@ -1074,7 +1079,8 @@ static int build_ranked(vrt_tree* t, int L, uint64_t n0, const float* d_root6, c
                 VRT_CUDA(cudaMemsetAsync(child_seen, 0, nn * 8, s));
                 k_expand_mask_r<<<nblk, 256, 0, s>>>(t->d_tri_in, tab, stride, cur->as<unsigned long long>(), (uint32_t)n, l,
                                                      t->level_morton[l].as<unsigned long long>(), child_seen,
-                                                     (n > 16 * nn && n >= (1ull << 20)) ? 1 : 0, t->tmp_b.as<uint8_t>(), bc);
+                                                     (n > 16 * nn && n >= (1ull << 20)) ? 1 : 0, iters, t->tmp_b.as<uint8_t>(),
+                                                     bc);
                 count_launch();
                 exclusive_scan_u32(bc, bc, nblk + 1ull, t->tmp_c.as<uint32_t>(), s);
                 k_node_counts<<<grid_for(nn, 256), 256, 0, s>>>(t->refs_s.as<unsigned long long>(), (uint32_t)nn, node_mask,
@@ -1112,9 +1118,10 @@ static int build_ranked(vrt_tree* t, int L, uint64_t n0, const float* d_root6, c
                         count_launch();
                 }
                 if (produced) {
-                        k_expand_emit_r<<<nblk, 256, 0, s>>>(cur->as<unsigned long long>(), (uint32_t)n,
-                                                             t->tmp_b.as<uint8_t>(), bc, node_mask, node_first,
-                                                             nxt->as<unsigned long long>(), leaf_cnt);
+                        k_expand_emit_r<<<nblk_emit, 256, 0, s>>>(cur->as<unsigned long long>(), (uint32_t)n,
+                                                                  t->tmp_b.as<uint8_t>(), bc, node_mask, node_first,
+                                                                  nxt->as<unsigned long long>(), leaf_cnt,
+                                                                  (uint32_t)(kPairsPerBlock / ppb));
                         count_launch();
                 }
                 n = produced;
