@@ -254,8 +254,15 @@ def run_ours(args):
     tree = None
     if rank == 0:
         capi.Octree.build(tri[:1024], nrm[:1024], 4).close()  # CUDA context + module load, outside the timing
+        # host triangles in -> octree resident in HBM, on a fresh handle.  The first full-size build of a
+        # process also grows the stream-ordered memory pool from nothing (reported as e2e_first_s); e2e_s is
+        # the same call on another fresh handle once the pool holds the scratch memory of a build, i.e. what
+        # a long-running process pays per scene
         t0 = time.perf_counter()
-        tree = capi.Octree.build(tri, nrm, depth)  # host triangles in -> octree resident in HBM (fresh handle)
+        capi.Octree.build(tri, nrm, depth).close()
+        build["e2e_first_s"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        tree = capi.Octree.build(tri, nrm, depth)
         build["e2e_s"] = time.perf_counter() - t0
         ms = []
         for _ in range(args.build_reps + 1):
@@ -499,6 +506,7 @@ def run_ours(args):
     b_tri = 36 + 12 * rho + 8 * nu
     build_out = {"mtris_per_s": T / (build["ms"] * 1e-3) / 1e6, "ms": build["ms"],
                  "e2e_mtris_per_s": T / build["e2e_s"] / 1e6, "e2e_s": build["e2e_s"],
+                 "e2e_first_s": build["e2e_first_s"],
                  "h2d_bytes": int(tri.nbytes + nrm.nbytes), "bytes_per_tri": b_tri,
                  "roofline_frac": b_tri * T / (build["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
                  "leaves": info["num_leaves"], "nodes": info["num_nodes"], "refs": info["num_refs"]}

@@ -1169,8 +1169,37 @@ static int build_ranked(vrt_tree* t, int L, uint64_t n0, const float* d_root6, c
         return assemble_blob(t, L, n, level_n, d_root6);
 }
 
+// CUDA loads kernels lazily, one by one, at their first launch (a few ms each for the large ones).
+// Which build kernels a scene needs depends on its depth and on the data (sorted or ranked path, dead
+// ends, oversize leaves), so the first build on a device loads them all up front: the cost is paid once
+// per process, at a predictable place, instead of in the middle of some later build.
+static void preload_build_kernels()
+{
+        static bool done = false;
+        if (done)
+                return;
+        done = true;
+        const void* kernels[] = {
+                (const void*)k_aabb_final,      (const void*)k_aabb_partial,    (const void*)k_alive_flags,
+                (const void*)k_alive_mask,      (const void*)k_axis_table,      (const void*)k_children_morton,
+                (const void*)k_collect_totals,  (const void*)k_compact_level,   (const void*)k_emit_leaves,
+                (const void*)k_emit_parents,    (const void*)k_expand_emit,     (const void*)k_expand_emit_r,
+                (const void*)k_expand_mask,     (const void*)k_expand_mask_r,   (const void*)k_head_flags,
+                (const void*)k_leaf_scatter,    (const void*)k_leaf_sort_big,   (const void*)k_leaf_sort_small,
+                (const void*)k_node_counts,     (const void*)k_pack_tris,       (const void*)k_parent_flags,
+                (const void*)k_publish_totals,  (const void*)k_root_emit,       (const void*)k_root_mask,
+                (const void*)k_scan_add,        (const void*)k_scan_tile,       (const void*)k_sort_hist,
+                (const void*)k_sort_scatter,    (const void*)k_write_interior,  (const void*)k_write_leaves,
+        };
+        cudaFuncAttributes a;
+        for (const void* k : kernels)
+                if (cudaFuncGetAttributes(&a, k) != cudaSuccess)
+                        cudaGetLastError();
+}
+
 int build_tree(vrt_tree* t, int max_depth)
 {
+        preload_build_kernels();
         cudaStream_t s = t->stream;
         const uint32_t T = t->hdr.num_tris;
         const int L = max_depth - 1;
