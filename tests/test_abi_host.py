@@ -135,3 +135,16 @@ def test_split_level_closed_form_equals_rounded_log2f():
     ref = np.log2(xs.astype(np.float64)).astype(np.float32).astype(np.int64)
     assert np.array_equal(split_level(xs), ref)
     assert (ref != np.floor(np.log2(xs.astype(np.float64)))).sum() > 100  # the rounded-up floats are in the sample
+
+
+def test_child_flag_bytes_pack_to_mask():
+    """The ranked octree build records "child c exists" as eight flag bytes per node and packs them into the
+    8-bit child mask with one multiply (k_node_counts, csrc/vrt_build.cu): byte c (0 or 1) -> bit c.  The
+    eight partial products land on distinct bit positions, so there are no carries; checked for all 256
+    patterns (and with garbage in the upper 7 bits of every byte, which the kernel masks off)."""
+    for m in range(256):
+        x = sum(((m >> c) & 1) << (8 * c) for c in range(8))
+        for noise in (0, 0xFEFEFEFEFEFEFEFE, 0xA4A4A4A4A4A4A4A4 & 0xFEFEFEFEFEFEFEFE):
+            v = (x | noise) & 0x0101010101010101
+            got = ((v * 0x0102040810204080) & 0xFFFFFFFFFFFFFFFF) >> 56
+            assert got == m, (m, hex(noise), got)

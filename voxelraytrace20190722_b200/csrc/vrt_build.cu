@@ -12,9 +12,14 @@
 //   * leaves hold triangle indices in ascending order.
 // Pipeline: root AABB reduction -> per-axis interval table -> root filter ->
 // L x expand (8 lanes per (triangle, cell) pair, one SAT test per lane; mask pass,
-// scan, emit pass: deterministic, no atomics; keys Morton<<tb | tri stay sorted by
-// (triangle, Morton)) -> stable LSD radix sort on the Morton bits -> unique ->
-// bottom-up parent derivation -> flat pointerless node array.
+// scan, emit pass: deterministic) -> flat pointerless node array, by one of two drivers:
+//   ranked (default, depth >= 5): the frontier carries node ranks, the node arrays come out
+//     of the expansion itself, the leaf reference lists out of a counting sort (see
+//     "RANKED top-down build" below);
+//   sorted (shallow trees, imports, oversize leaves): keys Morton<<tb | tri stay sorted by
+//     (triangle, Morton) -> stable LSD radix sort on the Morton bits -> unique -> bottom-up
+//     parent derivation.
+// Both produce the same bytes.
 #include <algorithm>
 #include <cfloat>
 #include <cstdlib>
