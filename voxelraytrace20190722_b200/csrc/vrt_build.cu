@@ -1264,15 +1264,13 @@ int build_tree(vrt_tree* t, int max_depth)
                         t->build_ms = ms;
                         return VRT_OK;
                 }
-                // a leaf with more than kLeafSortBig references: redo the expansion with Morton keys.
-                // keys_a still holds the level-0 frontier only if the ranked build did not swap it away:
-                // simply rebuild it
+                // a leaf with more than kLeafSortBig references (or no leaf at all): redo the expansion with
+                // Morton keys.  The ranked build has overwritten the level-0 frontier: rebuild it first.
                 const uint32_t nblk = (T + kPairsPerBlock - 1) / kPairsPerBlock;
-                uint32_t* bc = t->hist.as<uint32_t>();
                 if (t->keys_a.reserve(std::max<uint64_t>(T, 1) * 8) || t->tmp_b.reserve(T) ||
                     t->hist.reserve((nblk + 1ull) * 4) || t->tmp_c.reserve(scan_scratch_elems(nblk + 1ull) * 4))
                         return VRT_ERR_NOMEM;
-                bc = t->hist.as<uint32_t>();
+                uint32_t* bc = t->hist.as<uint32_t>();
                 VRT_CUDA(cudaMemsetAsync(bc + nblk, 0, 4, s));
                 k_root_mask<<<nblk, 256, 0, s>>>(t->d_tri_in, T, d_root6, t->tmp_b.as<uint8_t>(), bc);
                 exclusive_scan_u32(bc, bc, nblk + 1ull, t->tmp_c.as<uint32_t>(), s);
