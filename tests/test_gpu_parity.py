@@ -460,6 +460,25 @@ def test_render_async_pipeline_matches_sync(case, gpu):
         assert np.array_equal(e.view(np.uint32), b.numpy().view(np.uint32))
 
 
+def test_sync_waits_for_film_copies_of_large_frames(case, gpu):
+    """vrt_tree_sync() must also wait for the device->host film copies (they run on the handle's copy
+    stream, the kernels on two alternating streams): with 4K films the bytes are compared immediately
+    after sync(), three frames in flight, against the synchronous call."""
+    torch = pytest.importorskip("torch")
+    cam10 = case["cam10"]
+    nx, ny, spp = 3840, 2160, 1
+    cams = [gpu.Camera(cam10[0], cam10[1:4] + np.float32(0.02 * k), cam10[4:7], cam10[7:10], nx, ny, spp)
+            for k in range(3)]
+    tree = case["tree"]
+    bufs = [torch.full((ny, nx, 3), -7.0, dtype=torch.float32).pin_memory() for _ in cams]
+    for c, b in zip(cams, bufs):
+        tree.render_async(c, b.numpy())
+    tree.sync()
+    got = [b.numpy().copy() for b in bufs]  # snapshot right after sync(), before any other CUDA call
+    for c, g in zip(cams, got):
+        assert np.array_equal(tree.render(c).view(np.uint32), g.view(np.uint32))
+
+
 @pytest.mark.parametrize("world", [1, 3])
 def test_render_bands_async_assembles_host_frame(case, gpu, world):
     """vrt_render_bands_async: every "rank" (here: the ranks of a 3-GPU run one after the other on one GPU)

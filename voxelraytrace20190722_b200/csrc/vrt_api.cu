@@ -9,6 +9,7 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#include <sys/types.h>
 
 #include "vrt_exact.cuh"
 #include "vrt_internal.h"
@@ -134,6 +135,7 @@ void tree_bind_views(vrt_tree* t)
                 d.tab4[a] = reinterpret_cast<const float4*>(d.tab2[a]);
         }
         d.gi = nullptr;  // GI state belongs to one node array: vrt_gi_init after every (re)build
+        d.hull = nullptr;  // compute_hulls() follows every bind
         d.num_nodes = (uint32_t)h.num_nodes;
         d.num_leaves = (uint32_t)h.num_leaves;
         d.L = h.max_depth - 1;
@@ -429,7 +431,7 @@ using namespace vrt;
 uint64_t vrt_tree::scratch_bytes() const
 {
         uint64_t b = keys_a.cap + keys_b.cap + tmp_a.cap + tmp_b.cap + tmp_c.cap + hist.cap + refs_s.cap + tab_s.cap +
-                     io_in.cap + io_out.cap;
+                     io_in.cap + io_out.cap + hull_buf.cap;
         for (unsigned l = 0; l <= VRT_MAX_DEPTH; ++l)
                 b += level_morton[l].cap + level_first[l].cap + level_mask[l].cap;
         return b;
@@ -503,6 +505,7 @@ void vrt_tree_free(vrt_tree* t)
         t->tab_s.release();
         t->io_in.release();
         t->gi_buf.release();
+        t->hull_buf.release();
         t->gi_recs.release();
         t->mat_buf.release();
         t->io_out.release();
@@ -510,6 +513,8 @@ void vrt_tree_free(vrt_tree* t)
         t->film_dev[1].release();
         if (t->copy_stream)
                 cudaStreamDestroy(t->copy_stream);
+        if (t->alt_stream)
+                cudaStreamDestroy(t->alt_stream);
         for (int i = 0; i < 2; ++i) {
                 if (t->film_ready[i])
                         cudaEventDestroy(t->film_ready[i]);
@@ -657,6 +662,35 @@ int vrt_tree_blob_dev(const vrt_tree* t, const void** d_blob, uint64_t* bytes)
         return VRT_OK;
 }
 
+// A blob comes from another process or from a file: every size and offset of its header is checked
+// against the blob before a kernel may follow it (a truncated or corrupt checkpoint is VRT_ERR_ARG,
+// not an out-of-bounds read on the device).
+static bool blob_header_ok(const BlobHeader& h, uint64_t bytes)
+{
+        if (h.magic != kBlobMagic || h.bytes > bytes || h.bytes < kHeaderBytes)
+                return false;
+        if (h.max_depth < 1 || h.max_depth > (int)VRT_MAX_DEPTH)
+                return false;
+        const int L = h.max_depth - 1;
+        if (h.num_nodes >= 0xffffffffull || h.num_leaves > h.num_nodes || h.num_refs >= (1ull << 40))
+                return false;
+        if (h.level_offset[0] != 0)
+                return false;
+        for (int l = 0; l <= L; ++l)
+                if (h.level_offset[l + 1] < h.level_offset[l])
+                        return false;
+        if (h.level_offset[L + 1] != h.num_nodes || h.level_offset[L + 1] - h.level_offset[L] != h.num_leaves)
+                return false;
+        if (h.axis_tab_stride != (2ull << L))
+                return false;
+        auto fits = [&](uint64_t off, uint64_t count, uint64_t elem) {
+                return off >= kHeaderBytes && off <= h.bytes && count <= (h.bytes - off) / elem;
+        };
+        return fits(h.off_nodes, h.num_nodes, 8) && fits(h.off_leaf_morton, h.num_leaves, 8) &&
+               fits(h.off_leaf_refs, h.num_refs, 4) && fits(h.off_tri4, 3ull * h.num_tris, 16) &&
+               fits(h.off_nrm, 9ull * h.num_tris, 4) && fits(h.off_axis_tab, 3ull * h.axis_tab_stride, 8);
+}
+
 int vrt_tree_from_blob_dev(const void* d_blob, uint64_t bytes, vrt_tree** out)
 {
         if (!d_blob || !out || bytes < kHeaderBytes) {
@@ -673,8 +707,8 @@ int vrt_tree_from_blob_dev(const void* d_blob, uint64_t bytes, vrt_tree** out)
                 vrt_tree_free(t);
                 return VRT_ERR_CUDA;
         }
-        if (h.magic != kBlobMagic || h.bytes > bytes || h.max_depth < 1 || h.max_depth > (int)VRT_MAX_DEPTH) {
-                set_error("not a vrt octree blob (magic/size mismatch)");
+        if (!blob_header_ok(h, bytes)) {
+                set_error("not a valid vrt octree blob (magic, sizes or section offsets inconsistent)");
                 vrt_tree_free(t);
                 return VRT_ERR_ARG;
         }
@@ -690,6 +724,11 @@ int vrt_tree_from_blob_dev(const void* d_blob, uint64_t bytes, vrt_tree** out)
         }
         t->hdr = h;
         tree_bind_views(t);
+        rc = compute_hulls(t);
+        if (rc) {
+                vrt_tree_free(t);
+                return rc;
+        }
         *out = t;
         return VRT_OK;
 }
@@ -732,10 +771,10 @@ int vrt_tree_load(const char* path, vrt_tree** out)
                 set_error("cannot open %s", path);
                 return VRT_ERR_ARG;
         }
-        fseek(f, 0, SEEK_END);
-        const long sz = ftell(f);
-        fseek(f, 0, SEEK_SET);
-        if (sz < (long)kHeaderBytes) {
+        fseeko(f, 0, SEEK_END);
+        const off_t sz = ftello(f);
+        fseeko(f, 0, SEEK_SET);
+        if (sz < (off_t)kHeaderBytes) {
                 fclose(f);
                 set_error("%s is not a vrt octree checkpoint", path);
                 return VRT_ERR_ARG;
@@ -745,7 +784,7 @@ int vrt_tree_load(const char* path, vrt_tree** out)
         fclose(f);
         BlobHeader h;
         memcpy(&h, host.data(), sizeof h);
-        if (r != host.size() || h.magic != kBlobMagic || h.bytes > (uint64_t)sz) {
+        if (r != host.size() || !blob_header_ok(h, (uint64_t)sz)) {
                 set_error("%s is not a vrt octree checkpoint (magic/size mismatch)", path);
                 return VRT_ERR_ARG;
         }
@@ -907,6 +946,27 @@ static int trace_camera_common(const vrt_tree* tc, const vrt_camera* cam, const 
         return VRT_OK;
 }
 
+// Streams and events of the pipelined frame loops (vrt_render_camera_async / vrt_render_bands_async): a copy
+// stream for the device->host film copies and a second kernel stream, so that consecutive frames alternate
+// between two kernel streams (the persistent grid of frame k+1 starts while the last long rays of frame k
+// still run) while their copies queue up on the copy stream.
+static int async_pipeline_prepare(vrt_tree* t)
+{
+        if (!t->copy_stream) {
+                VRT_CUDA(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+                VRT_CUDA(cudaStreamCreateWithFlags(&t->alt_stream, cudaStreamNonBlocking));
+                for (int i = 0; i < 2; ++i) {
+                        VRT_CUDA(cudaEventCreateWithFlags(&t->film_ready[i], cudaEventDisableTiming));
+                        VRT_CUDA(cudaEventCreateWithFlags(&t->film_copied[i], cudaEventDisableTiming));
+                }
+        }
+        if (t->n_async_frames == 0)  // the alternate stream starts behind everything enqueued so far
+                VRT_CUDA(cudaStreamSynchronize(t->stream));
+        return VRT_OK;
+}
+// kernel stream of async frame k: even frames on the handle's stream, odd frames on the alternate one
+static cudaStream_t async_kernel_stream(const vrt_tree* t) { return (t->n_async_frames & 1) ? t->alt_stream : t->stream; }
+
 // Pipelined frame loop: the kernel of frame k+1 runs while frame k's film crosses PCIe.
 int vrt_render_camera_async(const vrt_tree* tc, const vrt_camera* cam, const vrt_shade* sh, int x0, int y0, int x1,
                             int y1, float* film_rgb)
@@ -925,13 +985,10 @@ int vrt_render_camera_async(const vrt_tree* tc, const vrt_camera* cam, const vrt
                 return VRT_ERR_ARG;
         }
         vrt_tree* t = const_cast<vrt_tree*>(tc);
-        if (!t->copy_stream) {
-                VRT_CUDA(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
-                for (int i = 0; i < 2; ++i) {
-                        VRT_CUDA(cudaEventCreateWithFlags(&t->film_ready[i], cudaEventDisableTiming));
-                        VRT_CUDA(cudaEventCreateWithFlags(&t->film_copied[i], cudaEventDisableTiming));
-                }
-        }
+        rc = async_pipeline_prepare(t);
+        if (rc)
+                return rc;
+        cudaStream_t ks = async_kernel_stream(t);
         const int k = (int)(t->n_async_frames & 1);
         const uint64_t bytes = npix * 12;
         if (t->film_dev[k].cap < bytes) {
@@ -940,11 +997,13 @@ int vrt_render_camera_async(const vrt_tree* tc, const vrt_camera* cam, const vrt
                         return VRT_ERR_NOMEM;
         }
         if (t->n_async_frames >= 2)  // the copy that last read this device film must be done
-                VRT_CUDA(cudaStreamWaitEvent(t->stream, t->film_copied[k], 0));
+                VRT_CUDA(cudaStreamWaitEvent(ks, t->film_copied[k], 0));
+        t->launch_stream = ks;
         rc = launch_trace_camera(t, cam, sh, x0, y0, x1, y1, t->film_dev[k].p, OUT_FILM);
+        t->launch_stream = nullptr;
         if (rc)
                 return rc;
-        VRT_CUDA(cudaEventRecord(t->film_ready[k], t->stream));
+        VRT_CUDA(cudaEventRecord(t->film_ready[k], ks));
         VRT_CUDA(cudaStreamWaitEvent(t->copy_stream, t->film_ready[k], 0));
         VRT_CUDA(cudaMemcpyAsync(film_rgb, t->film_dev[k].p, bytes, cudaMemcpyDeviceToHost, t->copy_stream));
         VRT_CUDA(cudaEventRecord(t->film_copied[k], t->copy_stream));
@@ -1067,13 +1126,10 @@ int vrt_render_bands_async(const vrt_tree* tc, const vrt_camera* cam, const vrt_
                 return VRT_ERR_ARG;
         }
         vrt_tree* t = const_cast<vrt_tree*>(tc);
-        if (!t->copy_stream) {
-                VRT_CUDA(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
-                for (int i = 0; i < 2; ++i) {
-                        VRT_CUDA(cudaEventCreateWithFlags(&t->film_ready[i], cudaEventDisableTiming));
-                        VRT_CUDA(cudaEventCreateWithFlags(&t->film_copied[i], cudaEventDisableTiming));
-                }
-        }
+        rc = async_pipeline_prepare(t);
+        if (rc)
+                return rc;
+        cudaStream_t ks = async_kernel_stream(t);
         const int k = (int)(t->n_async_frames & 1);
         const size_t row_bytes = (size_t)cam->nx * 12;
         const uint64_t bytes = (uint64_t)rows * row_bytes;
@@ -1083,13 +1139,15 @@ int vrt_render_bands_async(const vrt_tree* tc, const vrt_camera* cam, const vrt_
                         return VRT_ERR_NOMEM;
         }
         if (t->n_async_frames >= 2)  // the copy that last read this device buffer must be done
-                VRT_CUDA(cudaStreamWaitEvent(t->stream, t->film_copied[k], 0));
+                VRT_CUDA(cudaStreamWaitEvent(ks, t->film_copied[k], 0));
         const int y0 = b->band_first * b->band_h;
+        t->launch_stream = ks;
         rc = launch_trace_camera(t, cam, sh, 0, y0, cam->nx, y0 + rows, t->film_dev[k].p, OUT_FILM, b->band_h,
                                  b->band_stride * b->band_h);
+        t->launch_stream = nullptr;
         if (rc)
                 return rc;
-        VRT_CUDA(cudaEventRecord(t->film_ready[k], t->stream));
+        VRT_CUDA(cudaEventRecord(t->film_ready[k], ks));
         VRT_CUDA(cudaStreamWaitEvent(t->copy_stream, t->film_ready[k], 0));
         // full bands: one 2-D copy, "row" = one band of band_h film rows; then the last, shorter band
         const size_t band_bytes = (size_t)b->band_h * row_bytes;
@@ -1368,6 +1426,14 @@ int vrt_tree_sync(const vrt_tree* t)
                 return VRT_ERR_ARG;
         }
         VRT_CUDA(cudaStreamSynchronize(t->stream));
+        // the async frame loops also run kernels on alt_stream and film copies on copy_stream: after this
+        // call the films of every enqueued frame are in host memory (include/vrt.h)
+        if (t->alt_stream)
+                VRT_CUDA(cudaStreamSynchronize(t->alt_stream));
+        if (t->copy_stream)
+                VRT_CUDA(cudaStreamSynchronize(t->copy_stream));
+        // the next async frame starts a new sequence (its stream is ordered behind the handle's stream again)
+        const_cast<vrt_tree*>(t)->n_async_frames = 0;
         return VRT_OK;
 }
 

@@ -962,7 +962,7 @@ static int assemble_blob(vrt_tree* t, int L, uint64_t n, const uint64_t* level_n
         VRT_CUDA(cudaMemcpyAsync(base, &h, sizeof h, cudaMemcpyHostToDevice, s));
         VRT_CUDA(cudaStreamSynchronize(s));
         tree_bind_views(t);
-        return VRT_OK;
+        return compute_hulls(t);
 }
 
 int sort_keys_u64(vrt_tree* t, uint64_t n, int lo, int hi, unsigned long long** sorted)
@@ -1356,6 +1356,83 @@ int import_leaves(vrt_tree* t, int max_depth, const float root_aabb[6], uint64_t
         VRT_CUDA(cudaMemcpyAsync(d_root6, root_aabb, 24, cudaMemcpyHostToDevice, s));
         VRT_CUDA(cudaStreamSynchronize(s));
         return finish_from_keys(t, t->keys_a.as<unsigned long long>(), n, L, tb, false, d_root6);
+}
+
+// ---------------------------------------------------------------------------
+// Content hulls (round 2).  hull[i] of interior node i = per axis the smallest min plane and the
+// largest max plane over the node's non-empty LEAF cells, as the very floats of the leaf level of
+// the axis table (no arithmetic: min/max of existing values).  Bottom-up, one launch per level;
+// the parents of leaves read the leaf cells through leaf_morton, the levels above combine their
+// children's hulls.  The ray kernels skip a child whose hull the ray misses: for a tame ray
+// t(p) = (p - o) * dinv is monotone in p after rounding, so every leaf cell's per-axis slab
+// interval lies inside the hull's and a leaf the reference would accept implies
+// max(t0_hull, tmin) <= min(t1_hull, tmax); the contrapositive is the prune.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_hull_level(const uint2* __restrict__ nodes, const unsigned long long* __restrict__ leaf_morton,
+             const float2* __restrict__ tx, const float2* __restrict__ ty, const float2* __restrict__ tz,
+             uint64_t begin, uint64_t count, int child_is_leaf, uint64_t leaf_base, float2* __restrict__ hull)
+{
+        const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= count)
+                return;
+        const uint64_t node = begin + i;
+        const uint2 rec = nodes[node];
+        const uint32_t n = (uint32_t)__popc(rec.y & 0xffu);
+        const float inf = __int_as_float(0x7f800000);
+        float2 hx = make_float2(inf, -inf), hy = hx, hz = hx;
+        for (uint32_t c = 0; c < n; ++c) {
+                const uint64_t ch = (uint64_t)rec.x + c;
+                float2 bx, by, bz;
+                if (child_is_leaf) {
+                        const unsigned long long m = leaf_morton[ch - leaf_base];
+                        bx = tx[compact1by2(m >> 2)];
+                        by = ty[compact1by2(m >> 1)];
+                        bz = tz[compact1by2(m)];
+                } else {
+                        bx = hull[3 * ch];
+                        by = hull[3 * ch + 1];
+                        bz = hull[3 * ch + 2];
+                }
+                hx.x = fminf(hx.x, bx.x); hx.y = fmaxf(hx.y, bx.y);
+                hy.x = fminf(hy.x, by.x); hy.y = fmaxf(hy.y, by.y);
+                hz.x = fminf(hz.x, bz.x); hz.y = fmaxf(hz.y, bz.y);
+        }
+        hull[3 * node] = hx;
+        hull[3 * node + 1] = hy;
+        hull[3 * node + 2] = hz;
+}
+
+int compute_hulls(vrt_tree* t)
+{
+        const BlobHeader& h = t->hdr;
+        const int L = h.max_depth - 1;
+        t->dev.hull = nullptr;
+        static int enabled = -1;
+        if (enabled < 0) {
+                const char* e = getenv("VRT_HULL");
+                enabled = (e && e[0] == '0') ? 0 : 1;
+        }
+        if (!enabled || L < 1 || h.num_nodes == 0)
+                return VRT_OK;
+        const uint64_t interior = h.num_nodes - h.num_leaves;
+        if (t->hull_buf.reserve(std::max<uint64_t>(interior, 1) * 24))
+                return VRT_ERR_NOMEM;
+        float2* hull = t->hull_buf.as<float2>();
+        const uint64_t leaf_base = h.level_offset[L];
+        const uint64_t lv = 1ull << L;  // leaf-level entries of the axis table
+        for (int l = L - 1; l >= 0; --l) {
+                const uint64_t begin = h.level_offset[l], count = h.level_offset[l + 1] - begin;
+                if (!count)
+                        continue;
+                k_hull_level<<<grid_for(count, 256), 256, 0, t->stream>>>(t->dev.nodes, t->dev.leaf_morton, t->dev.tab2[0] + lv,
+                                                                          t->dev.tab2[1] + lv, t->dev.tab2[2] + lv, begin, count,
+                                                                          l + 1 == L ? 1 : 0, leaf_base, hull);
+                count_launch();
+        }
+        VRT_CUDA(cudaGetLastError());
+        t->dev.hull = hull;
+        return VRT_OK;
 }
 
 }  // namespace vrt

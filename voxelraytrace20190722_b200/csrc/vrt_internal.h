@@ -72,6 +72,11 @@ struct TreeDev {
                                 // children of cell x at level l
         const float2* tab2[3];
         const float* gi;  // per-node GI state (vrt_gi.cuh), or null before vrt_gi_init
+        // content hull of every INTERIOR node (round 2): per node three float2 (min,max) per axis = the
+        // extreme leaf-cell planes (floats of the axis table) over the node's non-empty leaves.  A ray whose
+        // slab interval over the hull is empty cannot pass the slab test of any leaf below (monotone rounding),
+        // so the subtree is skipped without changing any result.  Null: no pruning.
+        const float2* hull;
         // materials (vrt_set_materials), all null when unset: per-vertex texture coordinates, material id per
         // triangle, per material (kd.xyz, texture id or -1 as int bits), per texture (byte offset, w, h, channels)
         const float2* mat_uv;
@@ -128,9 +133,15 @@ struct vrt_tree {
         vrt::Scratch io_in, io_out;
         // GI rows: per-node coverage + illum[6], see vrt_gi.cuh
         vrt::Scratch gi_buf, gi_recs, mat_buf;
+        vrt::Scratch hull_buf;  // TreeDev::hull
         // pipelined host-film path (vrt_render_camera_async): two device films, a copy stream
         vrt::Scratch film_dev[2];
         cudaStream_t copy_stream = nullptr;
+        // the async frame loops alternate their kernels between `stream` and `alt_stream`, so that the head of
+        // frame k+1 fills the SMs the long-ray tail of frame k leaves idle; launch_stream (when set) overrides
+        // `stream` for the next trace launch
+        cudaStream_t alt_stream = nullptr;
+        mutable cudaStream_t launch_stream = nullptr;
         cudaEvent_t film_ready[2] = {}, film_copied[2] = {};
         mutable uint64_t n_async_frames = 0;
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // build timing
@@ -152,6 +163,8 @@ int tree_alloc(vrt_tree** out);
 void tree_bind_views(vrt_tree* t);
 // build pipeline (vrt_build.cu)
 int build_tree(vrt_tree* t, int max_depth);
+// per-node content hulls beside the blob (after tree_bind_views; every build / import / replica)
+int compute_hulls(vrt_tree* t);
 int import_leaves(vrt_tree* t, int max_depth, const float root_aabb[6], uint64_t num_leaves,
                   const uint32_t* leaf_cell, const uint32_t* leaf_count,
                   const uint32_t* leaf_refs);

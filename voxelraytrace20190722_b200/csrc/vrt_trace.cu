@@ -59,6 +59,7 @@ struct TraceParams {
         float root[6];
         float kd3[3];  // GI modes: the material's diffuse colour (untextured albedo)
         float gi_res;  // GI film: min_voxel_size of cone_trace (main.cc:69-70)
+        uint32_t lut_off;  // warp-synchronous kernels: byte offset of the mask table in dynamic shared memory
 };
 
 struct HitState {
@@ -79,12 +80,12 @@ struct WorkCount {
         uint32_t n_param, n_tie, n_unsafe;
 };
 
-// Triangle::isect + ray_march_isect for one leaf (voxel_octree.cc:99-129,438-460).
+// Triangle::isect + ray_march_isect for one leaf (voxel_octree.cc:99-129,438-460); rec = the leaf's node
+// record {first reference, reference count}.
 template <bool COUNT>
-__device__ __forceinline__ bool leaf_isect(const TreeDev& tr, uint32_t leaf_node, const float o[3],
-                                           const float d[3], HitState& hs, WorkCount& wc)
+__device__ __forceinline__ bool leaf_isect_rec(const TreeDev& tr, const uint2 rec, const float o[3],
+                                               const float d[3], HitState& hs, WorkCount& wc)
 {
-        const uint2 rec = __ldg(&tr.nodes[leaf_node]);
         if (COUNT) {
                 wc.n_leaf += 1;
                 wc.n_tri += rec.y;
@@ -121,6 +122,13 @@ __device__ __forceinline__ bool leaf_isect(const TreeDev& tr, uint32_t leaf_node
                 }
         }
         return found;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ bool leaf_isect(const TreeDev& tr, uint32_t leaf_node, const float o[3],
+                                           const float d[3], HitState& hs, WorkCount& wc)
+{
+        return leaf_isect_rec<COUNT>(tr, __ldg(&tr.nodes[leaf_node]), o, d, hs, wc);
 }
 
 // ISect of the winning triangle (voxel_octree.cc:449-454).
@@ -500,6 +508,23 @@ __device__ __forceinline__ int param_safe_levels(const float root[6], const floa
 __device__ unsigned long long g_param_check[4] = { 0, 0, 0, 0 };  // checked, mismatches, -, -
 #endif
 
+// Can the (tame) ray reach any non-empty leaf below interior node `node`?  Slab interval of the ray
+// over the node's content hull (TreeDev::hull) against the window, as an OVERLAP test: every leaf
+// cell below lies inside the hull plane by plane and rounding is monotone, so a leaf that passes the
+// reference's slab test implies max(t0,tmin) <= min(t1,tmax) here.  false = the subtree cannot
+// produce a hit; skipping it changes no result.
+__device__ __forceinline__ bool hull_reachable(const float2* __restrict__ hull, uint32_t node, const float o[3],
+                                               const float dinv[3], float tmin, float tmax)
+{
+        const float2 hx = __ldg(&hull[3ull * node]), hy = __ldg(&hull[3ull * node + 1]), hz = __ldg(&hull[3ull * node + 2]);
+        const float2 ax = mul2s(sub2s(hx.x, hx.y, o[0]), dinv[0]);
+        const float2 ay = mul2s(sub2s(hy.x, hy.y, o[1]), dinv[1]);
+        const float2 az = mul2s(sub2s(hz.x, hz.y, o[2]), dinv[2]);
+        const float t0 = fmax3(fminf(ax.x, ax.y), fminf(ay.x, ay.y), fminf(az.x, az.y));
+        const float t1 = fmin3(fmaxf(ax.x, ax.y), fmaxf(ay.x, ay.y), fmaxf(az.x, az.y));
+        return fmaxf(t0, tmin) <= fminf(t1, tmax);
+}
+
 // FAST path.  Node expansion is PARAMETRIC: with t(p) = (p-o)*dinv the nine child-plane
 // parameters of a node (three planes per axis; exactly the floats the reference's eight slab
 // tests are made of), a child's slab interval is the intersection of three per-axis intervals
@@ -549,7 +574,8 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
         // child is 2*i + bit and an ancestor i >> k.  The return stack is addressed through one
         // register holding this thread's shared-memory byte address of the next free record.
         int level = 0;
-        uint32_t x = 1, y = 1, z = 1, node = 0;
+        uint32_t x = 1, y = 1, z = 1;
+        uint2 rec = __ldg(&tr.nodes[0]);  // record of the node to expand (a child's is fetched with its hull)
         // visiting list of the node being iterated: 4 bits per entry, lowest first, entry =
         // 8 | child id -- an empty list is the value 0, so no separate count is carried
         uint32_t first, mask, list;
@@ -560,9 +586,8 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
         constexpr uint32_t kCol = stride * 4u;  // bytes between the three words of a record
         constexpr uint32_t kRec = 3u * kCol;    // bytes between records of one thread
         for (;;) {
-                // ---- expand `node` (level; x,y,z) -------------------------------------------
+                // ---- expand the node of `rec` (level; x,y,z) ---------------------------------
                 {
-                        const uint2 rec = __ldg(&tr.nodes[node]);
                         if (COUNT)
                                 wc.n_int += 1;
                         first = rec.x;
@@ -691,6 +716,11 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 }
                                 continue;
                         }
+                        rec = __ldg(&tr.nodes[child]);
+                        // content hull: skip a child under which the ray cannot reach a non-empty leaf
+                        // (not in the counting mode, which reports the reference algorithm's work)
+                        if (!COUNT && tr.hull != nullptr && !hull_reachable(tr.hull, child, o, dinv, tmin, tmax))
+                                continue;
                         if (list != 0u) {  // remember this level only if it has children left
                                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(first) : "memory");
                                 asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(sp), "n"(kCol),
@@ -703,7 +733,6 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                         x = cx;
                         y = cy;
                         z = cz;
-                        node = child;
                         break;
                 }
         }
@@ -727,6 +756,264 @@ __device__ __forceinline__ void trace_one(const TreeDev& tr, const float root[6]
                 trace_one_exact<COUNT>(tr, root, o, d, tmin, tmax, s_first, s_meta, s_list, hs, wc);
 }
 
+// Out-of-line copy of the per-ray traversal: the fallback of the warp-synchronous kernels (and
+// their shadow rays), so that the per-ray code exists once and off the hot path.  Everything goes
+// in and out BY VALUE: the caller's ray and hit state never have their address taken and stay
+// in registers on the hot path.
+struct PtResult {
+        HitState hs;
+        WorkCount wc;
+};
+template <bool COUNT>
+__device__ __noinline__ PtResult trace_one_nl(const TreeDev& tr, const float* root, float ox, float oy, float oz,
+                                              float dx, float dy, float dz, float tmin, float tmax, uint32_t* s_first)
+{
+        PtResult r;
+        r.wc = WorkCount{ 0, 0, 0, 0, 0, 0 };
+        const float o3[3] = { ox, oy, oz }, d3[3] = { dx, dy, dz };
+        const float r6[6] = { root[0], root[1], root[2], root[3], root[4], root[5] };
+        trace_one<COUNT>(tr, r6, o3, d3, tmin, tmax, s_first, s_first + kTraceThreads, s_first + 2 * kTraceThreads, r.hs,
+                         r.wc);
+        return r;
+}
+
+// ---------------------------------------------------------------------------
+// WARP-SYNCHRONOUS traversal (round 2).  The 32 rays of a warp tile share one traversal: the
+// warp walks the UNION of the nodes its rays visit with one stack, every lane evaluates the
+// node expansion for its own ray, and a lane takes part in a subtree only if its own ray would
+// enter it.  Measured on the headline frame (instrumented oracle): a ray expands 29.8 nodes, the
+// union over a 4x2-pixel x 4-sample tile is 33.4 nodes (28.5 rays per union node), so the warp
+// runs ONE instruction stream without divergence, node records and plane tables are loaded once
+// per warp, and the visit / stack bookkeeping is paid once per warp instead of once per lane.
+//
+// Why the shared visiting order is every ray's own order.  In the frame of the ray's direction
+// signs (S = child id ^ negmask; bit a of S set = far half of axis a) the children a ray enters
+// on a key-safe level without mid-plane ties are a CHAIN {} c {b0} c {b0,b1} c {x,y,z} visited in
+// that order (see trace_one_fast).  Ascending numeric S is a linear extension of set inclusion, so
+// a warp whose rays have the same direction signs can visit the children 0..7 in ascending S
+// and every lane sees its own children in its own (= the reference's travorder) order; depth
+// first recursion keeps that true for the leaves.  A lane stops at its first leaf with an
+// accepted triangle, exactly like ray_march (voxel_octree.cc:181-185).
+//
+// Node expansion per lane, without any ordering work: child S of the node is entered iff its
+// slab interval passes the reference's test.  With e0 <= em <= e1 the near / mid / far plane
+// parameters per axis (the very floats of the per-child slab tests), TL = max(e0x,e0y,e0z,0),
+// T1 = min(e1x,e1y,e1z):   t0_S = max(TL, em_a : a in S),  t1_S = min(T1, em_a : a not in S),
+// accepted (window [0,FLT_MAX], finite values) iff t0_S <= t1_S.
+//
+// Eligibility of a tile (else every lane runs the per-ray path): all rays tame, default window,
+// the same direction signs, every level key-safe for every ray.  A lane that meets a mid-plane
+// tie (ray through a shared edge: the closed test admits cells outside the chain, whose order is
+// the key order) leaves the warp traversal and is re-traced by the per-ray path afterwards.
+//
+// Children's node records are prefetched with cp.async into the warp's stack record while the
+// expansion arithmetic runs, so a descent (or a leaf visit) starts from shared memory instead
+// of a dependent global load.  Stack record r of a warp = two rows of 32 words:
+//   A[r][lane] = the lane's 8 accept bits at that node;   B[r][0..15] = the children's records,
+//   B[r][16..18] = first child, child mask | level << 8, children still to visit
+// (the rows are the warp's own slice of the per-ray stack columns, see below).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void* g)
+{
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+        asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+constexpr uint32_t kFull = 0xffffffffu;
+constexpr uint32_t kWsRedo = 0xfffffffeu;  // HitState::tri of a lane that left the warp traversal (mid-plane tie)
+constexpr int kWsLutBytes = 8 * 256;  // child mask -> mask in the S frame, per negmask
+
+// lut: the CTA's table [negmask][mask] -> bit S = mask bit (S ^ negmask)
+__device__ __forceinline__ void ws_fill_lut(uint8_t* lut)
+{
+        for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) {
+                const uint32_t ng = (uint32_t)i >> 8, m = (uint32_t)i & 255u;
+                uint32_t r = 0;
+#pragma unroll
+                for (uint32_t S = 0; S < 8; ++S)
+                        r |= ((m >> (S ^ ng)) & 1u) << S;
+                lut[i] = (uint8_t)r;
+        }
+        __syncthreads();
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void trace_tile_ws(const TreeDev& tr, const float root[6], const float o[3],
+                                              const float d[3], bool active, uint32_t neg, uint32_t* wsm,
+                                              const uint8_t* lut, HitState& hs, WorkCount& wc)
+{
+        const uint32_t lane = threadIdx.x & 31u;
+        hs.hit = false;
+        hs.tri = VRT_NO_TRI;
+        hs.leaf = VRT_NO_TRI;
+        hs.cx = hs.cy = hs.cz = 0xffffffffu;
+        hs.t = hs.u = hs.v = 0.f;
+        float dinv[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+                dinv[k] = slab_dinv(d[k]);
+        bool alive = active;
+        {
+                const float mn[3] = { root[0], root[1], root[2] };
+                const float mx[3] = { root[3], root[4], root[5] };
+                alive = alive && aabb_isect(mn, mx, o, dinv, 0.f, FLT_MAX);  // voxel_octree.cc:134
+        }
+        if (!__any_sync(kFull, alive))
+                return;
+        const uint32_t L = (uint32_t)tr.L;
+        const uint8_t* lutn = lut + neg * 256u;
+        // shared-memory byte addresses of this warp's rows: the warp only uses the words of its own
+        // lanes' per-ray stack columns (other warps of the CTA may be on the per-ray path), i.e. rows of
+        // 32 words every kTraceThreads words: A[r] = base + r * kWsRec, B[r] = A[r] + kWsRow
+        constexpr uint32_t kWsRow = kTraceThreads * 4u, kWsRec = 2u * kWsRow;
+        const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(wsm);
+        uint32_t level = 0, x = 1, y = 1, z = 1, sp = 0;
+        uint2 rec = __ldg(&tr.nodes[0]);
+        bool in = alive;
+        uint32_t first, mask, any8, acc8;
+        for (;;) {
+                // ---- expand the node whose record is `rec` (level; x,y,z) ---------------------
+                first = rec.x;
+                mask = rec.y & 0xffu;
+                {
+                        const float4 bx = __ldg(&tr.tab4[0][x]);
+                        const float4 by = __ldg(&tr.tab4[1][y]);
+                        const float4 bz = __ldg(&tr.tab4[2][z]);
+                        // children's records -> B[sp][0..15]; at most one batch per lane in flight
+                        cp_async_wait_all();
+                        __syncwarp();  // every lane has read its child record out of this row
+                        if (lane < (uint32_t)__popc(mask))
+                                cp_async8(sbase + sp * kWsRec + kWsRow + lane * 8u, &tr.nodes[first + lane]);
+                        const float2 ax = mul2s(sub2s(bx.x, bx.y, o[0]), dinv[0]);  // t(p0), t(pm)
+                        const float2 ay = mul2s(sub2s(by.x, by.y, o[1]), dinv[1]);
+                        const float2 az = mul2s(sub2s(bz.x, bz.y, o[2]), dinv[2]);
+                        const float ax2 = fmul(fsub(bx.w, o[0]), dinv[0]);  // t(p2)
+                        const float ay2 = fmul(fsub(by.w, o[1]), dinv[1]);
+                        const float az2 = fmul(fsub(bz.w, o[2]), dinv[2]);
+                        const float emx = ax.y, emy = ay.y, emz = az.y;
+                        const float TL = fmaxf(fmax3(fminf(ax.x, ax2), fminf(ay.x, ay2), fminf(az.x, az2)), 0.f);
+                        const float T1 = fmin3(fmaxf(ax.x, ax2), fmaxf(ay.x, ay2), fmaxf(az.x, az2));
+                        // S bits: x 4, y 2, z 1 (far half of that axis)
+                        const float lo1 = fmaxf(TL, emz), lo2 = fmaxf(TL, emy), lo4 = fmaxf(TL, emx);
+                        const float lo3 = fmax3(TL, emy, emz), lo5 = fmax3(TL, emx, emz), lo6 = fmax3(TL, emx, emy);
+                        const float lo7 = fmaxf(lo6, emz);
+                        const float hi6 = fminf(T1, emz), hi5 = fminf(T1, emy), hi3 = fminf(T1, emx);
+                        const float hi4 = fmin3(T1, emy, emz), hi2 = fmin3(T1, emx, emz), hi1 = fmin3(T1, emx, emy);
+                        const float hi0 = fminf(hi1, emz);
+                        uint32_t a = (TL <= hi0 ? 1u : 0u) | (lo1 <= hi1 ? 2u : 0u) | (lo2 <= hi2 ? 4u : 0u) |
+                                     (lo3 <= hi3 ? 8u : 0u) | (lo4 <= hi4 ? 16u : 0u) | (lo5 <= hi5 ? 32u : 0u) |
+                                     (lo6 <= hi6 ? 64u : 0u) | (lo7 <= T1 ? 128u : 0u);
+                        a &= (uint32_t)lutn[mask];
+                        const bool tie = (emx == emy) || (emy == emz) || (emx == emz);
+                        if (in && tie) {  // the chain argument does not hold: re-trace this ray alone
+                                hs.tri = kWsRedo;
+                                alive = false;
+                        }
+                        const bool use = in && !tie;
+                        acc8 = use ? a : 0u;
+                        if (COUNT && use) {
+                                wc.n_int += 1;
+                                wc.n_param += 1;
+                        }
+#ifdef VRT_PARAM_CHECK
+                        if (use) {
+                                const uint32_t list_s = expand_slab4(bx, by, bz, o[0], o[1], o[2], d[0], d[1], d[2], dinv[0],
+                                                                     dinv[1], dinv[2], mask, 0.f, FLT_MAX);
+                                uint32_t list_w = 0;
+                                for (int S = 7; S >= 0; --S)
+                                        if ((a >> S) & 1u)
+                                                list_w = (list_w << 4) | 8u | ((uint32_t)S ^ neg);
+                                atomicAdd(&g_param_check[0], 1ull);
+                                if (list_s != list_w)
+                                        atomicAdd(&g_param_check[1], 1ull);
+                        }
+#endif
+                        any8 = __reduce_or_sync(kFull, acc8);
+                }
+                // ---- visit the children in ascending S until the warp descends or is done ------
+                for (;;) {
+                        if (any8 == 0u) {
+                                if (sp == 0u)
+                                        return;
+                                --sp;
+                                const uint32_t ra = sbase + sp * kWsRec;
+                                uint32_t ml;
+                                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(acc8) : "r"(ra + lane * 4u));
+                                asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(first) : "r"(ra), "n"(kWsRow + 64u));
+                                asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(ml) : "r"(ra), "n"(kWsRow + 68u));
+                                asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(any8) : "r"(ra), "n"(kWsRow + 72u));
+                                mask = ml & 0xffu;
+                                const uint32_t nl = ml >> 8;
+                                x >>= (level - nl);
+                                y >>= (level - nl);
+                                z >>= (level - nl);
+                                level = nl;
+                                continue;
+                        }
+                        const uint32_t S = (uint32_t)__ffs((int)any8) - 1u;
+                        any8 &= any8 - 1u;
+                        const bool inc = alive && (((acc8 >> S) & 1u) != 0u);
+                        if (!__any_sync(kFull, inc))
+                                continue;  // (every ray that wanted this child has finished meanwhile)
+                        const uint32_t c = S ^ neg;
+                        const uint32_t k = (uint32_t)__popc(mask & ((1u << c) - 1u));
+                        cp_async_wait_all();
+                        __syncwarp();
+                        uint2 crec;
+                        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+%3];"
+                                     : "=r"(crec.x), "=r"(crec.y)
+                                     : "r"(sbase + sp * kWsRec + k * 8u), "n"(kWsRow));
+                        const uint32_t cx = 2u * x + ((c >> 2) & 1u);
+                        const uint32_t cy = 2u * y + ((c >> 1) & 1u);
+                        const uint32_t cz = 2u * z + (c & 1u);
+                        if (level + 1u == L) {
+                                bool found = false;
+                                if (inc)
+                                        found = leaf_isect_rec<COUNT>(tr, crec, o, d, hs, wc);
+                                if (found) {
+                                        hs.hit = true;
+                                        hs.leaf = first + k;
+                                        hs.cx = cx - (1u << L);
+                                        hs.cy = cy - (1u << L);
+                                        hs.cz = cz - (1u << L);
+                                        alive = false;
+                                }
+                                if (!__any_sync(kFull, alive))
+                                        return;
+                                continue;
+                        }
+                        // content hull of the child (see hull_reachable): lanes whose ray cannot reach a non-empty
+                        // leaf below leave the subtree; the warp skips it when no lane is left
+                        bool incr = inc;
+                        if (!COUNT && tr.hull != nullptr) {
+                                incr = inc && hull_reachable(tr.hull, first + k, o, dinv, 0.f, FLT_MAX);
+                                if (!__any_sync(kFull, incr))
+                                        continue;
+                        }
+                        if (any8 != 0u) {  // remember this node only if it has children left
+                                const uint32_t ra = sbase + sp * kWsRec;
+                                asm volatile("st.shared.u32 [%0], %1;" ::"r"(ra + lane * 4u), "r"(acc8) : "memory");
+                                if (lane == 0u)
+                                        asm volatile("st.shared.v4.u32 [%0+%4], {%1,%2,%3,%3};" ::"r"(ra), "r"(first),
+                                                     "r"(mask | (level << 8)), "r"(any8), "n"(kWsRow + 64u)
+                                                     : "memory");
+                                __syncwarp();
+                                ++sp;
+                        }
+                        ++level;
+                        x = cx;
+                        y = cy;
+                        z = cz;
+                        rec = crec;
+                        in = incr;
+                        break;
+                }
+        }
+}
+
 __device__ __forceinline__ void store_hit48(vrt_hit* out, const TreeDev& tr, const HitState& hs,
                                             const float o[3], const float d[3])
 {
@@ -745,7 +1032,7 @@ __device__ __forceinline__ void store_hit48(vrt_hit* out, const TreeDev& tr, con
 // second ray_march-semantics query from hit + eps*normal toward the light (config 5 of
 // BASELINE.json; harness-defined -- the reference itself has no shadow rays); it runs in
 // the same kernel, reusing the thread's traversal stack.
-template <bool COUNT>
+template <bool COUNT, bool NL>
 __device__ __forceinline__ void shade(const TraceParams& p, const HitState& hs, const float o[3],
                                       const float d[3], uint32_t* s_first, uint32_t* s_meta, uint32_t* s_list,
                                       WorkCount& wc, float rgb[3])
@@ -768,7 +1055,21 @@ __device__ __forceinline__ void shade(const TraceParams& p, const HitState& hs, 
                                       fadd(pos[2], fmul(p.shadow_eps, nrm[2])) };
                 const float sd[3] = { p.light[0], p.light[1], p.light[2] };
                 HitState sh;
-                trace_one<COUNT>(p.tree, p.root, so, sd, 0.f, FLT_MAX, s_first, s_meta, s_list, sh, wc);
+                if (NL) {
+                        const PtResult r = trace_one_nl<COUNT>(p.tree, p.root, so[0], so[1], so[2], sd[0], sd[1], sd[2], 0.f,
+                                                               FLT_MAX, s_first);
+                        sh.hit = r.hs.hit;
+                        if (COUNT) {
+                                wc.n_int += r.wc.n_int;
+                                wc.n_leaf += r.wc.n_leaf;
+                                wc.n_tri += r.wc.n_tri;
+                                wc.n_param += r.wc.n_param;
+                                wc.n_tie += r.wc.n_tie;
+                                wc.n_unsafe += r.wc.n_unsafe;
+                        }
+                } else {
+                        trace_one<COUNT>(p.tree, p.root, so, sd, 0.f, FLT_MAX, s_first, s_meta, s_list, sh, wc);
+                }
                 c = fmul(c, sh.hit ? 0.f : 1.f);
         }
         rgb[0] = rgb[1] = rgb[2] = c;
@@ -835,7 +1136,7 @@ k_trace_rays(const __grid_constant__ TraceParams p)
 
 // 64 registers (8 CTAs/SM) is fastest for the compact outputs; the modes that also
 // evaluate the ISect/normal/shading tail spill at 64 and run best at 80 (6 CTAs/SM).
-template <int MODE>
+template <int MODE, bool WS>
 #ifndef VRT_FILM_MIN_BLOCKS
 #define VRT_FILM_MIN_BLOCKS 7
 #endif
@@ -857,6 +1158,13 @@ k_trace_camera(const __grid_constant__ TraceParams p)
         const int lane = threadIdx.x & 31;
         const int W = p.x1 - p.x0, H = p.y1 - p.y0;
         const int spp = p.cam.spp;
+        // warp-synchronous path: this warp's stack rows and the CTA's child-mask table
+        uint32_t* wsm = s_stack + (threadIdx.x & ~31u);
+        const uint8_t* lut = reinterpret_cast<const uint8_t*>(s_stack) + p.lut_off;
+        const bool ws_ok = WS && p.tree.L >= 1 && p.tree.num_nodes != 0 && p.tree.tame != 0 && p.cam.tmin == 0.f &&
+                           p.cam.tmax == FLT_MAX;
+        if (WS)
+                ws_fill_lut(reinterpret_cast<uint8_t*>(s_stack) + p.lut_off);
         // warp tile: 8x4 pixels (spp 1) or 4x2 pixels x 4 samples (spp 4)
         const int tw = (spp == 4) ? 4 : 8, th = (spp == 4) ? 2 : 4;
         const int tiles_x = (W + tw - 1) / tw;
@@ -890,7 +1198,29 @@ k_trace_camera(const __grid_constant__ TraceParams p)
                 HitState hs;
                 hs.hit = false;
                 WorkCount wc = { 0, 0, 0, 0, 0, 0 };
-                if (active) {
+                if (WS) {
+                        if (active)
+                                gen_ray(p.cam, px, py, s, o, d);
+                        // the tile is traced by the warp as a whole when every ray qualifies (see trace_tile_ws)
+                        const uint32_t neg = (d[0] < 0.f ? 4u : 0u) | (d[1] < 0.f ? 2u : 0u) | (d[2] < 0.f ? 1u : 0u);
+                        const uint32_t am = __ballot_sync(0xffffffffu, active);
+                        const uint32_t neg0 = __shfl_sync(0xffffffffu, neg, am ? (__ffs((int)am) - 1) : 0);
+                        const bool elig = !active || (neg == neg0 && ray_is_tame(p.tree, o, d) &&
+                                                      param_safe_levels(p.root, o, d) >= p.tree.L);
+                        const bool tile_ws = ws_ok && am != 0u && __all_sync(0xffffffffu, elig);
+                        bool redo = false;
+                        if (tile_ws) {
+                                trace_tile_ws<MODE == OUT_COUNT>(p.tree, p.root, o, d, active, neg0, wsm, lut, hs, wc);
+                                redo = !hs.hit && hs.tri == kWsRedo;
+                        }
+                        if (active && (!tile_ws || redo)) {
+                                const PtResult r = trace_one_nl<MODE == OUT_COUNT>(p.tree, p.root, o[0], o[1], o[2], d[0], d[1],
+                                                                                   d[2], p.cam.tmin, p.cam.tmax, s_first);
+                                hs = r.hs;
+                                if (MODE == OUT_COUNT)
+                                        wc = r.wc;
+                        }
+                } else if (active) {
                         gen_ray(p.cam, px, py, s, o, d);
                         trace_one<MODE == OUT_COUNT>(p.tree, p.root, o, d, p.cam.tmin, p.cam.tmax, s_first, s_meta,
                                                      s_list, hs, wc);
@@ -955,7 +1285,7 @@ k_trace_camera(const __grid_constant__ TraceParams p)
                                 if (MODE == OUT_GI_FILM)
                                         shade_gi(p, hs, o, d, s_first, rgb);
                                 else
-                                        shade<MODE == OUT_COUNT>(p, hs, o, d, s_first, s_meta, s_list, wc, rgb);
+                                        shade<MODE == OUT_COUNT, WS>(p, hs, o, d, s_first, s_meta, s_list, wc, rgb);
                         }
                         // film->add(px,py, c * (1/spp)) in sample order (main.cc:119-122)
                         const float wgt = (spp == 4) ? .25f : 1.f;
@@ -1155,27 +1485,39 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
                 return VRT_ERR_ARG;
         }
         p.num_tiles = (uint32_t)tiles;
-        const size_t smem = stack_bytes(t, mode);
-        const void* kern = nullptr;
-        switch (mode) {
-        case OUT_HIT48: kern = (const void*)k_trace_camera<OUT_HIT48>; break;
-        case OUT_HIT16: kern = (const void*)k_trace_camera<OUT_HIT16>; break;
-        case OUT_COUNT: kern = (const void*)k_trace_camera<OUT_COUNT>; break;
-        case OUT_HIT16_FILM: kern = (const void*)k_trace_camera<OUT_HIT16_FILM>; break;
-        case OUT_SPLAT: kern = (const void*)k_trace_camera<OUT_SPLAT>; break;
-        case OUT_GI_FILM: kern = (const void*)k_trace_camera<OUT_GI_FILM>; break;
-        default: kern = (const void*)k_trace_camera<OUT_FILM>; break;
+        // warp-synchronous kernels (default; VRT_TRACE_WS=0 selects the per-ray kernels): the child-mask
+        // table of trace_tile_ws follows the stack in dynamic shared memory
+        static int use_ws = -1;
+        if (use_ws < 0) {
+                const char* e = getenv("VRT_TRACE_WS");
+                use_ws = (e && e[0] == '0') ? 0 : 1;
         }
+        const bool ws = use_ws != 0;
+        p.lut_off = (uint32_t)stack_bytes(t, mode);
+        const size_t smem = stack_bytes(t, mode) + (ws ? (size_t)kWsLutBytes : 0);
+        const void* kern = nullptr;
+#define VRT_PICK(M) kern = ws ? (const void*)k_trace_camera<M, true> : (const void*)k_trace_camera<M, false>
+        switch (mode) {
+        case OUT_HIT48: VRT_PICK(OUT_HIT48); break;
+        case OUT_HIT16: VRT_PICK(OUT_HIT16); break;
+        case OUT_COUNT: VRT_PICK(OUT_COUNT); break;
+        case OUT_HIT16_FILM: VRT_PICK(OUT_HIT16_FILM); break;
+        case OUT_SPLAT: VRT_PICK(OUT_SPLAT); break;
+        case OUT_GI_FILM: VRT_PICK(OUT_GI_FILM); break;
+        default: VRT_PICK(OUT_FILM); break;
+        }
+#undef VRT_PICK
         VRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int grid = persistent_grid(kern, smem);
         grid = (int)std::min<uint64_t>((uint64_t)grid, (tiles + 3) / 4);
-        VRT_CUDA(cudaMemsetAsync(p.queue, 0, 4, t->stream));
+        cudaStream_t ls = t->launch_stream ? t->launch_stream : t->stream;
+        VRT_CUDA(cudaMemsetAsync(p.queue, 0, 4, ls));
         const int slot = (int)(t->n_trace_launches % vrt_tree::kEvRing);
-        VRT_CUDA(cudaEventRecord(t->ring0[slot], t->stream));
+        VRT_CUDA(cudaEventRecord(t->ring0[slot], ls));
         void* args[] = { &p };
-        VRT_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(kTraceThreads), args, smem, t->stream));
+        VRT_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(kTraceThreads), args, smem, ls));
         count_launch();
-        VRT_CUDA(cudaEventRecord(t->ring1[slot], t->stream));
+        VRT_CUDA(cudaEventRecord(t->ring1[slot], ls));
         t->n_trace_launches++;
         return VRT_OK;
 }
