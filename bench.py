@@ -151,7 +151,27 @@ def gi_res_of(root_aabb, depth):
     return float(np.float32(((r[3:] - r[:3]) / np.float32(2.0 ** depth)).min()))
 
 
-def cpu_reference(tri, nrm, depth, cam10, spp, steps, warmup, sample=CPU_SAMPLE, gi=False):
+def parity_vs_reference(scene, tree, wl, cam10, nx, ny, spp):
+    """Parity of the CUDA path against the UNMODIFIED reference on the benched octree: every ray of the CPU sample
+    film (the reference's own render_mt + gen_rays + gi::ray_march, hit records kept) against tree.trace_camera on
+    the same camera -- hit flag, leaf cell, triangle, ISect.hit, ISect.normal, all bitwise -- and the leaf sets of
+    the two octrees (cells, counts, triangle lists).  The oracle is the checker here, never the thing measured."""
+    from voxelraytrace20190722_b200 import capi
+    _, rays, o = scene.render_mt(cam10, 1.0, nx, ny, spp, outputs=True)
+    cam = capi.Camera(cam10[0], cam10[1:4], cam10[4:7], cam10[7:10], nx, ny, spp)
+    g = tree.trace_camera(cam)
+    bad = (g["hit"] != o.hit) | (g["tri"] != o.tri) | (g["cell"] != o.cell).any(axis=1)
+    bad |= (g["pos"].view(np.uint32) != o.pos.view(np.uint32)).any(axis=1)
+    bad |= (g["nrm"].view(np.uint32) != o.nrm.view(np.uint32)).any(axis=1)
+    ours, theirs = tree.leaves(), scene.leaves()
+    leaf_ok = all(a.shape == b.shape and np.array_equal(a, b) for a, b in zip(ours, theirs))
+    return {"config": wl, "against": "oracle/_ref (unmodified reference): render_mt + gi::ray_march, gi::ray_march_init",
+            "film": f"{nx}x{ny}x{spp}", "rays": int(rays), "hits": int(o.hit.sum()), "mismatches": int(bad.sum()),
+            "compared": "hit, leaf cell, triangle, ISect.hit, ISect.normal (bitwise)",
+            "leaf_sets_bit_exact": bool(leaf_ok), "leaves": int(len(theirs[1])), "refs": int(len(theirs[2]))}
+
+
+def cpu_reference(tri, nrm, depth, cam10, spp, steps, warmup, sample=CPU_SAMPLE, gi=False, parity_tree=None, wl=None):
     from oracle.bindings import Ref
     ref = Ref()
     scene = ref.scene(tri, nrm)
@@ -163,6 +183,7 @@ def cpu_reference(tri, nrm, depth, cam10, spp, steps, warmup, sample=CPU_SAMPLE,
         if i >= warmup:
             times.append(sec)
     cores = ref.hardware_concurrency()
+    parity = parity_vs_reference(scene, parity_tree, wl, cam10, nx, ny, spp) if parity_tree is not None else None
     gi_out = None
     if gi:
         # GI rows on the reference: splat (sequential, bounded light film), filter, then the final trace() loop on
@@ -181,6 +202,7 @@ def cpu_reference(tri, nrm, depth, cam10, spp, steps, warmup, sample=CPU_SAMPLE,
                   "render_threads": cores,
                   "sample": f"light film {lx}x{ly}x4 (sequential, as the deterministic order requires), trace() film {gx}x{gy}x{spp}"}
     return dict(build_s=build_s, mtris=len(tri) / build_s / 1e6, ms_per_step=1e3 * float(np.mean(times)), gi=gi_out,
+                parity=parity,
                 mrays=rays / float(np.mean(times)) / 1e6, rays=rays, cores=cores,
                 sample=f"same scene/camera/spp at {nx}x{ny} ({rays} rays per step) through render_mt + gen_rays{spp} + "
                        f"gi::ray_march on {min(cores, 64)} pool threads; octree built once by gi::ray_march_init "
@@ -197,7 +219,11 @@ def run_reference(args):
         "impl": "reference", "metric": "Mrays/s octree traversal", "value": r["mrays"], "unit": "Mrays/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": workload_config(args.workload, len(tri), args.gpus),
+        "config": dict(workload_config(args.workload, len(tri), args.gpus),
+                       film=f"{CPU_SAMPLE[0]}x{CPU_SAMPLE[1]} sample of the {WORKLOADS[args.workload][4]}x"
+                            f"{WORKLOADS[args.workload][5]} film (same scene, camera, spp; rate metric)",
+                       rays_per_step=r["rays"],
+                       sharding="host threads: render_mt's 64 tiles on the thread pool (no GPU)"),
         "cpu_baseline": {"value": r["mrays"], "unit": "Mrays/s", "cores": r["cores"], "kind": "reference",
                          "sample": r["sample"]},
         "e2e": {"value": r["mrays"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -367,6 +393,18 @@ def run_ours(args):
     kern_ms = ms_per_step
     value = rays_per_step / (ms_per_step * 1e-3) / 1e6
 
+    # ---- the dominant kernel alone: one stream, CUDA events around every launch (no overlap with a neighbour) ----
+    tree.set_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        for i in range(args.steps):
+            tree.frame_bands_dev(cams[i % len(cams)], hits[0].data_ptr(), (fg.buffer(0).data_ptr() if use_gather else pf.ptr(0)),
+                                 vdist.BAND_H, rank, world, full_frame=not use_gather, shadow_eps=shadow_eps)
+    tk = torch.tensor([tree.mean_kernel_ms(min(args.steps, 64))], dtype=torch.float64, device=dev)
+    sync_all()
+    if world > 1:
+        td.all_reduce(tk, op=td.ReduceOp.MAX)
+    kern_ms_isolated = float(tk[0])
+
     # ---- e2e: host-buffer C-ABI call, film copied back to pinned host memory every step ----
     e2e_host_frame_ok = None
     e2e_note = None
@@ -496,7 +534,14 @@ def run_ours(args):
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_src,
-                "kernel": "k_trace_camera<HIT16_FILM>", "kernel_ms": kern_ms, "kernel_ms_event_pairs": kern_ms_events, "bytes_per_ray": b_ray,
+                "kernel": "k_trace_camera<HIT16_FILM>", "kernel_ms": kern_ms,
+                "kernel_ms_isolated": kern_ms_isolated,
+                "frac_isolated": b_ray * rays_per_launch / (kern_ms_isolated * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "timing": ("kernel_ms = CUDA-event time of the timed region / launches (consecutive frames alternate between "
+                           "two streams, so the tail of one launch overlaps the head of the next); kernel_ms_isolated = mean "
+                           "of per-launch CUDA-event pairs of the same launches issued on ONE stream after the timed region "
+                           "(comparable with the ncu launch list under profiles/)"),
+                "bytes_per_ray": b_ray,
                 "n_int": n_int, "n_leaf": n_leaf, "n_tri": n_tri, "hit_fraction": cnt["hits"] / cnt["rays"]}
 
     # ---- build metric ----
@@ -510,6 +555,29 @@ def run_ours(args):
                  "h2d_bytes": int(tri.nbytes + nrm.nbytes), "bytes_per_tri": b_tri,
                  "roofline_frac": b_tri * T / (build["ms"] * 1e-3) / 1e9 / peaks["hbm_gbs"],
                  "leaves": info["num_leaves"], "nodes": info["num_nodes"], "refs": info["num_refs"]}
+
+    # ---- BASELINE config 4: the 2 M-triangle soup voxelized at 2048^3 (build throughput), rank 0, N=1 ----
+    build_soup = None
+    if world == 1 and not args.no_build_soup and args.workload != "soup2m_2048_4k_spp4":
+        from voxelraytrace20190722_b200 import scenes as _sc
+        stri, snrm = _sc.make_scene("soup")
+        t0 = time.perf_counter()
+        stree = capi.Octree.build(stri, snrm, 12)
+        s_e2e = time.perf_counter() - t0
+        sms = []
+        for _ in range(args.build_reps + 1):
+            stree.rebuild(12)
+            sms.append(stree.info()["build_ms"])
+        sinfo = stree.info()
+        s_ms = float(np.mean(sms[1:])) if len(sms) > 1 else sms[0]
+        s_btri = 36 + 12 * sinfo["num_refs"] / len(stri) + 8 * sinfo["num_nodes"] / len(stri)
+        build_soup = {"workload": "soup 2,000,000 tris (PCG seed 12345) at max_depth 12 (2048^3)",
+                      "mtris_per_s": len(stri) / (s_ms * 1e-3) / 1e6, "ms": s_ms, "e2e_s": s_e2e,
+                      "e2e_mtris_per_s": len(stri) / s_e2e / 1e6, "bytes_per_tri": s_btri,
+                      "roofline_frac": s_btri * len(stri) / (s_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                      "leaves": sinfo["num_leaves"], "nodes": sinfo["num_nodes"], "refs": sinfo["num_refs"]}
+        stree.close()
+        del stri, snrm
 
     # ---- GI rows (SURVEY.md 8f "next"): splat / filter / trace() film, device-timed (rank 0, N=1) ----
     gi_out = None
@@ -547,9 +615,13 @@ def run_ours(args):
 
     # ---- cpu baseline (rank 0, N=1 only) ----
     cpu = None
+    parity = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = cpu_reference(tri, nrm, depth, cam10, spp, steps=1, warmup=0, gi=not args.no_gi)
+            tree.set_stream(0)
+            r = cpu_reference(tri, nrm, depth, cam10, spp, steps=1, warmup=0, gi=not args.no_gi, parity_tree=tree,
+                              wl=args.workload)
+            parity = r["parity"]
             cpu = {"value": r["mrays"], "unit": "Mrays/s", "cores": r["cores"], "kind": "reference",
                    "sample": r["sample"], "build_mtris_per_s": r["mtris"], "build_seconds": r["build_s"],
                    "gi": r["gi"]}
@@ -574,7 +646,9 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
+        "parity": parity,
         "build": build_out,
+        "build_soup": build_soup,
         "gi": gi_out,
         "octree": {"device_bytes": info["device_bytes"], "nodes": info["num_nodes"], "leaves": info["num_leaves"]},
         "frame_check": {"n_gpu_frame_equals_1_gpu_frame_bytewise": frame_check,
@@ -599,6 +673,7 @@ def main():
     ap.add_argument("--assemble", default="peer", choices=["peer", "gather"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gi", action="store_true", help="skip the GI rows (splat/filter/cone-trace film)")
+    ap.add_argument("--no-build-soup", action="store_true", help="skip the 2 M-triangle soup build (BASELINE config 4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

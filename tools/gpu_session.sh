@@ -1,13 +1,13 @@
 #!/bin/bash
-# One gpurun call: parity tests for the kernel variants, then perf + checksums of prebuilt library variants.
+# One gpurun call: parity tests, perf + checksums of prebuilt library variants, a short bench line.
 mkdir -p gpurun_out
 {
-echo "== pytest default (warp-synchronous + hull)"; python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-echo "== pytest VRT_TRACE_WS=0 (per-ray + hull)"; VRT_TRACE_WS=0 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-echo "== pytest VRT_TRACE_WS=0 VRT_HULL=0 (round-1 kernel)"; VRT_TRACE_WS=0 VRT_HULL=0 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-for s in "" _mb6 _mb5; do for ws in 0 1; do for hull in 0 1; do
-  echo "== variant '$s' ws=$ws hull=$hull"
-  VRT_LIB_SUFFIX=$s VRT_TRACE_WS=$ws VRT_HULL=$hull timeout 300 python tools/probe_quick.py 11 2>&1 | tail -2
-done; done; done
+echo "== pytest default"; python -m pytest tests -m gpu -x -q 2>&1 | tail -8
+echo "== pytest VRT_TRACE_WS=1"; VRT_TRACE_WS=1 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+for s in "" _tp _tp6; do
+  echo "== variant '$s'"
+  VRT_LIB_SUFFIX=$s timeout 300 python tools/probe_quick.py 11 2>&1 | tail -2
+done
+echo "== bench"; python bench.py --steps 10 --warmup 3 > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; tail -3 gpurun_out/bench_quick.err; python tools/show_bench.py gpurun_out/bench_quick.json
 } > gpurun_out/session.log 2>&1
 tail -60 gpurun_out/session.log

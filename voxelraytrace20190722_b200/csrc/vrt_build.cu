@@ -1371,7 +1371,7 @@ int import_leaves(vrt_tree* t, int max_depth, const float root_aabb[6], uint64_t
 __global__ void __launch_bounds__(256)
 k_hull_level(const uint2* __restrict__ nodes, const unsigned long long* __restrict__ leaf_morton,
              const float2* __restrict__ tx, const float2* __restrict__ ty, const float2* __restrict__ tz,
-             uint64_t begin, uint64_t count, int child_is_leaf, uint64_t leaf_base, float2* __restrict__ hull)
+             uint64_t begin, uint64_t count, int child_is_leaf, uint64_t leaf_base, float4* __restrict__ hull)
 {
         const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= count)
@@ -1390,17 +1390,17 @@ k_hull_level(const uint2* __restrict__ nodes, const unsigned long long* __restri
                         by = ty[compact1by2(m >> 1)];
                         bz = tz[compact1by2(m)];
                 } else {
-                        bx = hull[3 * ch];
-                        by = hull[3 * ch + 1];
-                        bz = hull[3 * ch + 2];
+                        const float4 ca = hull[2 * ch], cb = hull[2 * ch + 1];
+                        bx = make_float2(ca.z, ca.w);
+                        by = make_float2(cb.x, cb.y);
+                        bz = make_float2(cb.z, cb.w);
                 }
                 hx.x = fminf(hx.x, bx.x); hx.y = fmaxf(hx.y, bx.y);
                 hy.x = fminf(hy.x, by.x); hy.y = fmaxf(hy.y, by.y);
                 hz.x = fminf(hz.x, bz.x); hz.y = fmaxf(hz.y, bz.y);
         }
-        hull[3 * node] = hx;
-        hull[3 * node + 1] = hy;
-        hull[3 * node + 2] = hz;
+        hull[2 * node] = make_float4(__uint_as_float(rec.x), __uint_as_float(rec.y), hx.x, hx.y);
+        hull[2 * node + 1] = make_float4(hy.x, hy.y, hz.x, hz.y);
 }
 
 int compute_hulls(vrt_tree* t)
@@ -1416,9 +1416,9 @@ int compute_hulls(vrt_tree* t)
         if (!enabled || L < 1 || h.num_nodes == 0)
                 return VRT_OK;
         const uint64_t interior = h.num_nodes - h.num_leaves;
-        if (t->hull_buf.reserve(std::max<uint64_t>(interior, 1) * 24))
+        if (t->hull_buf.reserve(std::max<uint64_t>(interior, 1) * 32))
                 return VRT_ERR_NOMEM;
-        float2* hull = t->hull_buf.as<float2>();
+        float4* hull = t->hull_buf.as<float4>();
         const uint64_t leaf_base = h.level_offset[L];
         const uint64_t lv = 1ull << L;  // leaf-level entries of the axis table
         for (int l = L - 1; l >= 0; --l) {

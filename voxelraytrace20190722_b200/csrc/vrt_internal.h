@@ -72,11 +72,12 @@ struct TreeDev {
                                 // children of cell x at level l
         const float2* tab2[3];
         const float* gi;  // per-node GI state (vrt_gi.cuh), or null before vrt_gi_init
-        // content hull of every INTERIOR node (round 2): per node three float2 (min,max) per axis = the
-        // extreme leaf-cell planes (floats of the axis table) over the node's non-empty leaves.  A ray whose
-        // slab interval over the hull is empty cannot pass the slab test of any leaf below (monotone rounding),
-        // so the subtree is skipped without changing any result.  Null: no pruning.
-        const float2* hull;
+        // content hull of every INTERIOR node (round 2), fused with a copy of its node record into one
+        // 32-byte sector: float4 {first_child bits, child mask bits, x.min, x.max}, float4 {y.min, y.max, z.min,
+        // z.max}; the bounds are the extreme leaf-cell planes (floats of the axis table) over the node's
+        // non-empty leaves.  A ray whose slab interval over the hull is empty cannot pass the slab test of any
+        // leaf below (monotone rounding), so the subtree is skipped without changing any result.  Null: no pruning.
+        const float4* hull;
         // materials (vrt_set_materials), all null when unset: per-vertex texture coordinates, material id per
         // triangle, per material (kd.xyz, texture id or -1 as int bits), per texture (byte offset, w, h, channels)
         const float2* mat_uv;

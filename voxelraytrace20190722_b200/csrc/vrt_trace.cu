@@ -513,13 +513,18 @@ __device__ unsigned long long g_param_check[4] = { 0, 0, 0, 0 };  // checked, mi
 // cell below lies inside the hull plane by plane and rounding is monotone, so a leaf that passes the
 // reference's slab test implies max(t0,tmin) <= min(t1,tmax) here.  false = the subtree cannot
 // produce a hit; skipping it changes no result.
-__device__ __forceinline__ bool hull_reachable(const float2* __restrict__ hull, uint32_t node, const float o[3],
-                                               const float dinv[3], float tmin, float tmax)
+// volatile (= kept where it is written) read-only 16-byte load
+__device__ __forceinline__ void ldg_nc_f4(float4& v, const float4* p)
 {
-        const float2 hx = __ldg(&hull[3ull * node]), hy = __ldg(&hull[3ull * node + 1]), hz = __ldg(&hull[3ull * node + 2]);
-        const float2 ax = mul2s(sub2s(hx.x, hx.y, o[0]), dinv[0]);
-        const float2 ay = mul2s(sub2s(hy.x, hy.y, o[1]), dinv[1]);
-        const float2 az = mul2s(sub2s(hz.x, hz.y, o[2]), dinv[2]);
+        asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+}
+
+__device__ __forceinline__ bool hull_reachable(const float4 ha, const float4 hb, const float o[3], const float dinv[3],
+                                               float tmin, float tmax)
+{
+        const float2 ax = mul2s(sub2s(ha.z, ha.w, o[0]), dinv[0]);
+        const float2 ay = mul2s(sub2s(hb.x, hb.y, o[1]), dinv[1]);
+        const float2 az = mul2s(sub2s(hb.z, hb.w, o[2]), dinv[2]);
         const float t0 = fmax3(fminf(ax.x, ax.y), fminf(ay.x, ay.y), fminf(az.x, az.y));
         const float t1 = fmin3(fmaxf(ax.x, ax.y), fmaxf(ay.x, ay.y), fmaxf(az.x, az.y));
         return fmaxf(t0, tmin) <= fminf(t1, tmax);
@@ -576,6 +581,11 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
         int level = 0;
         uint32_t x = 1, y = 1, z = 1;
         uint2 rec = __ldg(&tr.nodes[0]);  // record of the node to expand (a child's is fetched with its hull)
+#ifdef VRT_TAB_PREFETCH
+        // the child's plane table entries are requested together with its hull record (their addresses only
+        // depend on the cell coordinates), so a descent costs one memory latency instead of two
+        float4 bx = __ldg(&tr.tab4[0][1]), by = __ldg(&tr.tab4[1][1]), bz = __ldg(&tr.tab4[2][1]);
+#endif
         // visiting list of the node being iterated: 4 bits per entry, lowest first, entry =
         // 8 | child id -- an empty list is the value 0, so no separate count is carried
         uint32_t first, mask, list;
@@ -592,9 +602,11 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 wc.n_int += 1;
                         first = rec.x;
                         mask = rec.y;
+#ifndef VRT_TAB_PREFETCH
                         const float4 bx = __ldg(&tr.tab4[0][x]);
                         const float4 by = __ldg(&tr.tab4[1][y]);
                         const float4 bz = __ldg(&tr.tab4[2][z]);
+#endif
                         bool use_slab = false;
                         {
                                 // t(p0), t(p1) packed, t(p2) scalar -- the reference's (plane-o)*dinv
@@ -716,11 +728,28 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 }
                                 continue;
                         }
-                        rec = __ldg(&tr.nodes[child]);
-                        // content hull: skip a child under which the ray cannot reach a non-empty leaf
-                        // (not in the counting mode, which reports the reference algorithm's work)
-                        if (!COUNT && tr.hull != nullptr && !hull_reachable(tr.hull, child, o, dinv, tmin, tmax))
-                                continue;
+                        // the child's node record, fused with its content hull: skip a child under which the
+                        // ray cannot reach a non-empty leaf (not in the counting mode, which reports the
+                        // reference algorithm's work)
+#ifdef VRT_TAB_PREFETCH
+                        float4 nbx, nby, nbz;
+                        ldg_nc_f4(nbx, &tr.tab4[0][cx]);
+                        ldg_nc_f4(nby, &tr.tab4[1][cy]);
+                        ldg_nc_f4(nbz, &tr.tab4[2][cz]);
+#endif
+                        if (!COUNT && tr.hull != nullptr) {
+                                const float4 ha = __ldg(&tr.hull[2ull * child]), hb = __ldg(&tr.hull[2ull * child + 1]);
+                                if (!hull_reachable(ha, hb, o, dinv, tmin, tmax))
+                                        continue;
+                                rec = make_uint2(__float_as_uint(ha.x), __float_as_uint(ha.y));
+                        } else {
+                                rec = __ldg(&tr.nodes[child]);
+                        }
+#ifdef VRT_TAB_PREFETCH
+                        bx = nbx;
+                        by = nby;
+                        bz = nbz;
+#endif
                         if (list != 0u) {  // remember this level only if it has children left
                                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(first) : "memory");
                                 asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(sp), "n"(kCol),
@@ -989,7 +1018,8 @@ __device__ __forceinline__ void trace_tile_ws(const TreeDev& tr, const float roo
                         // leaf below leave the subtree; the warp skips it when no lane is left
                         bool incr = inc;
                         if (!COUNT && tr.hull != nullptr) {
-                                incr = inc && hull_reachable(tr.hull, first + k, o, dinv, 0.f, FLT_MAX);
+                                const float4 ha = __ldg(&tr.hull[2ull * (first + k)]), hb = __ldg(&tr.hull[2ull * (first + k) + 1]);
+                                incr = inc && hull_reachable(ha, hb, o, dinv, 0.f, FLT_MAX);
                                 if (!__any_sync(kFull, incr))
                                         continue;
                         }
@@ -1485,12 +1515,12 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
                 return VRT_ERR_ARG;
         }
         p.num_tiles = (uint32_t)tiles;
-        // warp-synchronous kernels (default; VRT_TRACE_WS=0 selects the per-ray kernels): the child-mask
-        // table of trace_tile_ws follows the stack in dynamic shared memory
+        // per-ray kernels by default; VRT_TRACE_WS=1 selects the warp-synchronous kernels (measured slower so
+        // far): the child-mask table of trace_tile_ws follows the stack in dynamic shared memory
         static int use_ws = -1;
         if (use_ws < 0) {
                 const char* e = getenv("VRT_TRACE_WS");
-                use_ws = (e && e[0] == '0') ? 0 : 1;
+                use_ws = (e && e[0] == '1') ? 1 : 0;
         }
         const bool ws = use_ws != 0;
         p.lut_off = (uint32_t)stack_bytes(t, mode);
