@@ -513,12 +513,6 @@ __device__ unsigned long long g_param_check[4] = { 0, 0, 0, 0 };  // checked, mi
 // cell below lies inside the hull plane by plane and rounding is monotone, so a leaf that passes the
 // reference's slab test implies max(t0,tmin) <= min(t1,tmax) here.  false = the subtree cannot
 // produce a hit; skipping it changes no result.
-// volatile (= kept where it is written) read-only 16-byte load
-__device__ __forceinline__ void ldg_nc_f4(float4& v, const float4* p)
-{
-        asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-}
-
 __device__ __forceinline__ bool hull_reachable(const float4 ha, const float4 hb, const float o[3], const float dinv[3],
                                                float tmin, float tmax)
 {
@@ -581,11 +575,6 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
         int level = 0;
         uint32_t x = 1, y = 1, z = 1;
         uint2 rec = __ldg(&tr.nodes[0]);  // record of the node to expand (a child's is fetched with its hull)
-#ifdef VRT_TAB_PREFETCH
-        // the child's plane table entries are requested together with its hull record (their addresses only
-        // depend on the cell coordinates), so a descent costs one memory latency instead of two
-        float4 bx = __ldg(&tr.tab4[0][1]), by = __ldg(&tr.tab4[1][1]), bz = __ldg(&tr.tab4[2][1]);
-#endif
         // visiting list of the node being iterated: 4 bits per entry, lowest first, entry =
         // 8 | child id -- an empty list is the value 0, so no separate count is carried
         uint32_t first, mask, list;
@@ -602,11 +591,9 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 wc.n_int += 1;
                         first = rec.x;
                         mask = rec.y;
-#ifndef VRT_TAB_PREFETCH
                         const float4 bx = __ldg(&tr.tab4[0][x]);
                         const float4 by = __ldg(&tr.tab4[1][y]);
                         const float4 bz = __ldg(&tr.tab4[2][z]);
-#endif
                         bool use_slab = false;
                         {
                                 // t(p0), t(p1) packed, t(p2) scalar -- the reference's (plane-o)*dinv
@@ -731,12 +718,6 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                         // the child's node record, fused with its content hull: skip a child under which the
                         // ray cannot reach a non-empty leaf (not in the counting mode, which reports the
                         // reference algorithm's work)
-#ifdef VRT_TAB_PREFETCH
-                        float4 nbx, nby, nbz;
-                        ldg_nc_f4(nbx, &tr.tab4[0][cx]);
-                        ldg_nc_f4(nby, &tr.tab4[1][cy]);
-                        ldg_nc_f4(nbz, &tr.tab4[2][cz]);
-#endif
                         if (!COUNT && tr.hull != nullptr) {
                                 const float4 ha = __ldg(&tr.hull[2ull * child]), hb = __ldg(&tr.hull[2ull * child + 1]);
                                 if (!hull_reachable(ha, hb, o, dinv, tmin, tmax))
@@ -745,11 +726,6 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                         } else {
                                 rec = __ldg(&tr.nodes[child]);
                         }
-#ifdef VRT_TAB_PREFETCH
-                        bx = nbx;
-                        by = nby;
-                        bz = nbz;
-#endif
                         if (list != 0u) {  // remember this level only if it has children left
                                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(first) : "memory");
                                 asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(sp), "n"(kCol),
