@@ -1,13 +1,12 @@
 #!/bin/bash
-# One gpurun call: parity tests, perf + checksums of prebuilt library variants, a short bench line.
+# One gpurun call: parity tests, build probes (SAT8 on/off) with tree checksums, launch list of one build.
 mkdir -p gpurun_out
 {
 echo "== pytest default"; python -m pytest tests -m gpu -x -q 2>&1 | tail -8
-echo "== pytest VRT_TRACE_WS=1"; VRT_TRACE_WS=1 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-for s in "" _tp _tp6; do
-  echo "== variant '$s'"
-  VRT_LIB_SUFFIX=$s timeout 300 python tools/probe_quick.py 11 2>&1 | tail -2
-done
-echo "== bench"; python bench.py --steps 10 --warmup 3 > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; tail -3 gpurun_out/bench_quick.err; python tools/show_bench.py gpurun_out/bench_quick.json
+echo "== build sat8=1"; python tools/probe_build.py 2>&1 | tail -3
+echo "== build sat8=0"; VRT_BUILD_SAT8=0 python tools/probe_build.py 2>&1 | tail -3
+echo "== build sorted"; VRT_BUILD_SORTED=1 python tools/probe_build.py 2>&1 | tail -3
 } > gpurun_out/session.log 2>&1
-tail -60 gpurun_out/session.log
+tail -40 gpurun_out/session.log
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_build_r2c.csv python tools/probe_build_one.py > gpurun_out/ncu_build.log 2>&1
+tail -2 gpurun_out/ncu_build.log

@@ -544,6 +544,50 @@ k_expand_mask_r(const float* __restrict__ tri, const float2* __restrict__ tab, u
                 block_counts[blockIdx.x] = tot;
 }
 
+// Round 2: the mask pass with ONE thread per (triangle, cell) pair.  The thread evaluates all eight
+// children's tests at once (tri_overlaps_children8: the sub-expressions that are identical between children
+// are computed once -- about a third of the arithmetic of eight separate calls, and no 8-lane groups that
+// diverge at the early exits).  Same outputs as k_expand_mask_r; a block handles kPairsPerBlock pairs.
+__global__ void __launch_bounds__(256)
+k_expand_mask_r8(const float* __restrict__ tri, const float2* __restrict__ tab, uint64_t stride,
+                 const unsigned long long* __restrict__ in, uint32_t n_in, int level /* of the input cells */,
+                 const unsigned long long* __restrict__ node_morton, uint8_t* __restrict__ child_seen /* [nodes][8], zeroed */,
+                 int crowded, uint8_t* __restrict__ masks, uint32_t* __restrict__ block_counts)
+{
+        const uint32_t idx = blockIdx.x * kPairsPerBlock + threadIdx.x;
+        uint32_t m8 = 0;
+        if (idx < n_in) {
+                const unsigned long long key = in[idx];
+                const uint32_t t = (uint32_t)key;
+                const uint32_t node = (uint32_t)(key >> 32);
+                const unsigned long long m = node_morton[node];
+                // float4 view of the table: entry (1<<level)+x of an axis = (lo.min, lo.max, hi.min, hi.max) of
+                // the two children of cell x at `level`
+                const float4* tab4 = reinterpret_cast<const float4*>(tab);
+                const uint64_t s4 = stride >> 1;
+                const uint32_t base = 1u << level;
+                const float4 bx = tab4[0 * s4 + base + compact1by2(m >> 2)];
+                const float4 by = tab4[1 * s4 + base + compact1by2(m >> 1)];
+                const float4 bz = tab4[2 * s4 + base + compact1by2(m)];
+                const float* p = tri + 9ull * t;
+                const float v0[3] = { p[0], p[1], p[2] }, v1[3] = { p[3], p[4], p[5] }, v2[3] = { p[6], p[7], p[8] };
+                m8 = tri_overlaps_children8(bx, by, bz, v0, v1, v2);
+                masks[idx] = (uint8_t)m8;
+                // "child c of this node exists": plain byte stores of the constant 1 (see k_expand_mask_r)
+                uint32_t mm = m8;
+                while (mm) {
+                        const uint32_t c = __ffs((int)mm) - 1;
+                        mm &= mm - 1u;
+                        uint8_t* f = child_seen + 8ull * node + c;
+                        if (!crowded || !__ldcg(f))
+                                *f = 1;
+                }
+        }
+        const uint32_t tot = block_sum_256((uint32_t)__popc(m8));
+        if (threadIdx.x == 0)
+                block_counts[blockIdx.x] = tot;
+}
+
 // child mask (the 8 flag bytes packed into 8 bits) and children per node; *dead_ends counts the nodes
 // none of whose children any triangle reached
 __global__ void k_node_counts(const unsigned long long* __restrict__ child_seen, uint32_t n,
@@ -1067,7 +1111,14 @@ static int build_ranked(vrt_tree* t, int L, uint64_t n0, const float* d_root6, c
         uint64_t n = n0;
         for (int l = 0; l < L; ++l) {
                 const uint64_t nn = level_n[l];
-                const int iters = (n < (1ull << 20)) ? 1 : kPairsPerBlock / 32;
+                // mask pass: one thread per pair (k_expand_mask_r8, default) or eight lanes per pair
+                // (k_expand_mask_r, VRT_BUILD_SAT8=0: a block handles 32 * iters pairs)
+                static int sat8 = -1;
+                if (sat8 < 0) {
+                        const char* e = getenv("VRT_BUILD_SAT8");
+                        sat8 = (e && e[0] == '0') ? 0 : 1;
+                }
+                const int iters = sat8 ? kPairsPerBlock / 32 : ((n < (1ull << 20)) ? 1 : kPairsPerBlock / 32);
                 const uint32_t ppb = 32u * (uint32_t)iters;  // pairs per block of the mask pass
                 const uint32_t nblk = (uint32_t)((n + ppb - 1) / ppb);
                 const uint32_t nblk_emit = (uint32_t)((n + kPairsPerBlock - 1) / kPairsPerBlock);
@@ -1082,10 +1133,15 @@ static int build_ranked(vrt_tree* t, int L, uint64_t n0, const float* d_root6, c
                 VRT_CUDA(cudaMemsetAsync(bc + nblk, 0, 4, s));
                 uint8_t* child_seen = t->refs_s.as<uint8_t>();  // (the reference list is written after the last level)
                 VRT_CUDA(cudaMemsetAsync(child_seen, 0, nn * 8, s));
-                k_expand_mask_r<<<nblk, 256, 0, s>>>(t->d_tri_in, tab, stride, cur->as<unsigned long long>(), (uint32_t)n, l,
-                                                     t->level_morton[l].as<unsigned long long>(), child_seen,
-                                                     (n > 16 * nn && n >= (1ull << 20)) ? 1 : 0, iters, t->tmp_b.as<uint8_t>(),
-                                                     bc);
+                const int crowded = (n > 16 * nn && n >= (1ull << 20)) ? 1 : 0;
+                if (sat8)
+                        k_expand_mask_r8<<<nblk, 256, 0, s>>>(t->d_tri_in, tab, stride, cur->as<unsigned long long>(), (uint32_t)n,
+                                                              l, t->level_morton[l].as<unsigned long long>(), child_seen, crowded,
+                                                              t->tmp_b.as<uint8_t>(), bc);
+                else
+                        k_expand_mask_r<<<nblk, 256, 0, s>>>(t->d_tri_in, tab, stride, cur->as<unsigned long long>(), (uint32_t)n,
+                                                             l, t->level_morton[l].as<unsigned long long>(), child_seen, crowded,
+                                                             iters, t->tmp_b.as<uint8_t>(), bc);
                 count_launch();
                 exclusive_scan_u32(bc, bc, nblk + 1ull, t->tmp_c.as<uint32_t>(), s);
                 k_node_counts<<<grid_for(nn, 256), 256, 0, s>>>(t->refs_s.as<unsigned long long>(), (uint32_t)nn, node_mask,
@@ -1190,6 +1246,7 @@ static void preload_build_kernels()
                 (const void*)k_collect_totals,  (const void*)k_compact_level,   (const void*)k_emit_leaves,
                 (const void*)k_emit_parents,    (const void*)k_expand_emit,     (const void*)k_expand_emit_r,
                 (const void*)k_expand_mask,     (const void*)k_expand_mask_r,   (const void*)k_head_flags,
+                (const void*)k_expand_mask_r8,
                 (const void*)k_leaf_scatter,    (const void*)k_leaf_sort_big,   (const void*)k_leaf_sort_small,
                 (const void*)k_node_counts,     (const void*)k_pack_tris,       (const void*)k_parent_flags,
                 (const void*)k_publish_totals,  (const void*)k_root_emit,       (const void*)k_root_mask,

@@ -176,6 +176,158 @@ __device__ __forceinline__ bool tri_overlaps_aabb(const float mn[3], const float
 }
 
 // ---------------------------------------------------------------------------
+// The EIGHT Triangle::is_overlap calls of one triangle against the eight children of one cell
+// (insert's loop over children, voxel_octree.cc:45-50,61-64), evaluated by ONE thread (round 2).
+// Every float operation of the eight triBoxOverlap calls is kept, with the same operands in the same
+// order; what is shared are the sub-expressions that are literally identical between children: a
+// child's centre/half, the translated vertices and the edges only depend on the child's HALF per axis
+// (two values per axis, not eight), an edge-axis test only on two of the three halves (four variants,
+// not eight), and the normal's components likewise.  bx/by/bz = (lo.min, lo.max, hi.min, hi.max) of the
+// cell's two child intervals per axis.  Returns the 8 verdicts, bit c = child c (x bit 2, y bit 1, z bit 0).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool axis_sep2(float pa, float pb, float rad)
+{
+        const float mn = (pa < pb) ? pa : pb;
+        const float mx = (pa < pb) ? pb : pa;
+        return (mn > rad) || (mx < -rad);
+}
+
+__device__ __forceinline__ uint32_t tri_overlaps_children8(const float4 bx, const float4 by, const float4 bz,
+                                                           const float t0[3], const float t1[3], const float t2[3])
+{
+        const float4 bb[3] = { bx, by, bz };
+        float h[3][2], v0[3][2], v1[3][2], v2[3][2];
+        uint32_t boxok[3];  // bit s: the child half s of this axis passes the box-axis test
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+                boxok[a] = 0;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                        const float mn = s ? bb[a].z : bb[a].x, mx = s ? bb[a].w : bb[a].y;
+                        // centre=(min+max)*.5f, half=(max-min)/2.f (x/2.f == x*.5f bit for bit, denormals included)
+                        const float c = fmul(fadd(mn, mx), .5f);
+                        h[a][s] = fmul(fsub(mx, mn), .5f);
+                        v0[a][s] = fsub(t0[a], c);
+                        v1[a][s] = fsub(t1[a], c);
+                        v2[a][s] = fsub(t2[a], c);
+                        float lo = v0[a][s], hi = v0[a][s];
+                        if (v1[a][s] < lo) lo = v1[a][s];
+                        if (v1[a][s] > hi) hi = v1[a][s];
+                        if (v2[a][s] < lo) lo = v2[a][s];
+                        if (v2[a][s] > hi) hi = v2[a][s];
+                        if (!(lo > h[a][s] || hi < -h[a][s]))
+                                boxok[a] |= 1u << s;
+                }
+        }
+        // candidates: children whose three box-axis tests pass
+        uint32_t cand = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+                if (((boxok[0] >> (c >> 2)) & (boxok[1] >> ((c >> 1) & 1)) & (boxok[2] >> (c & 1)) & 1u) != 0u)
+                        cand |= 1u << c;
+        if (!cand)
+                return 0u;
+        float e0[3][2], e1[3][2], e2[3][2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                        e0[a][s] = fsub(v1[a][s], v0[a][s]);
+                        e1[a][s] = fsub(v2[a][s], v1[a][s]);
+                        e2[a][s] = fsub(v0[a][s], v2[a][s]);
+                }
+        // plane (tribox2.cc:181-183 + 42-63): normal = cross(e0, e1); component q depends on the halves of the
+        // two other axes
+        float n0[2][2], n1[2][2], n2[2][2];  // n0[sy][sz], n1[sz][sx], n2[sx][sy]
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                        n0[p][q] = fsub(fmul(e0[1][p], e1[2][q]), fmul(e0[2][q], e1[1][p]));
+                        n1[p][q] = fsub(fmul(e0[2][p], e1[0][q]), fmul(e0[0][q], e1[2][p]));
+                        n2[p][q] = fsub(fmul(e0[0][p], e1[1][q]), fmul(e0[1][q], e1[0][p]));
+                }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+                if (!((cand >> c) & 1u))
+                        continue;
+                const int sx = c >> 2, sy = (c >> 1) & 1, sz = c & 1;
+                const float nx = n0[sy][sz], ny = n1[sz][sx], nz = n2[sx][sy];
+                const float d = -fadd(fadd(fmul(nx, v0[0][sx]), fmul(ny, v0[1][sy])), fmul(nz, v0[2][sz]));
+                // vmin[q] = n[q] > 0 ? -h : h ; vmax = -vmin ;  n*(-h) == -(n*h) bit for bit
+                const float mx_ = fmul(nx, h[0][sx]), my_ = fmul(ny, h[1][sy]), mz_ = fmul(nz, h[2][sz]);
+                const float lx = (nx > 0.0f) ? -mx_ : mx_, ly = (ny > 0.0f) ? -my_ : my_, lz = (nz > 0.0f) ? -mz_ : mz_;
+                const float dmin = fadd(fadd(fadd(lx, ly), lz), d);
+                const float dmax = fadd(fadd(fadd(-lx, -ly), -lz), d);
+                if (dmin > 0.0f || !(dmax >= 0.0f))
+                        cand &= ~(1u << c);
+        }
+        if (!cand)
+                return 0u;
+        // edge axes.  X-type tests (AXISTEST_X01 / X2) use the y and z halves, Y-type x and z, Z-type x and y.
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                        {  // X-type, halves (sy, sz) = (p, q): children {p*2+q, 4+p*2+q}
+                                const uint32_t m = (1u << (p * 2 + q)) | (1u << (4 + p * 2 + q));
+                                if (cand & m) {
+                                        bool sep;
+                                        // edge 0: X01 (v0, v2); edge 1: X01 (v0, v2); edge 2: X2 (v0, v1)
+                                        sep = axis_sep2(fsub(fmul(e0[2][q], v0[1][p]), fmul(e0[1][p], v0[2][q])),
+                                                        fsub(fmul(e0[2][q], v2[1][p]), fmul(e0[1][p], v2[2][q])),
+                                                        fadd(fmul(fabsf(e0[2][q]), h[1][p]), fmul(fabsf(e0[1][p]), h[2][q])));
+                                        sep = sep || axis_sep2(fsub(fmul(e1[2][q], v0[1][p]), fmul(e1[1][p], v0[2][q])),
+                                                               fsub(fmul(e1[2][q], v2[1][p]), fmul(e1[1][p], v2[2][q])),
+                                                               fadd(fmul(fabsf(e1[2][q]), h[1][p]), fmul(fabsf(e1[1][p]), h[2][q])));
+                                        sep = sep || axis_sep2(fsub(fmul(e2[2][q], v0[1][p]), fmul(e2[1][p], v0[2][q])),
+                                                               fsub(fmul(e2[2][q], v1[1][p]), fmul(e2[1][p], v1[2][q])),
+                                                               fadd(fmul(fabsf(e2[2][q]), h[1][p]), fmul(fabsf(e2[1][p]), h[2][q])));
+                                        if (sep)
+                                                cand &= ~m;
+                                }
+                        }
+                        {  // Y-type, halves (sx, sz) = (p, q): children {p*4+q, p*4+2+q}
+                                const uint32_t m = (1u << (p * 4 + q)) | (1u << (p * 4 + 2 + q));
+                                if (cand & m) {
+                                        bool sep;
+                                        // edge 0: Y02 (v0, v2); edge 1: Y02 (v0, v2); edge 2: Y1 (v0, v1)
+                                        sep = axis_sep2(fadd(fmul(-e0[2][q], v0[0][p]), fmul(e0[0][p], v0[2][q])),
+                                                        fadd(fmul(-e0[2][q], v2[0][p]), fmul(e0[0][p], v2[2][q])),
+                                                        fadd(fmul(fabsf(e0[2][q]), h[0][p]), fmul(fabsf(e0[0][p]), h[2][q])));
+                                        sep = sep || axis_sep2(fadd(fmul(-e1[2][q], v0[0][p]), fmul(e1[0][p], v0[2][q])),
+                                                               fadd(fmul(-e1[2][q], v2[0][p]), fmul(e1[0][p], v2[2][q])),
+                                                               fadd(fmul(fabsf(e1[2][q]), h[0][p]), fmul(fabsf(e1[0][p]), h[2][q])));
+                                        sep = sep || axis_sep2(fadd(fmul(-e2[2][q], v0[0][p]), fmul(e2[0][p], v0[2][q])),
+                                                               fadd(fmul(-e2[2][q], v1[0][p]), fmul(e2[0][p], v1[2][q])),
+                                                               fadd(fmul(fabsf(e2[2][q]), h[0][p]), fmul(fabsf(e2[0][p]), h[2][q])));
+                                        if (sep)
+                                                cand &= ~m;
+                                }
+                        }
+                        {  // Z-type, halves (sx, sy) = (p, q): children {p*4+q*2, p*4+q*2+1}
+                                const uint32_t m = (1u << (p * 4 + q * 2)) | (1u << (p * 4 + q * 2 + 1));
+                                if (cand & m) {
+                                        bool sep;
+                                        // edge 0: Z12 (v2, v1); edge 1: Z0 (v0, v1); edge 2: Z12 (v2, v1)
+                                        sep = axis_sep2(fsub(fmul(e0[1][q], v2[0][p]), fmul(e0[0][p], v2[1][q])),
+                                                        fsub(fmul(e0[1][q], v1[0][p]), fmul(e0[0][p], v1[1][q])),
+                                                        fadd(fmul(fabsf(e0[1][q]), h[0][p]), fmul(fabsf(e0[0][p]), h[1][q])));
+                                        sep = sep || axis_sep2(fsub(fmul(e1[1][q], v0[0][p]), fmul(e1[0][p], v0[1][q])),
+                                                               fsub(fmul(e1[1][q], v1[0][p]), fmul(e1[0][p], v1[1][q])),
+                                                               fadd(fmul(fabsf(e1[1][q]), h[0][p]), fmul(fabsf(e1[0][p]), h[1][q])));
+                                        sep = sep || axis_sep2(fsub(fmul(e2[1][q], v2[0][p]), fmul(e2[0][p], v2[1][q])),
+                                                               fsub(fmul(e2[1][q], v1[0][p]), fmul(e2[0][p], v1[1][q])),
+                                                               fadd(fmul(fabsf(e2[1][q]), h[0][p]), fmul(fabsf(e2[0][p]), h[1][q])));
+                                        if (sep)
+                                                cand &= ~m;
+                                }
+                        }
+                }
+        return cand;
+}
+
+// ---------------------------------------------------------------------------
 // intersect_triangle3 (raytri.cc:197-249): double, two-sided, EPSILON 1e-6
 // (raytri.cc:9), inv_det computed before the sign branch, no test on t.
 // ---------------------------------------------------------------------------
