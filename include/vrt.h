@@ -320,6 +320,10 @@ int vrt_gi_render_camera_dev(const vrt_tree* tree, const vrt_camera* cam, const 
 /* out = {node expansions cross-checked against the slab expansion, mismatches}; counts only in
  * a library built with -DVRT_PARAM_CHECK (tests), {0,0} otherwise. */
 int vrt_debug_param_check(uint64_t out[2]);
+/* Test hook of the build's overflow guard: the per-level (triangle, cell) pair totals are 32-bit block
+ * counts; whenever a level could produce 2^32 pairs they are also summed in 64 bits on the device and the
+ * build returns VRT_ERR_CAPACITY instead of wrapping.  This runs that 64-bit sum on `n` host counts. */
+int vrt_debug_pair_total(const uint32_t* block_counts, uint64_t n, uint64_t* total);
 /* _dev launches are asynchronous with respect to the host: they return once the work is
  * enqueued on the tree's stream.  vrt_tree_sync waits for it. */
 int vrt_tree_sync(const vrt_tree* tree);

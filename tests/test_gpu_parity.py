@@ -291,7 +291,8 @@ def test_octree_checkpoint_roundtrip(gpu, tmp_path):
     path = str(tmp_path / "sphere.vrt")
     tree.save(path)
     rep = gpu.Octree.load(path)
-    assert rep.info()["num_nodes"] == tree.info()["num_nodes"]
+    tree_nodes = tree.info()["num_nodes"]
+    assert rep.info()["num_nodes"] == tree_nodes
     leaves_equal(rep.leaves(), tree.leaves())
     cam = gpu.Camera(CAM_SPHERE[0], CAM_SPHERE[1:4], CAM_SPHERE[4:7], CAM_SPHERE[7:10], 64, 64, 4)
     assert rep.trace_camera(cam).tobytes() == tree.trace_camera(cam).tobytes()
@@ -307,6 +308,47 @@ def test_octree_checkpoint_roundtrip(gpu, tmp_path):
         gpu.Octree.load(bad)
     with pytest.raises(gpu.VrtError):
         gpu.Octree.load(str(tmp_path / "missing.vrt"))
+    # a truncated file and a header whose counts / section offsets point outside the blob are refused
+    # (VRT_ERR_ARG) instead of being bound to the kernels
+    good = bytes(data[:0]) + open(path, "rb").read()
+    import struct
+    cases = {"truncated": good[: len(good) // 2], "short": good[:100]}
+    hdr = bytearray(good)
+    struct.pack_into("<Q", hdr, 48, 2**40)             # num_nodes far beyond the file
+    cases["num_nodes"] = bytes(hdr)
+    for off in range(56, 512 - 8, 8):                   # every 64-bit header word past the root box, one at a time
+        hdr = bytearray(good)
+        struct.pack_into("<Q", hdr, off, struct.unpack_from("<Q", hdr, off)[0] + 2**33)
+        cases[f"word{off}"] = bytes(hdr)
+    refused = 0
+    for name, blob in cases.items():
+        with open(bad, "wb") as f:
+            f.write(blob)
+        try:
+            t2 = gpu.Octree.load(bad)
+        except gpu.VrtError:
+            refused += 1
+            continue
+        # words the format does not use (padding behind the last field) may change freely: the tree must still work
+        assert t2.info()["num_nodes"] == tree_nodes, name
+        t2.close()
+    assert refused >= 18, refused
+
+
+def test_import_rejects_cells_outside_the_grid_and_duplicates(gpu, port):
+    tri, nrm = scenes.uv_sphere(32, 16)
+    orc = port.build(tri, nrm, 5)
+    cells, counts, refs = orc.leaves()
+    root = orc.root_aabb()
+    gpu.Octree.from_leaves(tri, nrm, 5, root, cells, counts, refs).close()
+    bad = cells.copy()
+    bad[3, 1] = 16  # leaf grid of max_depth 5 is 16^3
+    with pytest.raises(gpu.VrtError):
+        gpu.Octree.from_leaves(tri, nrm, 5, root, bad, counts, refs)
+    dup = cells.copy()
+    dup[7] = dup[2]
+    with pytest.raises(gpu.VrtError):
+        gpu.Octree.from_leaves(tri, nrm, 5, root, dup, counts, refs)
 
 
 def test_work_counters_match_oracle(case, gpu, port):
@@ -606,3 +648,14 @@ def test_maximum_depth(gpu, port):
     with pytest.raises(gpu.VrtError):
         gpu.Octree.build(tri, None, depth + 1)
     tree.close()
+
+
+def test_pair_total_guard_sums_in_64_bits(gpu):
+    """Block counts whose sum passes 2^32 (a level that would overflow the 32-bit frontier indices) are summed
+    without wrapping by the build's guard (vrt_build then reports VRT_ERR_CAPACITY instead of sizing the next
+    frontier from a wrapped total)."""
+    rng = np.random.default_rng(11)
+    c = rng.integers(0, 2**32, 100_000, dtype=np.uint64).astype(np.uint32)
+    assert gpu.debug_pair_total(c) == int(c.astype(np.uint64).sum()) > 2**32
+    assert gpu.debug_pair_total(np.array([2**31, 2**31, 5], np.uint32)) == 2**32 + 5
+    assert gpu.debug_pair_total(np.zeros(0, np.uint32)) == 0

@@ -67,7 +67,7 @@ SYMBOLS = [
     "vrt_render_camera", "vrt_render_camera_dev", "vrt_render_camera_async", "vrt_band_rows", "vrt_render_bands_dev", "vrt_render_bands_async",
     "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_frame_bands_peer_dev",
     "vrt_dev_alloc", "vrt_dev_free", "vrt_host_register", "vrt_host_unregister", "vrt_ipc_export", "vrt_ipc_open", "vrt_ipc_close", "vrt_tree_sync",
-    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_set_materials", "vrt_albedo", "vrt_gi_init", "vrt_gi_splat_camera", "vrt_gi_filter",
+    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_debug_pair_total", "vrt_set_materials", "vrt_albedo", "vrt_gi_init", "vrt_gi_splat_camera", "vrt_gi_filter",
     "vrt_gi_get_level", "vrt_gi_cone_trace", "vrt_gi_render_camera", "vrt_gi_render_camera_dev", "vrt_tribox_batch",
     "vrt_tri_overlap_aabb_batch", "vrt_raytri_batch", "vrt_aabb_isect_batch",
 ]
@@ -136,6 +136,7 @@ def load(build_if_missing: bool = True):
     L.vrt_ipc_close.argtypes = [vp]
     L.vrt_debug_general_order_calls.restype = u64
     L.vrt_debug_param_check.argtypes = [vp]
+    L.vrt_debug_pair_total.argtypes = [vp, u64, vp]
     L.vrt_gi_init.argtypes = [vp]
     L.vrt_build_indexed.argtypes = [vp, u64, vp, u64, vp, C.c_uint32, i32, C.POINTER(vp)]
     L.vrt_set_materials.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp]
@@ -496,6 +497,14 @@ def debug_param_check():
     c = np.zeros(2, np.uint64)
     _check(load().vrt_debug_param_check(_ptr(c)))
     return int(c[0]), int(c[1])
+
+
+def debug_pair_total(block_counts) -> int:
+    """64-bit device sum of 32-bit block counts (the build's pair-total overflow guard)."""
+    c = np.ascontiguousarray(block_counts, np.uint32)
+    out = np.zeros(1, np.uint64)
+    _check(load().vrt_debug_pair_total(_ptr(c), len(c), _ptr(out)))
+    return int(out[0])
 
 
 def dev_alloc(nbytes: int) -> int:

@@ -1412,6 +1412,28 @@ int vrt_debug_param_check(uint64_t out[2])
         return rc;
 }
 
+int vrt_debug_pair_total(const uint32_t* block_counts, uint64_t n, uint64_t* total)
+{
+        if ((!block_counts && n) || !total) {
+                set_error("null argument");
+                return VRT_ERR_ARG;
+        }
+        vrt_tree* t = nullptr;
+        int rc = tree_alloc(&t);
+        if (rc)
+                return rc;
+        DevBuf d;
+        rc = d.alloc(n * 4);
+        if (!rc && n && cudaMemcpy(d.p, block_counts, n * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+                cudaGetLastError();
+                rc = VRT_ERR_CUDA;
+        }
+        if (!rc)
+                rc = sum_u32_as_u64(t, static_cast<const uint32_t*>(d.p), n, total);
+        vrt_tree_free(t);
+        return rc;
+}
+
 uint64_t vrt_debug_general_order_calls(void)
 {
         unsigned long long n = 0;

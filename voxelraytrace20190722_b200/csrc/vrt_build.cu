@@ -473,6 +473,41 @@ static inline unsigned grid_for(uint64_t n, unsigned block)
         return (unsigned)std::max<uint64_t>(1, (n + block - 1) / block);
 }
 
+// Pair totals are carried in 32 bits (block counts, their scan, the frontier indices).  A level with n pairs can
+// produce up to 8n: whenever 8n could reach 2^32 the block counts are ALSO summed in 64 bits before the scan, and
+// the build stops with VRT_ERR_CAPACITY instead of sizing the next frontier from a wrapped total.
+__global__ void __launch_bounds__(256)
+k_sum_u32_u64(const uint32_t* __restrict__ v, uint64_t n, unsigned long long* __restrict__ out)
+{
+        unsigned long long acc = 0;
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+                acc += v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+                acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0 && acc)
+                atomicAdd(out, acc);
+}
+
+// sum of `n` device uint32 as a 64-bit host value (synchronises the stream)
+int sum_u32_as_u64(vrt_tree* t, const uint32_t* d_v, uint64_t n, uint64_t* out)
+{
+        unsigned long long* d_sum = reinterpret_cast<unsigned long long*>(t->d_counter + 58);
+        VRT_CUDA(cudaMemsetAsync(d_sum, 0, 8, t->stream));
+        if (n) {
+                k_sum_u32_u64<<<(unsigned)std::min<uint64_t>(1184, (n + 255) / 256), 256, 0, t->stream>>>(d_v, n, d_sum);
+                count_launch();
+        }
+        unsigned long long h = 0;
+        VRT_CUDA(cudaMemcpyAsync(&h, d_sum, 8, cudaMemcpyDeviceToHost, t->stream));
+        VRT_CUDA(cudaStreamSynchronize(t->stream));
+        *out = h;
+        return VRT_OK;
+}
+
+// true when the totals of a level fed by n pairs need the 64-bit check
+static inline bool pair_total_may_wrap(uint64_t n) { return n >= (1ull << 29); }
+
 // ---------------------------------------------------------------------------
 // RANKED top-down build (the default for trees of depth >= 5).  The level-synchronous expansion
 // above already visits every (triangle, non-empty cell) pair of every level, so the node arrays
@@ -1143,6 +1178,16 @@ static int build_ranked(vrt_tree* t, int L, uint64_t n0, const float* d_root6, c
                                                              l, t->level_morton[l].as<unsigned long long>(), child_seen, crowded,
                                                              iters, t->tmp_b.as<uint8_t>(), bc);
                 count_launch();
+                if (pair_total_may_wrap(n)) {
+                        uint64_t tot64 = 0;
+                        int rc64 = sum_u32_as_u64(t, bc, nblk, &tot64);
+                        if (rc64)
+                                return rc64;
+                        if (tot64 >= 0xfffffff0ull) {
+                                set_error("more than 2^32 (triangle, cell) pairs at level %d", l + 1);
+                                return VRT_ERR_CAPACITY;
+                        }
+                }
                 exclusive_scan_u32(bc, bc, nblk + 1ull, t->tmp_c.as<uint32_t>(), s);
                 k_node_counts<<<grid_for(nn, 256), 256, 0, s>>>(t->refs_s.as<unsigned long long>(), (uint32_t)nn, node_mask,
                                                                 node_cnt, d_tot + 2);
@@ -1347,6 +1392,16 @@ int build_tree(vrt_tree* t, int max_depth)
                                                    cur->as<unsigned long long>(), (uint32_t)n, l, tb,
                                                    t->tmp_b.as<uint8_t>(), bc);
                 count_launch();
+                if (pair_total_may_wrap(n)) {
+                        uint64_t tot64 = 0;
+                        int rc64 = sum_u32_as_u64(t, bc, nblk, &tot64);
+                        if (rc64)
+                                return rc64;
+                        if (tot64 >= 0xfffffff0ull) {
+                                set_error("more than 2^32 (triangle, cell) pairs at level %d", l + 1);
+                                return VRT_ERR_CAPACITY;
+                        }
+                }
                 exclusive_scan_u32(bc, bc, nblk + 1ull, t->tmp_c.as<uint32_t>(), s);
                 VRT_CUDA(cudaMemcpyAsync(t->h_counter, bc + nblk, 4, cudaMemcpyDeviceToHost, s));
                 VRT_CUDA(cudaStreamSynchronize(s));
@@ -1392,6 +1447,24 @@ int import_leaves(vrt_tree* t, int max_depth, const float root_aabb[6], uint64_t
         uint64_t n = 0;
         for (uint64_t i = 0; i < num_leaves; ++i)
                 n += leaf_count[i];
+        // every cell inside the leaf grid, no cell twice (a coordinate >= 2^L would spill into the Morton bits of
+        // another cell, a repeated cell would silently merge two reference lists)
+        {
+                std::vector<unsigned long long> codes(num_leaves);
+                for (uint64_t i = 0; i < num_leaves; ++i) {
+                        for (int a = 0; a < 3; ++a)
+                                if ((uint64_t)leaf_cell[3 * i + a] >> L) {
+                                        set_error("leaf_cell[%llu] lies outside the %d-level leaf grid", (unsigned long long)i, L);
+                                        return VRT_ERR_ARG;
+                                }
+                        codes[i] = morton_encode(leaf_cell[3 * i], leaf_cell[3 * i + 1], leaf_cell[3 * i + 2]);
+                }
+                std::sort(codes.begin(), codes.end());
+                if (std::adjacent_find(codes.begin(), codes.end()) != codes.end()) {
+                        set_error("leaf_cell lists the same cell twice");
+                        return VRT_ERR_ARG;
+                }
+        }
         std::vector<unsigned long long> keys(n);
         uint64_t k = 0;
         for (uint64_t i = 0; i < num_leaves; ++i) {

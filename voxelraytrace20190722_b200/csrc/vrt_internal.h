@@ -164,6 +164,8 @@ int tree_alloc(vrt_tree** out);
 void tree_bind_views(vrt_tree* t);
 // build pipeline (vrt_build.cu)
 int build_tree(vrt_tree* t, int max_depth);
+// 64-bit sum of n device uint32 (the overflow guard of the per-level pair totals); synchronises the stream
+int sum_u32_as_u64(vrt_tree* t, const uint32_t* d_v, uint64_t n, uint64_t* out);
 // per-node content hulls beside the blob (after tree_bind_views; every build / import / replica)
 int compute_hulls(vrt_tree* t);
 int import_leaves(vrt_tree* t, int max_depth, const float root_aabb[6], uint64_t num_leaves,
