@@ -7,7 +7,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <utility>
 #include <vector>
 #include <sys/types.h>
 
@@ -59,6 +61,30 @@ static void pool_setup_once()
         cudaGetLastError();
 }
 
+// Buffers that are dropped while work may still be reading them (a scratch buffer that has to grow in the middle
+// of a build, the buffers of a handle that is being freed) are parked here and freed at the next flush point --
+// ONE device synchronisation for all of them instead of one per buffer (a fresh handle's first build used to
+// spend most of its wall time in those synchronisations).
+static std::mutex g_parked_mu;
+static std::vector<std::pair<void*, size_t>> g_parked;
+static size_t g_parked_bytes = 0;
+
+void scratch_flush_deferred()
+{
+        std::vector<std::pair<void*, size_t>> v;
+        {
+                std::lock_guard<std::mutex> lk(g_parked_mu);
+                v.swap(g_parked);
+                g_parked_bytes = 0;
+        }
+        if (v.empty())
+                return;
+        cudaDeviceSynchronize();  // nothing may still be using the parked buffers
+        for (auto& e : v)
+                cudaFreeAsync(e.first, cudaStreamPerThread);
+        cudaGetLastError();
+}
+
 int Scratch::reserve(size_t bytes)
 {
         if (bytes <= cap && p)
@@ -66,15 +92,22 @@ int Scratch::reserve(size_t bytes)
         pool_setup_once();
         size_t want = std::max<size_t>(bytes, 256);
         if (p) {
-                want = std::max(want, cap + cap / 2);
+                want = std::max(want, cap * 2);
                 release();
+                if (g_parked_bytes > (8ull << 30))
+                        scratch_flush_deferred();
         }
         if (cudaMallocAsync(&p, want, cudaStreamPerThread) != cudaSuccess ||
             cudaStreamSynchronize(cudaStreamPerThread) != cudaSuccess) {
                 cudaGetLastError();
-                p = nullptr;
-                set_error("cudaMallocAsync(%zu) failed", want);
-                return VRT_ERR_NOMEM;
+                scratch_flush_deferred();  // give the parked memory back and try once more
+                if (cudaMallocAsync(&p, want, cudaStreamPerThread) != cudaSuccess ||
+                    cudaStreamSynchronize(cudaStreamPerThread) != cudaSuccess) {
+                        cudaGetLastError();
+                        p = nullptr;
+                        set_error("cudaMallocAsync(%zu) failed", want);
+                        return VRT_ERR_NOMEM;
+                }
         }
         cap = want;
         return 0;
@@ -83,8 +116,9 @@ int Scratch::reserve(size_t bytes)
 void Scratch::release()
 {
         if (p) {
-                cudaDeviceSynchronize();  // (what cudaFree did implicitly: nothing may still be using the buffer)
-                cudaFreeAsync(p, cudaStreamPerThread);
+                std::lock_guard<std::mutex> lk(g_parked_mu);
+                g_parked.emplace_back(p, cap);
+                g_parked_bytes += cap;
         }
         p = nullptr;
         cap = 0;
@@ -526,6 +560,7 @@ void vrt_tree_free(vrt_tree* t)
                 t->level_first[l].release();
                 t->level_mask[l].release();
         }
+        scratch_flush_deferred();
         if (t->d_counter)
                 cudaFree(t->d_counter);
         if (t->h_counter)

@@ -1041,6 +1041,7 @@ static int assemble_blob(vrt_tree* t, int L, uint64_t n, const uint64_t* level_n
         VRT_CUDA(cudaMemcpyAsync(base, &h, sizeof h, cudaMemcpyHostToDevice, s));
         VRT_CUDA(cudaStreamSynchronize(s));
         tree_bind_views(t);
+        scratch_flush_deferred();  // buffers that had to grow during this build
         return compute_hulls(t);
 }
 

@@ -94,6 +94,8 @@ struct TreeDev {
 void set_error(const char* fmt, ...);
 bool cuda_ok(cudaError_t e, const char* what);
 void count_launch(int n = 1);
+// frees the scratch buffers parked by Scratch::release (one device synchronisation for all of them)
+void scratch_flush_deferred();
 
 #define VRT_CUDA(expr)                                  \
         do {                                            \
