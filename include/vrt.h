@@ -139,6 +139,12 @@ int vrt_build(const float* tri_xyz, const float* tri_nrm, uint32_t num_tris,
               int max_depth, vrt_tree** out);
 int vrt_build_dev(const float* d_tri_xyz, const float* d_tri_nrm, uint32_t num_tris,
                   int max_depth, vrt_tree** out);
+/* vrt_build with flags.  VRT_BUILD_UNIT_NORMALS: tri_nrm holds Triangle::n_ as the reference's Triangle
+ * objects store it (already normalised by the ctor, voxel_octree.cc:426) and is kept verbatim -- what a
+ * binding that reads existing gi::Triangle objects must pass (cpp/vrt_dropin.cc). */
+#define VRT_BUILD_UNIT_NORMALS 1u
+int vrt_build_ex(const float* tri_xyz, const float* tri_nrm, uint32_t num_tris, int max_depth,
+                 uint32_t flags, vrt_tree** out);
 /* Indexed ingest (obj2voxel, voxel_octree.cc:305-371): the arrays tinyobj::LoadObj returns --
  * attrib.vertices[num_vertices][3], attrib.normals[num_normals][3] (NULL: geometric normals) and the
  * per-face-vertex tinyobj::index_t records index3[T][3] = {vertex_index, normal_index,

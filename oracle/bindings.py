@@ -43,7 +43,14 @@ def build_ref(force: bool = False) -> str | None:
     have_src = os.path.exists(os.path.join(
         os.environ.get("VRT_REFERENCE_DIR", "/root/reference"), "VoxelRayTrace20190722", "voxel_octree.cc"))
     harness = os.path.join(HERE, "ref_harness.cc")
-    stale = (not os.path.exists(REF_SO)) or os.path.getmtime(REF_SO) < os.path.getmtime(harness)
+    # (the same recipe also links the reference's main.cc against libvrt.so: oracle/_ref/main_dropin*)
+    dropin = os.path.join(HERE, "_ref", "main_dropin")
+    deps = [harness, os.path.join(HERE, "build_ref.sh"),
+            os.path.join(HERE, "..", "voxelraytrace20190722_b200", "cpp", "vrt_dropin.cc"),
+            os.path.join(HERE, "..", "include", "vrt.h")]
+    outs = [REF_SO] + ([dropin] if os.path.exists(os.path.join(HERE, "..", "voxelraytrace20190722_b200", "libvrt.so")) else [])
+    stale = any(not os.path.exists(o) for o in outs) or \
+        min(os.path.getmtime(o) for o in outs) < max(os.path.getmtime(d) for d in deps if os.path.exists(d))
     if have_src and (force or stale):
         subprocess.check_call(["bash", os.path.join(HERE, "build_ref.sh")])
     return REF_SO if os.path.exists(REF_SO) else None

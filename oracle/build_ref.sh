@@ -78,3 +78,54 @@ $CXX -shared -o "$OUT/libvrt_ref.so" "$TMP"/*.o -lpthread
         (cd "$REF" && sha256sum camera.cc voxel_octree.cc tribox2.cc raytri.cc graphics_math.h camera.h voxel_octree.h)
 } > "$OUT/BUILD_INFO.txt"
 echo "built $OUT/libvrt_ref.so"
+
+# ---------------------------------------------------------------------------------------------
+# DROP-IN link test (north star: "main.cc links against the GPU path as a drop-in").
+# The reference's OWN main.cc + voxel_octree.h + camera.h + voxel_octree.cc + camera.cc, from the
+# same throw-away copy, linked against libvrt.so through voxelraytrace20190722_b200/cpp/vrt_dropin.cc:
+#   * tribox2.cc and raytri.cc are NOT compiled: triBoxOverlap / intersect_triangle3 come from the binding;
+#   * voxel_octree.cc is compiled with -Dray_march_init=... -Dray_march=... (preprocessor renames, no edit),
+#     so its CPU build/traversal keep other names and gi::ray_march_init / gi::ray_march resolve to the
+#     binding (CUDA); obj2voxel, Triangle, texel_fetch, cone_trace stay the reference's own host code;
+#   * camera.cc is compiled with -DCamera=RefCpuCamera: Film stays the reference's, Camera is the binding's;
+#   * main.cc: ONLY the hard-coded Windows path of sponza.obj (main.cc:47) is replaced by ./dropin_scene.obj.
+#     main_dropin_small additionally shrinks the two films (main.cc:34-35,75) so that the per-ray launches of
+#     the test finish in seconds -- the geometry, cameras, depth and every call site are untouched.
+# Outputs: oracle/_ref/main_dropin, oracle/_ref/main_dropin_small (git-ignored, shipped by gpurun).
+# ---------------------------------------------------------------------------------------------
+PKG="$HERE/../voxelraytrace20190722_b200"
+if [ "${VRT_SKIP_DROPIN:-0}" != "1" ] && [ -f "$PKG/libvrt.so" ]; then
+        for f in main.cc stb_image_write.h; do cp "$REF/$f" "$TMP/src/$f"; done
+        grep -q 'sponza.obj"' "$TMP/src/main.cc"
+        sed -i 's#^\(\s*\)"C:.*sponza\.obj",#\1"./dropin_scene.obj",#' "$TMP/src/main.cc"
+        grep -q '"./dropin_scene.obj",' "$TMP/src/main.cc"
+        sed -e 's/int W = 1024;/int W = 96;/' -e 's/int H = 1024;/int H = 96;/' \
+            -e 's/Film sfilm(1, 1, 2048, 2048);/Film sfilm(1, 1, 128, 128);/' "$TMP/src/main.cc" > "$TMP/src/main_small.cc"
+        grep -q 'int W = 96;' "$TMP/src/main_small.cc" && grep -q 'Film sfilm(1, 1, 128, 128);' "$TMP/src/main_small.cc"
+        DFLAGS="-std=c++17 -O2 -ffp-contract=off -w -include $TMP/libm_shim.h -I$TMP/src -I$HERE/../include"
+        $CXX $DFLAGS -Dray_march_init=ref_cpu_ray_march_init -Dray_march=ref_cpu_ray_march -c "$TMP/src/voxel_octree.cc" -o "$TMP/d_voxel_octree.o" &
+        p1=$!
+        $CXX $DFLAGS -DCamera=RefCpuCamera -c "$TMP/src/camera.cc" -o "$TMP/d_camera.o" &
+        p2=$!
+        $CXX $DFLAGS -c "$PKG/cpp/vrt_dropin.cc" -o "$TMP/d_binding.o" &
+        p3=$!
+        $CXX $DFLAGS -c "$TMP/src/main.cc" -o "$TMP/d_main.o" &
+        p4=$!
+        $CXX $DFLAGS -c "$TMP/src/main_small.cc" -o "$TMP/d_main_small.o" &
+        p5=$!
+        for p in $p1 $p2 $p3 $p4 $p5; do wait "$p"; done
+        for m in main main_small; do
+                $CXX -o "$OUT/${m/main/main_dropin}" "$TMP/d_$m.o" "$TMP/d_voxel_octree.o" "$TMP/d_camera.o" "$TMP/d_binding.o" \
+                     "$TMP/tiny_obj_loader.o" -L"$PKG" -lvrt -lpthread -Wl,-rpath,'$ORIGIN/../../voxelraytrace20190722_b200'
+        done
+        # the same small main.cc linked against the reference's own objects only (CPU): the checker of the drop-in test
+        $CXX -o "$OUT/main_refcpu_small" "$TMP/d_main_small.o" "$TMP/camera.o" "$TMP/voxel_octree.o" "$TMP/tribox2.o" \
+             "$TMP/raytri.o" "$TMP/tiny_obj_loader.o" -lpthread
+        # the hot symbols of the drop-in binaries must come from the binding, the reference's CPU versions keep their renamed symbols
+        nm -C "$OUT/main_dropin" > "$TMP/syms.txt"
+        grep -q ' T gi::ray_march(gi::VoxelOctree' "$TMP/syms.txt"
+        grep -q 'gi::ref_cpu_ray_march(' "$TMP/syms.txt"
+        grep -q ' T triBoxOverlap' "$TMP/syms.txt"
+        grep -q ' T Camera::gen_rays4' "$TMP/syms.txt"
+        echo "built $OUT/main_dropin and $OUT/main_dropin_small (reference main.cc linked against libvrt.so)"
+fi

@@ -67,7 +67,7 @@ SYMBOLS = [
     "vrt_render_camera", "vrt_render_camera_dev", "vrt_render_camera_async", "vrt_band_rows", "vrt_render_bands_dev", "vrt_render_bands_async",
     "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_frame_bands_peer_dev",
     "vrt_dev_alloc", "vrt_dev_free", "vrt_host_register", "vrt_host_unregister", "vrt_ipc_export", "vrt_ipc_open", "vrt_ipc_close", "vrt_tree_sync",
-    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_debug_pair_total", "vrt_set_materials", "vrt_albedo", "vrt_gi_init", "vrt_gi_splat_camera", "vrt_gi_filter",
+    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_debug_pair_total", "vrt_build_ex", "vrt_set_materials", "vrt_albedo", "vrt_gi_init", "vrt_gi_splat_camera", "vrt_gi_filter",
     "vrt_gi_get_level", "vrt_gi_cone_trace", "vrt_gi_render_camera", "vrt_gi_render_camera_dev", "vrt_tribox_batch",
     "vrt_tri_overlap_aabb_batch", "vrt_raytri_batch", "vrt_aabb_isect_batch",
 ]

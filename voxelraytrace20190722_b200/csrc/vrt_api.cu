@@ -218,7 +218,8 @@ static int upload_inputs(vrt_tree* t, const float* tri, const float* nrm, uint32
         return VRT_OK;
 }
 
-static int build_common(const float* tri, const float* nrm, uint32_t T, int max_depth, bool dev, vrt_tree** out)
+static int build_common(const float* tri, const float* nrm, uint32_t T, int max_depth, bool dev, vrt_tree** out,
+                        uint32_t flags = 0)
 {
         if (!out || (T && !tri)) {
                 set_error("vrt_build: null argument");
@@ -233,6 +234,7 @@ static int build_common(const float* tri, const float* nrm, uint32_t T, int max_
         int rc = tree_alloc(&t);
         if (rc)
                 return rc;
+        t->unit_normals = (flags & VRT_BUILD_UNIT_NORMALS) != 0;
         rc = upload_inputs(t, tri, nrm, T, dev);
         if (!rc)
                 rc = build_tree(t, max_depth);
@@ -493,6 +495,16 @@ uint64_t vrt_launch_count(void) { return g_launches.load(); }
 int vrt_build(const float* tri_xyz, const float* tri_nrm, uint32_t num_tris, int max_depth, vrt_tree** out)
 {
         return build_common(tri_xyz, tri_nrm, num_tris, max_depth, false, out);
+}
+
+int vrt_build_ex(const float* tri_xyz, const float* tri_nrm, uint32_t num_tris, int max_depth, uint32_t flags,
+                 vrt_tree** out)
+{
+        if (flags & ~(uint32_t)VRT_BUILD_UNIT_NORMALS) {
+                set_error("vrt_build_ex: unknown flags 0x%x", flags);
+                return VRT_ERR_ARG;
+        }
+        return build_common(tri_xyz, tri_nrm, num_tris, max_depth, false, out, flags);
 }
 
 int vrt_build_indexed(const float* vertices, uint64_t num_vertices, const float* normals, uint64_t num_normals,
@@ -1189,7 +1201,12 @@ int vrt_render_bands_async(const vrt_tree* tc, const vrt_camera* cam, const vrt_
         const int full_bands = rows / b->band_h, tail_rows = rows % b->band_h;
         char* dst = reinterpret_cast<char*>(film_rgb_full) + (size_t)y0 * row_bytes;
         const char* src = static_cast<const char*>(t->film_dev[k].p);
-        if (full_bands)
+        static int dbg_no_copy = -1;  // VRT_DEBUG_NO_COPY=1: diagnostic only (frames never reach the host)
+        if (dbg_no_copy < 0) {
+                const char* e = getenv("VRT_DEBUG_NO_COPY");
+                dbg_no_copy = (e && e[0] == '1') ? 1 : 0;
+        }
+        if (full_bands && !dbg_no_copy)
                 VRT_CUDA(cudaMemcpy2DAsync(dst, (size_t)b->band_stride * band_bytes, src, band_bytes, band_bytes,
                                            (size_t)full_bands, cudaMemcpyDeviceToHost, t->copy_stream));
         if (tail_rows)

@@ -427,7 +427,7 @@ __global__ void k_write_leaves(const uint32_t* __restrict__ start, uint32_t n, u
 // vertices -> float4 x3 ; normals normalised like the Triangle ctor
 // (voxel_octree.cc:426); NULL normals -> geometric normal cross(p1-p0,p2-p0).
 __global__ void k_pack_tris(const float* __restrict__ tri, const float* __restrict__ nrm_in, uint32_t T,
-                            float4* __restrict__ tri4, float* __restrict__ nrm_out)
+                            float4* __restrict__ tri4, float* __restrict__ nrm_out, int unit_normals)
 {
         uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
         if (t >= T)
@@ -457,9 +457,13 @@ __global__ void k_pack_tris(const float* __restrict__ tri, const float* __restri
                 for (int k = 0; k < 9; ++k)
                         n[k] = g[k % 3];
         }
+        // (unit_normals: the caller hands over Triangle::n_ itself, already normalised by the Triangle ctor --
+        // normalising again would move the last bit)
+        if (!(unit_normals && nrm_in)) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k)
-                normalize3(n[3 * k], n[3 * k + 1], n[3 * k + 2]);
+                for (int k = 0; k < 3; ++k)
+                        normalize3(n[3 * k], n[3 * k + 1], n[3 * k + 2]);
+        }
 #pragma unroll
         for (int k = 0; k < 9; ++k)
                 nrm_out[9ull * t + k] = n[k];
@@ -1031,7 +1035,7 @@ static int assemble_blob(vrt_tree* t, int L, uint64_t n, const uint64_t* level_n
         if (T) {
                 k_pack_tris<<<grid_for(T, 256), 256, 0, s>>>(t->d_tri_in, t->d_nrm_in, T,
                                                              reinterpret_cast<float4*>(base + h.off_tri4),
-                                                             reinterpret_cast<float*>(base + h.off_nrm));
+                                                             reinterpret_cast<float*>(base + h.off_nrm), t->unit_normals ? 1 : 0);
                 count_launch();
         }
         k_axis_table<<<1, 1024, 0, s>>>(d_root6, reinterpret_cast<float2*>(base + h.off_axis_tab),

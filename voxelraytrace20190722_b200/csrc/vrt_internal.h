@@ -127,6 +127,7 @@ struct vrt_tree {
         // inputs kept for vrt_rebuild
         float* d_tri_in = nullptr;  // [T][9] as given
         float* d_nrm_in = nullptr;  // [T][9] as given, or null
+        bool unit_normals = false;  // VRT_BUILD_UNIT_NORMALS: d_nrm_in is stored verbatim
         // build scratch
         vrt::Scratch keys_a, keys_b, tmp_a, tmp_b, tmp_c, hist, refs_s, tab_s, level_morton[VRT_MAX_DEPTH + 1],
             level_first[VRT_MAX_DEPTH + 1], level_mask[VRT_MAX_DEPTH + 1];
