@@ -128,9 +128,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_scene(wl):
-    from voxelraytrace20190722_b200 import scenes
+OBJ_SCENE = {}  # filled by make_scene when the geometry comes from an OBJ file (--obj / Asset/sponza/sponza.obj)
+
+
+def make_scene(wl, obj=None):
+    """Geometry of the workload.  The "Sponza" workloads use the real asset when it is there (--obj PATH, or
+    Asset/sponza/sponza.obj next to the repo / $VRT_SPONZA_OBJ: SURVEY.md 7 step 2) -- OBJ + MTL + TGA read on the
+    host (voxelraytrace20190722_b200/assets.py), materials handed to vrt_set_materials -- else the procedural
+    atrium stand-in."""
+    from voxelraytrace20190722_b200 import assets, scenes
     scene, kw, depth, cam10, nx, ny, spp = WORKLOADS[wl]
+    if obj is None and scene == "atrium":
+        obj = assets.default_sponza_obj()
+    if obj:
+        sc = assets.load_scene(obj)
+        tri, nrm = assets.expand_triangles(sc)
+        if nrm is None:
+            raise SystemExit(f"bench.py: {obj} has faces without normals (obj2voxel asserts them, voxel_octree.cc:346)")
+        OBJ_SCENE.update(path=obj, scene=sc)
+        return tri, nrm, depth, np.asarray(cam10, np.float32), nx, ny, spp
     tri, nrm = scenes.make_scene(scene, **kw)
     return tri, nrm, depth, np.asarray(cam10, np.float32), nx, ny, spp
 
@@ -213,7 +229,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    tri, nrm, depth, cam10, nx, ny, spp = make_scene(args.workload)
+    tri, nrm, depth, cam10, nx, ny, spp = make_scene(args.workload, args.obj)
     r = cpu_reference(tri, nrm, depth, cam10, spp, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "Mrays/s octree traversal", "value": r["mrays"], "unit": "Mrays/s",
@@ -236,9 +252,15 @@ def run_reference(args):
 
 def workload_config(wl, ntris, gpus):
     scene, kw, depth, cam10, nx, ny, spp = WORKLOADS[wl]
+    if OBJ_SCENE:
+        sc = OBJ_SCENE["scene"]
+        scene_desc = (f"obj {OBJ_SCENE['path']} ({ntris} tris, {len(sc['materials'])} materials, {len(sc['textures'])} textures"
+                      + (f", missing textures {sc['missing_textures']}" if sc["missing_textures"] else "") + ")")
+    else:
+        scene_desc = f"{scene} ({ntris} tris" + ("; procedural Sponza stand-in, sponza.obj absent from the reference checkout)"
+                                                 if scene == "atrium" else ")")
     return {"workload": wl,
-            "scene": f"{scene} ({ntris} tris" + ("; procedural Sponza stand-in, sponza.obj absent from the reference checkout)"
-                                                  if scene == "atrium" else ")"),
+            "scene": scene_desc,
             "max_depth": depth, "leaf_grid": f"{2 ** (depth - 1)}^3", "film": f"{nx}x{ny}", "spp": spp,
             "rays_per_step": nx * ny * spp,
             "camera": ("64-frame orbit (SURVEY 8d config 5), one frame per step; value counts primary rays, every hit "
@@ -270,7 +292,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
 
-    tri, nrm, depth, cam10, nx, ny, spp = make_scene(args.workload)
+    tri, nrm, depth, cam10, nx, ny, spp = make_scene(args.workload, args.obj)
     T = len(tri)
     rays_per_step = nx * ny * spp
     launches0 = capi.launch_count()
@@ -297,6 +319,9 @@ def run_ours(args):
         build["ms"] = float(np.mean(ms[1:])) if len(ms) > 1 else ms[0]
     if world > 1:
         tree = vdist.replicate_octree(tree, dev)
+    if OBJ_SCENE and rank == 0 and world == 1:
+        sc = OBJ_SCENE["scene"]  # Triangle::get_albedo data for the GI rows (voxel_octree.cc:471-484)
+        tree.set_materials(sc["tri_uv"], sc["tri_mtl"], sc["kd"], sc["mtl_tex"], sc["textures"])
     info = tree.info()
     extra = EXTRAS.get(args.workload, {})
     shadow_eps = extra.get("shadow_eps")
@@ -670,6 +695,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--build-reps", type=int, default=3)
+    ap.add_argument("--obj", default=None,
+                    help="Wavefront OBJ (+ MTL + TGA) to use as the scene instead of the procedural stand-in; default: "
+                         "Asset/sponza/sponza.obj next to the repo or $VRT_SPONZA_OBJ when present")
     ap.add_argument("--assemble", default="peer", choices=["peer", "gather"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gi", action="store_true", help="skip the GI rows (splat/filter/cone-trace film)")
