@@ -247,6 +247,19 @@ int vrt_trace_bands16_dev(const vrt_tree* tree, const vrt_camera* cam,
  * process barrier, and the frame is complete.  Alternate between two host frames. */
 int vrt_render_bands_async(const vrt_tree* tree, const vrt_camera* cam, const vrt_shade* sh,
                            const vrt_bands* bands, float* film_rgb_full);
+/* Single-process multi-GPU render for C / C++ hosts (the thread pool of render_mt, camera.h:41-68, becomes N
+ * devices): replicate a built octree onto `num_devices` devices (devices == NULL: 0..num_devices-1; peer copies of
+ * the blob), then per frame deal the film's 8-row bands round-robin to the devices.  Every device runs the
+ * vrt_render_bands_async pipeline and DMA-copies its bands to their final rows of film_rgb_full (pinned host
+ * memory, e.g. vrt_host_register'ed); vrt_mgpu_sync (or the synchronous vrt_mgpu_render) completes the frame.
+ * The source tree stays the caller's and may be freed after vrt_mgpu_create. */
+typedef struct vrt_mgpu vrt_mgpu;
+int vrt_mgpu_create(const vrt_tree* tree, int num_devices, const int* devices, vrt_mgpu** out);
+int vrt_mgpu_num_devices(const vrt_mgpu* m);
+int vrt_mgpu_render_async(vrt_mgpu* m, const vrt_camera* cam, const vrt_shade* sh, float* film_rgb_full);
+int vrt_mgpu_sync(vrt_mgpu* m);
+int vrt_mgpu_render(vrt_mgpu* m, const vrt_camera* cam, const vrt_shade* sh, float* film_rgb_full);
+void vrt_mgpu_free(vrt_mgpu* m);
 /* Work counters of the reference algorithm for a camera frame:
  * counts[0..4] = rays traced, interior nodes expanded (travorder calls), non-empty
  * leaves visited, triangle tests, hits; counts[5..7] = kernel statistics: expansions done
@@ -326,6 +339,9 @@ int vrt_gi_render_camera_dev(const vrt_tree* tree, const vrt_camera* cam, const 
 /* out = {node expansions cross-checked against the slab expansion, mismatches}; counts only in
  * a library built with -DVRT_PARAM_CHECK (tests), {0,0} otherwise. */
 int vrt_debug_param_check(uint64_t out[2]);
+/* Test hook: switch the content-hull pruning of the ray kernels off / on for this handle (the hulls stay
+ * allocated), so that the pruned traversal can be compared with the unpruned one on the same tree. */
+int vrt_debug_set_hull(vrt_tree* tree, int on);
 /* Test hook of the build's overflow guard: the per-level (triangle, cell) pair totals are 32-bit block
  * counts; whenever a level could produce 2^32 pairs they are also summed in 64 bits on the device and the
  * build returns VRT_ERR_CAPACITY instead of wrapping.  This runs that 64-bit sum on `n` host counts. */

@@ -659,3 +659,31 @@ def test_pair_total_guard_sums_in_64_bits(gpu):
     assert gpu.debug_pair_total(c) == int(c.astype(np.uint64).sum()) > 2**32
     assert gpu.debug_pair_total(np.array([2**31, 2**31, 5], np.uint32)) == 2**32 + 5
     assert gpu.debug_pair_total(np.zeros(0, np.uint32)) == 0
+
+
+def test_single_process_multi_gpu_render_assembles_the_frame(case, gpu):
+    """vrt_mgpu_*: the C-ABI multi-GPU render for single-process hosts.  On this one-GPU box the "devices" are
+    three replicas on device 0 (and every visible device once, when there are more): bands dealt round-robin, every
+    replica DMA-copies its bands into ONE pinned host frame; the result equals vrt_render_camera bytewise, for
+    several frames in flight on two host frames."""
+    torch = pytest.importorskip("torch")
+    cam10 = case["cam10"]
+    nx, ny, spp = 200, 133, 4  # 133 rows: the last band is short and the replicas hold different row counts
+    cams = [gpu.Camera(cam10[0], cam10[1:4] + np.float32(0.01 * k), cam10[4:7], cam10[7:10], nx, ny, spp)
+            for k in range(4)]
+    tree = case["tree"]
+    expect = [tree.render(c) for c in cams]
+    ndev = gpu.device_count()
+    for devices in ([0, 0, 0], list(range(ndev)) if ndev > 1 else [0]):
+        mg = gpu.MultiGpu(tree, devices)
+        assert mg.num_devices == len(devices)
+        bufs = [torch.full((ny, nx, 3), -3.0, dtype=torch.float32).pin_memory() for _ in range(2)]
+        for k0 in (0, 2):
+            for k in (k0, k0 + 1):
+                mg.render_async(cams[k], bufs[k & 1].data_ptr())
+            mg.sync()
+            for k in (k0, k0 + 1):
+                assert np.array_equal(expect[k].view(np.uint32), bufs[k & 1].numpy().view(np.uint32)), (devices, k)
+        mg.render(cams[0], bufs[0].data_ptr())
+        assert np.array_equal(expect[0].view(np.uint32), bufs[0].numpy().view(np.uint32))
+        mg.close()

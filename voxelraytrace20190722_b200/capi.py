@@ -67,7 +67,8 @@ SYMBOLS = [
     "vrt_render_camera", "vrt_render_camera_dev", "vrt_render_camera_async", "vrt_band_rows", "vrt_render_bands_dev", "vrt_render_bands_async",
     "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_frame_bands_peer_dev",
     "vrt_dev_alloc", "vrt_dev_free", "vrt_host_register", "vrt_host_unregister", "vrt_ipc_export", "vrt_ipc_open", "vrt_ipc_close", "vrt_tree_sync",
-    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_debug_pair_total", "vrt_build_ex", "vrt_set_materials", "vrt_albedo", "vrt_gi_init", "vrt_gi_splat_camera", "vrt_gi_filter",
+    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_debug_pair_total", "vrt_debug_set_hull", "vrt_build_ex", "vrt_mgpu_create", "vrt_mgpu_num_devices",
+    "vrt_mgpu_render_async", "vrt_mgpu_sync", "vrt_mgpu_render", "vrt_mgpu_free", "vrt_set_materials", "vrt_albedo", "vrt_gi_init", "vrt_gi_splat_camera", "vrt_gi_filter",
     "vrt_gi_get_level", "vrt_gi_cone_trace", "vrt_gi_render_camera", "vrt_gi_render_camera_dev", "vrt_tribox_batch",
     "vrt_tri_overlap_aabb_batch", "vrt_raytri_batch", "vrt_aabb_isect_batch",
 ]
@@ -137,6 +138,14 @@ def load(build_if_missing: bool = True):
     L.vrt_debug_general_order_calls.restype = u64
     L.vrt_debug_param_check.argtypes = [vp]
     L.vrt_debug_pair_total.argtypes = [vp, u64, vp]
+    L.vrt_debug_set_hull.argtypes = [vp, i32]
+    L.vrt_mgpu_create.argtypes = [vp, i32, vp, C.POINTER(vp)]
+    L.vrt_mgpu_num_devices.argtypes = [vp]
+    L.vrt_mgpu_render_async.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), vp]
+    L.vrt_mgpu_render.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), vp]
+    L.vrt_mgpu_sync.argtypes = [vp]
+    L.vrt_mgpu_free.argtypes = [vp]
+    L.vrt_mgpu_free.restype = None
     L.vrt_gi_init.argtypes = [vp]
     L.vrt_build_indexed.argtypes = [vp, u64, vp, u64, vp, C.c_uint32, i32, C.POINTER(vp)]
     L.vrt_set_materials.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, C.c_uint32, vp]
@@ -396,6 +405,10 @@ class Octree:
     def sync(self):
         _check(load().vrt_tree_sync(self._h))
 
+    def debug_set_hull(self, on: bool):
+        """Test hook: content-hull pruning of the ray kernels off / on for this handle."""
+        _check(load().vrt_debug_set_hull(self._h, 1 if on else 0))
+
     def mean_kernel_ms(self, last_n):
         return float(load().vrt_mean_kernel_ms(self._h, int(last_n)))
 
@@ -497,6 +510,37 @@ def debug_param_check():
     c = np.zeros(2, np.uint64)
     _check(load().vrt_debug_param_check(_ptr(c)))
     return int(c[0]), int(c[1])
+
+
+class MultiGpu:
+    """vrt_mgpu_*: one process, N devices -- replicas of a built octree, every frame's 8-row bands dealt round-robin
+    to the devices and DMA-copied to their final rows of one (pinned) host frame."""
+
+    def __init__(self, tree: "Octree", devices):
+        dv = np.ascontiguousarray(devices, np.int32)
+        h = C.c_void_p()
+        _check(load().vrt_mgpu_create(tree._h, len(dv), _ptr(dv), C.byref(h)))
+        self._h = h
+
+    @property
+    def num_devices(self):
+        return int(load().vrt_mgpu_num_devices(self._h))
+
+    def render_async(self, cam: Camera, host_frame_ptr, light=None, kd=0.8, shadow_eps=None):
+        sh = _shade(light, kd, shadow_eps)
+        _check(load().vrt_mgpu_render_async(self._h, C.byref(cam.c), C.byref(sh), C.c_void_p(int(host_frame_ptr))))
+
+    def render(self, cam: Camera, host_frame_ptr, light=None, kd=0.8, shadow_eps=None):
+        sh = _shade(light, kd, shadow_eps)
+        _check(load().vrt_mgpu_render(self._h, C.byref(cam.c), C.byref(sh), C.c_void_p(int(host_frame_ptr))))
+
+    def sync(self):
+        _check(load().vrt_mgpu_sync(self._h))
+
+    def close(self):
+        if self._h:
+            load().vrt_mgpu_free(self._h)
+            self._h = None
 
 
 def debug_pair_total(block_counts) -> int:

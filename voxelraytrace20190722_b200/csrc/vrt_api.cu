@@ -170,6 +170,7 @@ void tree_bind_views(vrt_tree* t)
         }
         d.gi = nullptr;  // GI state belongs to one node array: vrt_gi_init after every (re)build
         d.hull = nullptr;  // compute_hulls() follows every bind
+        d.tri64 = nullptr;
         d.num_nodes = (uint32_t)h.num_nodes;
         d.num_leaves = (uint32_t)h.num_leaves;
         d.L = h.max_depth - 1;
@@ -467,7 +468,7 @@ using namespace vrt;
 uint64_t vrt_tree::scratch_bytes() const
 {
         uint64_t b = keys_a.cap + keys_b.cap + tmp_a.cap + tmp_b.cap + tmp_c.cap + hist.cap + refs_s.cap + tab_s.cap +
-                     io_in.cap + io_out.cap + hull_buf.cap;
+                     io_in.cap + io_out.cap + hull_buf.cap + tri64_buf.cap;
         for (unsigned l = 0; l <= VRT_MAX_DEPTH; ++l)
                 b += level_morton[l].cap + level_first[l].cap + level_mask[l].cap;
         return b;
@@ -552,6 +553,7 @@ void vrt_tree_free(vrt_tree* t)
         t->io_in.release();
         t->gi_buf.release();
         t->hull_buf.release();
+        t->tri64_buf.release();
         t->gi_recs.release();
         t->mat_buf.release();
         t->io_out.release();
@@ -1218,6 +1220,155 @@ int vrt_render_bands_async(const vrt_tree* tc, const vrt_camera* cam, const vrt_
         return VRT_OK;
 }
 
+// ---- single-process multi-GPU render (replaces render_mt camera.h:41-68 over N devices) -------
+// A C / C++ host (main.cc) owns ONE process: vrt_mgpu_create replicates a built octree onto the given devices
+// (peer copies of the blob over NVLink), vrt_mgpu_render_async deals the film's 8-row bands round-robin to the
+// devices -- each through its own vrt_render_bands_async pipeline, i.e. kernels alternating between two streams and
+// the device->host copies of its bands going straight to their final rows of the caller's frame -- and
+// vrt_mgpu_sync waits for all of them.  No collective in the data path: the path shards by image rows.
+struct vrt_mgpu {
+        std::vector<int> devices;
+        std::vector<vrt_tree*> trees;  // trees[i] lives on devices[i]; trees[0] is a replica too (the source stays the caller's)
+        int band_h = 8;
+};
+
+static int set_device_checked(int dev)
+{
+        VRT_CUDA(cudaSetDevice(dev));
+        return VRT_OK;
+}
+
+void vrt_mgpu_free(vrt_mgpu* m)
+{
+        if (!m)
+                return;
+        int cur = 0;
+        cudaGetDevice(&cur);
+        for (size_t i = 0; i < m->trees.size(); ++i) {
+                cudaSetDevice(m->devices[i]);
+                vrt_tree_free(m->trees[i]);
+        }
+        cudaSetDevice(cur);
+        delete m;
+}
+
+int vrt_mgpu_create(const vrt_tree* tree, int num_devices, const int* devices, vrt_mgpu** out)
+{
+        int rc = check_tree(tree);
+        if (rc)
+                return rc;
+        if (!out || num_devices < 1) {
+                set_error("vrt_mgpu_create: bad argument");
+                return VRT_ERR_ARG;
+        }
+        *out = nullptr;
+        int ndev = 0;
+        VRT_CUDA(cudaGetDeviceCount(&ndev));
+        vrt_mgpu* m = new (std::nothrow) vrt_mgpu();
+        if (!m)
+                return VRT_ERR_NOMEM;
+        for (int i = 0; i < num_devices; ++i) {
+                const int d = devices ? devices[i] : i;
+                if (d < 0 || d >= ndev) {
+                        set_error("vrt_mgpu_create: device %d does not exist (%d visible)", d, ndev);
+                        vrt_mgpu_free(m);
+                        return VRT_ERR_ARG;
+                }
+                m->devices.push_back(d);
+        }
+        const int src_dev = tree->device;
+        VRT_CUDA(cudaStreamSynchronize(tree->stream));
+        for (int i = 0; i < num_devices && !rc; ++i) {
+                const int d = m->devices[i];
+                rc = set_device_checked(d);
+                if (rc)
+                        break;
+                vrt_tree* rep = nullptr;
+                if (d == src_dev) {
+                        rc = vrt_tree_from_blob_dev(tree->blob, tree->hdr.bytes, &rep);
+                } else {
+                        void* tmp = nullptr;
+                        if (cudaMalloc(&tmp, tree->hdr.bytes) != cudaSuccess) {
+                                cudaGetLastError();
+                                set_error("vrt_mgpu_create: cudaMalloc(%llu) on device %d failed",
+                                          (unsigned long long)tree->hdr.bytes, d);
+                                rc = VRT_ERR_NOMEM;
+                        } else {
+                                if (cudaMemcpyPeer(tmp, d, tree->blob, src_dev, tree->hdr.bytes) != cudaSuccess) {
+                                        set_error("vrt_mgpu_create: peer copy %d -> %d failed: %s", src_dev, d,
+                                                  cudaGetErrorString(cudaGetLastError()));
+                                        rc = VRT_ERR_CUDA;
+                                } else {
+                                        rc = vrt_tree_from_blob_dev(tmp, tree->hdr.bytes, &rep);
+                                }
+                                cudaFree(tmp);
+                        }
+                }
+                if (!rc)
+                        m->trees.push_back(rep);
+        }
+        cudaSetDevice(src_dev);
+        if (rc) {
+                m->devices.resize(m->trees.size());
+                vrt_mgpu_free(m);
+                return rc;
+        }
+        *out = m;
+        return VRT_OK;
+}
+
+int vrt_mgpu_num_devices(const vrt_mgpu* m) { return m ? (int)m->trees.size() : 0; }
+
+int vrt_mgpu_render_async(vrt_mgpu* m, const vrt_camera* cam, const vrt_shade* sh, float* film_rgb_full)
+{
+        if (!m || m->trees.empty()) {
+                set_error("null multi-GPU handle");
+                return VRT_ERR_ARG;
+        }
+        int cur = 0;
+        VRT_CUDA(cudaGetDevice(&cur));
+        int rc = VRT_OK;
+        const int n = (int)m->trees.size();
+        for (int i = 0; i < n && !rc; ++i) {
+                rc = set_device_checked(m->devices[i]);
+                if (rc)
+                        break;
+                const vrt_bands b = { m->band_h, i, n };
+                if (cam && (long)i * m->band_h >= cam->ny)
+                        continue;  // more devices than bands
+                rc = vrt_render_bands_async(m->trees[i], cam, sh, &b, film_rgb_full);
+        }
+        cudaSetDevice(cur);
+        return rc;
+}
+
+int vrt_mgpu_sync(vrt_mgpu* m)
+{
+        if (!m) {
+                set_error("null multi-GPU handle");
+                return VRT_ERR_ARG;
+        }
+        int cur = 0;
+        VRT_CUDA(cudaGetDevice(&cur));
+        int rc = VRT_OK;
+        for (size_t i = 0; i < m->trees.size(); ++i) {
+                int r2 = set_device_checked(m->devices[i]);
+                if (!r2)
+                        r2 = vrt_tree_sync(m->trees[i]);
+                if (r2 && !rc)
+                        rc = r2;
+        }
+        cudaSetDevice(cur);
+        return rc;
+}
+
+int vrt_mgpu_render(vrt_mgpu* m, const vrt_camera* cam, const vrt_shade* sh, float* film_rgb_full)
+{
+        int rc = vrt_mgpu_render_async(m, cam, sh, film_rgb_full);
+        const int rs = vrt_mgpu_sync(m);
+        return rc ? rc : rs;
+}
+
 int vrt_trace_bands16_dev(const vrt_tree* t, const vrt_camera* cam, const vrt_bands* b, vrt_hit16* d_out)
 {
         return bands_common(t, cam, nullptr, b, d_out, OUT_HIT16);
@@ -1462,6 +1613,16 @@ int vrt_debug_param_check(uint64_t out[2])
         out[0] = v[0];
         out[1] = v[1];
         return rc;
+}
+
+int vrt_debug_set_hull(vrt_tree* t, int on)
+{
+        int rc = check_tree(t);
+        if (rc)
+                return rc;
+        VRT_CUDA(cudaStreamSynchronize(t->stream));
+        t->dev.hull = (on && t->hull_buf.p && t->hdr.max_depth > 1) ? t->hull_buf.as<float4>() : nullptr;
+        return VRT_OK;
 }
 
 int vrt_debug_pair_total(const uint32_t* block_counts, uint64_t n, uint64_t* total)

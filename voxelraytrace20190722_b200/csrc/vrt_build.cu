@@ -1538,11 +1538,47 @@ k_hull_level(const uint2* __restrict__ nodes, const unsigned long long* __restri
         hull[2 * node + 1] = make_float4(hy.x, hy.y, hz.x, hz.y);
 }
 
+// v0, e1 = v1 - v0, e2 = v2 - v0 in double: exactly the widening + SUB steps intersect_triangle3 starts with
+__global__ void __launch_bounds__(256)
+k_tri64(const float4* __restrict__ tri4, uint32_t T, double* __restrict__ out)
+{
+        const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+        if (t >= T)
+                return;
+        const float4 a = tri4[3ull * t], b = tri4[3ull * t + 1], c = tri4[3ull * t + 2];
+        const double av[3] = { (double)a.x, (double)a.y, (double)a.z };
+        const double bv[3] = { (double)b.x, (double)b.y, (double)b.z };
+        const double cv[3] = { (double)c.x, (double)c.y, (double)c.z };
+        double* o = out + 10ull * t;  // 80-byte records: 16-byte aligned for double2 loads
+        o[9] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+                o[k] = av[k];
+                o[3 + k] = dsub(bv[k], av[k]);
+                o[6 + k] = dsub(cv[k], av[k]);
+        }
+}
+
 int compute_hulls(vrt_tree* t)
 {
         const BlobHeader& h = t->hdr;
         const int L = h.max_depth - 1;
         t->dev.hull = nullptr;
+        t->dev.tri64 = nullptr;
+        {
+                static int tri64_on = -1;
+                if (tri64_on < 0) {
+                        const char* e = getenv("VRT_TRI64");
+                        tri64_on = (e && e[0] == '0') ? 0 : 1;
+                }
+                if (tri64_on && h.num_tris) {
+                        if (t->tri64_buf.reserve((uint64_t)h.num_tris * 80))
+                                return VRT_ERR_NOMEM;
+                        k_tri64<<<grid_for(h.num_tris, 256), 256, 0, t->stream>>>(t->dev.tri4, h.num_tris, t->tri64_buf.as<double>());
+                        count_launch();
+                        t->dev.tri64 = t->tri64_buf.as<double>();
+                }
+        }
         static int enabled = -1;
         if (enabled < 0) {
                 const char* e = getenv("VRT_HULL");

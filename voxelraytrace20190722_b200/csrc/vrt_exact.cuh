@@ -343,18 +343,31 @@ __device__ __forceinline__ void dcross(double o[3], const double a[3], const dou
         o[2] = dsub(dmul(a[0], b[1]), dmul(a[1], b[0]));
 }
 
+// intersect_triangle3 from the point where edge1 = vert1 - vert0 and edge2 = vert2 - vert0 are known
+__device__ __forceinline__ int ray_triangle3_edges(const double o[3], const double dir[3], const double a[3],
+                                                   const double e1[3], const double e2[3], double& t, double& u,
+                                                   double& v);
+
 __device__ __forceinline__ int ray_triangle3(const double o[3], const double dir[3],
                                              const double a[3], const double b[3],
                                              const double c[3], double& t, double& u,
                                              double& v)
 {
-        const double eps = 0.000001;
-        double e1[3], e2[3], tv[3], pv[3], qv[3];
+        double e1[3], e2[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
                 e1[k] = dsub(b[k], a[k]);
                 e2[k] = dsub(c[k], a[k]);
         }
+        return ray_triangle3_edges(o, dir, a, e1, e2, t, u, v);
+}
+
+__device__ __forceinline__ int ray_triangle3_edges(const double o[3], const double dir[3], const double a[3],
+                                                   const double e1[3], const double e2[3], double& t, double& u,
+                                                   double& v)
+{
+        const double eps = 0.000001;
+        double tv[3], pv[3], qv[3];
         dcross(pv, dir, e2);
         double det = ddot3(e1, pv);
 #pragma unroll

@@ -78,6 +78,10 @@ struct TreeDev {
         // non-empty leaves.  A ray whose slab interval over the hull is empty cannot pass the slab test of any
         // leaf below (monotone rounding), so the subtree is skipped without changing any result.  Null: no pruning.
         const float4* hull;
+        // triangles widened for the leaf test (round 2): per triangle ten doubles v0, e1 = v1 - v0, e2 = v2 - v0, pad --
+        // the first operations of intersect_triangle3 (raytri.cc:205-207) on the widened vertices, done once per
+        // build instead of once per (ray, triangle) test.  Null: the leaf test widens tri4 itself.
+        const double* tri64;
         // materials (vrt_set_materials), all null when unset: per-vertex texture coordinates, material id per
         // triangle, per material (kd.xyz, texture id or -1 as int bits), per texture (byte offset, w, h, channels)
         const float2* mat_uv;
@@ -138,6 +142,7 @@ struct vrt_tree {
         // GI rows: per-node coverage + illum[6], see vrt_gi.cuh
         vrt::Scratch gi_buf, gi_recs, mat_buf;
         vrt::Scratch hull_buf;  // TreeDev::hull
+        vrt::Scratch tri64_buf;  // TreeDev::tri64
         // pipelined host-film path (vrt_render_camera_async): two device films, a copy stream
         vrt::Scratch film_dev[2];
         cudaStream_t copy_stream = nullptr;
