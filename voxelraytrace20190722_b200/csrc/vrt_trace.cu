@@ -1158,6 +1158,13 @@ k_trace_rays(const __grid_constant__ TraceParams p)
 
 // 64 registers (8 CTAs/SM) is fastest for the compact outputs; the modes that also
 // evaluate the ISect/normal/shading tail spill at 64 and run best at 80 (6 CTAs/SM).
+// The per-ray records and the film are written once and never read by the kernel: streaming stores
+// (st.global.cs) keep them from displacing octree lines in L2 (-DVRT_PLAIN_STORES: ordinary stores).
+#ifdef VRT_PLAIN_STORES
+#define VRT_STORE_OUT(ptr, val) (*(ptr) = (val))
+#else
+#define VRT_STORE_OUT(ptr, val) __stcs((ptr), (val))
+#endif
 template <int MODE, bool WS>
 #ifndef VRT_FILM_MIN_BLOCKS
 #define VRT_FILM_MIN_BLOCKS 7
@@ -1291,7 +1298,7 @@ k_trace_camera(const __grid_constant__ TraceParams p)
                                 q.y = hs.tri;
                                 q.z = __float_as_uint(hs.hit ? hs.t : 0.f);
                                 q.w = hs.hit ? 1u : 0u;
-                                reinterpret_cast<uint4*>(p.out)[pix * spp + s] = q;
+                                VRT_STORE_OUT(reinterpret_cast<uint4*>(p.out) + (pix * spp + s), q);
                         }
                 } else {
                         if (MODE == OUT_HIT16_FILM && active) {
@@ -1300,7 +1307,7 @@ k_trace_camera(const __grid_constant__ TraceParams p)
                                 q.y = hs.tri;
                                 q.z = __float_as_uint(hs.hit ? hs.t : 0.f);
                                 q.w = hs.hit ? 1u : 0u;
-                                reinterpret_cast<uint4*>(p.out)[pix * spp + s] = q;
+                                VRT_STORE_OUT(reinterpret_cast<uint4*>(p.out) + (pix * spp + s), q);
                         }
                         float rgb[3] = { 0, 0, 0 };
                         if (active) {
@@ -1329,9 +1336,9 @@ k_trace_camera(const __grid_constant__ TraceParams p)
                                 if (MODE == OUT_HIT16_FILM && p.film_full)
                                         f = static_cast<float*>(p.out2) +
                                             ((unsigned long long)py * p.cam.nx + px) * 3ull;
-                                f[0] = acc[0];
-                                f[1] = acc[1];
-                                f[2] = acc[2];
+                                VRT_STORE_OUT(f + 0, acc[0]);
+                                VRT_STORE_OUT(f + 1, acc[1]);
+                                VRT_STORE_OUT(f + 2, acc[2]);
                         }
                 }
                 __syncwarp();
