@@ -631,7 +631,35 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         splat_ms, filter_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
         render_ms = min(ev[2].elapsed_time(ev[3]), ev[3].elapsed_time(ev[4]))
-        gi_out = {"splat_ms": splat_ms, "splat_mrays_per_s": lx * ly * lspp / (splat_ms * 1e-3) / 1e6,
+        # roofline entry of the GI film kernel: algorithmic bytes of the reference's cone trace (voxel_octree.cc:247-283)
+        # per ray = the primary traversal's bytes + 8 B per descent step of every sample's point location (the
+        # reference walks down from the root at every step) + 80 B per sample that reaches its level (coverage +
+        # illum[6]), counted by the instrumented oracle on a bounded film of the same scene / camera
+        gi_roof = None
+        if not args.no_cpu_baseline:
+            try:
+                from oracle.bindings import Port
+                t0 = time.perf_counter()
+                ptree = Port().build(tri, nrm, depth)
+                ptree.gi_reset()
+                ptree.gi_filter()
+                gx, gy = GI_CPU_SAMPLE
+                _, cc = ptree.gi_render_counted(cam10, 1.0, gx, gy, spp, res, GI_KD)
+                n_gi = gx * gy * spp
+                b_gi = b_ray + (8 * cc["descent_steps"] + 80 * cc["located"]) / n_gi
+                ach = b_gi * rays_per_step / (render_ms * 1e-3) / 1e9
+                gi_roof = {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": ach / peaks["hbm_gbs"], "bytes_per_ray": b_gi,
+                           "samples_per_ray": cc["samples"] / n_gi, "descent_steps_per_ray": cc["descent_steps"] / n_gi,
+                           "located_per_ray": cc["located"] / n_gi,
+                           "counted_on": f"{gx}x{gy}x{spp} film, oracle port (coverage from the filter; the counts do not "
+                                         f"depend on the light map), {time.perf_counter() - t0:.1f} s",
+                           "kernel": "k_trace_camera<GI_FILM>"}
+                del ptree
+            except Exception as e:  # the roofline entry is a report, never a reason to fail the bench
+                gi_roof = {"error": str(e)}
+        gi_out = {"roofline": gi_roof,
+                  "splat_ms": splat_ms, "splat_mrays_per_s": lx * ly * lspp / (splat_ms * 1e-3) / 1e6,
                   "light_film": f"{lx}x{ly}x{lspp} (main.cc:75-78)", "filter_ms": filter_ms,
                   "render_ms": render_ms, "render_mrays_per_s": rays_per_step / (render_ms * 1e-3) / 1e6,
                   "render": "trace() of main.cc:10-30 per sample: ray march + 6 cones + direct + albedo, same film as the headline",

@@ -266,6 +266,15 @@ class PortTree:
                                     float(np.float32(res)), kd, film)
         return film
 
+    def gi_render_counted(self, cam10, film_h, nx, ny, spp, res, kd=None):
+        """gi_render plus the cone trace's work counters: (film, {samples, descent_steps, located})."""
+        lib = self.port.lib
+        lib.orc_gi_counters_reset()
+        film = self.gi_render(cam10, film_h, nx, ny, spp, res, kd)
+        c = np.zeros(3, np.uint64)
+        lib.orc_gi_counters(c.ctypes.data_as(C.c_void_p))
+        return film, {"samples": int(c[0]), "descent_steps": int(c[1]), "located": int(c[2])}
+
 
 # ----------------------------------------------------------------------------
 class Ref:

@@ -1034,6 +1034,13 @@ static void orc_compute_illum(const orc_node* n, const float d[3], float out[3])
 
 /* voxel_octree.cc:247-283 cone_trace(root, cone, min_voxel_size); aperture .577350269f, step .1f,
  * litness_decay 1.f (voxel_octree.cc:216-225) */
+/* Work counters of the reference's cone trace (bench.py's roofline entry of the GI film): samples taken along the
+ * cones, descent steps of their point locations (one node record each), samples that reach their level and read
+ * the node's coverage + illum[6] (76 bytes).  Plain globals: the counting run is single-threaded. */
+static uint64_t g_cone_counts[3];
+void orc_gi_counters_reset(void) { memset(g_cone_counts, 0, sizeof g_cone_counts); }
+void orc_gi_counters(uint64_t out[3]) { memcpy(out, g_cone_counts, sizeof g_cone_counts); }
+
 static void orc_cone_trace_one(const orc_tree* t, const float o[3], const float d[3], float min_voxel_size,
                                float out[3])
 {
@@ -1052,7 +1059,9 @@ static void orc_cone_trace_one(const orc_tree* t, const float o[3], const float 
                         break;
                 int split_level = (int)log2f(maxdist / diam);
                 const orc_node* tree = root;
+                g_cone_counts[0]++;
                 while (tree->child[0] >= 0 && split_level) {
+                        g_cone_counts[1]++;
                         int i = 0;
                         i += (p[0] > (tree->mn[0] + tree->mx[0]) * .5f ? 4 : 0);
                         i += (p[1] > (tree->mn[1] + tree->mx[1]) * .5f ? 2 : 0);
@@ -1062,6 +1071,7 @@ static void orc_cone_trace_one(const orc_tree* t, const float o[3], const float 
                 }
                 if (split_level == 0) {
                         float illum[3];
+                        g_cone_counts[2]++;
                         orc_compute_illum(tree, nd, illum);
                         float transparency = orc_clampf(1.f - opacity, 0.f, 1.f);
                         float a = tree->coverage * step;
