@@ -3,6 +3,7 @@
 // handed to the C ABI; results are mapped back onto the reference's object model.
 #include "vrt_gi.h"
 
+#include <cmath>
 #include <cstring>
 #include <mutex>
 #include <stdexcept>
@@ -78,8 +79,17 @@ VoxelOctree* GpuTree::leaf(const uint32_t c[3])
 Triangle::Triangle(Vec3 p0, Vec3 p1, Vec3 p2, Vec3 n0, Vec3 n1, Vec3 n2)
         : p_{ p0, p1, p2 }, n_{ n0, n1, n2 }
 {
-        // AABB = min/max of the vertices (voxel_octree.cc:430); normals are normalised on
-        // the GPU when the tree is built (voxel_octree.cc:426), kept verbatim here.
+        // normals normalised like the reference ctor (voxel_octree.cc:426; jql::normalize = v / sqrtf(dot(v,v)),
+        // value_sum from 0; this file is compiled with -ffp-contract=off) -- ray_march_init hands them to the GPU
+        // build verbatim (VRT_BUILD_UNIT_NORMALS).  AABB = min/max of the vertices (voxel_octree.cc:430).
+        for (int v = 0; v < 3; ++v) {
+                float s = 0.f;
+                s += n_[v].x * n_[v].x;
+                s += n_[v].y * n_[v].y;
+                s += n_[v].z * n_[v].z;
+                const float l = std::sqrt(s);
+                n_[v] = Vec3{ n_[v].x / l, n_[v].y / l, n_[v].z / l };
+        }
         aabb_.min = aabb_.max = p0;
         for (int v = 1; v < 3; ++v)
                 for (int k = 0; k < 3; ++k) {
@@ -111,9 +121,22 @@ bool Triangle::isect(const Ray& ray, ISect* isect) const
         if (res != 1)
                 return false;
         if (isect) {
+                // the FP32 shell of Triangle::isect (voxel_octree.cc:449-454) around the GPU's FP64 result:
+                // u,v,w = clamp(.,0,1); normal = normalize(n0*w + n1*u + n2*v); hit = o + (float)t * d
+                auto clamp01 = [](float s) { return s > 1.f ? 1.f : (s < 0.f ? 0.f : s); };
+                const float u = clamp01((float)tuv[1]), v = clamp01((float)tuv[2]);
+                const float w = clamp01(1 - u - v);
+                Vec3 n;
+                for (int k = 0; k < 3; ++k)
+                        n[k] = (n_[0][k] * w + n_[1][k] * u) + n_[2][k] * v;
+                float s = 0.f;
+                s += n.x * n.x;
+                s += n.y * n.y;
+                s += n.z * n.z;
+                const float l = std::sqrt(s);
+                isect->normal = Vec3{ n.x / l, n.y / l, n.z / l };
                 const float t = (float)tuv[0];
                 isect->hit = Vec3{ ray.o.x + t * ray.d.x, ray.o.y + t * ray.d.y, ray.o.z + t * ray.d.z };
-                isect->normal = n_[0];
         }
         return true;
 }
@@ -128,7 +151,8 @@ void ray_march_init(VoxelOctree* root, std::vector<VoxelBase*>& voxels, int max_
                 std::memcpy(&tri[9 * i], voxels[i]->vertices(), 36);
                 std::memcpy(&nrm[9 * i], voxels[i]->normals(), 36);
         }
-        check(vrt_build(tri.data(), nrm.data(), (uint32_t)voxels.size(), max_depth, &g->tree), "gi::ray_march_init");
+        check(vrt_build_ex(tri.data(), nrm.data(), (uint32_t)voxels.size(), max_depth, VRT_BUILD_UNIT_NORMALS, &g->tree),
+              "gi::ray_march_init");
         vrt_tree_info info;
         check(vrt_tree_get_info(g->tree, &info), "vrt_tree_get_info");
         root->aabb.min = Vec3{ info.root_aabb[0], info.root_aabb[1], info.root_aabb[2] };
