@@ -342,6 +342,9 @@ int vrt_debug_param_check(uint64_t out[2]);
 /* Test hook: switch the content-hull pruning of the ray kernels off / on for this handle (the hulls stay
  * allocated), so that the pruned traversal can be compared with the unpruned one on the same tree. */
 int vrt_debug_set_hull(vrt_tree* tree, int on);
+/* Diagnostic (libraries built with -DVRT_HULL_STATS only, zeros otherwise): per tree level {node expansions, interior
+ * children visited, hull tests, hull prunes} of the per-ray kernel since the last call. */
+int vrt_debug_hull_stats(uint64_t out80[80]);
 /* Test hook of the build's overflow guard: the per-level (triangle, cell) pair totals are 32-bit block
  * counts; whenever a level could produce 2^32 pairs they are also summed in 64 bits on the device and the
  * build returns VRT_ERR_CAPACITY instead of wrapping.  This runs that 64-bit sum on `n` host counts. */

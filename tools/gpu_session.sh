@@ -1,9 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 {
-echo "== pytest"; python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-echo "== bench"; python bench.py > gpurun_out/bench_r2e.json 2> gpurun_out/bench_r2e.err; tail -3 gpurun_out/bench_r2e.err; python tools/show_bench.py gpurun_out/bench_r2e.json
-python -c "
-import json; d=json.loads(open('gpurun_out/bench_r2e.json').read().strip().splitlines()[-1]); print('gi', d.get('gi'))"
+echo "== pytest"; python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+for sa in 0.6 0.7 0.85 0.95; do echo "== VRT_HULL_SA=$sa"; VRT_HULL_SA=$sa python tools/probe_soup_frame.py 2>&1 | tail -2; done
 } > gpurun_out/session.log 2>&1
-tail -40 gpurun_out/session.log
+tail -30 gpurun_out/session.log

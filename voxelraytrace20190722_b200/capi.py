@@ -67,7 +67,7 @@ SYMBOLS = [
     "vrt_render_camera", "vrt_render_camera_dev", "vrt_render_camera_async", "vrt_band_rows", "vrt_render_bands_dev", "vrt_render_bands_async",
     "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_frame_bands_peer_dev",
     "vrt_dev_alloc", "vrt_dev_free", "vrt_host_register", "vrt_host_unregister", "vrt_ipc_export", "vrt_ipc_open", "vrt_ipc_close", "vrt_tree_sync",
-    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_debug_pair_total", "vrt_debug_set_hull", "vrt_build_ex", "vrt_mgpu_create", "vrt_mgpu_num_devices",
+    "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_debug_pair_total", "vrt_debug_set_hull", "vrt_debug_hull_stats", "vrt_build_ex", "vrt_mgpu_create", "vrt_mgpu_num_devices",
     "vrt_mgpu_render_async", "vrt_mgpu_sync", "vrt_mgpu_render", "vrt_mgpu_free", "vrt_set_materials", "vrt_albedo", "vrt_gi_init", "vrt_gi_splat_camera", "vrt_gi_filter",
     "vrt_gi_get_level", "vrt_gi_cone_trace", "vrt_gi_render_camera", "vrt_gi_render_camera_dev", "vrt_tribox_batch",
     "vrt_tri_overlap_aabb_batch", "vrt_raytri_batch", "vrt_aabb_isect_batch",
@@ -139,6 +139,7 @@ def load(build_if_missing: bool = True):
     L.vrt_debug_param_check.argtypes = [vp]
     L.vrt_debug_pair_total.argtypes = [vp, u64, vp]
     L.vrt_debug_set_hull.argtypes = [vp, i32]
+    L.vrt_debug_hull_stats.argtypes = [vp]
     L.vrt_mgpu_create.argtypes = [vp, i32, vp, C.POINTER(vp)]
     L.vrt_mgpu_num_devices.argtypes = [vp]
     L.vrt_mgpu_render_async.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), vp]
@@ -541,6 +542,13 @@ class MultiGpu:
         if self._h:
             load().vrt_mgpu_free(self._h)
             self._h = None
+
+
+def debug_hull_stats():
+    """[level][expansions, interior children visited, hull tests, prunes] (-DVRT_HULL_STATS builds)."""
+    c = np.zeros(80, np.uint64)
+    _check(load().vrt_debug_hull_stats(_ptr(c)))
+    return c.reshape(20, 4)
 
 
 def debug_pair_total(block_counts) -> int:

@@ -170,6 +170,7 @@ void tree_bind_views(vrt_tree* t)
         }
         d.gi = nullptr;  // GI state belongs to one node array: vrt_gi_init after every (re)build
         d.hull = nullptr;  // compute_hulls() follows every bind
+        d.tight8 = nullptr;
         d.tri64 = nullptr;
         d.num_nodes = (uint32_t)h.num_nodes;
         d.num_leaves = (uint32_t)h.num_leaves;
@@ -1615,6 +1616,15 @@ int vrt_debug_param_check(uint64_t out[2])
         return rc;
 }
 
+int vrt_debug_hull_stats(uint64_t out80[80])
+{
+        unsigned long long v[80];
+        int rc = hull_stats(v);
+        for (int i = 0; i < 80; ++i)
+                out80[i] = v[i];
+        return rc;
+}
+
 int vrt_debug_set_hull(vrt_tree* t, int on)
 {
         int rc = check_tree(t);
@@ -1622,6 +1632,8 @@ int vrt_debug_set_hull(vrt_tree* t, int on)
                 return rc;
         VRT_CUDA(cudaStreamSynchronize(t->stream));
         t->dev.hull = (on && t->hull_buf.p && t->hdr.max_depth > 1) ? t->hull_buf.as<float4>() : nullptr;
+        t->dev.tight8 = t->dev.hull ? reinterpret_cast<const uint8_t*>(t->dev.hull + 2ull * (t->hdr.num_nodes - t->hdr.num_leaves))
+                                    : nullptr;
         return VRT_OK;
 }
 

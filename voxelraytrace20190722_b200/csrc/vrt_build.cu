@@ -1505,36 +1505,60 @@ int import_leaves(vrt_tree* t, int max_depth, const float root_aabb[6], uint64_t
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_hull_level(const uint2* __restrict__ nodes, const unsigned long long* __restrict__ leaf_morton,
-             const float2* __restrict__ tx, const float2* __restrict__ ty, const float2* __restrict__ tz,
-             uint64_t begin, uint64_t count, int child_is_leaf, uint64_t leaf_base, float4* __restrict__ hull)
+             const float2* __restrict__ tab, uint64_t stride, int level /* of the nodes */, int L, uint64_t begin,
+             uint64_t count, uint64_t leaf_base, float4* __restrict__ hull, uint8_t* __restrict__ tight8,
+             unsigned long long* __restrict__ codes, float sa_max)
 {
         const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= count)
                 return;
         const uint64_t node = begin + i;
         const uint2 rec = nodes[node];
-        const uint32_t n = (uint32_t)__popc(rec.y & 0xffu);
+        const uint32_t mask = rec.y & 0xffu;
+        const bool child_is_leaf = (level + 1 == L);
+        const uint32_t cbase = 2u << level;  // table offset of the children's level
         const float inf = __int_as_float(0x7f800000);
         float2 hx = make_float2(inf, -inf), hy = hx, hz = hx;
-        for (uint32_t c = 0; c < n; ++c) {
-                const uint64_t ch = (uint64_t)rec.x + c;
+        unsigned long long code = 0;
+        uint32_t tight = 0, m = mask;
+        uint64_t ch = rec.x;
+        while (m) {
+                const uint32_t c = __ffs((int)m) - 1;
+                m &= m - 1u;
                 float2 bx, by, bz;
+                const unsigned long long cc = child_is_leaf ? leaf_morton[ch - leaf_base] : codes[ch];
+                code = cc >> 3;
+                const float2 cx = tab[0 * stride + cbase + compact1by2(cc >> 2)];  // the child's own cell
+                const float2 cy = tab[1 * stride + cbase + compact1by2(cc >> 1)];
+                const float2 cz = tab[2 * stride + cbase + compact1by2(cc)];
                 if (child_is_leaf) {
-                        const unsigned long long m = leaf_morton[ch - leaf_base];
-                        bx = tx[compact1by2(m >> 2)];
-                        by = ty[compact1by2(m >> 1)];
-                        bz = tz[compact1by2(m)];
+                        bx = cx;
+                        by = cy;
+                        bz = cz;
                 } else {
                         const float4 ca = hull[2 * ch], cb = hull[2 * ch + 1];
                         bx = make_float2(ca.z, ca.w);
                         by = make_float2(cb.x, cb.y);
                         bz = make_float2(cb.z, cb.w);
+                        // "tight": a ray that crosses the child's cell misses the child's content often enough to pay for
+                        // the test.  For convex bodies the mean projected area is proportional to the surface area, so
+                        // P(a line through the cell also meets the hull) ~ area(hull) / area(cell); the ray kernel only
+                        // tests children whose ratio is below `sa_max` (a heuristic: skipping a test never changes a
+                        // result, it only gives up a pruning opportunity).
+                        const float hx_ = bx.y - bx.x, hy_ = by.y - by.x, hz_ = bz.y - bz.x;
+                        const float ex_ = cx.y - cx.x, ey_ = cy.y - cy.x, ez_ = cz.y - cz.x;
+                        if (hx_ * hy_ + hy_ * hz_ + hz_ * hx_ <= sa_max * (ex_ * ey_ + ey_ * ez_ + ez_ * ex_))
+                                tight |= 1u << c;
                 }
                 hx.x = fminf(hx.x, bx.x); hx.y = fmaxf(hx.y, bx.y);
                 hy.x = fminf(hy.x, by.x); hy.y = fmaxf(hy.y, by.y);
                 hz.x = fminf(hz.x, bz.x); hz.y = fmaxf(hz.y, bz.y);
+                ++ch;
         }
-        hull[2 * node] = make_float4(__uint_as_float(rec.x), __uint_as_float(rec.y), hx.x, hx.y);
+        codes[node] = code;
+        // record: first child, child mask, then the hull; the tight-children mask goes to its own byte array
+        tight8[node] = (uint8_t)tight;
+        hull[2 * node] = make_float4(__uint_as_float(rec.x), __uint_as_float(mask), hx.x, hx.y);
         hull[2 * node + 1] = make_float4(hy.x, hy.y, hz.x, hz.y);
 }
 
@@ -1587,22 +1611,32 @@ int compute_hulls(vrt_tree* t)
         if (!enabled || L < 1 || h.num_nodes == 0)
                 return VRT_OK;
         const uint64_t interior = h.num_nodes - h.num_leaves;
-        if (t->hull_buf.reserve(std::max<uint64_t>(interior, 1) * 32))
+        if (t->hull_buf.reserve(std::max<uint64_t>(interior, 1) * 33))  // 32-byte records, then one flag byte per node
                 return VRT_ERR_NOMEM;
         float4* hull = t->hull_buf.as<float4>();
+        static float sa_max = -1.f;  // VRT_HULL_SA: area ratio below which a child's hull is tested (k_hull_level)
+        if (sa_max < 0.f) {
+                const char* e = getenv("VRT_HULL_SA");
+                sa_max = e ? (float)atof(e) : 0.7f;
+        }
+        // Morton codes of the interior nodes, bottom-up (a node's code = its first child's >> 3): scratch
+        if (t->keys_b.reserve(std::max<uint64_t>(interior, 1) * 8))
+                return VRT_ERR_NOMEM;
+        unsigned long long* codes = t->keys_b.as<unsigned long long>();
         const uint64_t leaf_base = h.level_offset[L];
-        const uint64_t lv = 1ull << L;  // leaf-level entries of the axis table
         for (int l = L - 1; l >= 0; --l) {
                 const uint64_t begin = h.level_offset[l], count = h.level_offset[l + 1] - begin;
                 if (!count)
                         continue;
-                k_hull_level<<<grid_for(count, 256), 256, 0, t->stream>>>(t->dev.nodes, t->dev.leaf_morton, t->dev.tab2[0] + lv,
-                                                                          t->dev.tab2[1] + lv, t->dev.tab2[2] + lv, begin, count,
-                                                                          l + 1 == L ? 1 : 0, leaf_base, hull);
+                k_hull_level<<<grid_for(count, 256), 256, 0, t->stream>>>(t->dev.nodes, t->dev.leaf_morton, t->dev.tab2[0],
+                                                                          h.axis_tab_stride, l, L, begin, count, leaf_base, hull,
+                                                                          reinterpret_cast<uint8_t*>(hull + 2ull * interior), codes,
+                                                                          sa_max);
                 count_launch();
         }
         VRT_CUDA(cudaGetLastError());
         t->dev.hull = hull;
+        t->dev.tight8 = reinterpret_cast<const uint8_t*>(hull + 2ull * interior);
         return VRT_OK;
 }
 

@@ -78,6 +78,9 @@ struct TreeDev {
         // non-empty leaves.  A ray whose slab interval over the hull is empty cannot pass the slab test of any
         // leaf below (monotone rounding), so the subtree is skipped without changing any result.  Null: no pruning.
         const float4* hull;
+        // per interior node: bit c = child c's hull is worth testing (k_hull_level); the hull records of the other
+        // children are never touched, their 8-byte node records are read instead
+        const uint8_t* tight8;
         // triangles widened for the leaf test (round 2): per triangle ten doubles v0, e1 = v1 - v0, e2 = v2 - v0, pad --
         // the first operations of intersect_triangle3 (raytri.cc:205-207) on the widened vertices, done once per
         // build instead of once per (ray, triangle) test.  Null: the leaf test widens tri4 itself.
@@ -195,6 +198,7 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
 // mean device time (ms) of the last n trace launches (waits for them)
 int trace_ms_mean(const vrt_tree* t, int last_n, double* ms);
 int general_order_calls(unsigned long long* out);
+int hull_stats(unsigned long long* out80);
 // GI (vrt_gi.cu)
 int gi_init(vrt_tree* t);
 int gi_splat_camera(vrt_tree* t, const vrt_camera* cam, const float kd[3]);

@@ -516,6 +516,9 @@ __device__ __forceinline__ int param_safe_levels(const float root[6], const floa
 #ifdef VRT_PARAM_CHECK
 __device__ unsigned long long g_param_check[4] = { 0, 0, 0, 0 };  // checked, mismatches, -, -
 #endif
+#ifdef VRT_HULL_STATS  // diagnostic build: [level][0..3] = expansions, visited interior children, hull tests, prunes
+__device__ unsigned long long g_hull_stats[20][4];
+#endif
 
 // Can the (tame) ray reach any non-empty leaf below interior node `node`?  Slab interval of the ray
 // over the node's content hull (TreeDev::hull) against the window, as an OVERLAP test: every leaf
@@ -583,12 +586,10 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
         // register holding this thread's shared-memory byte address of the next free record.
         int level = 0;
         uint32_t x = 1, y = 1, z = 1;
-        uint2 rec = __ldg(&tr.nodes[0]);  // record of the node to expand (a child's is fetched with its hull)
-        // (Rejected: clipping the children's verdicts to the hull's slab interval [t0, t1].  A leaf's interval lies
-        // inside its ancestors' HULL intervals, but not exactly inside its ancestors' CELL intervals -- the cell boxes
-        // of the float recurrence are not nested bit for bit -- so "cell interval misses the hull interval" can drop a
-        // grazing leaf: 3 of 3.7 M rays of the headline frame then report another leaf (instrumented oracle), and the
-        // GPU frame checksum changed.  The plain hull test only compares a ray with min/max of the leaves' own planes.)
+        // record of the node to expand (a tested child's comes with its hull record) and its node index (for the
+        // per-node flags of which children's hulls are worth testing)
+        uint2 rec = __ldg(&tr.nodes[0]);
+        uint32_t node = 0;
         // visiting list of the node being iterated: 4 bits per entry, lowest first, entry =
         // 8 | child id -- an empty list is the value 0, so no separate count is carried
         uint32_t first, mask, list;
@@ -603,8 +604,13 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                 {
                         if (COUNT)
                                 wc.n_int += 1;
+#ifdef VRT_HULL_STATS
+                        atomicAdd(&g_hull_stats[level][0], 1ull);
+#endif
                         first = rec.x;
-                        mask = rec.y;
+                        mask = rec.y;  // bits 0-7 child mask; bits 8-15 (below) children whose hull is worth testing
+                        if (!COUNT && tr.hull != nullptr)
+                                mask |= (uint32_t)__ldg(&tr.tight8[node]) << 8;
                         const float4 bx = __ldg(&tr.tab4[0][x]);
                         const float4 by = __ldg(&tr.tab4[1][y]);
                         const float4 bz = __ldg(&tr.tab4[2][z]);
@@ -704,8 +710,8 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(list) : "r"(sp), "n"(2u * kCol));
                                 if ((int32_t)m < 0)
                                         return;  // miss
-                                mask = m & 0xffu;
-                                const int nl = (int)(m >> 8);
+                                mask = m & 0xffffu;
+                                const int nl = (int)(m >> 16);
                                 x >>= (level - nl);
                                 y >>= (level - nl);
                                 z >>= (level - nl);
@@ -732,19 +738,31 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                         // the child's node record, fused with its content hull: skip a child under which the
                         // ray cannot reach a non-empty leaf (not in the counting mode, which reports the
                         // reference algorithm's work)
-                        if (!COUNT && tr.hull != nullptr) {
+                        // (only children flagged "tight" by the build are tested -- where the content fills most of
+                        // the cell the test rarely prunes -- and only their 32-byte hull records are read; the bits
+                        // are 0 without hulls and in the counting mode)
+#ifdef VRT_HULL_STATS
+                        atomicAdd(&g_hull_stats[level][1], 1ull);
+#endif
+                        if ((mask >> (8u + c)) & 1u) {
                                 const float4 ha = __ldg(&tr.hull[2ull * child]), hb = __ldg(&tr.hull[2ull * child + 1]);
                                 float h0, h1;
+#ifdef VRT_HULL_STATS
+                                atomicAdd(&g_hull_stats[level][2], 1ull);
+                                if (!hull_reachable(ha, hb, o, dinv, tmin, tmax, h0, h1))
+                                        atomicAdd(&g_hull_stats[level][3], 1ull);
+#endif
                                 if (!hull_reachable(ha, hb, o, dinv, tmin, tmax, h0, h1))
                                         continue;
                                 rec = make_uint2(__float_as_uint(ha.x), __float_as_uint(ha.y));
                         } else {
                                 rec = __ldg(&tr.nodes[child]);
                         }
+                        node = child;
                         if (list != 0u) {  // remember this level only if it has children left
                                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(first) : "memory");
                                 asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(sp), "n"(kCol),
-                                             "r"(mask + ((uint32_t)level << 8))
+                                             "r"(mask + ((uint32_t)level << 16))
                                              : "memory");
                                 asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(sp), "n"(2u * kCol), "r"(list) : "memory");
                                 sp += kRec;
@@ -1548,6 +1566,20 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         count_launch();
         VRT_CUDA(cudaEventRecord(t->ring1[slot], ls));
         t->n_trace_launches++;
+        return VRT_OK;
+}
+
+int hull_stats(unsigned long long* out80)
+{
+#ifdef VRT_HULL_STATS
+        VRT_CUDA(cudaDeviceSynchronize());
+        VRT_CUDA(cudaMemcpyFromSymbol(out80, g_hull_stats, sizeof(unsigned long long) * 80));
+        unsigned long long z[80] = { 0 };
+        VRT_CUDA(cudaMemcpyToSymbol(g_hull_stats, z, sizeof z));
+#else
+        for (int i = 0; i < 80; ++i)
+                out80[i] = 0;
+#endif
         return VRT_OK;
 }
 
