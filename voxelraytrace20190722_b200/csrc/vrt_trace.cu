@@ -716,7 +716,9 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                 y >>= (level - nl);
                                 z >>= (level - nl);
                                 level = nl;
-                                continue;
+                                // (fall through: only levels with children left are ever pushed, so the popped list is not
+                                // empty and the lane takes its next child in this same iteration -- lanes that pop and
+                                // lanes that do not then run the visit step together instead of one warp iteration apart)
                         }
                         const uint32_t c = list & 7u;
                         list >>= 4;
