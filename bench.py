@@ -530,7 +530,9 @@ def run_ours(args):
     if rank == 0:
         tree.set_stream(0)
         ref_film = torch.empty((ny, nx, 3), dtype=torch.float32, device=dev)
-        tree.render_dev(cam, ref_film.data_ptr(), shadow_eps=shadow_eps)
+        # the frame that was assembled last (timed loop with the gather, the single-stream loop with peer stores)
+        # shows the camera of step `steps - 1` (orbit workloads move the camera every step)
+        tree.render_dev(cams[(args.steps - 1) % len(cams)], ref_film.data_ptr(), shadow_eps=shadow_eps)
         tree.sync()
         got = fg.frame if use_gather else pf.frame(0)
         frame_check = bool(torch.equal(got.view(torch.int32), ref_film.view(torch.int32)))
