@@ -1,6 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 {
-for s in "" _hf; do echo "== variant '$s'"; VRT_LIB_SUFFIX=$s python tools/probe_soup_frame.py 2>&1 | tail -2; VRT_LIB_SUFFIX=$s python tools/probe_quick.py 11 2>&1 | tail -1 | cut -c1-220; done
+echo "== pytest"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+echo "== build"; timeout 300 python tools/probe_build.py 2>&1 | tail -3
+echo "== build sorted"; VRT_BUILD_SORTED=1 timeout 300 python tools/probe_build.py 2>&1 | tail -3
 } > gpurun_out/session.log 2>&1
 tail -30 gpurun_out/session.log

@@ -1,7 +1,7 @@
 // tools/l2bw.cu -- L2 read-bandwidth microbenchmark ("B200 L2 bandwidth: not
 // yet measured -- builder must microbenchmark").  Every thread block streams the whole
 // working set (LDG.128, .cg = L2 only) several times; working sets below the L2 capacity
-// measure L2 bandwidth, larger ones fall to HBM.   nvcc -O3 -arch=sm_100a l2bw.cu -o l2bw
+// measure L2 bandwidth, larger ones fall to HBM.   nvcc -O3 -arch=sm_100a -cudart shared l2bw.cu -o /tmp/l2bw   (build outside the repo tree)
 #include <cstdio>
 #include <cuda_runtime.h>
 __global__ void __launch_bounds__(1024) rd(const float4* __restrict__ p, size_t n, int reps, float* out)

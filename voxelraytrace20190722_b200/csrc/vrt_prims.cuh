@@ -77,38 +77,126 @@ k_scan_add(uint32_t* __restrict__ data, const uint32_t* __restrict__ tile_offs, 
         }
 }
 
+// Single-pass exclusive scan (round 2): decoupled look-back.  A tile takes a ticket (atomic counter, so
+// tiles start in ticket order and every predecessor of a running tile is running or done), scans its
+// 2048 elements, publishes its aggregate as (value | FLAG_AGG << 32), looks back over its predecessors'
+// status words until it meets an inclusive prefix, publishes its own inclusive prefix (FLAG_INC) and
+// writes the result: one kernel and 8 n bytes of traffic instead of tile scan + scan of the sums + add
+// pass (up to 5 launches and 16 n bytes).  status[] and the ticket are zeroed by one memset per scan.
+constexpr unsigned long long kScanAgg = 1ull << 32, kScanInc = 2ull << 32;
+
+__global__ void __launch_bounds__(kScanThreads)
+k_scan_lookback(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n,
+                unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket)
+{
+        __shared__ uint32_t warp_tot[kScanThreads / 32];
+        __shared__ uint32_t s_tile, s_prefix;
+        if (threadIdx.x == 0)
+                s_tile = atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        const uint64_t base = (uint64_t)tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+        uint32_t v[kScanItems];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+                const uint64_t k = base + i;
+                v[i] = (k < n) ? in[k] : 0u;
+                sum += v[i];
+        }
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o)
+                        inc += t;
+        }
+        if (lane == 31)
+                warp_tot[w] = inc;
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < kScanThreads / 32; ++i) {
+                const uint32_t t = warp_tot[i];
+                if (i < w)
+                        woff += t;
+                total += t;
+        }
+        // ---- publish the aggregate, look back, publish the inclusive prefix (warp 0) ----
+        if (w == 0) {
+                volatile unsigned long long* st = status;
+                if (lane == 0) {
+                        st[tile] = (tile == 0 ? kScanInc : kScanAgg) | total;
+                        __threadfence();
+                }
+                uint32_t prefix = 0;
+                if (tile != 0) {
+                        int j = (int)tile - 1 - lane;  // the 32 predecessors closest to this tile, lane 0 = nearest
+                        for (;;) {
+                                unsigned long long sv = kScanInc;  // lanes before tile 0 read an empty inclusive prefix
+                                if (j >= 0) {
+                                        do {
+                                                sv = st[j];
+                                        } while ((sv >> 32) == 0ull);
+                                }
+                                const uint32_t has_inc = __ballot_sync(0xffffffffu, (sv >> 32) == 2ull);
+                                // add everything up to and including the nearest predecessor with an inclusive prefix
+                                const int stop = has_inc ? (__ffs((int)has_inc) - 1) : 31;
+                                uint32_t add = (lane <= stop) ? (uint32_t)sv : 0u;
+#pragma unroll
+                                for (int o = 16; o > 0; o >>= 1)
+                                        add += __shfl_xor_sync(0xffffffffu, add, o);
+                                prefix += add;
+                                if (has_inc)
+                                        break;
+                                j -= 32;
+                        }
+                        if (lane == 0) {
+                                __threadfence();
+                                st[tile] = kScanInc | (unsigned long long)(uint32_t)(prefix + total);
+                        }
+                }
+                if (lane == 0)
+                        s_prefix = prefix;
+        }
+        __syncthreads();
+        uint32_t run = s_prefix + woff + inc - sum;
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+                const uint64_t k = base + i;
+                if (k < n)
+                        out[k] = run;
+                run += v[i];
+        }
+}
+
 // scratch must hold at least scan_scratch_elems(n) uint32.
 inline uint64_t scan_scratch_elems(uint64_t n)
 {
-        uint64_t tot = 0;
-        while (n > 1) {
-                n = (n + kScanTile - 1) / kScanTile;
-                tot += n + 1;
-                if (n == 1)
-                        break;
-        }
-        return tot + 8;
+        const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+        return 2 * tiles + 16;  // ticket + padding to 8 bytes + one 64-bit status word per tile
 }
 
-// Exclusive scan; returns nothing, total can be read from out[n-1]+in[n-1] by the
-// caller (or via the dedicated total slot if `d_total` != null: written as the
-// sum of all elements).
+// Exclusive scan (in place allowed); the total can be read from out[n-1] + in[n-1] by the caller.
 inline void exclusive_scan_u32(const uint32_t* in, uint32_t* out, uint64_t n, uint32_t* scratch,
                                cudaStream_t s)
 {
         if (n == 0)
                 return;
-        uint64_t tiles = (n + kScanTile - 1) / kScanTile;
+        const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
         if (tiles == 1) {
                 k_scan_tile<<<1, kScanThreads, 0, s>>>(in, out, nullptr, n);
                 count_launch();
                 return;
         }
-        uint32_t* sums = scratch;
-        k_scan_tile<<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, sums, n);
-        count_launch();
-        exclusive_scan_u32(sums, sums, tiles, scratch + tiles + 1, s);
-        k_scan_add<<<(unsigned)tiles, kScanThreads, 0, s>>>(out, sums, n);
+        // scratch: [ticket][pad..] then the status words at the next 8-byte boundary
+        uint32_t* ticket = scratch;
+        unsigned long long* status =
+                reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(scratch) + 8 + 7) & ~(uintptr_t)7);
+        const size_t bytes = (size_t)(reinterpret_cast<char*>(status + tiles) - reinterpret_cast<char*>(scratch));
+        cudaMemsetAsync(scratch, 0, bytes, s);
+        k_scan_lookback<<<(unsigned)tiles, kScanThreads, 0, s>>>(in, out, n, status, ticket);
         count_launch();
 }
 
