@@ -137,8 +137,8 @@ int tree_alloc(vrt_tree** out)
                 return VRT_ERR_NOMEM;
         if (!cuda_ok(cudaGetDevice(&t->device), "cudaGetDevice") ||
             !cuda_ok(cudaMalloc(&t->d_counter, 256), "cudaMalloc(counter)") ||
-            !cuda_ok(cudaMallocHost(&t->h_counter, 256), "cudaMallocHost(counter)") ||
-            !cuda_ok(cudaMemset(t->d_counter, 0, 256), "cudaMemset(counter)") ||
+            !cuda_ok(cudaHostAlloc(&t->h_counter, 256, cudaHostAllocMapped), "cudaHostAlloc(counter)") ||
+            !cuda_ok(cudaMemset(t->d_counter, 0, 256), "cudaMemset(counter)") || (memset(t->h_counter, 0, 256), false) ||
             !cuda_ok(cudaEventCreate(&t->ev0), "cudaEventCreate") ||
             !cuda_ok(cudaEventCreate(&t->ev1), "cudaEventCreate")) {
                 vrt_tree_free(t);

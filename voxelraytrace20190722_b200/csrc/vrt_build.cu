@@ -646,11 +646,36 @@ __global__ void k_node_counts(const unsigned long long* __restrict__ child_seen,
 
 // totals of one level in one place: out[0] = pairs produced, out[1] = nodes of the next level
 // (out[2] = dead ends so far, accumulated by k_node_counts)
+// `mailbox` (may be null) is page-locked HOST memory mapped into the device's address space: the three totals and
+// then a ticket are stored there directly, so the host learns them by polling one word instead of a copy + a
+// stream synchronisation per level (the stream never drains: the host enqueues the next level as soon as the
+// ticket shows up).
 __global__ void k_publish_totals(const uint32_t* __restrict__ pairs_total, const uint32_t* __restrict__ first_last,
-                                 const uint32_t* __restrict__ cnt_last, uint32_t* __restrict__ out)
+                                 const uint32_t* __restrict__ cnt_last, uint32_t* __restrict__ out,
+                                 volatile uint32_t* mailbox, uint32_t ticket)
 {
-        out[0] = *pairs_total;
-        out[1] = *first_last + *cnt_last;
+        const uint32_t a = *pairs_total, b = *first_last + *cnt_last;
+        out[0] = a;
+        out[1] = b;
+        if (mailbox) {
+                mailbox[0] = a;
+                mailbox[1] = b;
+                mailbox[2] = out[2];
+                __threadfence_system();
+                mailbox[3] = ticket;
+        }
+}
+
+// Host side of the mailbox: spin until the ticket arrives (with a periodic look at the stream, so that a failed
+// launch cannot hang the host).  Returns false when the stream finished without delivering the ticket.
+static bool wait_mailbox(cudaStream_t s, volatile uint32_t* mailbox, uint32_t ticket)
+{
+        for (uint64_t spin = 1;; ++spin) {
+                if (mailbox[3] == ticket)
+                        return true;
+                if ((spin & 0xfffffull) == 0 && cudaStreamQuery(s) != cudaErrorNotReady)
+                        return mailbox[3] == ticket;
+        }
 }
 
 // ---- dead ends.  A triangle can pass a cell's SAT test and fail all eight children's; the reference
@@ -1198,12 +1223,28 @@ static int build_ranked(vrt_tree* t, int L, uint64_t n0, const float* d_root6, c
                                                                 node_cnt, d_tot + 2);
                 count_launch();
                 exclusive_scan_u32(node_cnt, node_first, nn, t->tmp_c.as<uint32_t>(), s);
-                k_publish_totals<<<1, 1, 0, s>>>(bc + nblk, node_first + (nn - 1), node_cnt + (nn - 1), d_tot);
+                // totals to the host through the mapped mailbox (h_counter[16..19]; VRT_BUILD_MAILBOX=0: copy + sync)
+                static int use_mailbox = -1;
+                if (use_mailbox < 0) {
+                        const char* e = getenv("VRT_BUILD_MAILBOX");
+                        use_mailbox = (e && e[0] == '0') ? 0 : 1;
+                }
+                volatile uint32_t* mailbox = use_mailbox ? t->h_counter + 16 : nullptr;
+                const uint32_t ticket = ++t->mailbox_ticket;
+                k_publish_totals<<<1, 1, 0, s>>>(bc + nblk, node_first + (nn - 1), node_cnt + (nn - 1), d_tot, mailbox, ticket);
                 count_launch();
-                VRT_CUDA(cudaMemcpyAsync(t->h_counter, d_tot, 12, cudaMemcpyDeviceToHost, s));
-                VRT_CUDA(cudaStreamSynchronize(s));
-                const uint64_t produced = t->h_counter[0], nodes_next = t->h_counter[1];
-                dead_ends = t->h_counter[2];
+                uint64_t produced, nodes_next;
+                if (mailbox && wait_mailbox(s, mailbox, ticket)) {
+                        produced = mailbox[0];
+                        nodes_next = mailbox[1];
+                        dead_ends = mailbox[2];
+                } else {
+                        VRT_CUDA(cudaMemcpyAsync(t->h_counter, d_tot, 12, cudaMemcpyDeviceToHost, s));
+                        VRT_CUDA(cudaStreamSynchronize(s));
+                        produced = t->h_counter[0];
+                        nodes_next = t->h_counter[1];
+                        dead_ends = t->h_counter[2];
+                }
                 if (produced >= 0xfffffff0ull) {
                         set_error("more than 2^32 (triangle, cell) pairs at level %d", l + 1);
                         return VRT_ERR_CAPACITY;

@@ -139,7 +139,8 @@ struct vrt_tree {
         vrt::Scratch keys_a, keys_b, tmp_a, tmp_b, tmp_c, hist, refs_s, tab_s, level_morton[VRT_MAX_DEPTH + 1],
             level_first[VRT_MAX_DEPTH + 1], level_mask[VRT_MAX_DEPTH + 1];
         uint32_t* d_counter = nullptr;  // small device counter block
-        uint32_t* h_counter = nullptr;  // pinned mirror
+        uint32_t* h_counter = nullptr;  // pinned mirror (also mapped: words 16..19 are the build's host mailbox)
+        uint32_t mailbox_ticket = 0;
         // trace scratch (host-pointer entry points)
         vrt::Scratch io_in, io_out;
         // GI rows: per-node coverage + illum[6], see vrt_gi.cuh
