@@ -65,13 +65,18 @@ static void pool_setup_once()
 // of a build, the buffers of a handle that is being freed) are parked here and freed at the next flush point --
 // ONE device synchronisation for all of them instead of one per buffer (a fresh handle's first build used to
 // spend most of its wall time in those synchronisations).
+struct Parked {
+        void* p;
+        size_t bytes;
+        int device;
+};
 static std::mutex g_parked_mu;
-static std::vector<std::pair<void*, size_t>> g_parked;
+static std::vector<Parked> g_parked;
 static size_t g_parked_bytes = 0;
 
 void scratch_flush_deferred()
 {
-        std::vector<std::pair<void*, size_t>> v;
+        std::vector<Parked> v;
         {
                 std::lock_guard<std::mutex> lk(g_parked_mu);
                 v.swap(g_parked);
@@ -79,9 +84,21 @@ void scratch_flush_deferred()
         }
         if (v.empty())
                 return;
-        cudaDeviceSynchronize();  // nothing may still be using the parked buffers
-        for (auto& e : v)
-                cudaFreeAsync(e.first, cudaStreamPerThread);
+        // every buffer is freed on the device it lives on, after that device has drained (single-process
+        // multi-GPU hosts park buffers of several devices)
+        int cur = 0;
+        cudaGetDevice(&cur);
+        int synced = -1;
+        std::sort(v.begin(), v.end(), [](const Parked& a, const Parked& b) { return a.device < b.device; });
+        for (const Parked& e : v) {
+                if (e.device != synced) {
+                        cudaSetDevice(e.device);
+                        cudaDeviceSynchronize();  // nothing may still be using the parked buffers
+                        synced = e.device;
+                }
+                cudaFreeAsync(e.p, cudaStreamPerThread);
+        }
+        cudaSetDevice(cur);
         cudaGetLastError();
 }
 
@@ -116,8 +133,10 @@ int Scratch::reserve(size_t bytes)
 void Scratch::release()
 {
         if (p) {
+                int dev = 0;
+                cudaGetDevice(&dev);  // (a handle's buffers are only touched with its device current: check_tree)
                 std::lock_guard<std::mutex> lk(g_parked_mu);
-                g_parked.emplace_back(p, cap);
+                g_parked.push_back(Parked{ p, cap, dev });
                 g_parked_bytes += cap;
         }
         p = nullptr;
@@ -138,12 +157,13 @@ int tree_alloc(vrt_tree** out)
         if (!cuda_ok(cudaGetDevice(&t->device), "cudaGetDevice") ||
             !cuda_ok(cudaMalloc(&t->d_counter, 256), "cudaMalloc(counter)") ||
             !cuda_ok(cudaHostAlloc(&t->h_counter, 256, cudaHostAllocMapped), "cudaHostAlloc(counter)") ||
-            !cuda_ok(cudaMemset(t->d_counter, 0, 256), "cudaMemset(counter)") || (memset(t->h_counter, 0, 256), false) ||
+            !cuda_ok(cudaMemset(t->d_counter, 0, 256), "cudaMemset(counter)") ||
             !cuda_ok(cudaEventCreate(&t->ev0), "cudaEventCreate") ||
             !cuda_ok(cudaEventCreate(&t->ev1), "cudaEventCreate")) {
                 vrt_tree_free(t);
                 return VRT_ERR_CUDA;
         }
+        memset(t->h_counter, 0, 256);  // (words 16..19: the build's host mailbox, ticket 0 = nothing delivered)
         for (int i = 0; i < vrt_tree::kEvRing; ++i)
                 if (!cuda_ok(cudaEventCreate(&t->ring0[i]), "cudaEventCreate") ||
                     !cuda_ok(cudaEventCreate(&t->ring1[i]), "cudaEventCreate")) {
