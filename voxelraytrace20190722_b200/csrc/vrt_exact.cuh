@@ -459,8 +459,8 @@ struct CameraParams {
         int nx, ny, spp;
 };
 
-__device__ __forceinline__ void gen_ray(const CameraParams& cam, int px, int py, int s,
-                                        float o[3], float d[3])
+// direction of sample s of pixel (px,py): vector_transform(C, {x_, y_, z}) normalised by the Ray ctor
+__device__ __forceinline__ void gen_ray_dir(const CameraParams& cam, int px, int py, int s, float d[3])
 {
         // samples: gen_rays1 {4,4}/8 ; gen_rays4 {1,5},{3,1},{7,3},{5,7} /8
         float sx, sy;
@@ -475,9 +475,24 @@ __device__ __forceinline__ void gen_ray(const CameraParams& cam, int px, int py,
         const float y = (float)((cam.ny - 1 - py) - cam.ny / 2);
         const float x_ = fdiv(fadd(x, sx), (float)cam.nx);
         const float y_ = fdiv(fadd(y, sy), (float)cam.ny);
-        // point_transform(C,{0,0,0}) / vector_transform(C,{x_,y_,z})
-        // graphics_math.h:1063-1077 via dot(Mat4,Vec4) :552-562
-        float o4[4], d4[4];
+        // vector_transform(C,{x_,y_,z}): graphics_math.h:1063-1077 via dot(Mat4,Vec4) :552-562
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+                float b = fadd(0.f, fmul(cam.C[r], x_));
+                b = fadd(b, fmul(cam.C[4 + r], y_));
+                b = fadd(b, fmul(cam.C[8 + r], cam.z));
+                b = fadd(b, fmul(cam.C[12 + r], 0.f));
+                d[r] = b;
+        }
+        normalize3(d[0], d[1], d[2]);  // Ray ctor graphics_math.h:1159-1166
+}
+
+// origin of every ray of the camera: point_transform(C, {0,0,0}) -- the same four-term column sums and the
+// division by w as the reference, evaluated once per launch (the launcher runs the identical float operations on
+// the host, vrt_trace.cu camera_eye_host, and hands the result to the kernel)
+__device__ __forceinline__ void gen_ray_origin(const CameraParams& cam, float o[3])
+{
+        float o4[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
                 float a = fadd(0.f, fmul(cam.C[r], 0.f));
@@ -485,19 +500,17 @@ __device__ __forceinline__ void gen_ray(const CameraParams& cam, int px, int py,
                 a = fadd(a, fmul(cam.C[8 + r], 0.f));
                 a = fadd(a, fmul(cam.C[12 + r], 1.f));
                 o4[r] = a;
-                float b = fadd(0.f, fmul(cam.C[r], x_));
-                b = fadd(b, fmul(cam.C[4 + r], y_));
-                b = fadd(b, fmul(cam.C[8 + r], cam.z));
-                b = fadd(b, fmul(cam.C[12 + r], 0.f));
-                d4[r] = b;
         }
         o[0] = fdiv(o4[0], o4[3]);
         o[1] = fdiv(o4[1], o4[3]);
         o[2] = fdiv(o4[2], o4[3]);
-        d[0] = d4[0];
-        d[1] = d4[1];
-        d[2] = d4[2];
-        normalize3(d[0], d[1], d[2]);  // Ray ctor graphics_math.h:1159-1166
+}
+
+__device__ __forceinline__ void gen_ray(const CameraParams& cam, int px, int py, int s,
+                                        float o[3], float d[3])
+{
+        gen_ray_origin(cam, o);
+        gen_ray_dir(cam, px, py, s, d);
 }
 
 }  // namespace vrt
