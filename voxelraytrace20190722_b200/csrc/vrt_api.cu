@@ -158,6 +158,7 @@ int tree_alloc(vrt_tree** out)
             !cuda_ok(cudaMalloc(&t->d_counter, 256), "cudaMalloc(counter)") ||
             !cuda_ok(cudaHostAlloc(&t->h_counter, 256, cudaHostAllocMapped), "cudaHostAlloc(counter)") ||
             !cuda_ok(cudaMemset(t->d_counter, 0, 256), "cudaMemset(counter)") ||
+            !cuda_ok(cudaMalloc(&t->d_tile_queues, sizeof(uint32_t) * 8 * vrt_tree::kTileQueues), "cudaMalloc(tile queues)") ||
             !cuda_ok(cudaEventCreate(&t->ev0), "cudaEventCreate") ||
             !cuda_ok(cudaEventCreate(&t->ev1), "cudaEventCreate")) {
                 vrt_tree_free(t);
@@ -598,6 +599,8 @@ void vrt_tree_free(vrt_tree* t)
         scratch_flush_deferred();
         if (t->d_counter)
                 cudaFree(t->d_counter);
+        if (t->d_tile_queues)
+                cudaFree(t->d_tile_queues);
         if (t->h_counter)
                 cudaFreeHost(t->h_counter);
         if (t->ev0)

@@ -1597,9 +1597,10 @@ k_hull_level(const uint2* __restrict__ nodes, const unsigned long long* __restri
                 ++ch;
         }
         codes[node] = code;
-        // record: first child, child mask, then the hull; the tight-children mask goes to its own byte array
+        // record: first child, child mask | tight-children mask << 8, then the hull (the tight mask also goes to its
+        // own byte array for the statistics / debug readers)
         tight8[node] = (uint8_t)tight;
-        hull[2 * node] = make_float4(__uint_as_float(rec.x), __uint_as_float(mask), hx.x, hx.y);
+        hull[2 * node] = make_float4(__uint_as_float(rec.x), __uint_as_float(mask | (tight << 8)), hx.x, hx.y);
         hull[2 * node + 1] = make_float4(hy.x, hy.y, hz.x, hz.y);
 }
 

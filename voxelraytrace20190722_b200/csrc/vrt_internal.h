@@ -141,6 +141,9 @@ struct vrt_tree {
         uint32_t* d_counter = nullptr;  // small device counter block
         uint32_t* h_counter = nullptr;  // pinned mirror (also mapped: words 16..19 are the build's host mailbox)
         uint32_t mailbox_ticket = 0;
+        // per-SM tile queues of the camera kernels: 8 launch slots x kTileQueues counters (vrt_trace.cu)
+        static constexpr int kTileQueues = 256;
+        uint32_t* d_tile_queues = nullptr;
         // trace scratch (host-pointer entry points)
         vrt::Scratch io_in, io_out;
         // GI rows: per-node coverage + illum[6], see vrt_gi.cuh

@@ -50,8 +50,10 @@ struct TraceParams {
         void* out;
         void* out2;  // film when MODE == OUT_HIT16_FILM
         int film_full;  // out2 is the full [ny][nx][3] frame (peer-mapped): address by film row
-        uint32_t* queue;  // tile counter
+        uint32_t* queue;  // tile counter(s)
         uint32_t num_tiles;
+        // camera kernels: one tile queue per SM over a blocked tile order (see k_trace_camera)
+        uint32_t num_queues, queue_chunk, blocks_x, tiles_y;
         float light[3];
         float kd;
         float shadow_eps;
@@ -589,8 +591,17 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
         uint32_t x = 1, y = 1, z = 1;
         // record of the node to expand (a tested child's comes with its hull record) and its node index (for the
         // per-node flags of which children's hulls are worth testing)
-        uint2 rec = __ldg(&tr.nodes[0]);
-        uint32_t node = 0;
+        // (with hulls every interior node's record is read from its hull record, whose mask word also carries the
+        // tight-children flags in bits 8-15: the expansion needs no second per-node load)
+        const bool hulls = !COUNT && tr.hull != nullptr;
+        uint2 rec;
+        if (hulls) {
+                const float4 h0 = __ldg(&tr.hull[0]);
+                rec = make_uint2(__float_as_uint(h0.x), __float_as_uint(h0.y));
+        } else {
+                rec = __ldg(&tr.nodes[0]);
+                rec.y &= 0xffu;
+        }
         // visiting list of the node being iterated: 4 bits per entry, lowest first, entry =
         // 8 | child id -- an empty list is the value 0, so no separate count is carried
         uint32_t first, mask, list;
@@ -609,9 +620,7 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                         atomicAdd(&g_hull_stats[level][0], 1ull);
 #endif
                         first = rec.x;
-                        mask = rec.y;  // bits 0-7 child mask; bits 8-15 (below) children whose hull is worth testing
-                        if (!COUNT && tr.hull != nullptr)
-                                mask |= (uint32_t)__ldg(&tr.tight8[node]) << 8;
+                        mask = rec.y;  // bits 0-7 child mask; bits 8-15 children whose hull is worth testing (0 without hulls)
                         const float4 bx = __ldg(&tr.tab4[0][x]);
                         const float4 by = __ldg(&tr.tab4[1][y]);
                         const float4 bz = __ldg(&tr.tab4[2][z]);
@@ -747,21 +756,24 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
 #ifdef VRT_HULL_STATS
                         atomicAdd(&g_hull_stats[level][1], 1ull);
 #endif
-                        if ((mask >> (8u + c)) & 1u) {
-                                const float4 ha = __ldg(&tr.hull[2ull * child]), hb = __ldg(&tr.hull[2ull * child + 1]);
-                                float h0, h1;
+                        if (hulls) {
+                                const float4 ha = __ldg(&tr.hull[2ull * child]);
+                                if ((mask >> (8u + c)) & 1u) {
+                                        const float4 hb = __ldg(&tr.hull[2ull * child + 1]);
+                                        float h0, h1;
 #ifdef VRT_HULL_STATS
-                                atomicAdd(&g_hull_stats[level][2], 1ull);
-                                if (!hull_reachable(ha, hb, o, dinv, tmin, tmax, h0, h1))
-                                        atomicAdd(&g_hull_stats[level][3], 1ull);
+                                        atomicAdd(&g_hull_stats[level][2], 1ull);
+                                        if (!hull_reachable(ha, hb, o, dinv, tmin, tmax, h0, h1))
+                                                atomicAdd(&g_hull_stats[level][3], 1ull);
 #endif
-                                if (!hull_reachable(ha, hb, o, dinv, tmin, tmax, h0, h1))
-                                        continue;
+                                        if (!hull_reachable(ha, hb, o, dinv, tmin, tmax, h0, h1))
+                                                continue;
+                                }
                                 rec = make_uint2(__float_as_uint(ha.x), __float_as_uint(ha.y));
                         } else {
                                 rec = __ldg(&tr.nodes[child]);
+                                rec.y &= 0xffu;
                         }
-                        node = child;
                         if (list != 0u) {  // remember this level only if it has children left
                                 asm volatile("st.shared.u32 [%0], %1;" ::"r"(sp), "r"(first) : "memory");
                                 asm volatile("st.shared.u32 [%0+%1], %2;" ::"r"(sp), "n"(kCol),
@@ -1151,7 +1163,7 @@ k_trace_rays(const __grid_constant__ TraceParams p)
 {
         extern __shared__ uint32_t s_stack[];
         uint32_t* s_first = s_stack + threadIdx.x;
-        uint32_t* s_meta = s_first + kTraceThreads;  // record r, word w: s_stack[(3 * r + w) * threads + tid]
+        uint32_t* s_meta = s_first + kTraceThreads;  // record r, word w: s_first[(3 * r + w) * threads]
         uint32_t* s_list = s_meta + kTraceThreads;
         const unsigned long long nwarp_items = (p.num_rays + 31ull) / 32ull;
         const int lane = threadIdx.x & 31;
@@ -1177,8 +1189,10 @@ k_trace_rays(const __grid_constant__ TraceParams p)
         }
 }
 
-// 64 registers (8 CTAs/SM) is fastest for the compact outputs; the modes that also
-// evaluate the ISect/normal/shading tail spill at 64 and run best at 80 (6 CTAs/SM).
+// Every mode runs best at 72 registers (7 CTAs/SM).  Round 1 had the compact outputs at 64 registers (8 CTAs/SM);
+// since the tiles of an SM are neighbours on the film (per-SM queues below: L1 hit rate 73 -> 87 %) the warps wait
+// less on memory, and the 1/d values that 64 registers push into local memory (re-read in every expansion and hull
+// test) cost more than the eighth CTA hides: hit16 5.92 -> 5.72 ms per headline frame.
 // The per-ray records and the film are written once and never read by the kernel: streaming stores
 // (st.global.cs) keep them from displacing octree lines in L2 (-DVRT_PLAIN_STORES: ordinary stores).
 #ifdef VRT_PLAIN_STORES
@@ -1191,7 +1205,7 @@ template <int MODE, bool WS>
 #define VRT_FILM_MIN_BLOCKS 7
 #endif
 #ifndef VRT_HIT16_MIN_BLOCKS
-#define VRT_HIT16_MIN_BLOCKS 8
+#define VRT_HIT16_MIN_BLOCKS 7
 #endif
 #ifndef VRT_GI_MIN_BLOCKS
 #define VRT_GI_MIN_BLOCKS 5
@@ -1203,7 +1217,7 @@ k_trace_camera(const __grid_constant__ TraceParams p)
 {
         extern __shared__ uint32_t s_stack[];
         uint32_t* s_first = s_stack + threadIdx.x;
-        uint32_t* s_meta = s_first + kTraceThreads;  // record r, word w: s_stack[(3 * r + w) * threads + tid]
+        uint32_t* s_meta = s_first + kTraceThreads;  // record r, word w: s_first[(3 * r + w) * threads]
         uint32_t* s_list = s_meta + kTraceThreads;
         const int lane = threadIdx.x & 31;
         const int W = p.x1 - p.x0, H = p.y1 - p.y0;
@@ -1220,6 +1234,57 @@ k_trace_camera(const __grid_constant__ TraceParams p)
         const int tiles_x = (W + tw - 1) / tw;
         // the next tile index is fetched while the current tile is traced (the atomic's round
         // trip to L2 stays off the critical path)
+#ifndef VRT_TILE_GLOBAL
+        // Tile order and queues.  The tile sequence runs block by block over 8x8-tile blocks (row-major inside a
+        // block), and is cut into one contiguous range per SM; the warps of an SM pull from their SM's own counter, so
+        // the tiles in flight on one SM are neighbours on the film and their rays share node, hull and triangle
+        // records in that SM's L1.  An SM whose range is exhausted steals from the front of the following SMs'
+        // ranges.  qstate (lane 0) = current queue | queues still to be found empty << 16.
+        __shared__ uint32_t s_qstate[kTraceThreads / 32];  // (shared, not a register: only touched between tiles)
+        uint32_t* const qstate = &s_qstate[threadIdx.x >> 5];
+        {
+                uint32_t smid;
+                asm("mov.u32 %0, %%smid;" : "=r"(smid));
+                if (lane == 0)
+                        *qstate = (smid % p.num_queues) | (p.num_queues << 16);
+                __syncwarp();
+        }
+        // the ticket for the next tile is drawn while the current tile is traced (the atomic's round trip to L2
+        // stays off the critical path); everything but the atomic itself is warp-uniform
+        uint32_t next = 0;
+        if (lane == 0)
+                next = atomicAdd(p.queue + (*qstate & 0xffffu), 1u);
+        for (;;) {
+                uint32_t n = __shfl_sync(0xffffffffu, next, 0);
+                uint32_t qs = *qstate;
+                uint32_t tile = (qs & 0xffffu) * p.queue_chunk + n;
+                if (n >= p.queue_chunk || tile >= p.num_tiles) {  // this queue is exhausted: move on (rare)
+                        tile = 0xffffffffu;
+                        while ((qs -= 0x10000u) >> 16) {
+                                const uint32_t qv = ((qs & 0xffffu) + 1u == p.num_queues) ? 0u : (qs & 0xffffu) + 1u;
+                                qs = (qs & 0xffff0000u) | qv;
+                                if (lane == 0)
+                                        n = atomicAdd(p.queue + qv, 1u);
+                                n = __shfl_sync(0xffffffffu, n, 0);
+                                if (n < p.queue_chunk && qv * p.queue_chunk + n < p.num_tiles) {
+                                        tile = qv * p.queue_chunk + n;
+                                        break;
+                                }
+                        }
+                        __syncwarp();
+                        if (lane == 0)
+                                *qstate = qs;
+                        __syncwarp();
+                }
+                if (tile == 0xffffffffu)
+                        break;
+                if (lane == 0)
+                        next = atomicAdd(p.queue + (qs & 0xffffu), 1u);
+                const uint32_t blk = tile >> 6;
+                const uint32_t bly = blk / p.blocks_x, blx = blk - bly * p.blocks_x;
+                const int ty = (int)(bly * 8u + ((tile >> 3) & 7u)), tx = (int)(blx * 8u + (tile & 7u));
+                // (tiles in the padding of the blocked order lie beyond x1 / H: all their lanes are inactive)
+#else
         uint32_t next = 0;
         if (lane == 0)
                 next = atomicAdd(p.queue, 1u);
@@ -1230,6 +1295,7 @@ k_trace_camera(const __grid_constant__ TraceParams p)
                 if (lane == 0)
                         next = atomicAdd(p.queue, 1u);
                 const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+#endif
                 int s, lx, ly;
                 if (spp == 4) {
                         s = lane & 3;
@@ -1562,6 +1628,23 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
                 return VRT_ERR_ARG;
         }
         p.num_tiles = (uint32_t)tiles;
+#ifndef VRT_TILE_GLOBAL
+        {
+                const uint32_t tiles_x = (uint32_t)((x1 - x0 + tw - 1) / tw), tiles_y = (uint32_t)((y1 - y0 + th - 1) / th);
+                p.blocks_x = (tiles_x + 7u) / 8u;
+                p.tiles_y = tiles_y;
+                const uint64_t padded = (uint64_t)p.blocks_x * ((tiles_y + 7u) / 8u) * 64ull;
+                if (padded >= 0xfff00000ull) {
+                        set_error("too many tiles for one launch");
+                        return VRT_ERR_ARG;
+                }
+                p.num_tiles = (uint32_t)padded;
+                persistent_grid((const void*)k_trace_rays, 0);  // (g_sm_count)
+                p.num_queues = (uint32_t)std::min(g_sm_count, (int)vrt_tree::kTileQueues);
+                p.queue_chunk = (p.num_tiles + p.num_queues - 1u) / p.num_queues;
+                p.queue = t->d_tile_queues + (size_t)vrt_tree::kTileQueues * (t->n_trace_launches % 8);
+        }
+#endif
         // per-ray kernels by default; VRT_TRACE_WS=1 selects the warp-synchronous kernels (measured slower so
         // far): the child-mask table of trace_tile_ws follows the stack in dynamic shared memory
         static int use_ws = -1;
@@ -1588,7 +1671,11 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         int grid = persistent_grid(kern, smem);
         grid = (int)std::min<uint64_t>((uint64_t)grid, (tiles + 3) / 4);
         cudaStream_t ls = t->launch_stream ? t->launch_stream : t->stream;
+#ifndef VRT_TILE_GLOBAL
+        VRT_CUDA(cudaMemsetAsync(p.queue, 0, sizeof(uint32_t) * vrt_tree::kTileQueues, ls));
+#else
         VRT_CUDA(cudaMemsetAsync(p.queue, 0, 4, ls));
+#endif
         const int slot = (int)(t->n_trace_launches % vrt_tree::kEvRing);
         VRT_CUDA(cudaEventRecord(t->ring0[slot], ls));
         void* args[] = { &p };
