@@ -224,6 +224,27 @@ int vrt_render_camera_dev(const vrt_tree* tree, const vrt_camera* cam,
 int vrt_render_camera_async(const vrt_tree* tree, const vrt_camera* cam,
                             const vrt_shade* sh, int x0, int y0, int x1, int y1,
                             float* film_rgb);
+/* Film export encodings, fused into the store of a finished pixel (every film-writing entry point of the handle:
+ * vrt_render_camera*, vrt_render_bands*, vrt_frame_bands*, vrt_gi_render_camera*, vrt_mgpu_render*).  The reference
+ * keeps a float film and converts it after the render loop; on a multi-GPU node the float film is what saturates
+ * the host's device->host ingest, so the conversion runs in the ray kernel and the encoded film crosses PCIe:
+ *   VRT_FILM_F32   [ny][nx][3] float            Film::to_float_array, camera.cc:50-63 (default)
+ *   VRT_FILM_RGBE  [ny][nx][4] uint8 (R,G,B,E)  the pixel encoding stbi_write_hdr applies to that array
+ *                                               (main.cc:125-126; stbiw__linear_to_rgbe, stb_image_write.h:601-616);
+ *                                               vrt_hdr_file() turns it into the bytes of test2.hdr
+ *   VRT_FILM_RGB8  [ny][nx][3] uint8            Film::to_byte_array, camera.cc:27-48 (v * 255.9f, cast to uint8)
+ * With a format other than F32 the `float*` film arguments address bytes of that layout. */
+typedef enum vrt_film_format { VRT_FILM_F32 = 0, VRT_FILM_RGBE = 1, VRT_FILM_RGB8 = 2 } vrt_film_format;
+int vrt_set_film_format(vrt_tree* tree, int32_t format);
+int vrt_film_pixel_bytes(int32_t format); /* 12 / 4 / 3, or VRT_ERR_ARG */
+/* The same encodings applied on the device to a float film the caller already holds (host pointers;
+ * format = VRT_FILM_RGBE or VRT_FILM_RGB8; out = npix * vrt_film_pixel_bytes(format) bytes). */
+int vrt_film_encode(const vrt_tree* tree, const float* film_rgb, uint64_t npix, int32_t format, uint8_t* out);
+/* The file stbi_write_hdr(name, nx, ny, 3, film) writes (stb_image_write.h:635-740: header, then per scanline the
+ * 4-byte marker and the four components run-length encoded separately; flat pixels for nx < 8 or nx >= 32768),
+ * from the RGBE film.  Host code, no device involved.  Returns the number of bytes of the file, which are written
+ * to `out` if cap is large enough (call with cap = 0 to size the buffer); negative vrt_status on bad arguments. */
+int64_t vrt_hdr_file(const uint8_t* film_rgbe, int32_t nx, int32_t ny, uint8_t* out, uint64_t cap);
 /* Row-interleaved shard of the film for multi-GPU runs (replaces the
  * static 8x8 tile split of render_mt, camera.h:45-55): the film is cut into bands
  * of band_h rows; the call renders bands band_first, band_first+band_stride, ...
@@ -256,6 +277,7 @@ int vrt_render_bands_async(const vrt_tree* tree, const vrt_camera* cam, const vr
 typedef struct vrt_mgpu vrt_mgpu;
 int vrt_mgpu_create(const vrt_tree* tree, int num_devices, const int* devices, vrt_mgpu** out);
 int vrt_mgpu_num_devices(const vrt_mgpu* m);
+int vrt_mgpu_set_film_format(vrt_mgpu* m, int32_t format); /* vrt_set_film_format on every replica */
 int vrt_mgpu_render_async(vrt_mgpu* m, const vrt_camera* cam, const vrt_shade* sh, float* film_rgb_full);
 int vrt_mgpu_sync(vrt_mgpu* m);
 int vrt_mgpu_render(vrt_mgpu* m, const vrt_camera* cam, const vrt_shade* sh, float* film_rgb_full);

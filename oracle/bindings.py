@@ -110,7 +110,24 @@ class Port:
         # materials / textures
         L.orc_set_materials.argtypes = [C.c_void_p, _f32p, _u32p, C.c_uint32, _f32p, C.c_void_p, C.c_uint32, C.c_void_p,
                                         C.c_void_p]
+        L.orc_film_rgb8.argtypes = [_f32p, C.c_uint64, _u8p]
+        L.orc_film_rgbe.argtypes = [_f32p, C.c_uint64, _u8p]
         L.orc_albedo.argtypes = [C.c_void_p, _u32p, _f32p, C.c_uint64, _f32p, _f32p]
+
+    # -- film export ----------------------------------------------------------
+    def film_rgb8(self, film):
+        """Film::to_byte_array (camera.cc:27-48) of a float film [..., 3] -> uint8 [..., 3]."""
+        f = np.ascontiguousarray(film, np.float32)
+        out = np.zeros(f.shape, np.uint8)
+        self.lib.orc_film_rgb8(f.reshape(-1), f.size // 3, out.reshape(-1))
+        return out
+
+    def film_rgbe(self, film):
+        """stbiw__linear_to_rgbe (stb_image_write.h:601-616) per pixel: float [..., 3] -> uint8 [..., 4]."""
+        f = np.ascontiguousarray(film, np.float32)
+        out = np.zeros(f.shape[:-1] + (4,), np.uint8)
+        self.lib.orc_film_rgbe(f.reshape(-1), f.size // 3, out.reshape(-1))
+        return out
 
     # -- tree ---------------------------------------------------------------
     def build(self, tri, nrm, max_depth):
@@ -322,6 +339,9 @@ class Ref:
         L.ref_load_image.restype = C.c_uint64
         L.ref_load_image.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p,
                                      C.c_uint64]
+        L.ref_film_to_bytes.argtypes = [_f32p, C.c_int, C.c_int, _u8p]
+        L.ref_write_hdr.restype = C.c_uint64
+        L.ref_write_hdr.argtypes = [_f32p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
         L.ref_gi_render.restype = C.c_double
         L.ref_gi_render.argtypes = [C.c_void_p, _f32p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_float,
                                     _f32p, C.c_int]
@@ -362,6 +382,26 @@ class Ref:
         out = np.zeros(int(n), np.uint8)
         self.lib.ref_load_image(os.fsencode(path), C.byref(w), C.byref(h), C.byref(c), out.ctypes.data, int(n))
         return out.reshape(h.value, w.value, c.value)
+
+    def film_to_bytes(self, film):
+        """Film::to_byte_array() of the reference's own Film filled with `film` [n][n][3] (square: Film::set
+        indexes y*ny + x, camera.cc:12-15, which only addresses a square film correctly)."""
+        f = np.ascontiguousarray(film, np.float32)
+        ny, nx = f.shape[0], f.shape[1]
+        assert nx == ny
+        out = np.zeros((ny, nx, 3), np.uint8)
+        self.lib.ref_film_to_bytes(f.reshape(-1), nx, ny, out.reshape(-1))
+        return out
+
+    def write_hdr(self, film) -> bytes:
+        """The file stbi_write_hdr writes for Film::to_float_array() (main.cc:125-126)."""
+        f = np.ascontiguousarray(film, np.float32)
+        ny, nx = f.shape[0], f.shape[1]
+        assert nx == ny
+        n = int(self.lib.ref_write_hdr(f.reshape(-1), nx, ny, None, 0))
+        out = np.zeros(n, np.uint8)
+        self.lib.ref_write_hdr(f.reshape(-1), nx, ny, out.ctypes.data, n)
+        return out.tobytes()
 
     def camera_matrix(self, cam10):
         out = np.zeros(16, np.float32)

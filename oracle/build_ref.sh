@@ -34,7 +34,7 @@ trap 'rm -rf "$TMP"' EXIT
 mkdir -p "$TMP/src" "$OUT"
 for f in camera.cc camera.h voxel_octree.cc voxel_octree.h tribox2.cc tribox2.h \
          raytri.cc raytri.h tiny_obj_loader.cc tiny_obj_loader.h graphics_math.h \
-         util.h stb_image.h; do
+         util.h stb_image.h stb_image_write.h; do
         cp "$REF/$f" "$TMP/src/$f"
 done
 cp -r "$REF/thread_pool_cpp" "$TMP/src/thread_pool_cpp"

@@ -708,3 +708,50 @@ uint64_t ref_load_image(const char* path, int* w, int* hgt, int* channels, uint8
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Film export (main.cc:125-126, camera.cc:27-63): what the reference does with its float film.
+// ---------------------------------------------------------------------------
+#define STB_IMAGE_WRITE_IMPLEMENTATION
+#define STB_IMAGE_WRITE_STATIC
+#include "stb_image_write.h"
+
+extern "C" {
+
+// Film::to_byte_array() of a film whose pixels were set() to rgb[ny][nx][3]
+void ref_film_to_bytes(const float* rgb, int nx, int ny, uint8_t* out)
+{
+        Film film(1.f, 1.f, nx, ny);
+        for (int y = 0; y < ny; ++y)
+                for (int x = 0; x < nx; ++x) {
+                        const float* p = rgb + 3 * ((size_t)y * nx + x);
+                        film.set(x, y, Vec3{ p[0], p[1], p[2] });
+                }
+        const auto d = film.to_byte_array();
+        std::memcpy(out, d.data(), d.size());
+}
+
+// the bytes of the file stbi_write_hdr(name, nx, ny, 3, film.to_float_array().data()) writes; returns the size,
+// copies at most cap bytes
+uint64_t ref_write_hdr(const float* rgb, int nx, int ny, uint8_t* out, uint64_t cap)
+{
+        Film film(1.f, 1.f, nx, ny);
+        for (int y = 0; y < ny; ++y)
+                for (int x = 0; x < nx; ++x) {
+                        const float* p = rgb + 3 * ((size_t)y * nx + x);
+                        film.set(x, y, Vec3{ p[0], p[1], p[2] });
+                }
+        const auto d = film.to_float_array();
+        std::vector<uint8_t> bytes;
+        stbi_write_hdr_to_func(
+                [](void* ctx, void* data, int size) {
+                        auto* v = static_cast<std::vector<uint8_t>*>(ctx);
+                        v->insert(v->end(), static_cast<uint8_t*>(data), static_cast<uint8_t*>(data) + size);
+                },
+                &bytes, nx, ny, 3, d.data());
+        if (out)
+                std::memcpy(out, bytes.data(), bytes.size() < cap ? bytes.size() : cap);
+        return bytes.size();
+}
+
+}  // extern "C"

@@ -1197,3 +1197,46 @@ void orc_aabb_isect_batch(const float* aabbs6, const float* rays8, uint64_t n,
                 out[i] = (uint8_t)orc_aabb_isect(aabbs6 + 6 * i, aabbs6 + 6 * i + 3,
                                                  rays8 + 8 * i);
 }
+
+/* ------------------------------------------------------------------ */
+/* Film export (what the reference does with its float film)           */
+/* ------------------------------------------------------------------ */
+
+/* `(unsigned char)f` / static_cast<std::uint8_t>(f) as x86-64 compiles it: CVTTSS2SI to int32 (0x80000000 when the
+ * value does not fit or is NaN), low byte.  Written out so that the oracle does not depend on what THIS compiler
+ * makes of an out-of-range conversion. */
+static uint8_t orc_f2u8(float f)
+{
+        int32_t i = (fabsf(f) < 2147483648.0f) ? (int32_t)f : INT32_MIN;
+        return (uint8_t)((uint32_t)i & 0xffu);
+}
+
+/* Film::to_byte_array camera.cc:27-48: v = rawv * 255.9f, each component cast to uint8. */
+void orc_film_rgb8(const float* rgb, uint64_t npix, uint8_t* out)
+{
+        for (uint64_t i = 0; i < 3 * npix; ++i)
+                out[i] = orc_f2u8(rgb[i] * 255.9f);
+}
+
+/* stbiw__linear_to_rgbe stb_image_write.h:601-616 (stbiw__max is the `a > b ? a : b` macro). */
+static void orc_linear_to_rgbe(uint8_t rgbe[4], const float linear[3])
+{
+        float m12 = linear[1] > linear[2] ? linear[1] : linear[2];
+        float maxcomp = linear[0] > m12 ? linear[0] : m12;
+        if (maxcomp < 1e-32f) {
+                rgbe[0] = rgbe[1] = rgbe[2] = rgbe[3] = 0;
+        } else {
+                int exponent;
+                float normalize = (float)frexp(maxcomp, &exponent) * 256.0f / maxcomp;
+                rgbe[0] = orc_f2u8(linear[0] * normalize);
+                rgbe[1] = orc_f2u8(linear[1] * normalize);
+                rgbe[2] = orc_f2u8(linear[2] * normalize);
+                rgbe[3] = (uint8_t)(exponent + 128);
+        }
+}
+
+void orc_film_rgbe(const float* rgb, uint64_t npix, uint8_t* out)
+{
+        for (uint64_t i = 0; i < npix; ++i)
+                orc_linear_to_rgbe(out + 4 * i, rgb + 3 * i);
+}

@@ -138,3 +138,34 @@ def textured_case(seed=3, nu=48, nv=24):
     return dict(tri=tri, nrm=nrm, uv=uv, mtl=rng.integers(0, 4, T).astype(np.uint32),
                 kd=rng.uniform(0.2, 0.9, (4, 3)).astype(np.float32), mtl_tex=np.array([-1, 0, -1, 1], np.int32),
                 tex0=rng.integers(0, 256, (17, 23, 3), dtype=np.uint8), tex1=rng.integers(0, 256, (8, 8, 4), dtype=np.uint8))
+
+
+def export_test_film(ny=64, nx=64, seed=3):
+    """A float film [ny][nx][3] (square when it goes through the reference, see Ref.film_to_bytes) that exercises the export encodings: plain [0,1)
+    colours, constant runs of every length class of the RLE (3, 127, 128, 129 ...), exact zeros, values below the
+    1e-32 cut, powers of two and their neighbours, bright (> 1) and huge values, and a few negative components."""
+    rng = np.random.default_rng(seed)
+    f = rng.uniform(0.0, 1.0, (ny, nx, 3)).astype(np.float32)
+    if ny < 14:  # a small film: just the value classes, row by row as far as they fit
+        f[0, :, :] = rng.uniform(0, 3e-32, (nx, 3)).astype(np.float32)
+        f[1, :, :] = rng.uniform(1.0, 40.0, (nx, 3)).astype(np.float32)
+        f[2, :, 2] = -rng.uniform(0, 2.0, nx).astype(np.float32)
+        f[3, :, :] = 0.0
+        return f
+    f[1, :, :] = 0.25                       # one run over the whole row
+    f[2, 3:6, :] = f[2, 3, :]               # run of exactly 3
+    f[3, : nx - 1, 1] = 0.5                 # run that stops one short of the row end
+    f[4, :, :] = 0.0
+    f[5, :, :] = rng.uniform(0, 3e-32, (nx, 3)).astype(np.float32)
+    p2 = np.float32(2.0) ** rng.integers(-20, 12, nx).astype(np.float32)
+    f[6, :, 0] = p2
+    f[7, :, 0] = np.nextafter(p2, np.float32(0))
+    f[8, :, 0] = np.nextafter(p2, np.float32(np.inf))
+    f[9, :, :] = rng.uniform(1.0, 40.0, (nx, 3)).astype(np.float32)
+    f[10, :, :] = rng.uniform(0, 1e10, (nx, 3)).astype(np.float32)
+    f[11, :, 2] = -rng.uniform(0, 2.0, nx).astype(np.float32)
+    f[12, :, :] = 1.0
+    f[13, ::2, :] = 0.999999
+    if ny > 20:
+        f[14:20, :, :] = (f[14:20, :, :] * 4).astype(np.int32).astype(np.float32) / 4  # quantised: many short runs
+    return f

@@ -91,3 +91,19 @@ def test_textured_golden(port):
     nx, ny, spp = (int(v) for v in z["dims"])
     assert_bits_equal(tree.gi_render(z["cam10"], 1.0, nx, ny, spp, np.float32(z["res"]), np.array([0.7, 0.6, 0.5], np.float32)),
                       z["film"], "textured trace() film")
+
+
+def test_film_export_golden(port):
+    """Film::to_byte_array and stbi_write_hdr(Film::to_float_array) of the reference (tests/golden/make_golden_film.py)
+    against the restatement's per-pixel encoders and the product's host-side .hdr writer (vrt_hdr_file: header +
+    per-component RLE, no device involved)."""
+    from voxelraytrace20190722_b200 import capi
+    z = np.load(os.path.join(G, "film_export.npz"))
+    for name in ("wide", "big", "narrow"):
+        film = z[name]
+        assert_bits_equal(port.film_rgb8(film), z[name + "_rgb8"], name + " to_byte_array")
+        hdr = capi.hdr_file(port.film_rgbe(film))
+        assert hdr == z[name + "_hdr"].tobytes(), name + ": .hdr file differs from stbi_write_hdr's"
+    # the narrow film is written flat: its payload IS the per-pixel RGBE encoding
+    nar = z["narrow_hdr"].tobytes()
+    assert nar.endswith(port.film_rgbe(z["narrow"]).tobytes())

@@ -107,3 +107,14 @@ def test_textured_materials_live(port, ref, tmp_path):
     res = gi_res(b.root_aabb(), depth)
     assert_bits_equal(a.gi_render(CAM_SPHERE, 1.0, 48, 32, 4, res, GI_KD), b.gi_render(CAM_SPHERE, 1.0, 48, 32, 4, res, None, nthreads=4),
                       "textured trace() film")
+
+
+def test_film_export_live(port, ref):
+    """Film export (camera.cc:27-63, main.cc:125-126, stb_image_write.h:601-740): restatement and the product's
+    host-side .hdr writer against the reference's own Film + stbi_write_hdr on fresh random films."""
+    from tests.common import export_test_film
+    from voxelraytrace20190722_b200 import capi
+    for n, seed in ((96, 11), (7, 12), (8, 13), (200, 14)):
+        film = export_test_film(n, n, seed)
+        assert_bits_equal(port.film_rgb8(film), ref.film_to_bytes(film), "to_byte_array")
+        assert capi.hdr_file(port.film_rgbe(film)) == ref.write_hdr(film), f"{n}x{n} .hdr"

@@ -68,7 +68,8 @@ SYMBOLS = [
     "vrt_trace_bands16_dev", "vrt_count_camera", "vrt_frame_bands_dev", "vrt_frame_bands_peer_dev",
     "vrt_dev_alloc", "vrt_dev_free", "vrt_host_register", "vrt_host_unregister", "vrt_ipc_export", "vrt_ipc_open", "vrt_ipc_close", "vrt_tree_sync",
     "vrt_last_kernel_ms", "vrt_mean_kernel_ms", "vrt_debug_general_order_calls", "vrt_debug_param_check", "vrt_debug_pair_total", "vrt_debug_set_hull", "vrt_debug_hull_stats", "vrt_build_ex", "vrt_mgpu_create", "vrt_mgpu_num_devices",
-    "vrt_mgpu_render_async", "vrt_mgpu_sync", "vrt_mgpu_render", "vrt_mgpu_free", "vrt_set_materials", "vrt_albedo", "vrt_gi_init", "vrt_gi_splat_camera", "vrt_gi_filter",
+    "vrt_mgpu_render_async", "vrt_mgpu_sync", "vrt_mgpu_render", "vrt_mgpu_free", "vrt_set_film_format",
+    "vrt_film_pixel_bytes", "vrt_hdr_file", "vrt_mgpu_set_film_format", "vrt_film_encode", "vrt_set_materials", "vrt_albedo", "vrt_gi_init", "vrt_gi_splat_camera", "vrt_gi_filter",
     "vrt_gi_get_level", "vrt_gi_cone_trace", "vrt_gi_render_camera", "vrt_gi_render_camera_dev", "vrt_tribox_batch",
     "vrt_tri_overlap_aabb_batch", "vrt_raytri_batch", "vrt_aabb_isect_batch",
 ]
@@ -142,6 +143,12 @@ def load(build_if_missing: bool = True):
     L.vrt_debug_hull_stats.argtypes = [vp]
     L.vrt_mgpu_create.argtypes = [vp, i32, vp, C.POINTER(vp)]
     L.vrt_mgpu_num_devices.argtypes = [vp]
+    L.vrt_set_film_format.argtypes = [vp, C.c_int32]
+    L.vrt_mgpu_set_film_format.argtypes = [vp, C.c_int32]
+    L.vrt_film_pixel_bytes.argtypes = [C.c_int32]
+    L.vrt_film_encode.argtypes = [vp, vp, C.c_uint64, C.c_int32, vp]
+    L.vrt_hdr_file.restype = C.c_int64
+    L.vrt_hdr_file.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_uint64]
     L.vrt_mgpu_render_async.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), vp]
     L.vrt_mgpu_render.argtypes = [vp, C.POINTER(vrt_camera), C.POINTER(vrt_shade), vp]
     L.vrt_mgpu_sync.argtypes = [vp]
@@ -177,6 +184,12 @@ def load(build_if_missing: bool = True):
 def _check(rc):
     if rc != 0:
         raise VrtError(rc, load().vrt_last_error().decode(errors="replace"))
+
+
+def _check_pos(rc):
+    if rc < 0:
+        raise VrtError(rc, load().vrt_last_error().decode(errors="replace"))
+    return rc
 
 
 def _ptr(a):
@@ -368,12 +381,30 @@ class Octree:
         fn = load().vrt_trace_camera16_dev if compact else load().vrt_trace_camera_dev
         _check(fn(self._h, C.byref(cam.c), x0, y0, x1, y1, C.c_void_p(d_out_ptr)))
 
+    def set_film_format(self, fmt):
+        """'f32' (default), 'rgbe' (stbi_write_hdr's pixel encoding) or 'rgb8' (Film::to_byte_array): how every
+        film-writing call of this handle stores a finished pixel."""
+        self.film_format = FILM_FORMATS[fmt] if isinstance(fmt, str) else int(fmt)
+        _check(load().vrt_set_film_format(self._h, self.film_format))
+
+    def film_encode(self, film, fmt):
+        """Encode a float film [..., 3] on the device: 'rgbe' -> uint8 [..., 4], 'rgb8' -> uint8 [..., 3]."""
+        f = np.ascontiguousarray(film, np.float32)
+        code = FILM_FORMATS[fmt]
+        out = np.zeros(f.shape[:-1] + (4 if code == 1 else 3,), np.uint8)
+        _check(load().vrt_film_encode(self._h, _ptr(f), f.size // 3, code, _ptr(out)))
+        return out
+
+    def _film_array(self, h, w):
+        fmt = getattr(self, "film_format", 0)
+        return np.zeros((h, w, 3), np.float32) if fmt == 0 else np.zeros((h, w, 4 if fmt == 1 else 3), np.uint8)
+
     def render(self, cam: Camera, light=None, kd=0.8, rect=None, out=None, shadow_eps=None):
-        """Harness-shaded film (float RGB, [h,w,3]) through HOST buffers."""
+        """Harness-shaded film ([h,w,3] float, or the handle's film format) through HOST buffers."""
         x0, y0, x1, y1 = rect if rect else (0, 0, cam.nx, cam.ny)
         sh = _shade(light, kd, shadow_eps)
         if out is None:
-            out = np.zeros((y1 - y0, x1 - x0, 3), np.float32)
+            out = self._film_array(y1 - y0, x1 - x0)
         _check(load().vrt_render_camera(self._h, C.byref(cam.c), C.byref(sh), x0, y0, x1, y1, _ptr(out)))
         return out
 
@@ -513,6 +544,23 @@ def debug_param_check():
     return int(c[0]), int(c[1])
 
 
+FILM_FORMATS = {"f32": 0, "rgbe": 1, "rgb8": 2}
+
+
+def film_pixel_bytes(fmt) -> int:
+    return int(_check_pos(load().vrt_film_pixel_bytes(FILM_FORMATS[fmt] if isinstance(fmt, str) else int(fmt))))
+
+
+def hdr_file(film_rgbe) -> bytes:
+    """The bytes stbi_write_hdr writes for a film, from its RGBE encoding [ny][nx][4] (host code)."""
+    a = np.ascontiguousarray(film_rgbe, np.uint8)
+    ny, nx = a.shape[0], a.shape[1]
+    n = int(_check_pos(load().vrt_hdr_file(_ptr(a), nx, ny, None, 0)))
+    out = np.zeros(n, np.uint8)
+    _check_pos(load().vrt_hdr_file(_ptr(a), nx, ny, _ptr(out), n))
+    return out.tobytes()
+
+
 class MultiGpu:
     """vrt_mgpu_*: one process, N devices -- replicas of a built octree, every frame's 8-row bands dealt round-robin
     to the devices and DMA-copied to their final rows of one (pinned) host frame."""
@@ -537,6 +585,9 @@ class MultiGpu:
 
     def sync(self):
         _check(load().vrt_mgpu_sync(self._h))
+
+    def set_film_format(self, fmt):
+        _check(load().vrt_mgpu_set_film_format(self._h, FILM_FORMATS[fmt] if isinstance(fmt, str) else int(fmt)))
 
     def close(self):
         if self._h:

@@ -1008,7 +1008,7 @@ static int trace_camera_common(const vrt_tree* tc, const vrt_camera* cam, const 
         if (dev)
                 return launch_trace_camera(tc, cam, sh, x0, y0, x1, y1, out, mode, 0, 0, nullptr, 0, gi);
         vrt_tree* t = const_cast<vrt_tree*>(tc);
-        const uint64_t bytes = (mode == OUT_FILM || mode == OUT_GI_FILM) ? npix * 12 : npix * cam->spp * (mode == OUT_HIT48 ? 48 : 16);
+        const uint64_t bytes = (mode == OUT_FILM || mode == OUT_GI_FILM) ? npix * (uint64_t)vrt_film_pixel_bytes(tc->film_fmt) : npix * cam->spp * (mode == OUT_HIT48 ? 48 : 16);
         if (t->io_out.reserve(bytes))
                 return VRT_ERR_NOMEM;
         rc = launch_trace_camera(t, cam, sh, x0, y0, x1, y1, t->io_out.p, mode, 0, 0, nullptr, 0, gi);
@@ -1017,6 +1017,120 @@ static int trace_camera_common(const vrt_tree* tc, const vrt_camera* cam, const 
         VRT_CUDA(cudaMemcpyAsync(out, t->io_out.p, bytes, cudaMemcpyDeviceToHost, t->stream));
         VRT_CUDA(cudaStreamSynchronize(t->stream));
         return VRT_OK;
+}
+
+int vrt_film_pixel_bytes(int32_t format)
+{
+        switch (format) {
+        case VRT_FILM_F32: return 12;
+        case VRT_FILM_RGBE: return 4;
+        case VRT_FILM_RGB8: return 3;
+        default: set_error("unknown film format %d", (int)format); return VRT_ERR_ARG;
+        }
+}
+
+int vrt_set_film_format(vrt_tree* t, int32_t format)
+{
+        if (!t) {
+                set_error("null tree");
+                return VRT_ERR_ARG;
+        }
+        if (vrt_film_pixel_bytes(format) < 0)
+                return VRT_ERR_ARG;
+        t->film_fmt = format;
+        return VRT_OK;
+}
+
+// Encode an existing float film (host pointers) with the camera kernels' device functions.
+int vrt_film_encode(const vrt_tree* tc, const float* film_rgb, uint64_t npix, int32_t format, uint8_t* out)
+{
+        int rc = check_tree(tc);
+        if (rc)
+                return rc;
+        if (format != VRT_FILM_RGBE && format != VRT_FILM_RGB8) {
+                set_error("vrt_film_encode: format must be VRT_FILM_RGBE or VRT_FILM_RGB8");
+                return VRT_ERR_ARG;
+        }
+        if (!npix)
+                return VRT_OK;
+        if (!film_rgb || !out || npix >= (1ull << 40)) {
+                set_error("vrt_film_encode: bad argument");
+                return VRT_ERR_ARG;
+        }
+        vrt_tree* t = const_cast<vrt_tree*>(tc);
+        const uint64_t ob = npix * (uint64_t)vrt_film_pixel_bytes(format);
+        if (t->io_in.reserve(npix * 12) || t->io_out.reserve(ob))
+                return VRT_ERR_NOMEM;
+        VRT_CUDA(cudaMemcpyAsync(t->io_in.p, film_rgb, npix * 12, cudaMemcpyHostToDevice, t->stream));
+        rc = launch_film_encode(t, t->io_in.as<float>(), npix, format, t->io_out.as<uint8_t>());
+        if (rc)
+                return rc;
+        VRT_CUDA(cudaMemcpyAsync(out, t->io_out.p, ob, cudaMemcpyDeviceToHost, t->stream));
+        VRT_CUDA(cudaStreamSynchronize(t->stream));
+        return VRT_OK;
+}
+
+// stbi_write_hdr's file layout (stb_image_write.h:618-740) over an already encoded RGBE film: the header, then per
+// scanline either the flat pixels (nx < 8 or nx >= 32768) or the marker {2, 2, nx >> 8, nx & 255} followed by the
+// four components, each run-length encoded on its own: literal dumps of at most 128 bytes up to the next run of
+// three equal bytes, runs emitted in pieces of at most 127.
+int64_t vrt_hdr_file(const uint8_t* rgbe, int32_t nx, int32_t ny, uint8_t* out, uint64_t cap)
+{
+        if (!rgbe || nx <= 0 || ny <= 0 || (!out && cap)) {
+                set_error("vrt_hdr_file: bad argument");
+                return VRT_ERR_ARG;
+        }
+        uint64_t n = 0;
+        auto put = [&](const void* p, size_t len) {
+                if (n + len <= cap)
+                        memcpy(out + n, p, len);
+                n += len;
+        };
+        static const char header[] = "#?RADIANCE\n# Written by stb_image_write.h\nFORMAT=32-bit_rle_rgbe\n";
+        put(header, sizeof(header) - 1);
+        char buffer[128];
+        const int len = snprintf(buffer, sizeof buffer, "EXPOSURE=          1.0000000000000\n\n-Y %d +X %d\n", (int)ny, (int)nx);
+        put(buffer, (size_t)len);
+        std::vector<uint8_t> comp((size_t)nx);
+        for (int y = 0; y < ny; ++y) {
+                const uint8_t* row = rgbe + (size_t)y * nx * 4;
+                if (nx < 8 || nx >= 32768) {
+                        put(row, (size_t)nx * 4);
+                        continue;
+                }
+                const uint8_t marker[4] = { 2, 2, (uint8_t)((nx & 0xff00) >> 8), (uint8_t)(nx & 0xff) };
+                put(marker, 4);
+                for (int c = 0; c < 4; ++c) {
+                        for (int x = 0; x < nx; ++x)
+                                comp[x] = row[4 * (size_t)x + c];
+                        int x = 0;
+                        while (x < nx) {
+                                int r = x;  // first run of three equal bytes at or after x
+                                while (r + 2 < nx && !(comp[r] == comp[r + 1] && comp[r] == comp[r + 2]))
+                                        ++r;
+                                if (r + 2 >= nx)
+                                        r = nx;
+                                while (x < r) {  // literal bytes up to the run
+                                        const int l = std::min(r - x, 128);
+                                        const uint8_t lb = (uint8_t)l;
+                                        put(&lb, 1);
+                                        put(&comp[x], (size_t)l);
+                                        x += l;
+                                }
+                                if (r + 2 < nx) {  // the run itself
+                                        while (r < nx && comp[r] == comp[x])
+                                                ++r;
+                                        while (x < r) {
+                                                const int l = std::min(r - x, 127);
+                                                const uint8_t rb[2] = { (uint8_t)(l + 128), comp[x] };
+                                                put(rb, 2);
+                                                x += l;
+                                        }
+                                }
+                        }
+                }
+        }
+        return (int64_t)n;
 }
 
 // Streams and events of the pipelined frame loops (vrt_render_camera_async / vrt_render_bands_async): a copy
@@ -1063,7 +1177,7 @@ int vrt_render_camera_async(const vrt_tree* tc, const vrt_camera* cam, const vrt
                 return rc;
         cudaStream_t ks = async_kernel_stream(t);
         const int k = (int)(t->n_async_frames & 1);
-        const uint64_t bytes = npix * 12;
+        const uint64_t bytes = npix * (uint64_t)vrt_film_pixel_bytes(t->film_fmt);
         if (t->film_dev[k].cap < bytes) {
                 VRT_CUDA(cudaStreamSynchronize(t->copy_stream));  // nothing may still read the old buffer
                 if (t->film_dev[k].reserve(bytes))
@@ -1204,7 +1318,7 @@ int vrt_render_bands_async(const vrt_tree* tc, const vrt_camera* cam, const vrt_
                 return rc;
         cudaStream_t ks = async_kernel_stream(t);
         const int k = (int)(t->n_async_frames & 1);
-        const size_t row_bytes = (size_t)cam->nx * 12;
+        const size_t row_bytes = (size_t)cam->nx * (size_t)vrt_film_pixel_bytes(t->film_fmt);
         const uint64_t bytes = (uint64_t)rows * row_bytes;
         if (t->film_dev[k].cap < bytes) {
                 VRT_CUDA(cudaStreamSynchronize(t->copy_stream));  // nothing may still read the old buffer
@@ -1259,6 +1373,20 @@ struct vrt_mgpu {
 static int set_device_checked(int dev)
 {
         VRT_CUDA(cudaSetDevice(dev));
+        return VRT_OK;
+}
+
+int vrt_mgpu_set_film_format(vrt_mgpu* m, int32_t format)
+{
+        if (!m) {
+                set_error("null handle");
+                return VRT_ERR_ARG;
+        }
+        for (vrt_tree* t : m->trees) {
+                const int rc = vrt_set_film_format(t, format);
+                if (rc)
+                        return rc;
+        }
         return VRT_OK;
 }
 

@@ -513,4 +513,42 @@ __device__ __forceinline__ void gen_ray(const CameraParams& cam, int px, int py,
         gen_ray_dir(cam, px, py, s, d);
 }
 
+// ---------------------------------------------------------------------------
+// Film export encodings (the two formats the reference turns its float film into).
+// ---------------------------------------------------------------------------
+// float -> unsigned char as x86-64 compiles `(unsigned char)f` / static_cast<std::uint8_t>(f): CVTTSS2SI to a
+// 32-bit integer (0x80000000 for NaN and for |f| >= 2^31), then the low byte.  In range ([0,256)) this is the
+// plain truncation the C++ standard defines; outside it the standard leaves the result open and this is what the
+// reference binary does.
+__device__ __forceinline__ uint32_t f2u8_x86(float f)
+{
+        const int i = (fabsf(f) < 2147483648.f) ? __float2int_rz(f) : (int)0x80000000;
+        return (uint32_t)i & 0xffu;
+}
+
+// Film::to_byte_array (camera.cc:27-48): v = rawv * 255.9f, every component cast to std::uint8_t.
+__device__ __forceinline__ uint32_t film_rgb8(const float c[3])
+{
+        return f2u8_x86(fmul(c[0], 255.9f)) | (f2u8_x86(fmul(c[1], 255.9f)) << 8) | (f2u8_x86(fmul(c[2], 255.9f)) << 16);
+}
+
+// stbiw__linear_to_rgbe (stb_image_write.h:601-616), the pixel encoding of stbi_write_hdr(Film::to_float_array())
+// (main.cc:125-126): maxcomp by the `a > b ? a : b` macro, zero below 1e-32f, else
+// normalize = (float)frexp(maxcomp, &e) * 256.0f / maxcomp (left to right, single precision) and the three
+// components truncated to bytes, e + 128 as the fourth.  maxcomp >= 1e-32f is a normal float, so frexp's mantissa
+// and exponent are the float's own fields (finite films; stb's result for Inf/NaN pixels is not defined).
+__device__ __forceinline__ uint32_t film_rgbe(const float c[3])
+{
+        const float m12 = (c[1] > c[2]) ? c[1] : c[2];
+        const float mc = (c[0] > m12) ? c[0] : m12;
+        if (mc < 1e-32f)
+                return 0u;
+        const uint32_t b = __float_as_uint(mc);
+        const int e = (int)((b >> 23) & 0xffu) - 126;
+        const float frac = __uint_as_float((b & 0x807fffffu) | 0x3f000000u);
+        const float nrm = fdiv(fmul(frac, 256.0f), mc);
+        return f2u8_x86(fmul(c[0], nrm)) | (f2u8_x86(fmul(c[1], nrm)) << 8) | (f2u8_x86(fmul(c[2], nrm)) << 16) |
+               (((uint32_t)(e + 128) & 0xffu) << 24);
+}
+
 }  // namespace vrt

@@ -169,6 +169,7 @@ struct vrt_tree {
         mutable void* l2_window_stream = nullptr;
         mutable const void* l2_window_nodes = nullptr;
         mutable uint64_t l2_window_bytes = 0;
+        int film_fmt = 0;  // VRT_FILM_* of every film this handle's kernels write (vrt_set_film_format)
         double build_ms = 0;
         mutable double last_kernel_ms = 0;
         uint64_t scratch_bytes() const;
@@ -199,6 +200,7 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
                         int y0, int x1, int y1, void* d_out, OutMode mode, int band_h = 0,
                         int band_pitch = 0, void* d_out2 = nullptr, int film_full = 0,
                         const GiArgs* gi = nullptr);
+int launch_film_encode(const vrt_tree* t, const float* d_film, uint64_t npix, int fmt, uint8_t* d_out);
 // mean device time (ms) of the last n trace launches (waits for them)
 int trace_ms_mean(const vrt_tree* t, int last_n, double* ms);
 int general_order_calls(unsigned long long* out);

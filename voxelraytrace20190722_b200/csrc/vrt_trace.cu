@@ -50,6 +50,7 @@ struct TraceParams {
         void* out;
         void* out2;  // film when MODE == OUT_HIT16_FILM
         int film_full;  // out2 is the full [ny][nx][3] frame (peer-mapped): address by film row
+        int film_fmt;   // VRT_FILM_F32 / VRT_FILM_RGBE / VRT_FILM_RGB8: how a finished pixel is stored (include/vrt.h)
         uint32_t* queue;  // tile counter(s)
         uint32_t num_tiles;
         // camera kernels: one tile queue per SM over a blocked tile order (see k_trace_camera)
@@ -1429,17 +1430,56 @@ k_trace_camera(const __grid_constant__ TraceParams p)
                                 }
                         }
                         if (active && s == 0) {
-                                float* f = static_cast<float*>(MODE == OUT_HIT16_FILM ? p.out2 : p.out) + pix * 3ull;
-                                if (MODE == OUT_HIT16_FILM && p.film_full)
-                                        f = static_cast<float*>(p.out2) +
-                                            ((unsigned long long)py * p.cam.nx + px) * 3ull;
-                                VRT_STORE_OUT(f + 0, acc[0]);
-                                VRT_STORE_OUT(f + 1, acc[1]);
-                                VRT_STORE_OUT(f + 2, acc[2]);
+                                void* const film = (MODE == OUT_HIT16_FILM) ? p.out2 : p.out;
+                                const unsigned long long fpix = (MODE == OUT_HIT16_FILM && p.film_full)
+                                                                    ? (unsigned long long)py * p.cam.nx + px
+                                                                    : pix;
+                                if (p.film_fmt == VRT_FILM_F32) {
+                                        float* f = static_cast<float*>(film) + fpix * 3ull;
+                                        VRT_STORE_OUT(f + 0, acc[0]);
+                                        VRT_STORE_OUT(f + 1, acc[1]);
+                                        VRT_STORE_OUT(f + 2, acc[2]);
+                                } else if (p.film_fmt == VRT_FILM_RGBE) {  // the film as stbi_write_hdr encodes it
+                                        VRT_STORE_OUT(static_cast<uint32_t*>(film) + fpix, film_rgbe(acc));
+                                } else {  // Film::to_byte_array
+                                        const uint32_t v = film_rgb8(acc);
+                                        uint8_t* f = static_cast<uint8_t*>(film) + fpix * 3ull;
+                                        f[0] = (uint8_t)v;
+                                        f[1] = (uint8_t)(v >> 8);
+                                        f[2] = (uint8_t)(v >> 16);
+                                }
                         }
                 }
                 __syncwarp();
         }
+}
+
+// The film encodings of the camera kernels applied to a float film that already exists (vrt_film_encode).
+__global__ void __launch_bounds__(256) k_film_encode(const float* __restrict__ film, unsigned long long npix, int fmt,
+                                                     uint8_t* __restrict__ out)
+{
+        const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= npix)
+                return;
+        const float c[3] = { film[3 * i], film[3 * i + 1], film[3 * i + 2] };
+        if (fmt == VRT_FILM_RGBE) {
+                reinterpret_cast<uint32_t*>(out)[i] = film_rgbe(c);
+        } else {
+                const uint32_t v = film_rgb8(c);
+                out[3 * i] = (uint8_t)v;
+                out[3 * i + 1] = (uint8_t)(v >> 8);
+                out[3 * i + 2] = (uint8_t)(v >> 16);
+        }
+}
+
+int launch_film_encode(const vrt_tree* t, const float* d_film, uint64_t npix, int fmt, uint8_t* d_out)
+{
+        if (!npix)
+                return VRT_OK;
+        k_film_encode<<<(unsigned)((npix + 255) / 256), 256, 0, t->stream>>>(d_film, npix, fmt, d_out);
+        count_launch();
+        VRT_CUDA(cudaGetLastError());
+        return VRT_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -1607,6 +1647,7 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         p.out = d_out;
         p.out2 = d_out2;
         p.film_full = film_full;
+        p.film_fmt = t->film_fmt;
         if (gi) {
                 p.kd3[0] = gi->kd[0];
                 p.kd3[1] = gi->kd[1];

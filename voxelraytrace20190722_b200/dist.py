@@ -140,7 +140,7 @@ class SharedHostFrame:
     synchronised its handle and the ranks have met at a barrier.  Without an initialised
     process group it is simply `nbuf` pinned frames of one process."""
 
-    def __init__(self, ny, nx, nbuf: int = 2, dst: int = 0, pin: bool = True):
+    def __init__(self, ny, nx, nbuf: int = 2, dst: int = 0, pin: bool = True, fmt: str = "f32"):
         import mmap
         import os
         try:
@@ -151,7 +151,9 @@ class SharedHostFrame:
         self.world = dist.get_world_size() if on else 1
         self.rank = dist.get_rank() if on else 0
         self.ny, self.nx, self.nbuf, self.dst = ny, nx, nbuf, dst
-        self.frame_bytes = ny * nx * 12
+        self.fmt = fmt  # film format of the frames (capi.FILM_FORMATS): float RGB, RGBE or RGB8 bytes
+        self.pixel_bytes = {"f32": 12, "rgbe": 4, "rgb8": 3}[fmt]
+        self.frame_bytes = ny * nx * self.pixel_bytes
         self.stride = (self.frame_bytes + 4095) // 4096 * 4096  # page-aligned frames
         total = self.stride * nbuf
         # Failures (no /dev/shm, page-locking refused) are made COLLECTIVE: either every rank
@@ -197,9 +199,13 @@ class SharedHostFrame:
         return self.base + (k % self.nbuf) * self.stride
 
     def frame(self, k: int) -> np.ndarray:
-        """[ny, nx, 3] float32 numpy view of host frame k (any rank; the memory is shared)."""
+        """numpy view of host frame k (any rank; the memory is shared): [ny, nx, 3] float32, or uint8
+        [ny, nx, 4] / [ny, nx, 3] for the RGBE / RGB8 film formats."""
         o = (k % self.nbuf) * self.stride
-        return self._np[o:o + self.frame_bytes].view(np.float32).reshape(self.ny, self.nx, 3)
+        raw = self._np[o:o + self.frame_bytes]
+        if self.fmt == "f32":
+            return raw.view(np.float32).reshape(self.ny, self.nx, 3)
+        return raw.reshape(self.ny, self.nx, self.pixel_bytes)
 
     def close(self):
         if getattr(self, "_registered", False):
