@@ -109,7 +109,7 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         marks = getattr(self, "marks", {})
-        windows = [(marks[a], marks[b]) for a, b in (("t0", "t1"), ("e0", "e1")) if a in marks and b in marks]
+        windows = [(marks[a], marks[b]) for a, b in (("t0", "t1"), ("e0_f32", "e1_f32"), ("e0_rgbe", "e1_rgbe")) if a in marks and b in marks]
         for ts, r in self.rows:
             if windows and not any(lo <= ts <= hi + 0.06 for lo, hi in windows):
                 continue  # only samples taken while a timed region (value loop, e2e loop) was running
@@ -431,97 +431,118 @@ def run_ours(args):
     kern_ms_isolated = float(tk[0])
 
     # ---- e2e: host-buffer C-ABI call, film copied back to pinned host memory every step ----
-    e2e_host_frame_ok = None
-    e2e_note = None
-    if world == 1:
-        # frame loop through the host-buffer C ABI: vrt_render_camera_async enqueues the frame and
-        # its device->host copy (pinned film, alternating between two host buffers); the copy of
-        # frame k overlaps the kernel of frame k+1; every frame's film is in host memory when the
-        # timed region ends (vrt_tree_sync)
-        film_hosts = [torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
-        film_nps = [f.numpy() for f in film_hosts]
-        film_np = film_nps[0]
-        tree.set_stream(0)
-        for i in range(max(2, args.warmup // 2)):
-            tree.render_async(cams[i % len(cams)], film_nps[i & 1], shadow_eps=shadow_eps)
-        tree.sync()
-        sampler.mark("e0")
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            tree.render_async(cams[i % len(cams)], film_nps[i & 1], shadow_eps=shadow_eps)
-        tree.sync()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-        sampler.mark("e1")
-        # the synchronous single-frame call, for reference
-        t0 = time.perf_counter()
-        for _ in range(min(args.steps, 5)):
-            tree.render(cam, out=film_np, shadow_eps=shadow_eps)
-        e2e_sync_ms = (time.perf_counter() - t0) * 1e3 / min(args.steps, 5)
-        d2h = film_np.nbytes
-    else:
-        # N ranks: the same frame loop through vrt_render_bands_async -- every rank renders its
-        # bands and DMA-copies them to their final rows of a host frame that all ranks of the node
-        # map (POSIX shared memory, pinned in every process): N PCIe links in parallel, the copy of
-        # frame k overlapping the kernel of frame k+1; every frame is complete in host memory when
-        # the timed region ends (vrt_tree_sync on every rank + barrier)
+    # Measured for two film formats (include/vrt.h vrt_set_film_format): "rgbe" -- the film as main.cc:125-126
+    # delivers it (stbi_write_hdr's pixel encoding, 4 B/pixel, encoded in the ray kernel's pixel store) -- is the
+    # headline `e2e`; "f32" (Film::to_float_array, 12 B/pixel; round 1's e2e) is reported beside it as `e2e_f32`.
+    # The float film saturates this box's device->host ingest at 8 GPUs, the encoded one does not.
+    def measure_e2e(fmt):
+        note, host_ok, sync_ms = None, None, None
+        bpp = capi.film_pixel_bytes(fmt)
+        tree.set_film_format(fmt)
         try:
-            shf = vdist.SharedHostFrame(ny, nx, nbuf=2)
-        except RuntimeError as ex:  # raised on every rank or on none
-            shf = None
-            e2e_note = f"no shared pinned host frame ({ex}): per-frame barrier + copy from rank 0's GPU"
-        if shf is not None:
-            tree.set_stream(0)
-
-            def e2e_step(i):
-                tree.render_bands_async(cams[i % len(cams)], shf.ptr(i), vdist.BAND_H, rank, world,
-                                        shadow_eps=shadow_eps)
-
-            def e2e_drain():
+            if world == 1:
+                # frame loop through the host-buffer C ABI: vrt_render_camera_async enqueues the frame and its
+                # device->host copy (pinned film, alternating between two host buffers); the copy of frame k
+                # overlaps the kernel of frame k+1; every frame's film is in host memory when the timed region
+                # ends (vrt_tree_sync)
+                film_hosts = [torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory() if fmt == "f32" else
+                              torch.empty((ny, nx, bpp), dtype=torch.uint8).pin_memory() for _ in range(2)]
+                film_nps = [f.numpy() for f in film_hosts]
+                tree.set_stream(0)
+                for i in range(max(2, args.warmup // 2)):
+                    tree.render_async(cams[i % len(cams)], film_nps[i & 1], shadow_eps=shadow_eps)
                 tree.sync()
-        else:
-            film_host = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
+                sampler.mark("e0_" + fmt)
+                t0 = time.perf_counter()
+                for i in range(args.steps):
+                    tree.render_async(cams[i % len(cams)], film_nps[i & 1], shadow_eps=shadow_eps)
+                tree.sync()
+                ms = (time.perf_counter() - t0) * 1e3 / args.steps
+                sampler.mark("e1_" + fmt)
+                # the last frame of the loop against the synchronous single-frame call (also timed, for reference)
+                k_last = args.steps - 1
+                t0 = time.perf_counter()
+                for _ in range(min(args.steps, 5)):
+                    alone = tree.render(cams[k_last % len(cams)], shadow_eps=shadow_eps)
+                sync_ms = (time.perf_counter() - t0) * 1e3 / min(args.steps, 5)
+                host_ok = bool(np.array_equal(film_nps[k_last & 1].view(np.uint8), alone.view(np.uint8)))
+                return ms, ny * nx * bpp, host_ok, note, sync_ms
+            # N ranks: the same frame loop through vrt_render_bands_async -- every rank renders its bands and
+            # DMA-copies them to their final rows of a host frame that all ranks of the node map (POSIX shared
+            # memory, pinned in every process): N PCIe links in parallel, the copy of frame k overlapping the
+            # kernel of frame k+1; every frame is complete in host memory when the timed region ends
+            # (vrt_tree_sync on every rank + barrier)
+            try:
+                shf = vdist.SharedHostFrame(ny, nx, nbuf=2, fmt=fmt)
+            except RuntimeError as ex:  # raised on every rank or on none
+                shf = None
+                note = f"no shared pinned host frame ({ex}): per-frame barrier + copy from rank 0's GPU (float film)"
+            if shf is not None:
+                tree.set_stream(0)
+
+                def e2e_step(i):
+                    tree.render_bands_async(cams[i % len(cams)], shf.ptr(i), vdist.BAND_H, rank, world,
+                                            shadow_eps=shadow_eps)
+
+                def e2e_drain():
+                    tree.sync()
+            else:
+                tree.set_film_format("f32")
+                bpp = 12
+                film_host = torch.empty((ny, nx, 3), dtype=torch.float32).pin_memory() if rank == 0 else None
+                tree.set_stream(stream.cuda_stream)
+
+                def e2e_step(i):
+                    if use_gather:
+                        tree.render_bands_dev(cams[i % len(cams)], fg.buffer(0).data_ptr(), vdist.BAND_H, rank, world,
+                                              shadow_eps=shadow_eps)
+                        fg.gather_async(0)
+                        full = fg.assemble(0)
+                    else:
+                        tree.frame_bands_dev(cams[i % len(cams)], hits[0].data_ptr(), pf.ptr(0), vdist.BAND_H, rank, world,
+                                             full_frame=True, shadow_eps=shadow_eps)
+                        torch.cuda.synchronize(dev)
+                        td.barrier()  # every rank's pixels have landed in rank 0's frame
+                        full = pf.frame(0)
+                    if rank == 0:
+                        film_host.copy_(full, non_blocking=True)
+                    torch.cuda.synchronize(dev)
+
+                def e2e_drain():
+                    pass
+            for i in range(max(2, args.warmup // 2)):
+                e2e_step(i)
+            e2e_drain()
+            sync_all()
+            sampler.mark("e0_" + fmt)
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                e2e_step(i)
+            e2e_drain()
+            sync_all()
+            sampler.mark("e1_" + fmt)
+            tt = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=dev)
+            td.all_reduce(tt, op=td.ReduceOp.MAX)
+            ms = float(tt[0])
+            # the last host frame of the loop against the same camera rendered by rank 0 alone
+            if rank == 0:
+                k_last = args.steps - 1
+                alone = tree.render(cams[k_last % len(cams)], shadow_eps=shadow_eps)
+                got_host = shf.frame(k_last) if shf is not None else film_host.numpy()
+                host_ok = bool(np.array_equal(got_host.view(np.uint8), alone.view(np.uint8)))
+            if shf is not None:
+                sync_all()
+                shf.close()
+            return ms, ny * nx * bpp, host_ok, note, sync_ms
+        finally:
+            tree.set_film_format("f32")
             tree.set_stream(stream.cuda_stream)
 
-            def e2e_step(i):
-                if use_gather:
-                    tree.render_bands_dev(cams[i % len(cams)], fg.buffer(0).data_ptr(), vdist.BAND_H, rank, world,
-                                          shadow_eps=shadow_eps)
-                    fg.gather_async(0)
-                    full = fg.assemble(0)
-                else:
-                    tree.frame_bands_dev(cams[i % len(cams)], hits[0].data_ptr(), pf.ptr(0), vdist.BAND_H, rank, world,
-                                         full_frame=True, shadow_eps=shadow_eps)
-                    torch.cuda.synchronize(dev)
-                    td.barrier()  # every rank's pixels have landed in rank 0's frame
-                    full = pf.frame(0)
-                if rank == 0:
-                    film_host.copy_(full, non_blocking=True)
-                torch.cuda.synchronize(dev)
-
-            def e2e_drain():
-                pass
-        for i in range(max(2, args.warmup // 2)):
-            e2e_step(i)
-        e2e_drain()
-        sync_all()
-        sampler.mark("e0")
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            e2e_step(i)
-        e2e_drain()
-        sync_all()
-        sampler.mark("e1")
-        tt = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=dev)
-        td.all_reduce(tt, op=td.ReduceOp.MAX)
-        e2e_ms = float(tt[0])
-        d2h = ny * nx * 12
-        # the last host frame of the loop against the same camera rendered by rank 0 alone
-        if rank == 0:
-            k_last = args.steps - 1
-            alone = tree.render(cams[k_last % len(cams)], shadow_eps=shadow_eps)
-            got_host = shf.frame(k_last) if shf is not None else film_host.numpy()
-            e2e_host_frame_ok = bool(np.array_equal(got_host.view(np.uint32), alone.view(np.uint32)))
-        tree.set_stream(stream.cuda_stream)
+    f32_ms, f32_d2h, f32_ok, f32_note, f32_sync_ms = measure_e2e("f32")
+    e2e_ms, d2h, e2e_host_frame_ok, e2e_note, e2e_sync_ms = measure_e2e("rgbe")
+    e2e_f32 = {"value": rays_per_step / (f32_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": f32_ms,
+               "d2h_bytes_per_step": int(f32_d2h), "film": "f32 (Film::to_float_array, 12 B/pixel): round 1's e2e",
+               "host_frame_equals_1_gpu_render_bytewise": f32_ok, "sync_single_frame_ms": f32_sync_ms, "note": f32_note}
     e2e_value = rays_per_step / (e2e_ms * 1e-3) / 1e6
     clocks = sampler.stop() if rank == 0 else None
 
@@ -692,12 +713,16 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": 92, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms,
-                "call": ("vrt_render_camera_async per frame + vrt_tree_sync (camera struct in, shaded float film out to pinned "
+                "film": "rgbe: the film as main.cc:125-126 delivers it (stbi_write_hdr's pixel encoding, stb_image_write.h:"
+                        "601-616, 4 B/pixel), encoded in the ray kernel's pixel store (vrt_set_film_format); bytewise equal to "
+                        "the reference encoder on the float film (tests/test_gpu_film_export.py)",
+                "call": ("vrt_render_camera_async per frame + vrt_tree_sync (camera struct in, shaded film out to pinned "
                          "host; frame k's copy overlaps frame k+1's kernel)" if world == 1 else
                          "vrt_render_bands_async per rank and frame + vrt_tree_sync + barrier (camera struct in; every rank "
                          "DMA-copies its bands to their final rows of one host frame shared and pinned by all ranks; "
                          "frame k's copy overlaps frame k+1's kernel)"),
                 "sync_single_frame_ms": e2e_sync_ms if world == 1 else None, "note": e2e_note},
+        "e2e_f32": e2e_f32,
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
