@@ -577,6 +577,7 @@ void vrt_tree_free(vrt_tree* t)
         t->hull_buf.release();
         t->tri64_buf.release();
         t->gi_recs.release();
+        t->gi_steps.release();
         t->mat_buf.release();
         t->io_out.release();
         t->film_dev[0].release();
@@ -1738,7 +1739,10 @@ static int gi_render_common(const vrt_tree* tc, const vrt_camera* cam, const flo
                 set_error("vrt_gi_init has not been called on this tree");
                 return VRT_ERR_ARG;
         }
-        const GiArgs ga = { { kd[0], kd[1], kd[2] }, res };
+        GiArgs ga = { { kd[0], kd[1], kd[2] }, res };
+        rc = gi_step_table(tc, res, &ga.steps);
+        if (rc)
+                return rc;
         return trace_camera_common(tc, cam, nullptr, x0, y0, x1, y1, film, OUT_GI_FILM, dev, &ga);
 }
 

@@ -8,6 +8,7 @@
 // this file is the SEQUENTIAL member of that family (pixel order, samples in order), reproduced
 // exactly by summing every leaf's contributions in ray order.
 #include <algorithm>
+#include <cstdlib>
 
 #include "vrt_gi.cuh"
 
@@ -172,9 +173,41 @@ int gi_filter(vrt_tree* t)
         return VRT_OK;
 }
 
+struct GiRoot6 {
+        float v[6];
+};
+__global__ void k_gi_step_table(GiRoot6 root, float res, float4* tab)
+{
+        gi_step_table_fill(root.v, res, tab);
+}
+
+int gi_step_table(const vrt_tree* t, float res, const float4** d_steps)
+{
+        *d_steps = nullptr;
+        static int on = -1;  // VRT_GI_STEPS=0: every cone evaluates the marching arithmetic itself
+        if (on < 0) {
+                const char* e = getenv("VRT_GI_STEPS");
+                on = (e && e[0] == '0') ? 0 : 1;
+        }
+        if (!on)
+                return VRT_OK;
+        if (t->gi_steps.reserve((size_t)(kGiMaxSteps + 1) * sizeof(float4)))
+                return VRT_ERR_NOMEM;
+        GiRoot6 r;
+        for (int k = 0; k < 6; ++k)
+                r.v[k] = t->hdr.root_aabb[k];
+        cudaStream_t s = t->launch_stream ? t->launch_stream : t->stream;
+        k_gi_step_table<<<1, 1, 0, s>>>(r, res, t->gi_steps.as<float4>());
+        count_launch();
+        VRT_CUDA(cudaGetLastError());
+        *d_steps = t->gi_steps.as<float4>();
+        return VRT_OK;
+}
+
 struct GiPointParams {
         TreeDev tree;
         float root[6];
+        const float4* steps;
         const float* pos;
         const float* nrm;
         uint64_t n;
@@ -191,7 +224,7 @@ __global__ void __launch_bounds__(128) k_gi_cone_points(GiPointParams p)
         const float nrm[3] = { p.nrm[3 * i], p.nrm[3 * i + 1], p.nrm[3 * i + 2] };
         float out[3];
         extern __shared__ float s_gi_path[];
-        gi_cone_trace_point(p.tree, p.root, s_gi_path + threadIdx.x, blockDim.x, pos, nrm, p.res, out);
+        gi_cone_trace_point(p.tree, p.root, s_gi_path + threadIdx.x, blockDim.x, pos, nrm, p.res, p.steps, out);
         p.out[3 * i] = out[0];
         p.out[3 * i + 1] = out[1];
         p.out[3 * i + 2] = out[2];
@@ -214,6 +247,11 @@ int gi_cone_points(const vrt_tree* t, const float* d_pos, const float* d_nrm, ui
         p.n = n;
         p.res = res;
         p.out = d_out;
+        {
+                const int rc = gi_step_table(t, res, &p.steps);
+                if (rc)
+                        return rc;
+        }
         const size_t smem = (size_t)kGiPathWords * std::max(t->dev.L, 1) * 128 * sizeof(float);
         VRT_CUDA(cudaFuncSetAttribute(k_gi_cone_points, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_gi_cone_points<<<gi_grid(n, 128), 128, smem, t->stream>>>(p);

@@ -217,14 +217,88 @@ __device__ __forceinline__ uint32_t gi_locate(const TreeDev& tr, float* __restri
         return (l == s) ? node : kGiAbsent;
 }
 
-// cone_trace(root, cone, min_voxel_size) voxel_octree.cc:247-283.
-__device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[6], float* sc, int stride, GiPath& gp,
-                                            const float o[3], const float d[3], float min_voxel_size, float out[3])
+// ---------------------------------------------------------------------------
+// Step table.  The marching distances of cone_trace (voxel_octree.cc:252-281) do not depend on the cone:
+// dist_0 = mindist, dist_(k+1) = dist_k + step * diam_k with diam_k = max(mindist, 2 * aperture * dist_k), and with
+// them the sampled level int(log2f(maxdist / diam_k)) and the distance weight 1 / (1 + decay * dist_k) are functions
+// of (min_voxel_size, root box) alone.  One thread evaluates the reference's expressions once per launch
+// (gi_step_table_fill, the same float operations in the same order) and every cone of every ray reads the
+// results: two IEEE divisions, the logarithm and the distance bookkeeping leave the per-sample loop.
+// Layout: entry 0 = {count, truncated, dist to resume from, 0}; entry 1 + k = {dist_k, 1 / (1 + dist_k), level_k, 0}.
+// A march longer than the table (kGiMaxSteps) continues with the original loop.
+// ---------------------------------------------------------------------------
+constexpr int kGiMaxSteps = 511;
+constexpr float kGiAperture = 0.577350269f, kGiStep = .1f, kGiDecay = 1.f;
+
+__device__ __forceinline__ float gi_maxdist(const float root[6])
 {
-        const float aperture = 0.577350269f, step = .1f, decay = 1.f;
-        const float mindist = fmul(1.414f, min_voxel_size);
         const float sx = fsub(root[3], root[0]), sy = fsub(root[4], root[1]), sz = fsub(root[5], root[2]);
-        const float maxdist = __fsqrt_rn(dot3(sx, sy, sz, sx, sy, sz));
+        return __fsqrt_rn(dot3(sx, sy, sz, sx, sy, sz));
+}
+
+__device__ __forceinline__ void gi_step_table_fill(const float root[6], float min_voxel_size, float4* tab)
+{
+        const float mindist = fmul(1.414f, min_voxel_size);
+        const float maxdist = gi_maxdist(root);
+        float dist = mindist;
+        int n = 0;
+        bool truncated = false;
+        while (dist < maxdist) {
+                const float diam = std_max(mindist, fmul(fmul(kGiAperture, 2.f), dist));
+                if (maxdist < diam)
+                        break;
+                if (n == kGiMaxSteps) {
+                        truncated = true;
+                        break;
+                }
+                tab[1 + n] = make_float4(dist, fdiv(1.f, fadd(1.f, fmul(kGiDecay, dist))),
+                                         __int_as_float(gi_split_level(fdiv(maxdist, diam))), 0.f);
+                ++n;
+                dist = fadd(dist, fmul(kGiStep, diam));
+        }
+        tab[0] = make_float4(__int_as_float(n), __int_as_float(truncated ? 1 : 0), dist, 0.f);
+}
+
+// One sample of cone_trace (the loop body after the level is known) voxel_octree.cc:259-279.
+__device__ __forceinline__ void gi_cone_sample(const TreeDev& tr, float* sc, int stride, GiPath& gp, const float o[3],
+                                               const float d[3], const float coeff[6], float dist, int split_level,
+                                               float inv_w, float& opacity, float diffuse[3])
+{
+        const float p[3] = { fadd(o[0], fmul(d[0], dist)), fadd(o[1], fmul(d[1], dist)), fadd(o[2], fmul(d[2], dist)) };
+        // descend `split_level` levels (or to a leaf): deeper than the tree, or into an absent child
+        // (one of the reference's empty leaves, whose sample adds exact zeros) -> nothing to add
+        uint32_t node = kGiAbsent;
+        if (tr.num_nodes != 0 && split_level <= tr.L)
+                node = (split_level == 0) ? 0u : gi_locate(tr, sc, stride, gp, p, split_level);
+        if (node == kGiAbsent)
+                return;
+        const float4* g4 = reinterpret_cast<const float4*>(tr.gi + (size_t)kGiStride * node);
+        const float4 q0 = __ldg(g4), q1 = __ldg(g4 + 1), q2 = __ldg(g4 + 2), q3 = __ldg(g4 + 3), q4 = __ldg(g4 + 4);
+        const float il[18] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x,
+                               q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y };
+        const float coverage = q4.z;
+        float illum[3] = { 0.f, 0.f, 0.f };
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                        illum[k] = fadd(illum[k], fmul(coeff[i], il[3 * i + k]));
+        const float transparency = clampf(fsub(1.f, opacity), 0.f, 1.f);
+        const float a = fmul(coverage, kGiStep);
+        const float w = fmul(fmul(inv_w, transparency), coverage);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+                diffuse[k] = fadd(diffuse[k], fmul(w, illum[k]));
+        opacity = fadd(opacity, fmul(transparency, a));
+}
+
+// cone_trace(root, cone, min_voxel_size) voxel_octree.cc:247-283.  steps: the launch's step table, or null.
+__device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[6], float* sc, int stride, GiPath& gp,
+                                            const float o[3], const float d[3], float min_voxel_size,
+                                            const float4* __restrict__ steps, float out[3])
+{
+        const float mindist = fmul(1.414f, min_voxel_size);
+        const float maxdist = gi_maxdist(root);
         // compute_illum(-cone.d): the six lobe coefficients clamp(dot(illum_d[i], -d), 0, 1) do not depend
         // on the sample (illum_d[] = +x +y +z -x -y -z, voxel_octree.cc:19-20; jql::dot keeps the zero terms)
         float coeff[6];
@@ -236,39 +310,25 @@ __device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[
         }
         float dist = mindist, opacity = 0.f;
         float diffuse[3] = { 0.f, 0.f, 0.f };
-        while (dist < maxdist && opacity < 1.f) {
-                const float p[3] = { fadd(o[0], fmul(d[0], dist)), fadd(o[1], fmul(d[1], dist)),
-                                     fadd(o[2], fmul(d[2], dist)) };
-                const float diam = std_max(mindist, fmul(fmul(aperture, 2.f), dist));
+        bool rest = true;  // continue with the reference's own loop from `dist`
+        if (steps != nullptr) {
+                const float4 hdr = __ldg(steps);
+                const int n = __float_as_int(hdr.x);
+                int k = 0;
+                for (; k < n && opacity < 1.f; ++k) {
+                        const float4 st = __ldg(steps + 1 + k);
+                        gi_cone_sample(tr, sc, stride, gp, o, d, coeff, st.x, __float_as_int(st.z), st.y, opacity, diffuse);
+                }
+                rest = (k == n) && (__float_as_int(hdr.y) != 0);
+                dist = hdr.z;
+        }
+        while (rest && dist < maxdist && opacity < 1.f) {
+                const float diam = std_max(mindist, fmul(fmul(kGiAperture, 2.f), dist));
                 if (maxdist < diam)
                         break;
-                const int split_level = gi_split_level(fdiv(maxdist, diam));
-                // descend `split_level` levels (or to a leaf): deeper than the tree, or into an absent child
-                // (one of the reference's empty leaves, whose sample adds exact zeros) -> nothing to add
-                uint32_t node = kGiAbsent;
-                if (tr.num_nodes != 0 && split_level <= tr.L)
-                        node = (split_level == 0) ? 0u : gi_locate(tr, sc, stride, gp, p, split_level);
-                if (node != kGiAbsent) {
-                        const float4* g4 = reinterpret_cast<const float4*>(tr.gi + (size_t)kGiStride * node);
-                        const float4 q0 = __ldg(g4), q1 = __ldg(g4 + 1), q2 = __ldg(g4 + 2), q3 = __ldg(g4 + 3), q4 = __ldg(g4 + 4);
-                        const float il[18] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x,
-                                               q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y };
-                        const float coverage = q4.z;
-                        float illum[3] = { 0.f, 0.f, 0.f };
-#pragma unroll
-                        for (int i = 0; i < 6; ++i)
-#pragma unroll
-                                for (int k = 0; k < 3; ++k)
-                                        illum[k] = fadd(illum[k], fmul(coeff[i], il[3 * i + k]));
-                        const float transparency = clampf(fsub(1.f, opacity), 0.f, 1.f);
-                        const float a = fmul(coverage, step);
-                        const float w = fmul(fmul(fdiv(1.f, fadd(1.f, fmul(decay, dist))), transparency), coverage);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k)
-                                diffuse[k] = fadd(diffuse[k], fmul(w, illum[k]));
-                        opacity = fadd(opacity, fmul(transparency, a));
-                }
-                dist = fadd(dist, fmul(step, diam));
+                gi_cone_sample(tr, sc, stride, gp, o, d, coeff, dist, gi_split_level(fdiv(maxdist, diam)),
+                               fdiv(1.f, fadd(1.f, fmul(kGiDecay, dist))), opacity, diffuse);
+                dist = fadd(dist, fmul(kGiStep, diam));
         }
         out[0] = diffuse[0];
         out[1] = diffuse[1];
@@ -279,7 +339,8 @@ __device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[
 // and the six HemiCones :227-234.
 // sc: this thread's column of the path cache (kGiPathWords * L words, element stride `stride`).
 __device__ __forceinline__ void gi_cone_trace_point(const TreeDev& tr, const float root[6], float* sc, int stride,
-                                                    const float pos[3], const float n[3], float res, float out[3])
+                                                    const float pos[3], const float n[3], float res,
+                                                    const float4* __restrict__ steps, float out[3])
 {
         GiPath gp;
         gi_path_reset(gp);
@@ -306,7 +367,7 @@ __device__ __forceinline__ void gi_cone_trace_point(const TreeDev& tr, const flo
                 }
                 normalize3(d[0], d[1], d[2]);
                 float c[3];
-                gi_cone_one(tr, root, sc, stride, gp, pos, d, res, c);
+                gi_cone_one(tr, root, sc, stride, gp, pos, d, res, steps, c);
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                         diffuse[k] = fadd(diffuse[k], fmul(hemi[i][3], c[k]));

@@ -148,6 +148,7 @@ struct vrt_tree {
         vrt::Scratch io_in, io_out;
         // GI rows: per-node coverage + illum[6], see vrt_gi.cuh
         vrt::Scratch gi_buf, gi_recs, mat_buf;
+        mutable vrt::Scratch gi_steps;  // step table of the last cone trace launch
         vrt::Scratch hull_buf;  // TreeDev::hull
         vrt::Scratch tri64_buf;  // TreeDev::tri64
         // pipelined host-film path (vrt_render_camera_async): two device films, a copy stream
@@ -195,6 +196,7 @@ int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_
 struct GiArgs {  // OUT_SPLAT / OUT_GI_FILM: default material colour, cone-trace min_voxel_size
         float kd[3];
         float res;
+        const float4* steps = nullptr;  // step table of the cone trace for (res, root box), see gi_step_table
 };
 int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shade* sh, int x0,
                         int y0, int x1, int y1, void* d_out, OutMode mode, int band_h = 0,
@@ -209,6 +211,8 @@ int hull_stats(unsigned long long* out80);
 int gi_init(vrt_tree* t);
 int gi_splat_camera(vrt_tree* t, const vrt_camera* cam, const float kd[3]);
 int gi_filter(vrt_tree* t);
+// fills the tree's step table for `res` on its stream (vrt_gi.cuh) and returns the device pointer
+int gi_step_table(const vrt_tree* t, float res, const float4** d_steps);
 int gi_cone_points(const vrt_tree* t, const float* d_pos, const float* d_nrm, uint64_t n, float res, float* d_out);
 int gi_albedo_points(const vrt_tree* t, const uint32_t* d_tri, const float* d_pos, uint64_t n, const float kd[3], float* d_out);
 // sort `n` 64-bit keys held in t->keys_a on bits [lo,hi) with the build's radix sort (vrt_build.cu)

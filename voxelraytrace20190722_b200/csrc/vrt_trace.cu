@@ -37,6 +37,9 @@ namespace vrt {
 #ifndef VRT_TRACE_MIN_BLOCKS
 #define VRT_TRACE_MIN_BLOCKS 6  // k_trace_rays (48-byte records)
 #endif
+#ifndef VRT_EYE_ALL
+#define VRT_EYE_ALL 0
+#endif
 constexpr int kTraceThreads = VRT_TRACE_THREADS;
 constexpr int kMaxLevels = VRT_MAX_DEPTH;  // stack records per thread
 
@@ -62,6 +65,7 @@ struct TraceParams {
         float root[6];
         float kd3[3];  // GI modes: the material's diffuse colour (untextured albedo)
         float gi_res;  // GI film: min_voxel_size of cone_trace (main.cc:69-70)
+        const float4* gi_steps;  // GI film: the launch's step table (vrt_gi.cuh), or null
         uint32_t lut_off;  // warp-synchronous kernels: byte offset of the mask table in dynamic shared memory
         float eye[3];      // camera modes: the rays' common origin (camera_eye_host), bit-identical to gen_ray_origin
 };
@@ -1148,7 +1152,8 @@ __device__ __forceinline__ void shade_gi(const TraceParams& p, const HitState& h
         finish_isect(p.tree, hs, o, d, pos, nrm);
         gi_albedo(p.tree, hs.tri, pos, p.kd3, albedo);
         // the traversal is over: this thread's stack column doubles as the cone trace's path cache
-        gi_cone_trace_point(p.tree, p.root, reinterpret_cast<float*>(s_col), kTraceThreads, pos, nrm, p.gi_res, ind);
+        gi_cone_trace_point(p.tree, p.root, reinterpret_cast<float*>(s_col), kTraceThreads, pos, nrm, p.gi_res, p.gi_steps,
+                            ind);
         const float nd[3] = { -d[0], -d[1], -d[2] };
         gi_compute_illum(p.tree.gi + (size_t)kGiStride * hs.leaf, nd, dir);
 #pragma unroll
@@ -1341,7 +1346,7 @@ k_trace_camera(const __grid_constant__ TraceParams p)
                         // the common origin comes precomputed from the host in the record-only modes (-3.5 % there);
                         // the film modes keep computing it (measured: with it precomputed ptxas spills more in those
                         // instantiations and the frame step gets 5 % slower)
-                        if (MODE == OUT_HIT16 || MODE == OUT_HIT48) {
+                        if (VRT_EYE_ALL || MODE == OUT_HIT16 || MODE == OUT_HIT48) {
                                 o[0] = p.eye[0];
                                 o[1] = p.eye[1];
                                 o[2] = p.eye[2];
@@ -1653,6 +1658,7 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
                 p.kd3[1] = gi->kd[1];
                 p.kd3[2] = gi->kd[2];
                 p.gi_res = gi->res;
+                p.gi_steps = gi->steps;
         }
         if (sh) {
                 p.light[0] = sh->light_dir[0];
