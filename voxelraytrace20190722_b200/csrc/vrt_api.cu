@@ -190,6 +190,7 @@ void tree_bind_views(vrt_tree* t)
                 d.tab4[a] = reinterpret_cast<const float4*>(d.tab2[a]);
         }
         d.gi = nullptr;  // GI state belongs to one node array: vrt_gi_init after every (re)build
+        d.gi_ok = nullptr;
         d.hull = nullptr;  // compute_hulls() follows every bind
         d.tight8 = nullptr;
         d.tri64 = nullptr;
@@ -1591,7 +1592,8 @@ int vrt_gi_get_level(const vrt_tree* t, int level, float* coverage, float* illum
                 if (coverage)
                         coverage[i] = host[kGiStride * i + kGiCoverage];
                 if (illum18)
-                        memcpy(illum18 + 18 * i, &host[kGiStride * i], 18 * sizeof(float));
+                        for (int f = 0; f < 18; ++f)
+                                illum18[18 * i + f] = host[kGiStride * i + 4 * (f / 3) + f % 3];
         }
         return VRT_OK;
 }

@@ -22,10 +22,11 @@ static inline unsigned gi_grid(uint64_t n, unsigned block)
 int gi_init(vrt_tree* t)
 {
         const uint64_t n = std::max<uint64_t>(t->hdr.num_nodes, 1);
-        if (t->gi_buf.reserve(n * kGiStride * sizeof(float)))
+        if (t->gi_buf.reserve(n * kGiStride * sizeof(float) + 16))
                 return VRT_ERR_NOMEM;
-        VRT_CUDA(cudaMemsetAsync(t->gi_buf.p, 0, n * kGiStride * sizeof(float), t->stream));
+        VRT_CUDA(cudaMemsetAsync(t->gi_buf.p, 0, n * kGiStride * sizeof(float) + 16, t->stream));
         t->dev.gi = t->gi_buf.as<float>();
+        t->dev.gi_ok = reinterpret_cast<const uint32_t*>(t->gi_buf.as<float>() + n * kGiStride);
         return VRT_OK;
 }
 
@@ -49,7 +50,7 @@ __global__ void k_gi_accumulate(const unsigned long long* __restrict__ keys, uin
         float acc[18];
 #pragma unroll
         for (int f = 0; f < 18; ++f)
-                acc[f] = g[f];
+                acc[f] = g[4 * (f / 3) + f % 3];
         for (uint64_t j = i; j < n; ++j) {
                 const unsigned long long kj = keys[j];
                 if (kj == ~0ull || (uint32_t)(kj >> 32) != leaf)
@@ -69,7 +70,7 @@ __global__ void k_gi_accumulate(const unsigned long long* __restrict__ keys, uin
         }
 #pragma unroll
         for (int f = 0; f < 18; ++f)
-                g[f] = acc[f];
+                g[4 * (f / 3) + f % 3] = acc[f];
 }
 
 int gi_splat_camera(vrt_tree* t, const vrt_camera* cam, const float kd[3])
@@ -87,6 +88,8 @@ int gi_splat_camera(vrt_tree* t, const vrt_camera* cam, const float kd[3])
         }
         if (t->keys_a.reserve(R * 8) || t->gi_recs.reserve(R * 32))
                 return VRT_ERR_NOMEM;
+        // the light map changes: the filtered levels are stale until the next gi_filter (TreeDev::gi_ok)
+        VRT_CUDA(cudaMemsetAsync(const_cast<uint32_t*>(t->dev.gi_ok), 0, 4, t->stream));
         const GiArgs ga = { { kd[0], kd[1], kd[2] }, 0.f };
         int rc = launch_trace_camera(t, cam, nullptr, 0, 0, cam->nx, cam->ny, t->keys_a.p, OUT_SPLAT, 0, 0, t->gi_recs.p, 0,
                                      &ga);
@@ -111,8 +114,11 @@ int gi_splat_camera(vrt_tree* t, const vrt_camera* cam, const float kd[3])
 __global__ void k_gi_leaf_coverage(uint32_t first, uint32_t n, float* __restrict__ gi)
 {
         const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-        if (i < n)
-                gi[(size_t)kGiStride * (first + i) + kGiCoverage] = 1.f;
+        if (i < n) {
+#pragma unroll
+                for (int f = 0; f < 6; ++f)
+                        gi[(size_t)kGiStride * (first + i) + 4 * f + kGiCoverage] = 1.f;
+        }
 }
 
 // ... an interior node is the sum over its eight children in child order (absent children are the
@@ -132,19 +138,28 @@ __global__ void k_gi_filter_level(const uint2* __restrict__ nodes, uint32_t firs
                 if (!((rec.y >> c) & 1u))
                         continue;
                 const float4* g4 = reinterpret_cast<const float4*>(gi + (size_t)kGiStride * child);
-                const float4 q0 = g4[0], q1 = g4[1], q2 = g4[2], q3 = g4[3], q4 = g4[4];
-                const float v[19] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y,
-                                      q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z };
+                const float4 q0 = g4[0], q1 = g4[1], q2 = g4[2], q3 = g4[3], q4 = g4[4], q5 = g4[5];
+                const float v[19] = { q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z, q3.x,
+                                      q3.y, q3.z, q4.x, q4.y, q4.z, q5.x, q5.y, q5.z, q0.w };
 #pragma unroll
                 for (int f = 0; f < 19; ++f)
                         acc[f] = fadd(acc[f], v[f]);
                 ++child;
         }
-        float* g = gi + (size_t)kGiStride * (first + i);
+        float4* g = reinterpret_cast<float4*>(gi + (size_t)kGiStride * (first + i));
+        const float cov = fdiv(acc[18], 8.f);
 #pragma unroll
-        for (int f = 0; f < 18; ++f)
-                g[f] = fdiv(acc[f], 8.f);
-        g[kGiCoverage] = fdiv(acc[18], 8.f);
+        for (int f = 0; f < 6; ++f)
+                g[f] = make_float4(fdiv(acc[3 * f], 8.f), fdiv(acc[3 * f + 1], 8.f), fdiv(acc[3 * f + 2], 8.f), cov);
+}
+
+// TreeDev::gi_ok: the filter has run, and the root's values (hence every node's) are finite
+__global__ void k_gi_root_finite(const float* __restrict__ gi, uint32_t* __restrict__ ok)
+{
+        bool fin = true;
+        for (int f = 0; f < kGiStride; ++f)
+                fin = fin && (fabsf(gi[f]) <= 3.402823466e+38f);
+        *ok = fin ? 1u : 0u;
 }
 
 int gi_filter(vrt_tree* t)
@@ -169,6 +184,8 @@ int gi_filter(vrt_tree* t)
                                                                           (uint32_t)n, gi);
                 count_launch();
         }
+        k_gi_root_finite<<<1, 1, 0, t->stream>>>(gi, const_cast<uint32_t*>(t->dev.gi_ok));
+        count_launch();
         VRT_CUDA(cudaGetLastError());
         return VRT_OK;
 }

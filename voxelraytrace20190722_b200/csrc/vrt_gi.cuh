@@ -1,7 +1,7 @@
 // vrt_gi.cuh -- device side of the GI rows: VoxelOctree::compute_illum
 // (voxel_octree.h:71-81), cone_trace / orthonormal_basis / HemiCones (voxel_octree.cc:216-303)
 // on the flat node array.  Per-node GI state lives in a side array of kGiStride floats per
-// node: illum[6][3] (the six axis lobes), coverage, one pad float (80 B = five LDG.128).
+// node: six float4 {illum r, g, b, coverage}, one per axis lobe (96 B; a cone sample reads three of them).
 // Arithmetic follows the reference expression by expression (vrt_exact.cuh rules: no FMA,
 // IEEE division and sqrt).  One deviation, documented in DESIGN.md: int(std::log2f(x)) is
 // evaluated for the correctly rounded log2f (gi_split_level) -- the host libm's log2f is not
@@ -90,9 +90,10 @@ __device__ __forceinline__ void gi_albedo(const TreeDev& tr, uint32_t tri, const
 __device__ __forceinline__ void gi_compute_illum(const float* __restrict__ g, const float d[3], float out[3])
 {
         const float4* g4 = reinterpret_cast<const float4*>(g);
-        const float4 q0 = __ldg(g4), q1 = __ldg(g4 + 1), q2 = __ldg(g4 + 2), q3 = __ldg(g4 + 3), q4 = __ldg(g4 + 4);
-        const float il[18] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x,
-                               q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y };
+        const float4 q0 = __ldg(g4), q1 = __ldg(g4 + 1), q2 = __ldg(g4 + 2), q3 = __ldg(g4 + 3), q4 = __ldg(g4 + 4),
+                     q5 = __ldg(g4 + 5);
+        const float il[18] = { q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z,
+                               q3.x, q3.y, q3.z, q4.x, q4.y, q4.z, q5.x, q5.y, q5.z };
         out[0] = out[1] = out[2] = 0.f;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
@@ -261,8 +262,8 @@ __device__ __forceinline__ void gi_step_table_fill(const float root[6], float mi
 
 // One sample of cone_trace (the loop body after the level is known) voxel_octree.cc:259-279.
 __device__ __forceinline__ void gi_cone_sample(const TreeDev& tr, float* sc, int stride, GiPath& gp, const float o[3],
-                                               const float d[3], const float coeff[6], float dist, int split_level,
-                                               float inv_w, float& opacity, float diffuse[3])
+                                               const float d[3], const float coeff[6], int lobes, float dist,
+                                               int split_level, float inv_w, float& opacity, float diffuse[3])
 {
         const float p[3] = { fadd(o[0], fmul(d[0], dist)), fadd(o[1], fmul(d[1], dist)), fadd(o[2], fmul(d[2], dist)) };
         // descend `split_level` levels (or to a leaf): deeper than the tree, or into an absent child
@@ -273,16 +274,31 @@ __device__ __forceinline__ void gi_cone_sample(const TreeDev& tr, float* sc, int
         if (node == kGiAbsent)
                 return;
         const float4* g4 = reinterpret_cast<const float4*>(tr.gi + (size_t)kGiStride * node);
-        const float4 q0 = __ldg(g4), q1 = __ldg(g4 + 1), q2 = __ldg(g4 + 2), q3 = __ldg(g4 + 3), q4 = __ldg(g4 + 4);
-        const float il[18] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x,
-                               q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y };
-        const float coverage = q4.z;
         float illum[3] = { 0.f, 0.f, 0.f };
+        float coverage;
+        if (lobes >= 0) {
+                // Only the three lobes that face the cone: per axis one of (+a, -a) has the coefficient
+                // clamp(<= 0) = +-0, and 0 * il = +-0 added to the running sum changes nothing -- the sum starts at
+                // +0 and can never be -0 (x + y is -0 only for x = y = -0), the il are finite (TreeDev::gi_ok).  The
+                // remaining terms are added in the reference's order: lobes = their indices, ascending, 3 bits each;
+                // coeff[0..2] = their coefficients in that order.
+                const float4 a = __ldg(g4 + (lobes & 7)), b = __ldg(g4 + ((lobes >> 3) & 7)), c = __ldg(g4 + (lobes >> 6));
+                illum[0] = fadd(fadd(fadd(0.f, fmul(coeff[0], a.x)), fmul(coeff[1], b.x)), fmul(coeff[2], c.x));
+                illum[1] = fadd(fadd(fadd(0.f, fmul(coeff[0], a.y)), fmul(coeff[1], b.y)), fmul(coeff[2], c.y));
+                illum[2] = fadd(fadd(fadd(0.f, fmul(coeff[0], a.z)), fmul(coeff[1], b.z)), fmul(coeff[2], c.z));
+                coverage = a.w;
+        } else {
+                const float4 q0 = __ldg(g4), q1 = __ldg(g4 + 1), q2 = __ldg(g4 + 2), q3 = __ldg(g4 + 3), q4 = __ldg(g4 + 4),
+                             q5 = __ldg(g4 + 5);
+                const float il[18] = { q0.x, q0.y, q0.z, q1.x, q1.y, q1.z, q2.x, q2.y, q2.z,
+                                       q3.x, q3.y, q3.z, q4.x, q4.y, q4.z, q5.x, q5.y, q5.z };
+                coverage = q0.w;
 #pragma unroll
-        for (int i = 0; i < 6; ++i)
+                for (int i = 0; i < 6; ++i)
 #pragma unroll
-                for (int k = 0; k < 3; ++k)
-                        illum[k] = fadd(illum[k], fmul(coeff[i], il[3 * i + k]));
+                        for (int k = 0; k < 3; ++k)
+                                illum[k] = fadd(illum[k], fmul(coeff[i], il[3 * i + k]));
+        }
         const float transparency = clampf(fsub(1.f, opacity), 0.f, 1.f);
         const float a = fmul(coverage, kGiStep);
         const float w = fmul(fmul(inv_w, transparency), coverage);
@@ -295,7 +311,7 @@ __device__ __forceinline__ void gi_cone_sample(const TreeDev& tr, float* sc, int
 // cone_trace(root, cone, min_voxel_size) voxel_octree.cc:247-283.  steps: the launch's step table, or null.
 __device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[6], float* sc, int stride, GiPath& gp,
                                             const float o[3], const float d[3], float min_voxel_size,
-                                            const float4* __restrict__ steps, float out[3])
+                                            const float4* __restrict__ steps, bool lobes3, float out[3])
 {
         const float mindist = fmul(1.414f, min_voxel_size);
         const float maxdist = gi_maxdist(root);
@@ -308,6 +324,31 @@ __device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[
                 const float ax = (i % 3 == 0) ? sg : 0.f, ay = (i % 3 == 1) ? sg : 0.f, az = (i % 3 == 2) ? sg : 0.f;
                 coeff[i] = clampf(dot3(ax, ay, az, -d[0], -d[1], -d[2]), 0.f, 1.f);
         }
+        // the three lobes that face the cone, sorted by lobe index (= the order of the reference's sum), with their
+        // coefficients moved to coeff[0..2]; or -1: all six (see gi_cone_sample)
+        int lobes = -1;
+        if (lobes3) {
+                int k0 = (-d[0] > 0.f) ? 0 : 3, k1 = (-d[1] > 0.f) ? 1 : 4, k2 = (-d[2] > 0.f) ? 2 : 5;
+                float c0 = (k0 == 0) ? coeff[0] : coeff[3], c1 = (k1 == 1) ? coeff[1] : coeff[4],
+                      c2 = (k2 == 2) ? coeff[2] : coeff[5];
+#define VRT_CSWAP(ka, ca, kb, cb)                 \
+        if (ka > kb) {                            \
+                const int tk = ka;                \
+                ka = kb;                          \
+                kb = tk;                          \
+                const float tc = ca;              \
+                ca = cb;                          \
+                cb = tc;                          \
+        }
+                VRT_CSWAP(k0, c0, k1, c1)
+                VRT_CSWAP(k1, c1, k2, c2)
+                VRT_CSWAP(k0, c0, k1, c1)
+#undef VRT_CSWAP
+                lobes = k0 | (k1 << 3) | (k2 << 6);
+                coeff[0] = c0;
+                coeff[1] = c1;
+                coeff[2] = c2;
+        }
         float dist = mindist, opacity = 0.f;
         float diffuse[3] = { 0.f, 0.f, 0.f };
         bool rest = true;  // continue with the reference's own loop from `dist`
@@ -317,7 +358,7 @@ __device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[
                 int k = 0;
                 for (; k < n && opacity < 1.f; ++k) {
                         const float4 st = __ldg(steps + 1 + k);
-                        gi_cone_sample(tr, sc, stride, gp, o, d, coeff, st.x, __float_as_int(st.z), st.y, opacity, diffuse);
+                        gi_cone_sample(tr, sc, stride, gp, o, d, coeff, lobes, st.x, __float_as_int(st.z), st.y, opacity, diffuse);
                 }
                 rest = (k == n) && (__float_as_int(hdr.y) != 0);
                 dist = hdr.z;
@@ -326,7 +367,7 @@ __device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[
                 const float diam = std_max(mindist, fmul(fmul(kGiAperture, 2.f), dist));
                 if (maxdist < diam)
                         break;
-                gi_cone_sample(tr, sc, stride, gp, o, d, coeff, dist, gi_split_level(fdiv(maxdist, diam)),
+                gi_cone_sample(tr, sc, stride, gp, o, d, coeff, lobes, dist, gi_split_level(fdiv(maxdist, diam)),
                                fdiv(1.f, fadd(1.f, fmul(kGiDecay, dist))), opacity, diffuse);
                 dist = fadd(dist, fmul(kGiStep, diam));
         }
@@ -344,6 +385,7 @@ __device__ __forceinline__ void gi_cone_trace_point(const TreeDev& tr, const flo
 {
         GiPath gp;
         gi_path_reset(gp);
+        const bool lobes3 = tr.gi_ok != nullptr && __ldg(tr.gi_ok) != 0u;
         const float hemi[6][4] = {
                 { 0.000000f, 0.000000f, 1.0f, 0.25f },   { 0.000000f, 0.866025f, 0.5f, 0.15f },
                 { 0.823639f, 0.267617f, 0.5f, 0.15f },   { 0.509037f, -0.700629f, 0.5f, 0.15f },
@@ -367,7 +409,7 @@ __device__ __forceinline__ void gi_cone_trace_point(const TreeDev& tr, const flo
                 }
                 normalize3(d[0], d[1], d[2]);
                 float c[3];
-                gi_cone_one(tr, root, sc, stride, gp, pos, d, res, steps, c);
+                gi_cone_one(tr, root, sc, stride, gp, pos, d, res, steps, lobes3, c);
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                         diffuse[k] = fadd(diffuse[k], fmul(hemi[i][3], c[k]));

@@ -55,8 +55,11 @@ struct BlobHeader {
 static_assert(sizeof(BlobHeader) <= 512, "header grew");
 constexpr uint64_t kBlobMagic = 0x3142305452565856ull;  // "VXVRT0B1"
 constexpr uint64_t kHeaderBytes = 512;
-constexpr int kGiStride = 20;    // floats of GI state per node: illum[6][3], coverage, pad (vrt_gi.cuh)
-constexpr int kGiCoverage = 18;
+// floats of GI state per node (vrt_gi.cuh): six lobes (+x +y +z -x -y -z), each one float4 {illum r, g, b, coverage}
+// -- the node's coverage is repeated in every lobe so that a cone sample, which needs the three lobes facing the cone
+// and the coverage, is three LDG.128
+constexpr int kGiStride = 24;
+constexpr int kGiCoverage = 3;
 
 inline uint64_t align256(uint64_t x) { return (x + 255ull) & ~255ull; }
 
@@ -72,6 +75,10 @@ struct TreeDev {
                                 // children of cell x at level l
         const float2* tab2[3];
         const float* gi;  // per-node GI state (vrt_gi.cuh), or null before vrt_gi_init
+        // one word behind the GI state: 1 when cone_trace_init_filter has run since the last change of the light map AND
+        // the root's filtered values are all finite -- then EVERY node's values are finite (a non-finite value
+        // propagates up the sums of the filter), which is what lets a cone sample skip its zero-coefficient lobes
+        const uint32_t* gi_ok;
         // content hull of every INTERIOR node (round 2), fused with a copy of its node record into one
         // 32-byte sector: float4 {first_child bits, child mask bits, x.min, x.max}, float4 {y.min, y.max, z.min,
         // z.max}; the bounds are the extreme leaf-cell planes (floats of the axis table) over the node's
