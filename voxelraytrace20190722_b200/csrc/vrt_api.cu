@@ -1788,9 +1788,7 @@ int vrt_debug_set_hull(vrt_tree* t, int on)
         if (rc)
                 return rc;
         VRT_CUDA(cudaStreamSynchronize(t->stream));
-        t->dev.hull = (on && t->hull_buf.p && t->hdr.max_depth > 1) ? t->hull_buf.as<float4>() : nullptr;
-        t->dev.tight8 = t->dev.hull ? reinterpret_cast<const uint8_t*>(t->dev.hull + 2ull * (t->hdr.num_nodes - t->hdr.num_leaves))
-                                    : nullptr;
+        t->dev.rec_mask = on ? 0xffffu : 0x00ffu;
         return VRT_OK;
 }
 

@@ -1650,7 +1650,8 @@ int compute_hulls(vrt_tree* t)
                 const char* e = getenv("VRT_HULL");
                 enabled = (e && e[0] == '0') ? 0 : 1;
         }
-        if (!enabled || L < 1 || h.num_nodes == 0)
+        t->dev.rec_mask = enabled ? 0xffffu : 0x00ffu;  // (VRT_HULL=0: the records are built, the tests are off)
+        if (L < 1 || h.num_nodes == 0)
                 return VRT_OK;
         const uint64_t interior = h.num_nodes - h.num_leaves;
         if (t->hull_buf.reserve(std::max<uint64_t>(interior, 1) * 33))  // 32-byte records, then one flag byte per node

@@ -88,6 +88,7 @@ struct TreeDev {
         // per interior node: bit c = child c's hull is worth testing (k_hull_level); the hull records of the other
         // children are never touched, their 8-byte node records are read instead
         const uint8_t* tight8;
+        uint32_t rec_mask;  // 0xffff: hull tests on; 0x00ff: the tight flags are cleared from every record read (off)
         // triangles widened for the leaf test (round 2): per triangle ten doubles v0, e1 = v1 - v0, e2 = v2 - v0, pad --
         // the first operations of intersect_triangle3 (raytri.cc:205-207) on the widened vertices, done once per
         // build instead of once per (ray, triangle) test.  Null: the leaf test widens tri4 itself.

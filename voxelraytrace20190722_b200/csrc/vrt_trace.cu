@@ -597,13 +597,13 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
         uint32_t x = 1, y = 1, z = 1;
         // record of the node to expand (a tested child's comes with its hull record) and its node index (for the
         // per-node flags of which children's hulls are worth testing)
-        // (with hulls every interior node's record is read from its hull record, whose mask word also carries the
-        // tight-children flags in bits 8-15: the expansion needs no second per-node load)
-        const bool hulls = !COUNT && tr.hull != nullptr;
+        // (outside the counting mode every interior node's record is read from its hull record, whose mask word also
+        // carries the tight-children flags in bits 8-15: the expansion needs no second per-node load; tr.rec_mask
+        // = 0x00ff clears the flags -- the "hulls off" switch of the tests)
         uint2 rec;
-        if (hulls) {
+        if (!COUNT) {
                 const float4 h0 = __ldg(&tr.hull[0]);
-                rec = make_uint2(__float_as_uint(h0.x), __float_as_uint(h0.y));
+                rec = make_uint2(__float_as_uint(h0.x), __float_as_uint(h0.y) & tr.rec_mask);
         } else {
                 rec = __ldg(&tr.nodes[0]);
                 rec.y &= 0xffu;
@@ -762,7 +762,7 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
 #ifdef VRT_HULL_STATS
                         atomicAdd(&g_hull_stats[level][1], 1ull);
 #endif
-                        if (hulls) {
+                        if (!COUNT) {
                                 const float4 ha = __ldg(&tr.hull[2ull * child]);
                                 if ((mask >> (8u + c)) & 1u) {
                                         const float4 hb = __ldg(&tr.hull[2ull * child + 1]);
@@ -775,7 +775,7 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                         if (!hull_reachable(ha, hb, o, dinv, tmin, tmax, h0, h1))
                                                 continue;
                                 }
-                                rec = make_uint2(__float_as_uint(ha.x), __float_as_uint(ha.y));
+                                rec = make_uint2(__float_as_uint(ha.x), __float_as_uint(ha.y) & tr.rec_mask);
                         } else {
                                 rec = __ldg(&tr.nodes[child]);
                                 rec.y &= 0xffu;
@@ -1047,7 +1047,7 @@ __device__ __forceinline__ void trace_tile_ws(const TreeDev& tr, const float roo
                         // content hull of the child (see hull_reachable): lanes whose ray cannot reach a non-empty
                         // leaf below leave the subtree; the warp skips it when no lane is left
                         bool incr = inc;
-                        if (!COUNT && tr.hull != nullptr) {
+                        if (!COUNT && (tr.rec_mask & 0x100u)) {
                                 const float4 ha = __ldg(&tr.hull[2ull * (first + k)]), hb = __ldg(&tr.hull[2ull * (first + k) + 1]);
                                 float h0, h1;
                                 incr = inc && hull_reachable(ha, hb, o, dinv, 0.f, FLT_MAX, h0, h1);
@@ -1599,6 +1599,17 @@ static void apply_l2_window(const vrt_tree* t)
         t->l2_window_bytes = bytes;
 }
 
+// every tree with interior levels carries hull records (compute_hulls after every build / import / replica): the
+// ray kernels read the node records from them
+static int check_hull_records(const vrt_tree* t)
+{
+        if (t->hdr.num_nodes != 0 && t->dev.L >= 1 && t->dev.hull == nullptr) {
+                set_error("octree has no hull records (compute_hulls did not run)");
+                return VRT_ERR_STATE;
+        }
+        return VRT_OK;
+}
+
 static void fill_common(const vrt_tree* t, TraceParams& p)
 {
         apply_l2_window(t);
@@ -1618,6 +1629,8 @@ int launch_trace_rays(const vrt_tree* t, const vrt_ray* d_rays, uint64_t n, vrt_
                 set_error("too many rays for one launch");
                 return VRT_ERR_ARG;
         }
+        if (int rc = check_hull_records(t))
+                return rc;
         TraceParams p{};
         fill_common(t, p);
         p.rays = d_rays;
@@ -1661,6 +1674,8 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
 {
         if (x1 <= x0 || y1 <= y0)
                 return VRT_OK;
+        if (int rc = check_hull_records(t))
+                return rc;
         TraceParams p{};
         fill_common(t, p);
         for (int k = 0; k < 16; ++k)
