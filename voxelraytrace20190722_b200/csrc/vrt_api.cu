@@ -177,6 +177,7 @@ int tree_alloc(vrt_tree** out)
 
 void tree_bind_views(vrt_tree* t)
 {
+        t->n_builds++;  // (tables derived from the blob, e.g. the origin-relative axis tables, are stale now)
         const BlobHeader& h = t->hdr;
         char* base = static_cast<char*>(t->blob);
         TreeDev& d = t->dev;
@@ -579,6 +580,10 @@ void vrt_tree_free(vrt_tree* t)
         t->tri64_buf.release();
         t->gi_recs.release();
         t->gi_steps.release();
+        t->tabrel_buf.release();
+        for (auto& rs : t->tabrel_slot)
+                if (rs.ev)
+                        cudaEventDestroy(rs.ev);
         t->mat_buf.release();
         t->io_out.release();
         t->film_dev[0].release();

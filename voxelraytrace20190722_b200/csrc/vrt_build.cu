@@ -1631,19 +1631,12 @@ int compute_hulls(vrt_tree* t)
         const int L = h.max_depth - 1;
         t->dev.hull = nullptr;
         t->dev.tri64 = nullptr;
-        {
-                static int tri64_on = -1;
-                if (tri64_on < 0) {
-                        const char* e = getenv("VRT_TRI64");
-                        tri64_on = (e && e[0] == '0') ? 0 : 1;
-                }
-                if (tri64_on && h.num_tris) {
-                        if (t->tri64_buf.reserve((uint64_t)h.num_tris * 80))
-                                return VRT_ERR_NOMEM;
-                        k_tri64<<<grid_for(h.num_tris, 256), 256, 0, t->stream>>>(t->dev.tri4, h.num_tris, t->tri64_buf.as<double>());
-                        count_launch();
-                        t->dev.tri64 = t->tri64_buf.as<double>();
-                }
+        if (h.num_tris) {
+                if (t->tri64_buf.reserve((uint64_t)h.num_tris * 80))
+                        return VRT_ERR_NOMEM;
+                k_tri64<<<grid_for(h.num_tris, 256), 256, 0, t->stream>>>(t->dev.tri4, h.num_tris, t->tri64_buf.as<double>());
+                count_launch();
+                t->dev.tri64 = t->tri64_buf.as<double>();
         }
         static int enabled = -1;
         if (enabled < 0) {

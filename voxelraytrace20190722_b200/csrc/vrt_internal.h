@@ -178,6 +178,19 @@ struct vrt_tree {
         mutable void* l2_window_stream = nullptr;
         mutable const void* l2_window_nodes = nullptr;
         mutable uint64_t l2_window_bytes = 0;
+        // origin-relative axis tables of the camera launches (vrt_trace.cu tab_rel_for_launch)
+        static constexpr int kRelSlots = 8;
+        struct RelSlot {
+                float eye[3] = { 0, 0, 0 };
+                bool valid = false, done = false;
+                cudaEvent_t ev = nullptr;
+                cudaStream_t stream = nullptr;
+        };
+        mutable vrt::Scratch tabrel_buf;
+        mutable RelSlot tabrel_slot[kRelSlots];
+        mutable const void* tabrel_blob = nullptr;
+        mutable uint64_t tabrel_build = ~0ull;
+        uint64_t n_builds = 0;  // bumped whenever the blob's contents change (tree_bind_views)
         int film_fmt = 0;  // VRT_FILM_* of every film this handle's kernels write (vrt_set_film_format)
         double build_ms = 0;
         mutable double last_kernel_ms = 0;

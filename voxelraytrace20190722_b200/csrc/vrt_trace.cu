@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstdlib>
+#include <cstring>
 
 #include "vrt_exact.cuh"
 #include "vrt_gi.cuh"
@@ -69,6 +70,10 @@ struct TraceParams {
         const float4* gi_steps;  // GI film: the launch's step table (vrt_gi.cuh), or null
         uint32_t lut_off;  // warp-synchronous kernels: byte offset of the mask table in dynamic shared memory
         float eye[3];      // camera modes: the rays' common origin (camera_eye_host), bit-identical to gen_ray_origin
+        // camera modes: the axis tables with the common origin already subtracted, rel[a][i] = tab4[a][i] - eye[a]
+        // (k_tab_rel: the reference's (plane - o) of every slab test, evaluated once per table entry instead of once
+        // per ray and node); null: the expansion subtracts itself
+        const float4* tabrel[3];
 };
 
 struct HitState {
@@ -106,21 +111,12 @@ __device__ __forceinline__ bool leaf_isect_rec(const TreeDev& tr, const uint2 re
         for (uint32_t i = 0; i < rec.y; ++i) {
                 const uint32_t ti = __ldg(&tr.leaf_refs[rec.x + i]);
                 double dt, du, dv;
-                if (tr.tri64 != nullptr) {  // v0, e1, e2 already widened and subtracted (k_tri64)
+                {  // v0, e1, e2 already widened and subtracted (k_tri64, every tree with triangles has them)
                         const double2* q = reinterpret_cast<const double2*>(tr.tri64 + 10ull * ti);  // 80-byte records
                         const double2 q0 = __ldg(q), q1 = __ldg(q + 1), q2 = __ldg(q + 2), q3 = __ldg(q + 3);
                         const double q4 = __ldg(tr.tri64 + 10ull * ti + 8);
                         const double a[3] = { q0.x, q0.y, q1.x }, e1[3] = { q1.y, q2.x, q2.y }, e2[3] = { q3.x, q3.y, q4 };
                         if (ray_triangle3_edges(od, dd, a, e1, e2, dt, du, dv) != 1)
-                                continue;
-                } else {
-                        const float4 a4 = __ldg(&tr.tri4[3ull * ti + 0]);
-                        const float4 b4 = __ldg(&tr.tri4[3ull * ti + 1]);
-                        const float4 c4 = __ldg(&tr.tri4[3ull * ti + 2]);
-                        const double a[3] = { (double)a4.x, (double)a4.y, (double)a4.z };
-                        const double b[3] = { (double)b4.x, (double)b4.y, (double)b4.z };
-                        const double c[3] = { (double)c4.x, (double)c4.y, (double)c4.z };
-                        if (ray_triangle3(od, dd, a, b, c, dt, du, dv) != 1)
                                 continue;
                 }
                 // hit = o + (float)dt * d ; depth = length(hit - o)   voxel_octree.cc:454,114
@@ -557,10 +553,11 @@ __device__ __forceinline__ bool hull_reachable(const float4 ha, const float4 hb,
 // not key-safe (param_safe_levels), the node is expanded by expand_slab instead.  Each cell
 // knows its own t0 (entry breakpoint) and t1 (next breakpoint), so the reference's window test
 // slab_accept(t0,t1,tmin,tmax) is evaluated on the same values.
-template <bool COUNT>
+template <bool COUNT, bool REL>
 __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float root[6], const float o[3],
                                                const float d[3], float tmin, float tmax, uint32_t* s_first,
-                                               uint32_t* s_meta, uint32_t* s_list, HitState& hs, WorkCount& wc)
+                                               uint32_t* s_meta, uint32_t* s_list, HitState& hs, WorkCount& wc,
+                                               const float4* const* rel)
 {
         float dinv[3];
 #pragma unroll
@@ -627,18 +624,26 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
 #endif
                         first = rec.x;
                         mask = rec.y;  // bits 0-7 child mask; bits 8-15 children whose hull is worth testing (0 without hulls)
-                        const float4 bx = __ldg(&tr.tab4[0][x]);
-                        const float4 by = __ldg(&tr.tab4[1][y]);
-                        const float4 bz = __ldg(&tr.tab4[2][z]);
+                        // REL: (plane - o) comes from the launch's table (the same subtraction, done once per entry)
+                        float4 bx, by, bz;
+                        if (REL) {
+                                bx = __ldg(&rel[0][x]);
+                                by = __ldg(&rel[1][y]);
+                                bz = __ldg(&rel[2][z]);
+                        } else {
+                                bx = __ldg(&tr.tab4[0][x]);
+                                by = __ldg(&tr.tab4[1][y]);
+                                bz = __ldg(&tr.tab4[2][z]);
+                        }
                         bool use_slab = false;
                         {
                                 // t(p0), t(p1) packed, t(p2) scalar -- the reference's (plane-o)*dinv
-                                const float2 ax = mul2s(sub2s(bx.x, bx.y, o[0]), dinv[0]);
-                                const float2 ay = mul2s(sub2s(by.x, by.y, o[1]), dinv[1]);
-                                const float2 az = mul2s(sub2s(bz.x, bz.y, o[2]), dinv[2]);
-                                const float ax2 = fmul(fsub(bx.w, o[0]), dinv[0]);
-                                const float ay2 = fmul(fsub(by.w, o[1]), dinv[1]);
-                                const float az2 = fmul(fsub(bz.w, o[2]), dinv[2]);
+                                const float2 ax = mul2s(REL ? make_float2(bx.x, bx.y) : sub2s(bx.x, bx.y, o[0]), dinv[0]);
+                                const float2 ay = mul2s(REL ? make_float2(by.x, by.y) : sub2s(by.x, by.y, o[1]), dinv[1]);
+                                const float2 az = mul2s(REL ? make_float2(bz.x, bz.y) : sub2s(bz.x, bz.y, o[2]), dinv[2]);
+                                const float ax2 = fmul(REL ? bx.w : fsub(bx.w, o[0]), dinv[0]);
+                                const float ay2 = fmul(REL ? by.w : fsub(by.w, o[1]), dinv[1]);
+                                const float az2 = fmul(REL ? bz.w : fsub(bz.w, o[2]), dinv[2]);
                                 const float emx = ax.y, emy = ay.y, emz = az.y;
                                 const float T0 = fmax3(fminf(ax.x, ax2), fminf(ay.x, ay2), fminf(az.x, az2));
                                 const float T1 = fmin3(fmaxf(ax.x, ax2), fmaxf(ay.x, ay2), fmaxf(az.x, az2));
@@ -703,6 +708,11 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
                                         list = a0 ? ((list << 4) | c0) : list;
 #ifdef VRT_PARAM_CHECK
                                         {
+                                                if (REL) {
+                                                        bx = __ldg(&tr.tab4[0][x]);
+                                                        by = __ldg(&tr.tab4[1][y]);
+                                                        bz = __ldg(&tr.tab4[2][z]);
+                                                }
                                                 const uint32_t list_s = expand_slab4(bx, by, bz, o[0], o[1], o[2], d[0], d[1], d[2], dinv[0],
                                                                                      dinv[1], dinv[2], mask, tmin, tmax);
                                                 atomicAdd(&g_param_check[0], 1ull);
@@ -712,9 +722,15 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
 #endif
                                 }
                         }
-                        if (use_slab)
+                        if (use_slab) {
+                                if (REL) {  // the slab expansion works on the planes themselves
+                                        bx = __ldg(&tr.tab4[0][x]);
+                                        by = __ldg(&tr.tab4[1][y]);
+                                        bz = __ldg(&tr.tab4[2][z]);
+                                }
                                 list = expand_slab4(bx, by, bz, o[0], o[1], o[2], d[0], d[1], d[2], dinv[0], dinv[1], dinv[2],
                                                     mask, tmin, tmax);
+                        }
                 }
                 // ---- visit children in order until we descend, hit, or run out -----------------
                 for (;;) {
@@ -797,10 +813,11 @@ __device__ __forceinline__ void trace_one_fast(const TreeDev& tr, const float ro
         }
 }
 
-template <bool COUNT>
+template <bool COUNT, bool REL = false>
 __device__ __forceinline__ void trace_one(const TreeDev& tr, const float root[6], const float o[3],
                                           const float d[3], float tmin, float tmax, uint32_t* s_first,
-                                          uint32_t* s_meta, uint32_t* s_list, HitState& hs, WorkCount& wc)
+                                          uint32_t* s_meta, uint32_t* s_list, HitState& hs, WorkCount& wc,
+                                          const float4* const* rel = nullptr)
 {
         hs.hit = false;
         hs.tri = VRT_NO_TRI;
@@ -810,7 +827,7 @@ __device__ __forceinline__ void trace_one(const TreeDev& tr, const float root[6]
         if (tr.num_nodes == 0)
                 return;
         if (ray_is_tame(tr, o, d))
-                trace_one_fast<COUNT>(tr, root, o, d, tmin, tmax, s_first, s_meta, s_list, hs, wc);
+                trace_one_fast<COUNT, REL>(tr, root, o, d, tmin, tmax, s_first, s_meta, s_list, hs, wc, rel);
         else
                 trace_one_exact<COUNT>(tr, root, o, d, tmin, tmax, s_first, s_meta, s_list, hs, wc);
 }
@@ -1383,8 +1400,9 @@ k_trace_camera(const __grid_constant__ TraceParams p)
                         } else {
                                 gen_ray(p.cam, px, py, s, o, d);
                         }
-                        trace_one<MODE == OUT_COUNT>(p.tree, p.root, o, d, p.cam.tmin, p.cam.tmax, s_first, s_meta,
-                                                     s_list, hs, wc);
+                        // (every camera launch carries the origin-relative plane table, see launch_trace_camera)
+                        trace_one<MODE == OUT_COUNT, MODE != OUT_COUNT>(p.tree, p.root, o, d, p.cam.tmin, p.cam.tmax, s_first,
+                                                                        s_meta, s_list, hs, wc, p.tabrel);
                 }
                 const unsigned long long pix = (unsigned long long)ry * W + (px - p.x0);
                 if (MODE == OUT_HIT48) {
@@ -1486,6 +1504,69 @@ k_trace_camera(const __grid_constant__ TraceParams p)
                 }
                 __syncwarp();
         }
+}
+
+// Origin-relative axis tables of a camera launch: rel[i] = tab[i] - eye[axis] for the three axes (contiguous:
+// n4 float4 entries per axis).  fsub = the reference's (plane - o), rounded once, exactly as the expansion would.
+__global__ void __launch_bounds__(256) k_tab_rel(const float4* __restrict__ tab, uint32_t n4, float ex, float ey, float ez,
+                                                 float4* __restrict__ rel)
+{
+        const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= 3u * n4)
+                return;
+        const float e = (i < n4) ? ex : (i < 2u * n4) ? ey : ez;
+        const float4 t = tab[i];
+        rel[i] = make_float4(fsub(t.x, e), fsub(t.y, e), fsub(t.z, e), fsub(t.w, e));
+}
+
+// The table for (tree contents, eye), cached per handle: a frame loop with a fixed camera builds it once.  Slots are
+// reused round-robin by launch number (launches of consecutive frames may overlap on two streams); a launch on
+// another stream than the one that filled the slot waits for the fill through the slot's event.
+static int tab_rel_for_launch(const vrt_tree* t, const float eye[3], cudaStream_t ls, const float4* out[3])
+{
+        const uint64_t n4 = t->hdr.axis_tab_stride / 2;  // float4 entries per axis
+        const uint64_t slot_bytes = 3 * n4 * sizeof(float4);
+        if (t->tabrel_buf.cap < vrt_tree::kRelSlots * slot_bytes || t->tabrel_blob != t->blob ||
+            t->tabrel_build != t->n_builds) {
+                VRT_CUDA(cudaDeviceSynchronize());  // (first launch after a build: nothing may still read the old tables)
+                if (t->tabrel_buf.reserve(vrt_tree::kRelSlots * slot_bytes))
+                        return VRT_ERR_NOMEM;
+                for (auto& s : t->tabrel_slot)
+                        s.valid = false;
+                t->tabrel_blob = t->blob;
+                t->tabrel_build = t->n_builds;
+        }
+        int k = -1;
+        for (int i = 0; i < vrt_tree::kRelSlots; ++i)
+                if (t->tabrel_slot[i].valid && memcmp(t->tabrel_slot[i].eye, eye, 12) == 0)
+                        k = i;
+        if (k < 0) {
+                k = (int)(t->n_trace_launches % vrt_tree::kRelSlots);
+                auto& s = t->tabrel_slot[k];
+                if (!s.ev)
+                        VRT_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+                float4* dst = reinterpret_cast<float4*>(static_cast<char*>(t->tabrel_buf.p) + k * slot_bytes);
+                k_tab_rel<<<(unsigned)((3 * n4 + 255) / 256), 256, 0, ls>>>(t->dev.tab4[0], (uint32_t)n4, eye[0], eye[1], eye[2], dst);
+                count_launch();
+                VRT_CUDA(cudaGetLastError());
+                VRT_CUDA(cudaEventRecord(s.ev, ls));
+                memcpy(s.eye, eye, 12);
+                s.valid = true;
+                s.done = false;
+                s.stream = ls;
+        }
+        auto& s = t->tabrel_slot[k];
+        if (!s.done) {
+                if (cudaEventQuery(s.ev) == cudaSuccess)
+                        s.done = true;
+                else if (s.stream != ls)
+                        VRT_CUDA(cudaStreamWaitEvent(ls, s.ev, 0));
+                cudaGetLastError();  // (cudaErrorNotReady is not an error here)
+        }
+        const float4* base = reinterpret_cast<const float4*>(static_cast<const char*>(t->tabrel_buf.p) + k * slot_bytes);
+        for (int a = 0; a < 3; ++a)
+                out[a] = base + a * n4;
+        return VRT_OK;
 }
 
 // The film encodings of the camera kernels applied to a float film that already exists (vrt_film_encode).
@@ -1603,8 +1684,8 @@ static void apply_l2_window(const vrt_tree* t)
 // ray kernels read the node records from them
 static int check_hull_records(const vrt_tree* t)
 {
-        if (t->hdr.num_nodes != 0 && t->dev.L >= 1 && t->dev.hull == nullptr) {
-                set_error("octree has no hull records (compute_hulls did not run)");
+        if (t->hdr.num_nodes != 0 && ((t->dev.L >= 1 && t->dev.hull == nullptr) || (t->hdr.num_tris && t->dev.tri64 == nullptr))) {
+                set_error("octree has no hull / widened-triangle records (compute_hulls did not run)");
                 return VRT_ERR_STATE;
         }
         return VRT_OK;
@@ -1762,6 +1843,11 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         int grid = persistent_grid(kern, smem);
         grid = (int)std::min<uint64_t>((uint64_t)grid, (tiles + 3) / 4);
         cudaStream_t ls = t->launch_stream ? t->launch_stream : t->stream;
+        if (mode != OUT_COUNT && t->hdr.num_nodes != 0 && t->dev.L >= 1) {
+                const int rc = tab_rel_for_launch(t, p.eye, ls, p.tabrel);
+                if (rc)
+                        return rc;
+        }
 #ifndef VRT_TILE_GLOBAL
         VRT_CUDA(cudaMemsetAsync(p.queue, 0, sizeof(uint32_t) * vrt_tree::kTileQueues, ls));
 #else
