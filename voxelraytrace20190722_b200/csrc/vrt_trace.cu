@@ -42,6 +42,10 @@ namespace vrt {
 #define VRT_EYE_ALL 0
 #endif
 constexpr int kTraceThreads = VRT_TRACE_THREADS;
+#ifndef VRT_TILE_BLOCK_LOG
+#define VRT_TILE_BLOCK_LOG 3
+#endif
+constexpr uint32_t kTileBlockLog = VRT_TILE_BLOCK_LOG;  // the tile order runs over (1 << log) x (1 << log)-tile blocks
 constexpr uint32_t kQueueBitmap = 248;  // per-SM tile queues: counters [0, 248), exhausted-queue bitmap [248, 256)
 constexpr int kMaxLevels = VRT_MAX_DEPTH;  // stack records per thread
 
@@ -1332,9 +1336,10 @@ k_trace_camera(const __grid_constant__ TraceParams p)
                         break;
                 if (lane == 0)
                         next = atomicAdd(p.queue + qv, 1u);
-                const uint32_t blk = tile >> 6;
+                const uint32_t blk = tile >> (2 * kTileBlockLog);
                 const uint32_t bly = blk / p.blocks_x, blx = blk - bly * p.blocks_x;
-                const int ty = (int)(bly * 8u + ((tile >> 3) & 7u)), tx = (int)(blx * 8u + (tile & 7u));
+                const int ty = (int)((bly << kTileBlockLog) + ((tile >> kTileBlockLog) & ((1u << kTileBlockLog) - 1u))),
+                          tx = (int)((blx << kTileBlockLog) + (tile & ((1u << kTileBlockLog) - 1u)));
                 // (tiles in the padding of the blocked order lie beyond x1 / H: all their lanes are inactive)
 #else
         uint32_t next = 0;
@@ -1803,9 +1808,10 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
 #ifndef VRT_TILE_GLOBAL
         {
                 const uint32_t tiles_x = (uint32_t)((x1 - x0 + tw - 1) / tw), tiles_y = (uint32_t)((y1 - y0 + th - 1) / th);
-                p.blocks_x = (tiles_x + 7u) / 8u;
+                constexpr uint32_t bs = 1u << kTileBlockLog;
+                p.blocks_x = (tiles_x + bs - 1u) / bs;
                 p.tiles_y = tiles_y;
-                const uint64_t padded = (uint64_t)p.blocks_x * ((tiles_y + 7u) / 8u) * 64ull;
+                const uint64_t padded = (uint64_t)p.blocks_x * ((tiles_y + bs - 1u) / bs) * (uint64_t)(bs * bs);
                 if (padded >= 0xfff00000ull) {
                         set_error("too many tiles for one launch");
                         return VRT_ERR_ARG;
