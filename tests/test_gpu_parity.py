@@ -502,6 +502,27 @@ def test_render_async_pipeline_matches_sync(case, gpu):
         assert np.array_equal(e.view(np.uint32), b.numpy().view(np.uint32))
 
 
+def test_async_frames_with_many_eyes(case, gpu):
+    """The camera kernels read the axis tables relative to the launch's eye from a per-handle cache of eight slots
+    (vrt_trace.cu tab_rel_for_launch).  Thirty pipelined frames that cycle through eleven eye positions -- hits and
+    refills of the slots interleaved, launches alternating between the two kernel streams -- must equal the
+    synchronous renders of the same cameras."""
+    torch = pytest.importorskip("torch")
+    cam10 = case["cam10"]
+    nx, ny, spp = 320, 180, 4
+    eyes = [cam10[1:4] + np.float32(0.004 * k) * np.array([1, -1, 0.5], np.float32) for k in range(11)]
+    cams = [gpu.Camera(cam10[0], e, cam10[4:7], cam10[7:10], nx, ny, spp) for e in eyes]
+    tree = case["tree"]
+    expect = [tree.render(c) for c in cams]
+    order = [(7 * i + (i // 3)) % len(cams) for i in range(30)]
+    bufs = [torch.full((ny, nx, 3), -3.0, dtype=torch.float32).pin_memory() for _ in order]
+    for k, b in zip(order, bufs):
+        tree.render_async(cams[k], b.numpy())
+    tree.sync()
+    for k, b in zip(order, bufs):
+        assert np.array_equal(expect[k].view(np.uint32), b.numpy().view(np.uint32)), k
+
+
 def test_sync_waits_for_film_copies_of_large_frames(case, gpu):
     """vrt_tree_sync() must also wait for the device->host film copies (they run on the handle's copy
     stream, the kernels on two alternating streams): with 4K films the bytes are compared immediately

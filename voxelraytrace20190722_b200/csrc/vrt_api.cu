@@ -582,8 +582,10 @@ void vrt_tree_free(vrt_tree* t)
         t->gi_steps.release();
         t->tabrel_buf.release();
         for (auto& rs : t->tabrel_slot)
-                if (rs.ev)
+                if (rs.ev) {
                         cudaEventDestroy(rs.ev);
+                        cudaEventDestroy(rs.ev_read);
+                }
         t->mat_buf.release();
         t->io_out.release();
         t->film_dev[0].release();

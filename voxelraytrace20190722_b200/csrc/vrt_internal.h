@@ -183,9 +183,12 @@ struct vrt_tree {
         struct RelSlot {
                 float eye[3] = { 0, 0, 0 };
                 bool valid = false, done = false;
-                cudaEvent_t ev = nullptr;
+                cudaEvent_t ev = nullptr, ev_read = nullptr;  // table filled / last launch that reads it enqueued
                 cudaStream_t stream = nullptr;
+                uint64_t last_use = 0;
         };
+        mutable uint64_t tabrel_clock = 0;
+        mutable int tabrel_cur = 0;
         mutable vrt::Scratch tabrel_buf;
         mutable RelSlot tabrel_slot[kRelSlots];
         mutable const void* tabrel_blob = nullptr;

@@ -1546,10 +1546,18 @@ static int tab_rel_for_launch(const vrt_tree* t, const float eye[3], cudaStream_
                 if (t->tabrel_slot[i].valid && memcmp(t->tabrel_slot[i].eye, eye, 12) == 0)
                         k = i;
         if (k < 0) {
-                k = (int)(t->n_trace_launches % vrt_tree::kRelSlots);
+                // least recently used slot; its last reader (possibly queued on the other stream) goes first
+                k = 0;
+                for (int i = 1; i < vrt_tree::kRelSlots; ++i)
+                        if (t->tabrel_slot[i].last_use < t->tabrel_slot[k].last_use)
+                                k = i;
                 auto& s = t->tabrel_slot[k];
-                if (!s.ev)
+                if (!s.ev) {
                         VRT_CUDA(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+                        VRT_CUDA(cudaEventCreateWithFlags(&s.ev_read, cudaEventDisableTiming));
+                } else if (s.valid) {
+                        VRT_CUDA(cudaStreamWaitEvent(ls, s.ev_read, 0));
+                }
                 float4* dst = reinterpret_cast<float4*>(static_cast<char*>(t->tabrel_buf.p) + k * slot_bytes);
                 k_tab_rel<<<(unsigned)((3 * n4 + 255) / 256), 256, 0, ls>>>(t->dev.tab4[0], (uint32_t)n4, eye[0], eye[1], eye[2], dst);
                 count_launch();
@@ -1568,6 +1576,8 @@ static int tab_rel_for_launch(const vrt_tree* t, const float eye[3], cudaStream_
                         VRT_CUDA(cudaStreamWaitEvent(ls, s.ev, 0));
                 cudaGetLastError();  // (cudaErrorNotReady is not an error here)
         }
+        s.last_use = ++t->tabrel_clock;
+        t->tabrel_cur = k;
         const float4* base = reinterpret_cast<const float4*>(static_cast<const char*>(t->tabrel_buf.p) + k * slot_bytes);
         for (int a = 0; a < 3; ++a)
                 out[a] = base + a * n4;
@@ -1849,7 +1859,8 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         int grid = persistent_grid(kern, smem);
         grid = (int)std::min<uint64_t>((uint64_t)grid, (tiles + 3) / 4);
         cudaStream_t ls = t->launch_stream ? t->launch_stream : t->stream;
-        if (mode != OUT_COUNT && t->hdr.num_nodes != 0 && t->dev.L >= 1) {
+        const bool use_rel = mode != OUT_COUNT && t->hdr.num_nodes != 0 && t->dev.L >= 1;
+        if (use_rel) {
                 const int rc = tab_rel_for_launch(t, p.eye, ls, p.tabrel);
                 if (rc)
                         return rc;
@@ -1865,6 +1876,8 @@ int launch_trace_camera(const vrt_tree* t, const vrt_camera* cam, const vrt_shad
         VRT_CUDA(cudaLaunchKernel(kern, dim3(grid), dim3(kTraceThreads), args, smem, ls));
         count_launch();
         VRT_CUDA(cudaEventRecord(t->ring1[slot], ls));
+        if (use_rel)  // (a later launch that re-fills this table slot waits for this reader)
+                VRT_CUDA(cudaEventRecord(t->tabrel_slot[t->tabrel_cur].ev_read, ls));
         t->n_trace_launches++;
         return VRT_OK;
 }
