@@ -91,7 +91,7 @@ struct TreeDev {
         uint32_t rec_mask;  // 0xffff: hull tests on; 0x00ff: the tight flags are cleared from every record read (off)
         // triangles widened for the leaf test (round 2): per triangle ten doubles v0, e1 = v1 - v0, e2 = v2 - v0, pad --
         // the first operations of intersect_triangle3 (raytri.cc:205-207) on the widened vertices, done once per
-        // build instead of once per (ray, triangle) test.  Null: the leaf test widens tri4 itself.
+        // build instead of once per (ray, triangle) test.  Every tree with triangles has them (compute_hulls).
         const double* tri64;
         // materials (vrt_set_materials), all null when unset: per-vertex texture coordinates, material id per
         // triangle, per material (kd.xyz, texture id or -1 as int bits), per texture (byte offset, w, h, channels)
