@@ -10,13 +10,19 @@ final camera (main.cc:112-115), 3840x2160 film, gen_rays4 -> 33,177,600 primary 
 per step.  A step = one frame = one launch of the persistent ray kernel per GPU.
 
   value     Mrays/s with everything resident in HBM: per step every rank traces its 8-row
-            bands and writes 16-byte hit records + the shaded film bands to HBM; N>1: the film
-            bands are gathered to rank 0 (NCCL, double-buffered under the next frame's kernel)
-            and re-ordered into the frame inside the timed region
+            bands and writes 16-byte hit records to HBM and the shaded pixels straight into
+            rank 0's frame (peer stores over NVLink inside the ray kernel; --assemble gather:
+            NCCL gather + re-order copy instead), all inside the timed region
   e2e       Mrays/s through the host-buffer C-ABI call (vrt_render_camera_async; N>1:
-            vrt_render_bands_async on every rank): camera in, shaded float film copied back to
+            vrt_render_bands_async on every rank): camera in, shaded film copied back to
             pinned host memory inside the timed region (N>1: one host frame shared by the ranks,
-            every rank DMA-copies its own bands)
+            every rank DMA-copies its own bands).  The film travels as main.cc writes it
+            (stbi_write_hdr's RGBE pixels, encoded in the ray kernel); e2e_f32 is the same
+            loop with the float film (12 B/pixel), which the host's PCIe ingest caps at 8 GPUs
+  config5   BASELINE.json configs[4] in the same run: 2048^3, 7680x4320, orbit, primary +
+            shadow rays (a few frames; the full line: --workload atrium2048_8k_orbit_shadow)
+  parity    the bench's CPU sample (640x360x4 rays) and the leaf sets of the 1024^3 octrees,
+            compared with the unmodified reference inside the run
   roofline  algorithmic bytes per ray (8*N_int + 8*N_leaf + 40*N_tri + 16,
             N_* counted on the same frame) * rays / kernel time, against the measured HBM
             copy bandwidth of MEASURED_PEAKS.json
@@ -270,6 +276,102 @@ def workload_config(wl, ntris, gpus):
             "l2": "inputs larger than L2: octree blob > 126 MB and every step writes 16 B/ray of hit records + 12 B/pixel of film"}
 
 
+def make_cams(capi, wl, cam10, nx, ny, spp):
+    """The workload's cameras: one fixed camera, or the frames of an orbit (EXTRAS)."""
+    extra = EXTRAS.get(wl, {})
+    if not extra.get("orbit"):
+        return [capi.Camera(cam10[0], cam10[1:4], cam10[4:7], cam10[7:10], nx, ny, spp)]
+    n_orb, c, r, h = extra["orbit"], np.asarray(extra["orbit_c"]), extra["orbit_r"], extra["orbit_h"]
+    cams = []
+    for k in range(n_orb):
+        a = 2 * np.pi * k / n_orb
+        eye = c + np.array([r * np.cos(a), h, r * np.sin(a)])
+        cams.append(capi.Camera(cam10[0], eye.astype(np.float32), c.astype(np.float32), (0, 1, 0), nx, ny, spp))
+    return cams
+
+
+def config5_block(args, capi, vdist, torch, world, rank, dev, tri, nrm):
+    """BASELINE.json configs[4] inside the default run (every rank calls this): the same triangles voxelized at 2048^3,
+    7680x4320 x 4 spp, camera orbit, primary rays + one shadow ray per hit, bands over all GPUs, frames assembled on
+    rank 0 by the kernel's own stores.  A few frames only (the full line: --workload atrium2048_8k_orbit_shadow)."""
+    wl = "atrium2048_8k_orbit_shadow"
+    _, _, depth, cam10, nx, ny, spp = WORKLOADS[wl]
+    shadow_eps = EXTRAS[wl]["shadow_eps"]
+    if world > 1:
+        import torch.distributed as td
+    t0 = time.perf_counter()
+    tree = capi.Octree.build(tri, nrm, depth) if rank == 0 else None
+    build_s = time.perf_counter() - t0
+    if world > 1:
+        tree = vdist.replicate_octree(tree, dev)
+    cams = make_cams(capi, wl, cam10, nx, ny, spp)
+    rows = vdist.max_band_rows(ny, world)
+    hits = [torch.empty((rows, nx * spp * 4), dtype=torch.int32, device=dev) for _ in range(2)]
+    pf = vdist.PeerFrame(ny, nx, dev)
+    stream = torch.cuda.current_stream(dev)
+    S = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+
+    def step(i):
+        with torch.cuda.stream(S[i & 1]):
+            tree.set_stream(S[i & 1].cuda_stream)
+            tree.frame_bands_dev(cams[i % len(cams)], hits[i & 1].data_ptr(), pf.ptr(i & 1), vdist.BAND_H, rank, world,
+                                 full_frame=True, shadow_eps=shadow_eps)
+
+    def sync_all():
+        stream.wait_stream(S[0])
+        stream.wait_stream(S[1])
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            td.barrier()
+            torch.cuda.synchronize(dev)
+
+    steps = max(2, min(args.steps, 8))
+    for i in range(3):
+        step(i)
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    S[0].wait_stream(stream)
+    S[1].wait_stream(stream)
+    for i in range(steps):
+        step(i)
+    stream.wait_stream(S[0])
+    stream.wait_stream(S[1])
+    e1.record(stream)
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+    ms = float(t[0])
+    # the frame assembled last (single-stream loop: step `steps - 1` again) against rank 0 alone
+    tree.set_stream(stream.cuda_stream)
+    tree.frame_bands_dev(cams[(steps - 1) % len(cams)], hits[0].data_ptr(), pf.ptr(0), vdist.BAND_H, rank, world,
+                         full_frame=True, shadow_eps=shadow_eps)
+    sync_all()
+    ok = None
+    if rank == 0:
+        tree.set_stream(0)
+        alone = torch.empty((ny, nx, 3), dtype=torch.float32, device=dev)
+        tree.render_dev(cams[(steps - 1) % len(cams)], alone.data_ptr(), shadow_eps=shadow_eps)
+        tree.sync()
+        ok = bool(torch.equal(pf.frame(0).view(torch.int32), alone.view(torch.int32)))
+        del alone
+    info = tree.info()
+    sync_all()
+    if rank != 0:
+        pf.close()  # (the peers unmap before rank 0 frees)
+    sync_all()
+    if rank == 0:
+        pf.close()
+    del hits
+    tree.close()
+    return {"workload": wl, "config": "BASELINE.json configs[4]: atrium at 2048^3, 7680x4320, gen_rays4, 64-frame orbit, "
+                                      "primary + one shadow ray per hit (traced in the same launch)",
+            "steps": steps, "ms_per_frame": ms, "primary_mrays_per_s": nx * ny * spp / (ms * 1e-3) / 1e6,
+            "n_gpu_frame_equals_1_gpu_frame_bytewise": ok, "octree_nodes": info["num_nodes"],
+            "octree_device_bytes": info["device_bytes"], "build_e2e_s": build_s if rank == 0 else None}
+
+
 # ----------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------
@@ -325,15 +427,7 @@ def run_ours(args):
     info = tree.info()
     extra = EXTRAS.get(args.workload, {})
     shadow_eps = extra.get("shadow_eps")
-    if extra.get("orbit"):
-        n_orb, c, r, h = extra["orbit"], np.asarray(extra["orbit_c"]), extra["orbit_r"], extra["orbit_h"]
-        cams = []
-        for k in range(n_orb):
-            a = 2 * np.pi * k / n_orb
-            eye = c + np.array([r * np.cos(a), h, r * np.sin(a)])
-            cams.append(capi.Camera(cam10[0], eye.astype(np.float32), c.astype(np.float32), (0, 1, 0), nx, ny, spp))
-    else:
-        cams = [capi.Camera(cam10[0], cam10[1:4], cam10[4:7], cam10[7:10], nx, ny, spp)]
+    cams = make_cams(capi, args.workload, cam10, nx, ny, spp)
     cam = cams[0]
     stream = torch.cuda.current_stream(dev)
     tree.set_stream(stream.cuda_stream)
@@ -559,6 +653,14 @@ def run_ours(args):
         frame_check = bool(torch.equal(got.view(torch.int32), ref_film.view(torch.int32)))
         del ref_film
 
+    # ---- BASELINE config 5 in the same run (default workload only; all ranks) ----
+    cfg5 = None
+    if args.workload == DEFAULT_WORKLOAD and not args.no_config5 and not OBJ_SCENE:
+        try:
+            cfg5 = config5_block(args, capi, vdist, torch, world, rank, dev, tri, nrm)
+        except Exception as ex:  # noqa: BLE001 -- reported in the line, the headline numbers stand
+            cfg5 = {"workload": "atrium2048_8k_orbit_shadow", "error": repr(ex)}
+
     if rank != 0:
         if world > 1:
             td.destroy_process_group()
@@ -729,6 +831,7 @@ def run_ours(args):
         "parity": parity,
         "build": build_out,
         "build_soup": build_soup,
+        "config5": cfg5,
         "gi": gi_out,
         "octree": {"device_bytes": info["device_bytes"], "nodes": info["num_nodes"], "leaves": info["num_leaves"]},
         "frame_check": {"n_gpu_frame_equals_1_gpu_frame_bytewise": frame_check,
@@ -757,6 +860,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gi", action="store_true", help="skip the GI rows (splat/filter/cone-trace film)")
     ap.add_argument("--no-build-soup", action="store_true", help="skip the 2 M-triangle soup build (BASELINE config 4)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the BASELINE config 5 block (2048^3, 8K orbit + shadow rays)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
