@@ -148,3 +148,25 @@ def test_child_flag_bytes_pack_to_mask():
             v = (x | noise) & 0x0101010101010101
             got = ((v * 0x0102040810204080) & 0xFFFFFFFFFFFFFFFF) >> 56
             assert got == m, (m, hex(noise), got)
+
+
+def test_hdr_file_host_only():
+    """vrt_hdr_file / vrt_film_pixel_bytes are host code: they work without a device.  Header text, flat scanlines for
+    narrow films, argument errors."""
+    from voxelraytrace20190722_b200 import capi
+    capi.load()
+    assert [capi.film_pixel_bytes(f) for f in ("f32", "rgbe", "rgb8")] == [12, 4, 3]
+    with pytest.raises(capi.VrtError):
+        capi.film_pixel_bytes(9)
+    rgbe = (np.arange(5 * 3 * 4) % 256).astype(np.uint8).reshape(3, 5, 4)
+    f = capi.hdr_file(rgbe)
+    head = b"#?RADIANCE\n# Written by stb_image_write.h\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=          1.0000000000000\n\n-Y 3 +X 5\n"
+    assert f == head + rgbe.tobytes()  # nx < 8: the pixels as they are
+    wide = np.zeros((2, 40, 4), np.uint8)
+    wide[:, :, 3] = 128
+    g = capi.hdr_file(wide)
+    # per scanline: marker 2 2 0 40, then per component one run of 40 (length byte 128 + 40, value)
+    line = bytes([2, 2, 0, 40]) + bytes([168, 0]) * 3 + bytes([168, 128])
+    assert g.endswith(line + line) and len(g) == len(g[:g.index(b"+X 40\n") + 6]) + 2 * len(line)
+    L = capi.load()
+    assert L.vrt_hdr_file(None, 4, 4, None, 0) < 0 and L.vrt_hdr_file(rgbe.ctypes.data, 0, 4, None, 0) < 0

@@ -80,6 +80,51 @@ def test_banded_gather_world2(ny):
     assert ok.value == 1
 
 
+def _worker_shared_bytes(rank, world, port, ny, nx, fmt, ok):
+    """The shared host frame in the encoded film formats (4 / 3 bytes per pixel): frame size, page-aligned frame
+    stride and the band rows of every rank."""
+    import torch.distributed as td
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from voxelraytrace20190722_b200 import dist as vdist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    bpp = {"rgbe": 4, "rgb8": 3}[fmt]
+    shf = vdist.SharedHostFrame(ny, nx, nbuf=2, pin=False, fmt=fmt)
+    for f in range(2):
+        fr = shf.frame(f)
+        assert fr.dtype == np.uint8 and fr.shape == (ny, nx, bpp)
+        k = rank
+        while k * vdist.BAND_H < ny:
+            for y in range(k * vdist.BAND_H, min((k + 1) * vdist.BAND_H, ny)):
+                fr[y, :, :] = ((y * 7 + np.arange(nx)[:, None] * 3 + np.arange(bpp)[None, :] + f) % 251).astype(np.uint8)
+            k += world
+    td.barrier()
+    if rank == 0:
+        y, x, c = np.meshgrid(np.arange(ny), np.arange(nx), np.arange(bpp), indexing="ij")
+        good = all(np.array_equal(shf.frame(f), ((y * 7 + x * 3 + c + f) % 251).astype(np.uint8)) for f in range(2))
+        good = good and shf.frame_bytes == ny * nx * bpp and (shf.ptr(1) - shf.ptr(0)) % 4096 == 0 \
+            and shf.ptr(1) - shf.ptr(0) >= shf.frame_bytes
+        ok.value = int(good)
+    td.barrier()
+    shf.close()
+    td.destroy_process_group()
+
+
+@pytest.mark.parametrize("fmt", ["rgbe", "rgb8"])
+def test_shared_host_frame_encoded_formats_world2(fmt):
+    ctx = mp.get_context("spawn")
+    ok = ctx.Value("i", 0)
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_shared_bytes, args=(r, 2, port, 45, 24, fmt, ok)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert ok.value == 1
+
+
 def _worker_shared(rank, world, port, ny, nx, ok):
     import torch.distributed as td
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
