@@ -208,7 +208,7 @@ int gi_step_table(const vrt_tree* t, float res, const float4** d_steps)
         }
         if (!on)
                 return VRT_OK;
-        if (t->gi_steps.reserve((size_t)(kGiMaxSteps + 1) * sizeof(float4)))
+        if (t->gi_steps.reserve((size_t)(kGiMaxSteps + 2) * sizeof(float4)))  // (+1: the cone loop reads one entry ahead)
                 return VRT_ERR_NOMEM;
         GiRoot6 r;
         for (int k = 0; k < 6; ++k)

@@ -356,9 +356,13 @@ __device__ __forceinline__ void gi_cone_one(const TreeDev& tr, const float root[
                 const float4 hdr = __ldg(steps);
                 const int n = __float_as_int(hdr.x);
                 int k = 0;
+                // (the entry of step k + 1 is requested before step k is sampled: entry 1 + n exists, the table has
+                // kGiMaxSteps + 2 entries)
+                float4 st = __ldg(steps + 1);
                 for (; k < n && opacity < 1.f; ++k) {
-                        const float4 st = __ldg(steps + 1 + k);
-                        gi_cone_sample(tr, sc, stride, gp, o, d, coeff, lobes, st.x, __float_as_int(st.z), st.y, opacity, diffuse);
+                        const float4 cur = st;
+                        st = __ldg(steps + 2 + k);
+                        gi_cone_sample(tr, sc, stride, gp, o, d, coeff, lobes, cur.x, __float_as_int(cur.z), cur.y, opacity, diffuse);
                 }
                 rest = (k == n) && (__float_as_int(hdr.y) != 0);
                 dist = hdr.z;
