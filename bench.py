@@ -299,9 +299,7 @@ def config5_block(args, capi, vdist, torch, world, rank, dev, tri, nrm):
     shadow_eps = EXTRAS[wl]["shadow_eps"]
     if world > 1:
         import torch.distributed as td
-    t0 = time.perf_counter()
     tree = capi.Octree.build(tri, nrm, depth) if rank == 0 else None
-    build_s = time.perf_counter() - t0
     if world > 1:
         tree = vdist.replicate_octree(tree, dev)
     cams = make_cams(capi, wl, cam10, nx, ny, spp)
@@ -369,7 +367,7 @@ def config5_block(args, capi, vdist, torch, world, rank, dev, tri, nrm):
                                       "primary + one shadow ray per hit (traced in the same launch)",
             "steps": steps, "ms_per_frame": ms, "primary_mrays_per_s": nx * ny * spp / (ms * 1e-3) / 1e6,
             "n_gpu_frame_equals_1_gpu_frame_bytewise": ok, "octree_nodes": info["num_nodes"],
-            "octree_device_bytes": info["device_bytes"], "build_e2e_s": build_s if rank == 0 else None}
+            "octree_device_bytes": info["device_bytes"]}
 
 
 # ----------------------------------------------------------------------------
