@@ -170,3 +170,34 @@ def test_hdr_file_host_only():
     assert g.endswith(line + line) and len(g) == len(g[:g.index(b"+X 40\n") + 6]) + 2 * len(line)
     L = capi.load()
     assert L.vrt_hdr_file(None, 4, 4, None, 0) < 0 and L.vrt_hdr_file(rgbe.ctypes.data, 0, 4, None, 0) < 0
+
+
+@pytest.mark.parametrize("w,h,spp", [(3840, 2160, 4), (120, 70, 4), (136, 72, 1), (37, 5, 1), (7680, 270, 4), (8, 4, 1)])
+def test_tile_order_covers_every_tile_once(w, h, spp):
+    """Host-side restatement of the camera kernels' tile order (vrt_trace.cu: 8x8-tile blocks, one contiguous range
+    of the padded sequence per SM queue): every tile of the film appears exactly once, padding tiles lie outside
+    the film, and the per-queue ranges tile the padded sequence."""
+    tw, th = (4, 2) if spp == 4 else (8, 4)
+    tiles_x, tiles_y = -(-w // tw), -(-h // th)
+    B = 3
+    bs = 1 << B
+    blocks_x, blocks_y = -(-tiles_x // bs), -(-tiles_y // bs)
+    padded = blocks_x * blocks_y * bs * bs
+    q = np.arange(padded, dtype=np.int64)
+    blk = q >> (2 * B)
+    bly, blx = blk // blocks_x, blk % blocks_x
+    ty = (bly << B) + ((q >> B) & (bs - 1))
+    tx = (blx << B) + (q & (bs - 1))
+    inside = (tx < tiles_x) & (ty < tiles_y)
+    assert inside.sum() == tiles_x * tiles_y
+    assert len(np.unique(ty[inside] * tiles_x + tx[inside])) == tiles_x * tiles_y
+    # a padding tile has no active lane: its first pixel is already outside the film
+    assert np.all((tx[~inside] * tw >= w) | (ty[~inside] * th >= h))
+    for nq in (148, 132, 1):
+        chunk = -(-padded // nq)
+        covered = np.zeros(padded, bool)
+        for v in range(nq):
+            n = np.arange(chunk)
+            t = v * chunk + n
+            covered[t[t < padded]] = True
+        assert covered.all() and chunk * nq >= padded
